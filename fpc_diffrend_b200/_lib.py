@@ -1,0 +1,85 @@
+"""ctypes loader for libfpc_b200.so — the C-ABI declared in include/fpc_b200.h.
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libfpc_b200.so')
+HEADER_PATH = os.path.join(_HERE, '..', 'include', 'fpc_b200.h')
+
+_lib = None
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+_F = _c.c_float
+_Z = _c.c_size_t
+_L = _c.c_longlong
+
+# name -> (restype, argtypes); kept in the order of include/fpc_b200.h
+SIGNATURES = {
+    'fpc_abi_version': (_I, []),
+    'fpc_last_error': (_c.c_char_p, []),
+    'fpc_check_device': (_I, []),
+    'fpc_rasterize_scratch_bytes': (_Z, [_I, _I, _I, _I]),
+    'fpc_rasterize_fwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    'fpc_rasterize_bwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    'fpc_interpolate_fwd': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
+    'fpc_interpolate_bwd': (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    'fpc_texture_linear_fwd': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
+    'fpc_texture_linear_bwd': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'fpc_topology_scratch_bytes': (_Z, [_I]),
+    'fpc_topology_build': (_I, [_P, _I, _I, _P, _P, _Z, _P]),
+    'fpc_antialias_fwd': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'fpc_antialias_bwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'fpc_blend_fwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    'fpc_blend_bwd_scratch_bytes': (_Z, [_I, _I, _I]),
+    'fpc_blend_bwd': (_I, [_P, _P, _I, _I, _I, _P, _P, _Z, _P]),
+    'fpc_pose_mvp_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    'fpc_pose_mvp_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    'fpc_project_fwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    'fpc_project_bwd_scratch_bytes': (_Z, [_I, _I, _I]),
+    'fpc_project_bwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    'fpc_image_loss_scratch_bytes': (_Z, [_I, _I, _I, _I]),
+    'fpc_image_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _Z, _P]),
+    'fpc_adam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P]),
+    'fpc_adam_advance': (_I, [_P, _P]),
+    'fpc_quat_renorm': (_I, [_P, _I, _I, _P]),
+}
+
+
+def header_symbols():
+    """Function names declared in include/fpc_b200.h (used by the CPU tests to check the exports)."""
+    with open(HEADER_PATH) as f:
+        src = f.read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(fpc_[a-z0-9_]+)\s*\(', src)))
+
+
+def load():
+    """Load the shared library (no GPU needed for loading); raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'libfpc_b200.so not found at %s — build it with `python -m fpc_diffrend_b200.build`; '
+                'there is no CPU or PyTorch fallback for the fit hot path' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError('fpc_b200: %s' % load().fpc_last_error().decode())
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,76 @@
+// Shared helpers for the sm_100a kernels of the fit hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fpc_b200.h"
+
+// ---- error plumbing (C-ABI never throws; see include/fpc_b200.h) -------------------------------------
+void fpc_set_error(const char* fmt, ...);
+
+#define FPC_CHECK_ARG(cond, ...)                                   \
+    do {                                                           \
+        if (!(cond)) { fpc_set_error(__VA_ARGS__); return FPC_ERR_INVALID_ARGUMENT; } \
+    } while (0)
+
+#define FPC_CUDA(call)                                             \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) {                                  \
+            fpc_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return FPC_ERR_CUDA;                                   \
+        }                                                          \
+    } while (0)
+
+#define FPC_LAUNCH_CHECK()                                         \
+    do {                                                           \
+        cudaError_t e__ = cudaGetLastError();                      \
+        if (e__ != cudaSuccess) {                                  \
+            fpc_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return FPC_ERR_CUDA;                                   \
+        }                                                          \
+    } while (0)
+
+static inline int fpc_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- exact fp32 ops: never contracted to FMA, so coverage / depth decisions are bit-identical to the
+//      CPU golden model compiled with -ffp-contract=off (DESIGN.md "Rasterizer semantics") ----------------
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+
+// rast.w holds float(tri_id + 1); ids < 2^24 are exact in fp32
+__device__ __forceinline__ int rast_tri(float w) { return (int)w - 1; }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Shading formula of SURVEY App. A.1 (perspective-correct barycentrics from clip-space vertices).
+struct Shade { float u, v, zw, iw; };
+
+__device__ __forceinline__ Shade shade_pixel(const float4& p0, const float4& p1, const float4& p2,
+                                             float fx, float fy)
+{
+    float p0x = xsub(p0.x, xmul(fx, p0.w)), p0y = xsub(p0.y, xmul(fy, p0.w));
+    float p1x = xsub(p1.x, xmul(fx, p1.w)), p1y = xsub(p1.y, xmul(fy, p1.w));
+    float p2x = xsub(p2.x, xmul(fx, p2.w)), p2y = xsub(p2.y, xmul(fy, p2.w));
+    float a0 = xsub(xmul(p1x, p2y), xmul(p1y, p2x));
+    float a1 = xsub(xmul(p2x, p0y), xmul(p2y, p0x));
+    float a2 = xsub(xmul(p0x, p1y), xmul(p0y, p1x));
+    float at = xadd(xadd(a0, a1), a2);
+    float iw = xdiv(1.0f, at);
+    Shade s;
+    s.iw = iw;
+    s.u = xmul(a0, iw);
+    s.v = xmul(a1, iw);
+    float z = xadd(xadd(xmul(p0.z, a0), xmul(p1.z, a1)), xmul(p2.z, a2));
+    float w = xadd(xadd(xmul(p0.w, a0), xmul(p1.w, a1)), xmul(p2.w, a2));
+    s.zw = xdiv(z, w);
+    return s;
+}
+
+// pixel centre in NDC: fx = (2/W) * px + (1/W - 1), evaluated as separate mul/add
+__device__ __forceinline__ float pixel_ndc(int p, float scale, float offset) { return xadd(xmul(scale, (float)p), offset); }

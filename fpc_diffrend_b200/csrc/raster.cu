@@ -1,0 +1,405 @@
+// Tile-binned fixed-point software rasterizer for sm_100a  (replaces dr.rasterize, reference fit.py:151).
+//
+// Pipeline per call (no host read-back, all buffers caller-owned):
+//   k_setup : one thread per (instance, triangle): snap to 1/16 px, bbox -> 64x64-px bins touched.
+//             small triangles (<= 2x2 bins) bump per-bin counters, large ones go to a per-instance list.
+//   k_scan  : per instance exclusive scan of the bin counters (bin list offsets; capacity 4T per instance).
+//   k_fill  : one thread per (instance, triangle): append the triangle to its bins' lists.
+//   k_fine  : one CTA per (bin, instance): a 64x64 array of 64-bit (depth,id) keys lives in shared memory;
+//             threads stage one triangle each from the bin list, walk its bbox and atomicMin the key of every
+//             covered pixel; after a barrier the CTA shades its 4096 pixels straight from the keys and
+//             writes rast / rast_db — the key buffer never touches HBM.
+// Semantics (bit-identical to oracle/golden.c): DESIGN.md "Rasterizer semantics".
+#include "common.cuh"
+
+namespace {
+
+constexpr int BIN = 64;              // bin edge in pixels
+constexpr int BIN_LOG2 = 6;
+constexpr int FINE_THREADS = 256;
+constexpr float SNAP_LIMIT = 16777216.0f;
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+struct RasterParams {
+    const float* pos;
+    const int32_t* tri;
+    int N, V, T, H, W;
+    int BW, BH, NB;
+    float xs, xo, ys, yo;            // pixel -> NDC
+    float sxs, sys;                  // NDC -> 1/16 px:  8*W, 8*H
+    int* bin_count;                  // [N*NB]
+    int* bin_cursor;                 // [N*NB]
+    int* large_count;                // [N]
+    int* bin_offset;                 // [N*NB]
+    int* tri_info;                   // [N*T]
+    int* pairs;                      // [N*4T]
+    int* large_list;                 // [N*T]
+};
+
+struct SnappedTri {
+    int x0, y0, x1, y1, x2, y2;      // 1/16 px, oriented to positive area
+    int pxa, pxb, pya, pyb;          // candidate pixel range clamped to the image
+};
+
+__device__ __forceinline__ bool snap_vertex(const float4& p, float sxs, float sys, int& sx, int& sy)
+{
+    if (!(p.w > 0.f)) return false;
+    float rw = xdiv(1.0f, p.w);
+    float xf = xadd(xmul(xmul(p.x, rw), sxs), sxs);
+    float yf = xadd(xmul(xmul(p.y, rw), sys), sys);
+    if (!(fabsf(xf) < SNAP_LIMIT) || !(fabsf(yf) < SNAP_LIMIT)) return false;
+    sx = __float2int_rn(xf);
+    sy = __float2int_rn(yf);
+    return true;
+}
+
+// Returns false when the triangle produces no fragments at all.
+__device__ __forceinline__ bool setup_triangle(const float4& p0, const float4& p1, const float4& p2,
+                                               const RasterParams& rp, SnappedTri& s)
+{
+    if (!snap_vertex(p0, rp.sxs, rp.sys, s.x0, s.y0) || !snap_vertex(p1, rp.sxs, rp.sys, s.x1, s.y1) ||
+        !snap_vertex(p2, rp.sxs, rp.sys, s.x2, s.y2))
+        return false;
+    long long area = (long long)(s.x1 - s.x0) * (s.y2 - s.y0) - (long long)(s.x2 - s.x0) * (s.y1 - s.y0);
+    if (area == 0) return false;
+    if (area < 0) { int tx = s.x1, ty = s.y1; s.x1 = s.x2; s.y1 = s.y2; s.x2 = tx; s.y2 = ty; }
+    int minx = min(s.x0, min(s.x1, s.x2)), maxx = max(s.x0, max(s.x1, s.x2));
+    int miny = min(s.y0, min(s.y1, s.y2)), maxy = max(s.y0, max(s.y1, s.y2));
+    s.pxa = max((minx - 8 + 15) >> 4, 0);
+    s.pxb = min((maxx - 8) >> 4, rp.W - 1);
+    s.pya = max((miny - 8 + 15) >> 4, 0);
+    s.pyb = min((maxy - 8) >> 4, rp.H - 1);
+    return s.pxa <= s.pxb && s.pya <= s.pyb;
+}
+
+__device__ __forceinline__ bool load_triangle(const RasterParams& rp, int n, int t, float4& p0, float4& p1, float4& p2)
+{
+    int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+    if ((unsigned)i0 >= (unsigned)rp.V || (unsigned)i1 >= (unsigned)rp.V || (unsigned)i2 >= (unsigned)rp.V) return false;
+    const float* P = rp.pos + (size_t)n * rp.V * 4;
+    p0 = ldg4(P + 4 * (size_t)i0);
+    p1 = ldg4(P + 4 * (size_t)i1);
+    p2 = ldg4(P + 4 * (size_t)i2);
+    return true;
+}
+
+// tri_info: bits 0..9 bx0, 10..19 by0, 20 (nbx-1), 21 (nby-1), 22..23 class (0 none, 1 small, 2 large)
+__global__ void __launch_bounds__(256) k_setup(RasterParams rp)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)rp.N * rp.T) return;
+    int n = (int)(gid / rp.T), t = (int)(gid - (long long)n * rp.T);
+    float4 p0, p1, p2;
+    SnappedTri s;
+    int info = 0;
+    if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
+        int bx0 = s.pxa >> BIN_LOG2, bx1 = s.pxb >> BIN_LOG2, by0 = s.pya >> BIN_LOG2, by1 = s.pyb >> BIN_LOG2;
+        if (bx1 - bx0 > 1 || by1 - by0 > 1) {
+            int slot = atomicAdd(rp.large_count + n, 1);
+            rp.large_list[(size_t)n * rp.T + slot] = t;
+            info = 2 << 22;
+        } else {
+            info = bx0 | (by0 << 10) | ((bx1 - bx0) << 20) | ((by1 - by0) << 21) | (1 << 22);
+            for (int by = by0; by <= by1; by++)
+                for (int bx = bx0; bx <= bx1; bx++) atomicAdd(rp.bin_count + (size_t)n * rp.NB + by * rp.BW + bx, 1);
+        }
+    }
+    rp.tri_info[gid] = info;
+}
+
+// one CTA per instance; NB is small (256 at 1024^2, 1024 at 2048^2)
+__global__ void __launch_bounds__(256) k_scan(RasterParams rp)
+{
+    __shared__ int warp_sums[8];
+    __shared__ int carry;
+    int n = blockIdx.x;
+    const int* cnt = rp.bin_count + (size_t)n * rp.NB;
+    int* off = rp.bin_offset + (size_t)n * rp.NB;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < rp.NB; base += 256) {
+        int i = base + threadIdx.x;
+        int v = (i < rp.NB) ? cnt[i] : 0;
+        int x = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, d);
+            if ((threadIdx.x & 31) >= d) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < (threadIdx.x >> 5); w++) wbase += warp_sums[w];
+        int c = carry;
+        if (i < rp.NB) off[i] = c + wbase + x - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c + wbase + x;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill(RasterParams rp)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)rp.N * rp.T) return;
+    int info = rp.tri_info[gid];
+    if ((info >> 22) != 1) return;
+    int n = (int)(gid / rp.T), t = (int)(gid - (long long)n * rp.T);
+    int bx0 = info & 1023, by0 = (info >> 10) & 1023, nbx = (info >> 20) & 1, nby = (info >> 21) & 1;
+    for (int by = by0; by <= by0 + nby; by++)
+        for (int bx = bx0; bx <= bx0 + nbx; bx++) {
+            size_t b = (size_t)n * rp.NB + by * rp.BW + bx;
+            int slot = atomicAdd(rp.bin_cursor + b, 1);
+            rp.pairs[(size_t)n * 4 * rp.T + rp.bin_offset[b] + slot] = t;
+        }
+}
+
+__device__ __forceinline__ unsigned depth_key(float zw)
+{
+    unsigned b = __float_as_uint(zw);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+struct EdgeEval {
+    long long e0, e1, e2;            // edge functions (+ fill-rule bias) at the first pixel of the walk
+    long long ax0, ax1, ax2;         // step per +1 px in x
+    long long ay0, ay1, ay2;         // step per +1 px in y
+};
+
+__device__ __forceinline__ long long edge_bias(long long dx, long long dy)
+{
+    return (dy > 0 || (dy == 0 && dx < 0)) ? 0 : -1;
+}
+
+__device__ __forceinline__ void edge_setup(const SnappedTri& s, int px, int py, EdgeEval& e)
+{
+    long long sx = 16 * px + 8, sy = 16 * py + 8;
+    long long ex0 = s.x1 - s.x0, ey0 = s.y1 - s.y0;
+    long long ex1 = s.x2 - s.x1, ey1 = s.y2 - s.y1;
+    long long ex2 = s.x0 - s.x2, ey2 = s.y0 - s.y2;
+    e.e0 = ex0 * (sy - s.y0) - ey0 * (sx - s.x0) + edge_bias(ex0, ey0);
+    e.e1 = ex1 * (sy - s.y1) - ey1 * (sx - s.x1) + edge_bias(ex1, ey1);
+    e.e2 = ex2 * (sy - s.y2) - ey2 * (sx - s.x2) + edge_bias(ex2, ey2);
+    e.ax0 = -16 * ey0; e.ax1 = -16 * ey1; e.ax2 = -16 * ey2;
+    e.ay0 = 16 * ex0;  e.ay1 = 16 * ex1;  e.ay2 = 16 * ex2;
+}
+
+__device__ __forceinline__ void emit_fragment(unsigned long long* keys, const RasterParams& rp, const float4& p0,
+                                              const float4& p1, const float4& p2, int t, int px, int py, int lx, int ly)
+{
+    float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
+    Shade sh = shade_pixel(p0, p1, p2, fx, fy);
+    if (!(sh.zw >= -1.f && sh.zw <= 1.f)) return;
+    unsigned long long key = ((unsigned long long)depth_key(sh.zw) << 32) | (unsigned)t;
+    atomicMin(keys + ly * BIN + lx, key);
+}
+
+__global__ void __launch_bounds__(FINE_THREADS) k_fine(RasterParams rp, float* __restrict__ rast, float* __restrict__ rast_db)
+{
+    __shared__ unsigned long long keys[BIN * BIN];
+    const int bin = blockIdx.x, n = blockIdx.y;
+    const int bx = bin % rp.BW, by = bin / rp.BW;
+    const int ox = bx * BIN, oy = by * BIN;                   // bin origin in pixels
+    const int lim_x = min(ox + BIN, rp.W) - 1, lim_y = min(oy + BIN, rp.H) - 1;
+    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
+    const int nlarge = rp.large_count[n];
+
+    for (int i = threadIdx.x; i < BIN * BIN; i += FINE_THREADS) keys[i] = KEY_EMPTY;
+    __syncthreads();
+
+    // ---- small triangles: one thread per triangle of the bin list ----
+    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
+    for (int i = threadIdx.x; i < count; i += FINE_THREADS) {
+        int t = list[i];
+        float4 p0, p1, p2;
+        SnappedTri s;
+        if (!load_triangle(rp, n, t, p0, p1, p2) || !setup_triangle(p0, p1, p2, rp, s)) continue;
+        int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
+        if (xa > xb || ya > yb) continue;
+        EdgeEval e;
+        edge_setup(s, xa, ya, e);
+        for (int py = ya; py <= yb; py++) {
+            long long r0 = e.e0, r1 = e.e1, r2 = e.e2;
+            for (int px = xa; px <= xb; px++) {
+                if ((r0 | r1 | r2) >= 0) emit_fragment(keys, rp, p0, p1, p2, t, px, py, px - ox, py - oy);
+                r0 += e.ax0; r1 += e.ax1; r2 += e.ax2;
+            }
+            e.e0 += e.ay0; e.e1 += e.ay1; e.e2 += e.ay2;
+        }
+    }
+
+    // ---- large triangles: the whole CTA cooperates on each one (16 pixels per thread) ----
+    const int* llist = rp.large_list + (size_t)n * rp.T;
+    for (int i = 0; i < nlarge; i++) {
+        int t = llist[i];
+        float4 p0, p1, p2;
+        SnappedTri s;
+        if (!load_triangle(rp, n, t, p0, p1, p2) || !setup_triangle(p0, p1, p2, rp, s)) continue;
+        int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
+        if (xa > xb || ya > yb) continue;
+        EdgeEval e;
+        edge_setup(s, ox, oy, e);
+        for (int idx = threadIdx.x; idx < BIN * BIN; idx += FINE_THREADS) {
+            int lx = idx & (BIN - 1), ly = idx >> BIN_LOG2;
+            int px = ox + lx, py = oy + ly;
+            if (px < xa || px > xb || py < ya || py > yb) continue;
+            long long r0 = e.e0 + lx * e.ax0 + ly * e.ay0;
+            long long r1 = e.e1 + lx * e.ax1 + ly * e.ay1;
+            long long r2 = e.e2 + lx * e.ax2 + ly * e.ay2;
+            if ((r0 | r1 | r2) >= 0) emit_fragment(keys, rp, p0, p1, p2, t, px, py, lx, ly);
+        }
+    }
+    __syncthreads();
+
+    // ---- shade: (u, v, z/w, id+1) and the barycentric pixel differentials ----
+    const float* P = rp.pos + (size_t)n * rp.V * 4;
+    for (int idx = threadIdx.x; idx < BIN * BIN; idx += FINE_THREADS) {
+        int lx = idx & (BIN - 1), ly = idx >> BIN_LOG2;
+        int px = ox + lx, py = oy + ly;
+        if (px >= rp.W || py >= rp.H) continue;
+        size_t pi = ((size_t)n * rp.H + py) * rp.W + px;
+        unsigned long long key = keys[idx];
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f), odb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (key != KEY_EMPTY) {
+            int t = (int)(key & 0xFFFFFFFFu);
+            int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+            float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
+            float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
+            Shade sh = shade_pixel(p0, p1, p2, fx, fy);
+            out = make_float4(clamp01(sh.u), clamp01(sh.v), fminf(fmaxf(sh.zw, -1.f), 1.f), (float)(t + 1));
+            if (rast_db) {
+                float b0 = sh.u, b1 = sh.v;
+                float dfxdx = xmul(rp.xs, sh.iw), dfydy = xmul(rp.ys, sh.iw);
+                float da0dx = xsub(xmul(p2.y, p1.w), xmul(p1.y, p2.w)), da0dy = xsub(xmul(p1.x, p2.w), xmul(p2.x, p1.w));
+                float da1dx = xsub(xmul(p0.y, p2.w), xmul(p2.y, p0.w)), da1dy = xsub(xmul(p2.x, p0.w), xmul(p0.x, p2.w));
+                float da2dx = xsub(xmul(p1.y, p0.w), xmul(p0.y, p1.w)), da2dy = xsub(xmul(p0.x, p1.w), xmul(p1.x, p0.w));
+                float datdx = xadd(xadd(da0dx, da1dx), da2dx), datdy = xadd(xadd(da0dy, da1dy), da2dy);
+                odb.x = xmul(dfxdx, xsub(xmul(b0, datdx), da0dx));
+                odb.y = xmul(dfydy, xsub(xmul(b0, datdy), da0dy));
+                odb.z = xmul(dfxdx, xsub(xmul(b1, datdx), da1dx));
+                odb.w = xmul(dfydy, xsub(xmul(b1, datdy), da1dy));
+            }
+        }
+        reinterpret_cast<float4*>(rast)[pi] = out;
+        if (rast_db) reinterpret_cast<float4*>(rast_db)[pi] = odb;
+    }
+}
+
+// d pos from (d u, d v): one thread per pixel, float atomics into grad_pos (upstream's scheme).
+__global__ void __launch_bounds__(256) k_raster_bwd(const float* __restrict__ pos, const int32_t* __restrict__ tri,
+                                                    const float* __restrict__ rast, const float* __restrict__ dy,
+                                                    int N, int V, int T, int H, int W, float xs, float xo, float ys, float yo,
+                                                    float* __restrict__ grad_pos)
+{
+    long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= (long long)N * H * W) return;
+    float4 r = ldg4(rast + 4 * pi);
+    int t = rast_tri(r.w);
+    if (t < 0 || t >= T) return;
+    float4 g = ldg4(dy + 4 * pi);
+    if (g.x == 0.f && g.y == 0.f) return;
+    int px = (int)(pi % W), py = (int)((pi / W) % H), n = (int)(pi / ((long long)W * H));
+    int i0 = __ldg(tri + 3 * t), i1 = __ldg(tri + 3 * t + 1), i2 = __ldg(tri + 3 * t + 2);
+    const float* P = pos + (size_t)n * V * 4;
+    float4 q0 = ldg4(P + 4 * (size_t)i0), q1 = ldg4(P + 4 * (size_t)i1), q2 = ldg4(P + 4 * (size_t)i2);
+    float fx = pixel_ndc(px, xs, xo), fy = pixel_ndc(py, ys, yo);
+    float p0x = q0.x - fx * q0.w, p0y = q0.y - fy * q0.w;
+    float p1x = q1.x - fx * q1.w, p1y = q1.y - fy * q1.w;
+    float p2x = q2.x - fx * q2.w, p2y = q2.y - fy * q2.w;
+    float a0 = p1x * p2y - p1y * p2x, a1 = p2x * p0y - p2y * p0x, a2 = p0x * p1y - p0y * p1x;
+    float iw = 1.f / (a0 + a1 + a2);
+    float u = a0 * iw, v = a1 * iw;
+    float gbb = g.x * u + g.y * v;
+    float g0 = iw * (g.x - gbb), g1 = iw * (g.y - gbb), g2 = -iw * gbb;
+    float g0x = -g1 * p2y + g2 * p1y, g0y = g1 * p2x - g2 * p1x;
+    float g1x = g0 * p2y - g2 * p0y, g1y = -g0 * p2x + g2 * p0x;
+    float g2x = -g0 * p1y + g1 * p0y, g2y = g0 * p1x - g1 * p0x;
+    float* G = grad_pos + (size_t)n * V * 4;
+    atomicAdd(G + 4 * (size_t)i0 + 0, g0x); atomicAdd(G + 4 * (size_t)i0 + 1, g0y); atomicAdd(G + 4 * (size_t)i0 + 3, -fx * g0x - fy * g0y);
+    atomicAdd(G + 4 * (size_t)i1 + 0, g1x); atomicAdd(G + 4 * (size_t)i1 + 1, g1y); atomicAdd(G + 4 * (size_t)i1 + 3, -fx * g1x - fy * g1y);
+    atomicAdd(G + 4 * (size_t)i2 + 0, g2x); atomicAdd(G + 4 * (size_t)i2 + 1, g2y); atomicAdd(G + 4 * (size_t)i2 + 3, -fx * g2x - fy * g2y);
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct ScratchLayout {
+    size_t zero_bytes;               // leading region that must be zeroed each call
+    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, total;
+};
+
+ScratchLayout raster_layout(int N, int T, int NB)
+{
+    ScratchLayout L;
+    size_t o = 0;
+    L.off_count = o;       o += align_up((size_t)N * NB * 4);
+    L.off_cursor = o;      o += align_up((size_t)N * NB * 4);
+    L.off_large_count = o; o += align_up((size_t)N * 4);
+    L.zero_bytes = o;
+    L.off_offset = o;      o += align_up((size_t)N * NB * 4);
+    L.off_info = o;        o += align_up((size_t)N * T * 4);
+    L.off_pairs = o;       o += align_up((size_t)N * T * 16);
+    L.off_large = o;       o += align_up((size_t)N * T * 4);
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+extern "C" size_t fpc_rasterize_scratch_bytes(int N, int T, int H, int W)
+{
+    if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return 256;
+    int NB = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
+    return raster_layout(N, T, NB).total;
+}
+
+extern "C" int fpc_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
+                                 float* rast, float* rast_db, void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FPC_CHECK_ARG(pos && tri && rast, "rasterize_fwd: pos, tri and rast must be non-null");
+    FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "rasterize_fwd: N, V, T, H, W must be positive (got %d %d %d %d %d)", N, V, T, H, W);
+    FPC_CHECK_ARG(T < (1 << 24), "rasterize_fwd: at most 2^24-1 triangles (got %d)", T);
+    FPC_CHECK_ARG(H <= 65536 && W <= 65536 && N <= 65535, "rasterize_fwd: resolution <= 65536^2 and N <= 65535 (got %dx%d, N=%d)", H, W, N);
+    RasterParams rp;
+    rp.pos = pos; rp.tri = tri; rp.N = N; rp.V = V; rp.T = T; rp.H = H; rp.W = W;
+    rp.BW = fpc_div_up(W, BIN); rp.BH = fpc_div_up(H, BIN); rp.NB = rp.BW * rp.BH;
+    ScratchLayout L = raster_layout(N, T, rp.NB);
+    FPC_CHECK_ARG(scratch && scratch_bytes >= L.total, "rasterize_fwd: scratch too small (%zu < %zu bytes)", scratch_bytes, L.total);
+    rp.xs = 2.0f / (float)W; rp.xo = 1.0f / (float)W - 1.0f;
+    rp.ys = 2.0f / (float)H; rp.yo = 1.0f / (float)H - 1.0f;
+    rp.sxs = 8.0f * (float)W; rp.sys = 8.0f * (float)H;
+    char* s = (char*)scratch;
+    rp.bin_count = (int*)(s + L.off_count);
+    rp.bin_cursor = (int*)(s + L.off_cursor);
+    rp.large_count = (int*)(s + L.off_large_count);
+    rp.bin_offset = (int*)(s + L.off_offset);
+    rp.tri_info = (int*)(s + L.off_info);
+    rp.pairs = (int*)(s + L.off_pairs);
+    rp.large_list = (int*)(s + L.off_large);
+
+    FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
+    long long nt = (long long)N * T;
+    k_setup<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);
+    FPC_LAUNCH_CHECK();
+    k_scan<<<N, 256, 0, stream>>>(rp);
+    FPC_LAUNCH_CHECK();
+    k_fill<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);
+    FPC_LAUNCH_CHECK();
+    k_fine<<<dim3(rp.NB, N), FINE_THREADS, 0, stream>>>(rp, rast, rast_db);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+extern "C" int fpc_rasterize_bwd(const float* pos, const int32_t* tri, const float* rast, const float* dy,
+                                 int N, int V, int T, int H, int W, float* grad_pos, fpc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FPC_CHECK_ARG(pos && tri && rast && dy && grad_pos, "rasterize_bwd: null pointer argument");
+    FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "rasterize_bwd: N, V, T, H, W must be positive");
+    FPC_CUDA(cudaMemsetAsync(grad_pos, 0, (size_t)N * V * 4 * sizeof(float), stream));
+    long long npx = (long long)N * H * W;
+    k_raster_bwd<<<fpc_div_up(npx, 256), 256, 0, stream>>>(pos, tri, rast, dy, N, V, T, H, W, 2.0f / (float)W,
+                                                            1.0f / (float)W - 1.0f, 2.0f / (float)H,
+                                                            1.0f / (float)H - 1.0f, grad_pos);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}

@@ -1,0 +1,282 @@
+"""Fit driver: the per-iteration analysis-by-synthesis loop on device (role of the reference's fit.py).
+
+One `FitSession.iteration()` is the body of the reference's hot loop (fit.py:524-642) for ALL cameras of ALL
+frames of the local batch at once (north-star parameterisation V_f = base + D w_f, per-frame pose (t_f, q_f)):
+
+    pose -> MVP (fit.py:546-553)  ->  blend (fit.py:103-129)  ->  clip transform (camera.py:11-23)
+    -> rasterize -> interpolate -> [texture] -> [antialias] (fit.py:151-160) -> background + loss (fit.py:161,579)
+    -> backward of all of it (fit.py:611) -> Adam + LambdaLR (fit.py:612-613) -> quaternion renorm (fit.py:616-618)
+
+Everything is enqueued on the current CUDA stream through the C-ABI (include/fpc_b200.h) with persistent
+buffers and no host synchronisation, so the whole iteration can be captured once into a CUDA graph and
+replayed (`capture()` / `replay()`).  PyTorch only owns the device memory, the stream and (for the
+camera-split mode) the NCCL all-reduce of the small gradient vector.
+
+Loss convention for a batch: sum over frames of the mean over that frame's cameras of the reference's
+single-view loss mean((ref - 255 colour)^2); per-frame gradients therefore do not depend on the batch size.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import _check_device
+
+BG = 45.0 / 255.0  # fit.py:161
+
+
+@dataclass
+class FitConfig:
+    # defaults are the reference's shipped settings (main.py:13-18,30)
+    resolution: tuple = (1024, 1024)      # (H, W)
+    shading: str = 'vcol'                 # 'vcol' (BASELINE config 2) or 'texture' (fit.py:157-158)
+    antialias: bool = False               # fit.py:160
+    lr_base: float = 1e-3                 # activations  (main.py:14 "10e-4")
+    lr_t: float = 1e-5                    # main.py:17
+    lr_q: float = 1e-5                    # main.py:18
+    lr_ramp: float = 0.005                # main.py:16
+    max_iter: int = 80000                 # main.py:13
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    bg: float = BG
+    quat_norm: str = 'row'                # 'row' (default) or 'frobenius' (reference quirk)
+    optimize_pose: bool = True
+    cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class FitSession:
+    def __init__(self, rig, n_frames, config=None, device=None):
+        """rig: an object with v_base [3V], pos_idx [T,3], uv, uv_idx, D [3V,B], vcol [V,3], tex [Ht,Wt,Ch], P, A [C,4,4]
+        (numpy, e.g. fpc_diffrend_b200.rig.Rig)."""
+        self.cfg = config or FitConfig()
+        cfg = self.cfg
+        if not torch.cuda.is_available():
+            raise RuntimeError('FitSession needs a CUDA device (sm_100a); there is no CPU path')
+        self.device = torch.device(device if device is not None else ('cuda:%d' % torch.cuda.current_device()))
+        dev = self.device
+        _lib.load()
+        _check_device(torch.empty(1, device=dev))
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.F = int(n_frames)
+        self.V = rig.v_base.shape[0] // 3
+        self.T = rig.pos_idx.shape[0]
+        self.B = rig.D.shape[1]
+        c0, c1 = cfg.cam_slice if cfg.cam_slice is not None else (0, rig.P.shape[0])
+        self.C_total = rig.P.shape[0]
+        self.C = c1 - c0
+        self.H, self.W = cfg.resolution
+        F, V, T, B, C, H, W = self.F, self.V, self.T, self.B, self.C, self.H, self.W
+        self.N = F * C
+
+        # constants
+        self.v_base = torch.tensor(rig.v_base, **f32)
+        self.D = torch.tensor(rig.D, **f32).contiguous()
+        self.pos_idx = torch.tensor(rig.pos_idx, dtype=torch.int32, device=dev).contiguous()
+        self.P = torch.tensor(rig.P[c0:c1], **f32).reshape(C, 16).contiguous()
+        self.A = torch.tensor(rig.A[c0:c1], **f32).reshape(C, 16).contiguous()
+        if cfg.shading == 'vcol':
+            self.attr = torch.tensor(rig.vcol, **f32).reshape(1, V, -1).contiguous()
+            self.attr_idx = self.pos_idx
+            self.tex = None
+            self.Ch = self.attr.shape[2]
+        elif cfg.shading == 'texture':
+            self.attr = torch.tensor(rig.uv, **f32).reshape(1, -1, 2).contiguous()
+            self.attr_idx = torch.tensor(rig.uv_idx, dtype=torch.int32, device=dev).contiguous()
+            self.tex = torch.tensor(rig.tex, **f32).reshape((1,) + tuple(rig.tex.shape)).contiguous()
+            self.Ch = self.tex.shape[3]
+        else:
+            raise ValueError("shading must be 'vcol' or 'texture'")
+        Ch = self.Ch
+
+        # parameters (packed so that one all-reduce / one Adam launch covers them): [w | t | q]
+        nw, nt, nq = F * B, F * 3, F * 4
+        self.params = torch.zeros(nw + nt + nq, **f32)
+        self.grads = torch.zeros_like(self.params)
+        self.adam_m = torch.zeros_like(self.params)
+        self.adam_v = torch.zeros_like(self.params)
+        self.w = self.params[:nw].view(F, B)
+        self.t = self.params[nw:nw + nt].view(F, 3)
+        self.q = self.params[nw + nt:].view(F, 4)
+        self.q[:, 3] = 1.0
+        self.d_w = self.grads[:nw].view(F, B)
+        self.d_t = self.grads[nw:nw + nt].view(F, 3)
+        self.d_q = self.grads[nw + nt:].view(F, 4)
+        self.step_count = torch.zeros(1, **f32)
+        self.loss = torch.zeros(1, **f32)
+
+        # per-iteration buffers
+        self.mvp = torch.empty(self.N, 16, **f32)
+        self.verts = torch.empty(F, V * 3, **f32)
+        self.pos_clip = torch.empty(self.N, V, 4, **f32)
+        self.rast = torch.empty(self.N, H, W, 4, **f32)
+        self.colour = torch.empty(self.N, H, W, Ch, **f32)
+        self.d_colour = torch.empty(self.N, H, W, Ch, **f32)
+        self.g_rast = torch.empty(self.N, H, W, 4, **f32)
+        self.g_pos = torch.empty(self.N, V, 4, **f32)
+        self.g_attr = torch.empty_like(self.attr)
+        self.d_verts = torch.empty(F, V * 3, **f32)
+        self.d_mvp = torch.empty(self.N, 16, **f32)
+        if cfg.shading == 'texture':
+            self.texc = torch.empty(self.N, H, W, 2, **f32)
+            self.g_texc = torch.empty(self.N, H, W, 2, **f32)
+        if cfg.antialias:
+            self.colour_aa = torch.empty(self.N, H, W, Ch, **f32)
+            self.g_colour_pre = torch.empty(self.N, H, W, Ch, **f32)
+            self.g_pos_aa = torch.empty(self.N, V, 4, **f32)
+            self.tri_opp = torch.empty(T, 3, dtype=torch.int32, device=dev)
+            sc = torch.empty(int(_lib.load().fpc_topology_scratch_bytes(T)), dtype=torch.uint8, device=dev)
+            _lib.call('fpc_topology_build', _p(self.pos_idx), T, V, _p(self.tri_opp), _p(sc), sc.numel(), self._stream())
+        self.ref = None
+
+        L = _lib.load()
+        nbytes = max(L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_blend_bwd_scratch_bytes(V * 3, B, F),
+                     L.fpc_project_bwd_scratch_bytes(F, C, V), L.fpc_image_loss_scratch_bytes(self.N, H, W, Ch))
+        self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        self.graph = None
+        self.launches_per_iteration = 0
+
+    # ---- plumbing ------------------------------------------------------------------------------------
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def set_reference(self, frames):
+        """frames [F, C_local, H, W, Ch] float32 grey levels on the 0..255 scale (already clipped / flipped as
+        fit.py:531-533 does); device tensor or host array (copied once, frames stay resident on device)."""
+        ref = torch.as_tensor(frames, dtype=torch.float32).to(self.device, non_blocking=True)
+        assert tuple(ref.shape) == (self.F, self.C, self.H, self.W, self.Ch), (tuple(ref.shape), (self.F, self.C, self.H, self.W, self.Ch))
+        self.ref = ref.reshape(self.N, self.H, self.W, self.Ch).contiguous()
+
+    def set_parameters(self, w=None, t=None, q=None):
+        if w is not None:
+            self.w.copy_(torch.as_tensor(w, dtype=torch.float32))
+        if t is not None:
+            self.t.copy_(torch.as_tensor(t, dtype=torch.float32))
+        if q is not None:
+            self.q.copy_(torch.as_tensor(q, dtype=torch.float32))
+
+    # ---- one iteration -------------------------------------------------------------------------------
+    def forward(self, with_loss=True):
+        """Render all local views with the current parameters; returns the composited image tensor [N,H,W,Ch]
+        when with_loss is False (used to synthesise reference frames), else fills self.loss / self.d_colour."""
+        cfg, s, call = self.cfg, self._stream(), _lib.call
+        F, V, T, B, C, H, W, N, Ch = self.F, self.V, self.T, self.B, self.C, self.H, self.W, self.N, self.Ch
+        n = 0
+        call('fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, F, C, _p(self.mvp), s); n += 1
+        call('fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
+        call('fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
+        call('fpc_rasterize_fwd', _p(self.pos_clip), _p(self.pos_idx), N, V, T, H, W, _p(self.rast), None,
+             _p(self.scratch), self.scratch.numel(), s); n += 4
+        if cfg.shading == 'vcol':
+            call('fpc_interpolate_fwd', _p(self.attr), 1, V, Ch, _p(self.rast), _p(self.attr_idx), N, T, H, W, _p(self.colour), s); n += 1
+        else:
+            call('fpc_interpolate_fwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), N, T, H, W, _p(self.texc), s); n += 1
+            call('fpc_texture_linear_fwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), N, H, W, _p(self.colour), s); n += 1
+        final = self.colour
+        if cfg.antialias:
+            call('fpc_antialias_fwd', _p(self.colour), _p(self.rast), _p(self.pos_clip), _p(self.pos_idx), _p(self.tri_opp),
+                 N, V, T, H, W, Ch, _p(self.colour_aa), s); n += 1
+            final = self.colour_aa
+        if not with_loss:
+            comp = torch.where(self.rast[..., 3:] > 0, final, torch.tensor(cfg.bg, device=self.device))
+            return comp
+        assert self.ref is not None, 'call set_reference() first'
+        call('fpc_image_loss_fwd_bwd', _p(final), _p(self.rast), _p(self.ref), N, H, W, Ch, cfg.bg, 1.0 / self.C_total,
+             _p(self.loss), _p(self.d_colour), None, _p(self.scratch), self.scratch.numel(), s); n += 2
+        return n
+
+    def backward(self):
+        cfg, s, call = self.cfg, self._stream(), _lib.call
+        F, V, T, B, C, H, W, N, Ch = self.F, self.V, self.T, self.B, self.C, self.H, self.W, self.N, self.Ch
+        n = 0
+        g_colour = self.d_colour
+        if cfg.antialias:
+            call('fpc_antialias_bwd', _p(self.colour), _p(self.rast), _p(self.pos_clip), _p(self.pos_idx), _p(self.tri_opp),
+                 _p(self.d_colour), N, V, T, H, W, Ch, _p(self.g_colour_pre), _p(self.g_pos_aa), s); n += 2
+            g_colour = self.g_colour_pre
+        if cfg.shading == 'vcol':
+            call('fpc_interpolate_bwd', _p(self.attr), 1, V, Ch, _p(self.rast), _p(self.attr_idx), _p(g_colour), N, T, H, W,
+                 _p(self.g_attr), _p(self.g_rast), s); n += 2
+        else:
+            call('fpc_texture_linear_bwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), _p(g_colour),
+                 N, H, W, None, _p(self.g_texc), s); n += 1
+            call('fpc_interpolate_bwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), _p(self.g_texc),
+                 N, T, H, W, _p(self.g_attr), _p(self.g_rast), s); n += 2
+        call('fpc_rasterize_bwd', _p(self.pos_clip), _p(self.pos_idx), _p(self.rast), _p(self.g_rast), N, V, T, H, W,
+             _p(self.g_pos), s); n += 2
+        if cfg.antialias:
+            self.g_pos.add_(self.g_pos_aa); n += 1
+        call('fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
+             _p(self.scratch), self.scratch.numel(), s); n += 2
+        call('fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
+        call('fpc_pose_mvp_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.d_mvp), F, C,
+             _p(self.d_t), _p(self.d_q), s); n += 1
+        return n
+
+    def optimizer_step(self):
+        cfg, s, call = self.cfg, self._stream(), _lib.call
+        F, B = self.F, self.B
+        n = 0
+        if cfg.cam_slice is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.grads)   # the only exchange of the camera-split mode: (B+7) F floats
+        nw = F * B
+        adam = lambda off, cnt, lr: call('fpc_adam_step', ctypes.c_void_p(self.params.data_ptr() + 4 * off),
+                                         ctypes.c_void_p(self.grads.data_ptr() + 4 * off),
+                                         ctypes.c_void_p(self.adam_m.data_ptr() + 4 * off),
+                                         ctypes.c_void_p(self.adam_v.data_ptr() + 4 * off), cnt, lr, cfg.beta1, cfg.beta2,
+                                         cfg.eps, cfg.lr_ramp, float(cfg.max_iter), _p(self.step_count), s)
+        adam(0, nw, cfg.lr_base); n += 1
+        if cfg.optimize_pose:
+            adam(nw, F * 3, cfg.lr_t); n += 1
+            adam(nw + F * 3, F * 4, cfg.lr_q); n += 1
+            call('fpc_quat_renorm', _p(self.q), F, 1 if cfg.quat_norm == 'frobenius' else 0, s); n += 1
+        call('fpc_adam_advance', _p(self.step_count), s); n += 1
+        return n
+
+    def iteration(self):
+        """Enqueue one full fit iteration (forward + backward + Adam) on the current stream. Returns the number
+        of kernel launches it issued."""
+        n = self.forward() + self.backward() + self.optimizer_step()
+        self.launches_per_iteration = n
+        return n
+
+    # ---- CUDA graph ----------------------------------------------------------------------------------
+    def capture(self):
+        """Capture one iteration into a CUDA graph (after a warm-up iteration on a side stream)."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.iteration()
+        return self.graph
+
+    def replay(self):
+        self.graph.replay()
+
+    # ---- results -------------------------------------------------------------------------------------
+    def result_vertices(self):
+        """[F, 3V] blended vertices of the current parameters (fit.py:642 `result`)."""
+        _lib.call('fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), self.V * 3, self.B, self.F, _p(self.verts), self._stream())
+        return self.verts.clone()
+
+
+def synthesize_reference(rig, w_true, t_true, q_true, config, device=None):
+    """Render reference frames from ground-truth parameters with the kernels themselves, x255, clipped to [0,140]
+    (fit.py:531) -> [F, C, H, W, Ch] float32 on device."""
+    F = w_true.shape[0]
+    s = FitSession(rig, F, config, device)
+    s.set_parameters(w_true, t_true, q_true)
+    img = s.forward(with_loss=False)
+    ref = torch.clamp(img * 255.0, 0.0, 140.0)
+    return ref.reshape(F, s.C, s.H, s.W, s.Ch).contiguous()

@@ -1,0 +1,149 @@
+/*
+ * fpc_b200.h — C-ABI of the B200-native fit hot path (libfpc_b200.so).
+ *
+ * This is the drop-in boundary for the per-iteration analysis-by-synthesis path of fpc-diffrend
+ * (reference: /root/reference/src/torch/fit.py:524-642).  Each entry point states the reference
+ * interface it replaces.  For the four rendering ops that interface is the nvdiffrast plugin the
+ * reference binds through `import nvdiffrast.torch as dr` (fit.py:13): upstream plugin functions
+ * `rasterize_fwd_cuda / rasterize_grad / interpolate_fwd / interpolate_grad / texture_fwd /
+ * texture_grad_linear / antialias_construct_topology_hash / antialias_fwd / antialias_grad`
+ * (SURVEY.md §8(b)).  The binding a maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers on the current CUDA device unless
+ *     a parameter says "host"; float = IEEE fp32, indices = int32; tensors are dense, row-major,
+ *     contiguous with the shapes given in brackets;
+ *   - every function returns 0 (FPC_OK) or an fpc_status; it never throws and never synchronises the
+ *     device; work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     there is no host read-back on any path, so a whole fit iteration can be captured in a CUDA graph;
+ *   - `fpc_last_error()` returns a thread-local, human-readable description of the last failure;
+ *   - scratch memory is caller-owned: ask `*_scratch_bytes()` and pass a device buffer of at least that size.
+ *     The same scratch buffer must not be used by two concurrently running streams;
+ *   - outputs documented as "overwritten" need no initialisation by the caller.
+ *   - image row 0 is the BOTTOM row (NDC y = -1), as in nvdiffrast; rast = (u, v, z/w, float(tri_id+1)),
+ *     all four zero on background pixels.
+ */
+#ifndef FPC_B200_H
+#define FPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum fpc_status {
+    FPC_OK = 0,
+    FPC_ERR_INVALID_ARGUMENT = 1,
+    FPC_ERR_CUDA = 2,
+    FPC_ERR_UNSUPPORTED = 3
+} fpc_status;
+
+typedef void* fpc_stream_t; /* cudaStream_t */
+
+#define FPC_B200_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int fpc_abi_version(void);
+const char* fpc_last_error(void);
+/* Fails (FPC_ERR_UNSUPPORTED) unless the current device is compute capability 10.x: there is no fallback path. */
+int fpc_check_device(void);
+
+/* ---- rasterize   (replaces dr.rasterize, fit.py:151; plugin rasterize_fwd_cuda / rasterize_grad) --- */
+/* Bytes of scratch needed by fpc_rasterize_fwd for N instances of T triangles at HxW. */
+size_t fpc_rasterize_scratch_bytes(int N, int T, int H, int W);
+/* pos [N,V,4] clip space, tri [T,3]  ->  rast [N,H,W,4], rast_db [N,H,W,4] (may be NULL).  Overwritten. */
+int fpc_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
+                      float* rast, float* rast_db, void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+/* dy [N,H,W,4] (only d u, d v are used; d(z/w), d(id) ignored as upstream) -> grad_pos [N,V,4], overwritten
+ * (x, y, w components; z = 0).  Gradients w.r.t. rast_db are not supported (mip path). */
+int fpc_rasterize_bwd(const float* pos, const int32_t* tri, const float* rast, const float* dy,
+                      int N, int V, int T, int H, int W, float* grad_pos, fpc_stream_t stream);
+
+/* ---- interpolate (replaces dr.interpolate, fit.py:157; plugin interpolate_fwd / interpolate_grad) -- */
+/* attr [Na,Vt,A] with Na in {1,N} (1 = broadcast over instances), rast [N,H,W,4], tri [T,3] -> out [N,H,W,A] */
+int fpc_interpolate_fwd(const float* attr, int Na, int Vt, int A, const float* rast, const int32_t* tri,
+                        int N, int T, int H, int W, float* out, fpc_stream_t stream);
+/* dy [N,H,W,A] -> grad_attr [Na,Vt,A] (overwritten; summed over instances when Na == 1),
+ *                 grad_rast [N,H,W,4] = (d u, d v, 0, 0) (overwritten) */
+int fpc_interpolate_bwd(const float* attr, int Na, int Vt, int A, const float* rast, const int32_t* tri,
+                        const float* dy, int N, int T, int H, int W, float* grad_attr, float* grad_rast,
+                        fpc_stream_t stream);
+
+/* ---- texture, filter_mode='linear', boundary_mode='wrap'
+ *      (replaces dr.texture(..., filter_mode='linear'), fit.py:158; plugin texture_fwd / texture_grad_linear) */
+/* tex [Nt,Ht,Wt,C] with Nt in {1,N}, uv [N,H,W,2] -> out [N,H,W,C] */
+int fpc_texture_linear_fwd(const float* tex, int Nt, int Ht, int Wt, int C, const float* uv,
+                           int N, int H, int W, float* out, fpc_stream_t stream);
+/* dy [N,H,W,C] -> grad_tex [Nt,Ht,Wt,C] (overwritten; may be NULL to skip it), grad_uv [N,H,W,2] (overwritten) */
+int fpc_texture_linear_bwd(const float* tex, int Nt, int Ht, int Wt, int C, const float* uv, const float* dy,
+                           int N, int H, int W, float* grad_tex, float* grad_uv, fpc_stream_t stream);
+
+/* ---- antialias   (replaces dr.antialias, fit.py:160; plugin antialias_construct_topology_hash /
+ *      antialias_fwd / antialias_grad).  The per-call edge hash of upstream is replaced by a per-topology
+ *      adjacency table tri_opp [T,3]: opposite vertex across edge e (e0=(v1,v2), e1=(v2,v0), e2=(v0,v1)), -1 = none. */
+size_t fpc_topology_scratch_bytes(int T);
+int fpc_topology_build(const int32_t* tri, int T, int V, int32_t* tri_opp, void* scratch, size_t scratch_bytes,
+                       fpc_stream_t stream);
+/* color [N,H,W,C], rast [N,H,W,4], pos [N,V,4], tri [T,3], tri_opp [T,3] -> out [N,H,W,C] */
+int fpc_antialias_fwd(const float* color, const float* rast, const float* pos, const int32_t* tri,
+                      const int32_t* tri_opp, int N, int V, int T, int H, int W, int C, float* out,
+                      fpc_stream_t stream);
+/* dy [N,H,W,C] -> grad_color [N,H,W,C], grad_pos [N,V,4] (both overwritten) */
+int fpc_antialias_bwd(const float* color, const float* rast, const float* pos, const int32_t* tri,
+                      const int32_t* tri_opp, const float* dy, int N, int V, int T, int H, int W, int C,
+                      float* grad_color, float* grad_pos, fpc_stream_t stream);
+
+/* ---- blendshape combination (replaces fit.blend, fit.py:103-129, north-star form V = base + D w) ---- */
+/* D [R,B] (R = 3V rows, xyz interleaved), base [R], w [F,B]  ->  verts [F,R] */
+int fpc_blend_fwd(const float* D, const float* base, const float* w, int R, int B, int F, float* verts,
+                  fpc_stream_t stream);
+/* transpose gradient: d_verts [F,R] -> d_w [F,B] (overwritten) = D^T d_verts.  Deterministic two-stage reduction. */
+size_t fpc_blend_bwd_scratch_bytes(int R, int B, int F);
+int fpc_blend_bwd(const float* D, const float* d_verts, int R, int B, int F, float* d_w,
+                  void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
+/* ---- pose + projection (replaces the MVP chain fit.py:546-553 with camera.rigid_grad camera.py:128-132 and
+ *      roma.unitquat_to_rotmat, and camera.transform_clip camera.py:11-23) --------------------------------- */
+/* P [C,16], A [C,16] (= MV @ translate(0,170,0)), row-major 4x4; t [F,3], q [F,4] XYZW (not normalised);
+ * t_cam [C,3] / q_cam [C,4] per-camera corrections (fit.py:443-448) or NULL for identity
+ * -> mvp [F*C,16], instance n = f*C + c:   mvp = P_c @ Rigid(t_f,q_f) @ Rigid(t_cam_c,q_cam_c) @ A_c */
+int fpc_pose_mvp_fwd(const float* P, const float* A, const float* t, const float* q,
+                     const float* t_cam, const float* q_cam, int F, int C, float* mvp, fpc_stream_t stream);
+/* d_mvp [F*C,16] -> d_t [F,3], d_q [F,4] (overwritten) */
+int fpc_pose_mvp_bwd(const float* P, const float* A, const float* t, const float* q,
+                     const float* t_cam, const float* q_cam, const float* d_mvp, int F, int C,
+                     float* d_t, float* d_q, fpc_stream_t stream);
+/* verts [F,V,3], mvp [F*C,16] -> pos_clip [F*C,V,4] */
+int fpc_project_fwd(const float* verts, const float* mvp, int F, int C, int V, float* pos_clip, fpc_stream_t stream);
+/* d_pos_clip [F*C,V,4] -> d_verts [F,V,3] (overwritten), d_mvp [F*C,16] (overwritten) */
+size_t fpc_project_bwd_scratch_bytes(int F, int C, int V);
+int fpc_project_bwd(const float* verts, const float* mvp, const float* d_pos_clip, int F, int C, int V,
+                    float* d_verts, float* d_mvp, void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
+/* ---- background composite + image loss (replaces fit.py:161 and the first term of fit.py:579) --------------
+ * colour [N,H,W,C], rast [N,H,W,4], ref [N,H,W,C] (grey levels, 0..255 scale):
+ *   comp = rast.w > 0 ? colour : bg;   loss = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2
+ * -> loss [1] (overwritten), d_colour [N,H,W,C] (overwritten; 0 on background), comp [N,H,W,C] or NULL. */
+size_t fpc_image_loss_scratch_bytes(int N, int H, int W, int C);
+int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, const float* ref, int N, int H, int W, int C,
+                           float bg, float scale, float* loss, float* d_colour, float* comp,
+                           void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
+/* ---- Adam (replaces torch.optim.Adam + LambdaLR + quaternion renorm, fit.py:493-505,610-618) ---------------
+ * p, g, m, v [n]; state [2] device floats: state[0] = step count (incremented here), state[1] unused.
+ * lr_eff = lr * lr_ramp^(step/max_iter) with step counted before the increment (LambdaLR semantics).
+ * torch.optim.Adam update rule with bias correction, betas (b1,b2), eps, no weight decay / amsgrad. */
+int fpc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                  float lr_ramp, float max_iter, const float* step_count, fpc_stream_t stream);
+/* step_count [1] += 1 (device side, so the iteration stays graph-capturable) */
+int fpc_adam_advance(float* step_count, fpc_stream_t stream);
+/* q [n,4] /= norm.  mode 0: per-row norm (default of this build);  mode 1: Frobenius norm of the whole tensor
+ * (the reference's quirk, fit.py:616-618). */
+int fpc_quat_renorm(float* q, int n, int mode, fpc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPC_B200_H */

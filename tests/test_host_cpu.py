@@ -1,0 +1,140 @@
+"""CPU tests: host-side mirror of the reference's camera code, rig generator, C-ABI exports."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from fpc_diffrend_b200 import _lib, camera, rig as rigmod
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope='module')
+def kat():
+    with open(os.path.join(HERE, 'golden', 'camera_kat.json')) as f:
+        return json.load(f)
+
+
+def test_camera_matches_reference_kat(kat):
+    """camera.py mirror == the reference's own camera.py on the real calibration (bit-exact fp32)."""
+    for name, c in kat['cameras'].items():
+        P = camera.intrinsic_to_projection(np.asarray(c['intrinsic'], np.float32))
+        MV = camera.extrinsic_to_modelview(np.asarray(c['rotation'], np.float32), np.asarray(c['translation'], np.float32))
+        assert np.array_equal(P, np.asarray(c['P'], np.float32)), name
+        assert np.array_equal(MV, np.asarray(c['MV'], np.float32)), name
+        Pc, Ac = camera.camera_constants([c])
+        assert np.array_equal(Ac[0], np.asarray(c['A'], np.float32)), name
+        mvp = (Pc[0] @ Ac[0]).astype(np.float32)
+        assert np.array_equal(mvp, np.asarray(c['MVP'], np.float32)), name
+
+
+def test_survey_appendix_c3_values(kat):
+    c = kat['cameras']['pod2primary']
+    assert abs(c['P'][0][0] - 12.083149909973145) < 1e-6
+    assert abs(c['P'][1][1] - 8.954282760620117) < 1e-6
+    np.testing.assert_allclose(c['clip'][0], [-9.326126, -56.269230, 171.465439, 171.468292], rtol=1e-6)
+
+
+def test_unitquat_to_rotmat_is_rotation():
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    R = camera.unitquat_to_rotmat(q)
+    np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-12)
+    assert abs(np.linalg.det(R) - 1.0) < 1e-12
+    # identity quaternion (0,0,0,1) -> identity (XYZW order, fit.py:446-447)
+    np.testing.assert_allclose(camera.unitquat_to_rotmat([0, 0, 0, 1]), np.eye(3))
+    # 90 degrees about z
+    s = np.sqrt(0.5)
+    np.testing.assert_allclose(camera.unitquat_to_rotmat([0, 0, s, s]) @ [1, 0, 0], [0, 1, 0], atol=1e-12)
+
+
+@pytest.mark.parametrize('nv', [1000, 2500])
+def test_rig_counts(nv):
+    r = rigmod.make_rig(n_vertices=nv, n_shapes=4, n_cams=2, width=64, height=64, tex_size=16)
+    assert r.V == nv and r.T == 2 * nv - 4                     # closed genus-0: T = 2V - 4
+    assert r.uv.shape[0] > nv                                   # seam duplicates: Vt > V
+    assert (r.uv_idx != r.pos_idx).any()
+    assert r.uv.min() > 0 and r.uv.max() < 1
+    assert r.D.shape == (3 * nv, 4) and r.D.dtype == np.float32
+    assert r.pos_idx.min() == 0 and r.pos_idx.max() == nv - 1
+    # every edge is shared by exactly two triangles (closed manifold)
+    e = np.sort(np.concatenate([r.pos_idx[:, [0, 1]], r.pos_idx[:, [1, 2]], r.pos_idx[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert (cnt == 2).all()
+    assert list(r.calib.keys()) == ['pod1primary', 'pod1secondary']
+    assert set(r.calib['pod1primary'].keys()) == {'distortion', 'intrinsic', 'rotation', 'translation'}
+
+
+def test_obj_roundtrip(tmp_path, tiny_rig):
+    """write_obj follows the reference's OBJ conventions (data.py:17-39): parse it back the way MeshData does."""
+    p = tmp_path / 'base.obj'
+    rigmod.write_obj(str(p), tiny_rig.v_base, tiny_rig.uv, tiny_rig.pos_idx, tiny_rig.uv_idx)
+    verts, uv, faces, fuv = [], [], [], []
+    for line in open(p):
+        if line.startswith('v '):
+            verts.extend(float(x) for x in line.strip().split(' ')[1:])
+        elif line.startswith('vt '):
+            uv.append([float(x) for x in line.strip().split(' ')[1:]])
+        elif line.startswith('f '):
+            idx = [l.split('/') for l in line.strip().split(' ')[1:]]
+            assert len(idx) == 3
+            faces.append([int(x[0]) - 1 for x in idx])
+            fuv.append([int(x[1]) - 1 for x in idx])
+    assert np.array_equal(np.asarray(verts, np.float32), tiny_rig.v_base)
+    assert np.array_equal(np.asarray(faces, np.int32), tiny_rig.pos_idx)
+    assert np.array_equal(np.asarray(fuv, np.int32), tiny_rig.uv_idx)
+    assert np.array_equal(np.asarray(uv, np.float32), tiny_rig.uv)
+
+
+# ---- C-ABI ------------------------------------------------------------------------------------------------
+
+def test_library_exports_every_header_symbol():
+    lib = _lib.load()
+    names = _lib.header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), 'libfpc_b200.so does not export %s declared in include/fpc_b200.h' % n
+    assert set(names) == set(_lib.SIGNATURES.keys())
+    assert lib.fpc_abi_version() == 1
+
+
+def test_argument_errors_do_not_throw_and_set_message():
+    """Error convention: int status + fpc_last_error(), validated before any CUDA work."""
+    lib = _lib.load()
+    st = lib.fpc_rasterize_fwd(None, None, 1, 1, 1, 8, 8, None, None, None, 0, None)
+    assert st == 1
+    assert b'rasterize_fwd' in lib.fpc_last_error()
+    st = lib.fpc_interpolate_fwd(ctypes.c_void_p(8), 3, 4, 2, ctypes.c_void_p(8), ctypes.c_void_p(8), 2, 1, 4, 4, ctypes.c_void_p(8), None)
+    assert st == 1 and b'attr batch must be 1 or N' in lib.fpc_last_error()
+    st = lib.fpc_texture_linear_fwd(ctypes.c_void_p(8), 1, 0, 4, 1, ctypes.c_void_p(8), 1, 4, 4, ctypes.c_void_p(8), None)
+    assert st == 1
+    st = lib.fpc_quat_renorm(ctypes.c_void_p(8), 4, 7, None)
+    assert st == 1 and b'mode' in lib.fpc_last_error()
+    with pytest.raises(RuntimeError, match='fpc_b200'):
+        _lib.call('fpc_blend_fwd', None, None, None, 1, 1, 1, None, None)
+
+
+def test_scratch_size_queries():
+    lib = _lib.load()
+    small = lib.fpc_rasterize_scratch_bytes(1, 2000, 128, 128)
+    big = lib.fpc_rasterize_scratch_bytes(9, 39996, 1024, 1024)
+    assert 0 < small < big < 64 * 2 ** 20
+    assert lib.fpc_blend_bwd_scratch_bytes(60000, 200, 1) > 0
+    assert lib.fpc_topology_scratch_bytes(39996) >= 6 * 39996 * 16
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    import fpc_diffrend_b200.ops as dr
+    ctx = dr.RasterizeGLContext(device='cuda')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        dr.rasterize(ctx, torch.zeros(1, 3, 4), torch.zeros(1, 3, dtype=torch.int32), resolution=(8, 8))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        dr.interpolate(torch.zeros(1, 3, 2), torch.zeros(1, 4, 4, 4), torch.zeros(1, 3, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match='range mode'):
+        dr.rasterize(ctx, torch.zeros(3, 4), torch.zeros(1, 3, dtype=torch.int32), resolution=(8, 8), ranges=torch.zeros(1, 2))
+    with pytest.raises(RuntimeError, match='linear'):
+        dr.texture(torch.zeros(1, 4, 4, 1), torch.zeros(1, 4, 4, 2), filter_mode='nearest')

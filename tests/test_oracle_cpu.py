@@ -1,0 +1,217 @@
+"""CPU tests that pin the oracle: golden rasterizer semantics (known-answer cases), and its analytic backward
+passes against float64 torch autograd of the forward formulas (oracle/torch_ref.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import clip_positions
+from oracle import golden as G
+from oracle import torch_ref as TR
+
+
+def _quad(z0=0.0, z1=0.0):
+    # two triangles sharing the diagonal of the square [-0.5,0.5]^2, w = 1
+    pos = np.array([[[-0.5, -0.5, z0, 1], [0.5, -0.5, z0, 1], [0.5, 0.5, z1, 1], [-0.5, 0.5, z1, 1]]], np.float32)
+    tri = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    return pos, tri
+
+
+def test_raster_watertight_and_layout():
+    pos, tri = _quad()
+    rast, db, _ = G.rasterize_fwd(pos, tri, (16, 16))
+    ids = rast[0, ..., 3]
+    # square covers pixel centres in (-0.5,0.5): pixels 4..11 in both axes; shared diagonal drawn exactly once
+    assert (ids[4:12, 4:12] > 0).all()
+    assert (ids > 0).sum() == 64
+    assert set(np.unique(ids)) == {0.0, 1.0, 2.0}
+    # background is all zeros in all four channels and in db
+    assert (rast[0][ids == 0] == 0).all() and (db[0][ids == 0] == 0).all()
+    # barycentrics: weight of vertex 2 is 1-u-v; at pixel (x=11,y=4) (near vertex 1 of triangle 0) v ~ 1
+    assert rast[0, 4, 11, 1] > 0.8 and rast[0, 4, 11, 3] == 1.0
+    # row 0 is the bottom: triangle 0 (0,1,2) owns the lower-right half
+    assert ids[5, 10] == 1.0 and ids[10, 5] == 2.0
+
+
+def test_raster_depth_order_and_tie_break():
+    pos, tri = _quad()
+    # duplicate the quad behind (z=0.5) and in front (z=-0.5): the front one must win everywhere
+    far = pos.copy(); far[..., 2] = 0.5
+    near = pos.copy(); near[..., 2] = -0.5
+    P = np.concatenate([pos, far, near], axis=1)
+    T = np.concatenate([tri, tri + 4, tri + 8])
+    rast, _, sec = G.rasterize_fwd(P, T, (16, 16), with_second=True)
+    ids = rast[0, ..., 3]
+    assert set(np.unique(ids[ids > 0])) == {5.0, 6.0}
+    np.testing.assert_allclose(rast[0, ..., 2][ids > 0], -0.5)
+    np.testing.assert_allclose(sec[0][ids > 0], 0.0)
+    # exact depth tie: the lower triangle index wins (in-order LESS)
+    P2 = np.concatenate([pos, pos], axis=1)
+    T2 = np.concatenate([tri + 4, tri])           # triangles 0,1 use the second copy, 2,3 the first
+    rast2, _, _ = G.rasterize_fwd(P2, T2, (16, 16))
+    assert set(np.unique(rast2[0, ..., 3])) == {0.0, 1.0, 2.0}
+
+
+def test_raster_drops_behind_camera_and_depth_range():
+    pos, tri = _quad()
+    behind = pos.copy(); behind[0, 1, 3] = -1.0      # vertex 1 belongs to triangle 0 only: it is dropped (no clipper yet)
+    rast, _, _ = G.rasterize_fwd(behind, tri, (16, 16))
+    assert (rast[0, ..., 3] == 2.0).sum() > 0 and (rast[0, ..., 3] == 1.0).sum() == 0
+    outside = pos.copy(); outside[..., 2] = 1.5      # z/w beyond the far plane: discarded
+    rast, _, _ = G.rasterize_fwd(outside, tri, (16, 16))
+    assert (rast == 0).all()
+    degenerate = pos.copy(); degenerate[0, 2] = degenerate[0, 1]
+    rast, _, _ = G.rasterize_fwd(degenerate, np.array([[0, 1, 2]], np.int32), (16, 16))
+    assert (rast == 0).all()
+
+
+def test_raster_matches_float64_barycentrics(tiny_rig):
+    pc = clip_positions(tiny_rig, w=np.linspace(0, 0.5, 16))
+    rast, db, sec = G.rasterize_fwd(pc, tiny_rig.pos_idx, (128, 128), with_second=True)
+    cov = (rast[..., 3] > 0).mean()
+    assert 0.2 < cov < 0.4                                       # 25-30 % coverage
+    tid = torch.tensor(rast[..., 3]).long() - 1
+    u, v, zw = TR.barycentrics(torch.tensor(pc).double(), torch.tensor(tiny_rig.pos_idx), tid, 128, 128)
+    assert np.abs(u.numpy() - rast[..., 0]).max() < 2e-5
+    assert np.abs(v.numpy() - rast[..., 1]).max() < 2e-5
+    assert np.abs(zw.numpy() - rast[..., 2]).max() < 1e-6
+    # db = analytic pixel differentials of (u, v): check against central differences of the fp64 formula
+    H = W = 128
+    fg = rast[..., 3] > 0
+    du_dx = np.zeros_like(rast[..., 0]); dv_dy = np.zeros_like(du_dx)
+    inner = fg[:, 1:-1, 1:-1] & (rast[:, 1:-1, 2:, 3] == rast[:, 1:-1, 1:-1, 3]) & (rast[:, 1:-1, :-2, 3] == rast[:, 1:-1, 1:-1, 3])
+    un = u.numpy()
+    du_dx_fd = (un[:, 1:-1, 2:] - un[:, 1:-1, :-2]) / 2
+    sel = inner & (un[:, 1:-1, 2:] > 0) & (un[:, 1:-1, 2:] < 1) & (un[:, 1:-1, :-2] > 0) & (un[:, 1:-1, :-2] < 1)
+    assert sel.sum() > 50
+    np.testing.assert_allclose(db[:, 1:-1, 1:-1, 0][sel], du_dx_fd[sel], atol=2e-4)
+
+
+def _rand_like(a, seed):
+    return np.random.default_rng(seed).normal(size=a.shape).astype(np.float32)
+
+
+def test_rasterize_bwd_matches_autograd(tiny_rig):
+    pc = clip_positions(tiny_rig, w=np.linspace(0, 0.5, 16))
+    rast, _, _ = G.rasterize_fwd(pc, tiny_rig.pos_idx, (128, 128))
+    dy = _rand_like(rast, 1)
+    g = G.rasterize_bwd(pc, tiny_rig.pos_idx, rast, dy)
+    pos = torch.tensor(pc).double().requires_grad_(True)
+    tid = torch.tensor(rast[..., 3]).long() - 1
+    u, v, zw = TR.barycentrics(pos, torch.tensor(tiny_rig.pos_idx), tid, 128, 128)
+    (u * torch.tensor(dy[..., 0]).double() + v * torch.tensor(dy[..., 1]).double()).sum().backward()
+    ref = pos.grad.numpy()
+    assert np.abs(ref[..., 2]).max() == 0 and np.abs(g[..., 2]).max() == 0   # no gradient to clip z
+    scale = np.abs(ref).max()
+    assert scale > 0
+    assert np.abs(g - ref).max() / scale < 1e-4
+
+
+@pytest.mark.parametrize('A,bc', [(2, True), (3, True), (5, False)])
+def test_interpolate_matches_autograd(small_rig3, A, bc):
+    r = small_rig3
+    pc = clip_positions(r)
+    H, W = 152, 200
+    rast, _, _ = G.rasterize_fwd(pc, r.pos_idx, (H, W))
+    N = rast.shape[0]
+    rng = np.random.default_rng(2)
+    if A == 2:
+        attr, idx = r.uv[None], r.uv_idx
+    else:
+        attr, idx = rng.normal(size=(1 if bc else N, r.V, A)).astype(np.float32), r.pos_idx
+    out = G.interpolate_fwd(attr, rast, idx)
+    at = torch.tensor(attr).double().requires_grad_(True)
+    ra = torch.tensor(rast).double().requires_grad_(True)
+    ref = TR.interpolate(at, ra, torch.tensor(idx))
+    assert np.abs(out - ref.detach().numpy()).max() < 1e-5
+    dy = _rand_like(out, 3)
+    ga, gr = G.interpolate_bwd(attr, rast, idx, dy)
+    (ref * torch.tensor(dy).double()).sum().backward()
+    assert np.abs(ga - at.grad.numpy()).max() / np.abs(at.grad.numpy()).max() < 1e-4
+    assert np.abs(gr[..., :2] - ra.grad.numpy()[..., :2]).max() / np.abs(ra.grad.numpy()).max() < 1e-4
+    assert (gr[..., 2:] == 0).all()
+    assert (out[rast[..., 3] == 0] == 0).all()
+
+
+@pytest.mark.parametrize('C,Nt', [(1, 1), (3, 1), (2, 2)])
+def test_texture_matches_autograd(C, Nt):
+    rng = np.random.default_rng(4)
+    N, H, W, Ht, Wt = 2, 9, 11, 8, 16
+    tex = rng.random((Nt, Ht, Wt, C)).astype(np.float32)
+    uv = rng.uniform(-1.5, 2.5, size=(N, H, W, 2)).astype(np.float32)   # exercises wrap on both sides
+    uv[0, 0, 0] = (0.0, 0.0)                                             # background texel corner (App. A.3)
+    uv[0, 0, 1] = (1.0 - 1e-7, 0.5 / Ht)
+    out = G.texture_linear_fwd(tex, uv)
+    tt = torch.tensor(tex).double().requires_grad_(True)
+    tu = torch.tensor(uv).double().requires_grad_(True)
+    ref = TR.texture_linear(tt, tu)
+    assert np.abs(out - ref.detach().numpy()).max() < 1e-5
+    # uv = (0,0) samples the wrapped corner average
+    np.testing.assert_allclose(out[0, 0, 0], 0.25 * (tex[0, 0, 0] + tex[0, 0, -1] + tex[0, -1, 0] + tex[0, -1, -1]), rtol=1e-6)
+    dy = _rand_like(out, 5)
+    gt, guv = G.texture_linear_bwd(tex, uv, dy)
+    (ref * torch.tensor(dy).double()).sum().backward()
+    assert np.abs(gt - tt.grad.numpy()).max() / np.abs(tt.grad.numpy()).max() < 1e-4
+    # fp32 rounding of the fractional position changes d/duv by ~1e-5 relative; compare at 1e-3 of the max
+    assert np.abs(guv - tu.grad.numpy()).max() / np.abs(tu.grad.numpy()).max() < 1e-3
+
+
+def test_topology(tiny_rig):
+    opp = G.topology_build(tiny_rig.pos_idx)
+    assert opp.shape == (tiny_rig.T, 3) and (opp >= 0).all()       # closed mesh: every edge has a wing
+    tri = tiny_rig.pos_idx
+    # brute force on a few triangles
+    for t in (0, 7, 1234):
+        for e in range(3):
+            va, vb = tri[t, (e + 1) % 3], tri[t, (e + 2) % 3]
+            cands = [s for s in range(tri.shape[0]) if s != t and va in tri[s] and vb in tri[s]]
+            assert len(cands) == 1
+            third = [x for x in tri[cands[0]] if x != va and x != vb][0]
+            assert opp[t, e] == third
+    # open mesh: boundary edges have no opposite vertex
+    opp2 = G.topology_build(np.array([[0, 1, 2], [0, 2, 3]], np.int32))
+    assert opp2.tolist() == [[-1, 3, -1], [-1, -1, 1]]
+
+
+def test_antialias_matches_autograd(small_rig3):
+    r = small_rig3
+    pc = clip_positions(r, w=np.linspace(0, 0.4, 8))
+    H, W = 152, 200
+    rast, _, _ = G.rasterize_fwd(pc, r.pos_idx, (H, W))
+    rng = np.random.default_rng(6)
+    col = rng.random(rast.shape[:3] + (3,)).astype(np.float32)
+    opp = G.topology_build(r.pos_idx)
+    out = G.antialias_fwd(col, rast, pc, r.pos_idx, opp)
+    changed = (np.abs(out - col).max(axis=-1) > 0)
+    assert 50 < changed.sum() < 0.1 * changed.size                 # only silhouette pixels are touched
+    tc = torch.tensor(col).double().requires_grad_(True)
+    tp = torch.tensor(pc).double().requires_grad_(True)
+    ref = TR.antialias(tc, torch.tensor(rast).double(), tp, torch.tensor(r.pos_idx), torch.tensor(opp))
+    # the fp64 restatement can flip a marginal silhouette decision; allow a handful of pixels
+    bad = np.abs(out - ref.detach().numpy()).max(axis=-1) > 1e-4
+    assert bad.sum() <= 4, bad.sum()
+    dy = _rand_like(out, 7)
+    dy[bad] = 0
+    gc, gp = G.antialias_bwd(col, rast, pc, r.pos_idx, dy, opp)
+    (ref * torch.tensor(dy).double()).sum().backward()
+    assert np.abs(gc - tc.grad.numpy()).max() < 1e-3
+    ref_gp = tp.grad.numpy()
+    # position gradient: golden uses the 1e-3 px regulariser on 1/dy (App. A.4), autograd the exact derivative
+    denom = np.abs(ref_gp).max()
+    assert denom > 0
+    assert np.abs(gp - ref_gp).max() / denom < 2e-2
+    assert np.abs(gp[..., 2]).max() == 0
+
+
+def test_torch_stages(tiny_rig):
+    r = tiny_rig
+    w = torch.linspace(0, 1, r.B)
+    v = G.blend(torch.tensor(r.v_base), torch.tensor(r.D), w)
+    np.testing.assert_allclose(v.numpy(), r.v_base + r.D @ w.numpy(), rtol=1e-5, atol=1e-5)
+    ident = G.mvp_chain(torch.tensor(r.P[0]), torch.tensor(r.A[0]), torch.zeros(3), torch.tensor([0., 0, 0, 1]))
+    np.testing.assert_allclose(ident.numpy(), r.P[0] @ r.A[0], rtol=1e-6)
+    img = G.render(ident, v.reshape(-1, 3), torch.tensor(r.pos_idx), (128, 128), vcol=torch.tensor(r.vcol),
+                   use_antialias=False)
+    assert img.shape == (128, 128, 3)
+    assert torch.allclose(img[0, 0], torch.tensor(G.BG))            # corner pixel is background 45/255
+    ref = torch.clamp(img * 255, 0, 140)
+    assert float(G.image_loss(ref, img)) < 1e-6

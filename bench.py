@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — fit iterations/s of the B200-native hot path (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config1|config3]
+
+A "step" is one fit iteration (forward + backward + Adam) over ALL 9 views of every frame of the local batch.
+N = 1 workload: BASELINE.json configs[1] — 20k-vertex / 40k-triangle rig, 200 blendshapes, 9 calibrated cameras
+at 1024x1024, single frame, vertex-colour shading.  N > 1: one process per GPU (torchrun), every rank fits its
+own frame(s) of the sequence (frames are independent units: no data-path collective) -> weak scaling.
+
+value   : steps/s x N with all inputs resident in HBM, K replays of the captured CUDA graph, CUDA events,
+          barrier + synchronize on both sides, max over ranks.
+e2e     : the same metric through FitSession.iteration_from_host(): every step uploads that step's reference
+          frames from pinned host memory and reads the loss back.
+roofline: the dominant kernel group (largest share of the step), timed per launch with CUDA events in an eager
+          pass of the same K steps; achieved = algorithmic bytes of that op (SURVEY §8(d) formulas)
+          / its mean duration; peak = MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference: the CPU oracle (oracle/: torch CPU stages + scalar golden rasterizer, OpenMP
+          over views) timed on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'fit iters/s (fwd+bwd+Adam, 9 views, 1024^2)'
+UNIT = 'iters/s'
+
+WORKLOADS = {
+    # name: (V, B, cams, H, W, frames per GPU, shading, antialias, tex)
+    'config1': dict(V=1000, B=16, C=1, H=128, W=128, F=1, shading='vcol', aa=False, tex=64,
+                    desc='BASELINE configs[0]: 1k-vertex/2k-tri rig, 16 blendshapes, 1 camera 128x128, 1 frame'),
+    'config2': dict(V=20000, B=200, C=9, H=1024, W=1024, F=1, shading='vcol', aa=False, tex=64,
+                    desc='BASELINE configs[1]: 20k-vertex/40k-tri rig, 200 blendshapes, 9 cameras 1024x1024, single frame, vertex-colour shading'),
+    'config3': dict(V=20000, B=200, C=9, H=1024, W=1024, F=8, shading='texture', aa=True, tex=1024,
+                    desc='BASELINE configs[2] at 8 frames/GPU: textured + antialias'),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic inputs (seeded)
+# ---------------------------------------------------------------------------------------------------------
+
+def make_inputs(wl, n_frames, frame_seed=1):
+    from fpc_diffrend_b200 import rig as rigmod
+    rig = rigmod.make_rig(n_vertices=wl['V'], n_shapes=wl['B'], n_cams=wl['C'], width=wl['W'], height=wl['H'],
+                          tex_size=wl['tex'], seed=0)
+    w_true, t_true, q_true = rigmod.make_targets(n_frames, wl['B'], seed=frame_seed)
+    return rig, w_true, t_true, q_true
+
+
+# ---------------------------------------------------------------------------------------------------------
+# algorithmic bytes per op (SURVEY §8(d) "ALGORITHMIC bytes"; restated in DESIGN.md)
+# ---------------------------------------------------------------------------------------------------------
+
+def algorithmic_bytes(wl, F, Vt):
+    V, B, C, H, W = wl['V'], wl['B'], wl['C'], wl['H'], wl['W']
+    T = 2 * V - 4
+    N = F * C
+    px = N * H * W
+    geo = N * 16 * V + 12 * T
+    Ch = 3 if wl['shading'] == 'vcol' else 1
+    A = Ch if wl['shading'] == 'vcol' else 2
+    Va = V if wl['shading'] == 'vcol' else Vt
+    R = 3 * V
+    b = {
+        'blend_fwd': 4 * (R * B + R + B * F + R * F),
+        'blend_bwd': 4 * (R * B + R * F + B * F),
+        'project_fwd': 4 * (R * F) + 64 * N + 16 * N * V,
+        'project_bwd': 4 * (R * F) + 64 * N + 16 * N * V + 12 * V * F,
+        'rasterize_fwd': 16 * px + geo,
+        'rasterize_bwd': 32 * px + geo + 16 * N * V,
+        'interpolate_fwd': (16 + 4 * A) * px + 12 * T + 4 * A * Va,
+        'interpolate_bwd': (4 * A + 16 + 16) * px + 12 * T + 8 * A * Va,
+        'image_loss': (4 * Ch + 4 * Ch + 4 + 4 * Ch) * px,
+        'adam': 28 * F * (B + 7),
+        'pose_mvp_fwd': 64 * 3 * N,
+        'pose_mvp_bwd': 64 * 3 * N,
+    }
+    if wl['shading'] == 'texture':
+        b['texture_fwd'] = (8 + 4 * Ch) * px + 4 * Ch * wl['tex'] ** 2
+        b['texture_bwd'] = (4 * Ch + 8 + 8) * px + 4 * Ch * wl['tex'] ** 2
+    if wl['aa']:
+        b['antialias_fwd'] = (4 * Ch + 16 + 4 * Ch) * px + geo
+        b['antialias_bwd'] = (4 * Ch + 4 * Ch + 16 + 4 * Ch) * px + geo + 16 * N * V
+    return b
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.tmp = None
+
+    def start(self):
+        try:
+            self.tmp = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(nme)
+        os.unlink(self.tmp.name)
+        if sm:
+            out = {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU oracle arm (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------------
+
+def cpu_oracle_rate(wl, budget_s=15.0, max_iters=10):
+    """Fit iterations/s of the CPU oracle (torch CPU blend/project/loss + golden rasterizer with autograd +
+    torch Adam) on one frame of the workload; bounded sample: 1 warm-up + up to max_iters timed iterations."""
+    import torch
+    from oracle import golden as G
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    rig, w_true, t_true, q_true = make_inputs(wl, 1)
+    H, W, C = wl['H'], wl['W'], wl['C']
+    tri = torch.tensor(rig.pos_idx)
+    opp = torch.tensor(G.topology_build(rig.pos_idx)) if wl['aa'] else None
+    base, D = torch.tensor(rig.v_base), torch.tensor(rig.D)
+    Ps, As = torch.tensor(rig.P), torch.tensor(rig.A)
+    vcol = torch.tensor(rig.vcol)
+    uv, uv_idx, tex = torch.tensor(rig.uv), torch.tensor(rig.uv_idx), torch.tensor(rig.tex)
+
+    def render_all(w, t, q):
+        """All C views of one frame as ONE batched golden call per op (OpenMP over views inside golden.c)."""
+        verts = G.blend(base, D, w).reshape(-1, 3)
+        pcs = torch.cat([G.transform_clip(G.mvp_chain(Ps[c], As[c], t, q), verts) for c in range(C)])
+        rast, _ = G.rasterize(pcs, tri, (H, W))
+        if wl['shading'] == 'vcol':
+            col = G.interpolate(vcol[None], rast, tri)
+        else:
+            col = G.texture(tex[None], G.interpolate(uv[None], rast, uv_idx))
+        if wl['aa']:
+            col = G.antialias(col, rast, pcs, tri, opp)
+        return torch.where(rast[..., 3:] > 0, col, torch.tensor(G.BG))
+
+    with torch.no_grad():
+        ref = torch.clamp(render_all(torch.tensor(w_true[0]), torch.tensor(t_true[0]), torch.tensor(q_true[0])) * 255, 0, 140)
+    w = torch.zeros(wl['B'], requires_grad=True)
+    t = torch.zeros(3, requires_grad=True)
+    q = torch.tensor([0., 0, 0, 1], requires_grad=True)
+    opt = torch.optim.Adam([{'params': w, 'lr': 1e-3}, {'params': t, 'lr': 1e-5}, {'params': q, 'lr': 1e-5}])
+
+    def step():
+        img = render_all(w, t, q)
+        loss = sum(G.image_loss(ref[c], img[c]) for c in range(C)) / C
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            q.div_(q.norm())
+        return float(loss.detach())
+
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_iters and (n == 0 or time.perf_counter() - t0 < budget_s):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, cores, '%d fit iteration(s) of one frame (all %d views) after 1 warm-up, %.1f s' % (n, C, dt)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rate, cores, sample = cpu_oracle_rate(wl, budget_s=40.0, max_iters=max(1, min(args.steps, 5)))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1000.0 / rate, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl['desc'], 'note': 'CPU oracle port (nvdiffrast has no CPU backend; reference GPU path not installable offline)'},
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the fit hot path has no CPU fallback (use --impl reference for the CPU oracle)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    F = wl['F']
+    # frames of the sequence are sharded by rank: rank r owns frames [r*F, (r+1)*F)
+    rig, w_all, t_all, q_all = make_inputs(wl, F * world)
+    sl = slice(rank * F, (rank + 1) * F)
+    cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'])
+    ref = synthesize_reference(rig, w_all[sl], t_all[sl], q_all[sl], cfg)
+    sess = FitSession(rig, F, cfg)
+    sess.set_reference(ref)
+    ref_host = ref.cpu().pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+    del ref
+    torch.cuda.empty_cache()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt)
+
+    launches = sess.iteration()           # first eager iteration (also warms the allocator)
+    use_graph = not args.no_graph
+    if use_graph:
+        sess.capture()
+    step = sess.replay if use_graph else sess.iteration
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / args.steps
+    value = world * F * 1000.0 / ms_per_step / F    # iterations/s summed over ranks (each rank iterates its own frames)
+    frames_per_s = world * F * 1000.0 / ms_per_step
+
+    # ---- e2e: host buffers in, loss out, every step ----
+    for _ in range(3):
+        sess.iteration_from_host(ref_host, loss_host)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        sess.iteration_from_host(ref_host, loss_host)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0 if world == 1 else 0.0)) / args.steps
+    e2e = {'value': world * 1000.0 / e2e_ms, 'unit': UNIT, 'h2d_bytes_per_step': int(ref_host.numel() * 4),
+           'd2h_bytes_per_step': 4}
+
+    # ---- roofline: per-op CUDA-event timing over an eager pass of the same K steps ----
+    sess.stage_events = {}
+    for _ in range(args.steps):
+        sess.iteration()
+    torch.cuda.synchronize()
+    stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in sess.stage_events.items()}
+    sess.stage_events = None
+    total_stage = sum(stage_ms.values())
+    top = max(stage_ms, key=stage_ms.get)
+    alg = algorithmic_bytes(wl, F, rig.uv.shape[0])
+    peak, peak_src = measured_peak()
+    achieved = alg[top] / (stage_ms[top] * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[top],
+                'avg_ms_per_launch': stage_ms[top], 'share_of_step': stage_ms[top] / total_stage}
+    stages = {k: {'ms': round(v, 4), 'share': round(v / total_stage, 4),
+                  'GBps_algorithmic': round(alg[k] / (v * 1e-3) / 1e9, 1) if k in alg and v > 0 else None}
+              for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': wl['desc'], 'frames_per_gpu': F, 'frames_fitted_per_s': frames_per_s,
+                   'sharding': 'frames over ranks, no data-path collective' if world > 1 else 'single GPU',
+                   'cache': 'per-step working set (~GBs of per-pixel buffers) exceeds the 126 MB L2; D (48 MB) and geometry stay L2-resident across steps',
+                   'launch': 'CUDA graph replay' if use_graph else 'eager', 'loss_final': float(sess.loss)},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches * args.steps), 'roofline': roofline, 'stages': stages,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        rate, cores, sample = cpu_oracle_rate(wl)
+        line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+    elif world > 1:
+        line['cpu_baseline'] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == '__main__':
+    main()

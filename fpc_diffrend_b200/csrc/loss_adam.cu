@@ -111,9 +111,10 @@ __global__ void __launch_bounds__(256) k_quat_renorm(float* __restrict__ q, int 
     if (mode == 0) {
         int i = blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= n) return;
-        float4 v = reinterpret_cast<float4*>(q)[i];
-        float s = rsqrtf(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
-        reinterpret_cast<float4*>(q)[i] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+        // q may sit at any 4-byte offset inside a packed parameter buffer: scalar accesses
+        float x = q[4 * i], y = q[4 * i + 1], z = q[4 * i + 2], w = q[4 * i + 3];
+        float s = 1.f / sqrtf(x * x + y * y + z * z + w * w);
+        q[4 * i] = x * s; q[4 * i + 1] = y * s; q[4 * i + 2] = z * s; q[4 * i + 3] = w * s;
         return;
     }
     // Frobenius: single CTA

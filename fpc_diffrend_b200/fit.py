@@ -141,6 +141,7 @@ class FitSession:
         self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         self.graph = None
         self.launches_per_iteration = 0
+        self.stage_events = None          # when a dict: stage name -> list of (start, end) CUDA events (bench.py)
 
     # ---- plumbing ------------------------------------------------------------------------------------
     @staticmethod
@@ -154,6 +155,24 @@ class FitSession:
         assert tuple(ref.shape) == (self.F, self.C, self.H, self.W, self.Ch), (tuple(ref.shape), (self.F, self.C, self.H, self.W, self.Ch))
         self.ref = ref.reshape(self.N, self.H, self.W, self.Ch).contiguous()
 
+    def iteration_from_host(self, frames_host, loss_host=None):
+        """The call a user of the drop-in makes per step with HOST buffers: upload this step's reference frames
+        (pinned host memory -> the resident device buffer), run one iteration (the captured graph when there is
+        one), read the loss back.  Returns the loss as a float (this synchronises the stream)."""
+        src = frames_host.reshape(self.N, self.H, self.W, self.Ch)
+        if self.ref is None:
+            self.ref = torch.empty(self.N, self.H, self.W, self.Ch, dtype=torch.float32, device=self.device)
+        self.ref.copy_(src, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.iteration()
+        if loss_host is None:
+            return float(self.loss)
+        loss_host.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+
     def set_parameters(self, w=None, t=None, q=None):
         if w is not None:
             self.w.copy_(torch.as_tensor(w, dtype=torch.float32))
@@ -162,72 +181,83 @@ class FitSession:
         if q is not None:
             self.q.copy_(torch.as_tensor(q, dtype=torch.float32))
 
+    def _timed(self, stage, name, *args):
+        """C-ABI call, bracketed by CUDA events on the launching stream when stage profiling is on."""
+        if self.stage_events is None:
+            _lib.call(name, *args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call(name, *args)
+        e1.record()
+        self.stage_events.setdefault(stage, []).append((e0, e1))
+
     # ---- one iteration -------------------------------------------------------------------------------
     def forward(self, with_loss=True):
         """Render all local views with the current parameters; returns the composited image tensor [N,H,W,Ch]
         when with_loss is False (used to synthesise reference frames), else fills self.loss / self.d_colour."""
-        cfg, s, call = self.cfg, self._stream(), _lib.call
+        cfg, s, call = self.cfg, self._stream(), self._timed
         F, V, T, B, C, H, W, N, Ch = self.F, self.V, self.T, self.B, self.C, self.H, self.W, self.N, self.Ch
         n = 0
-        call('fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, F, C, _p(self.mvp), s); n += 1
-        call('fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
-        call('fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
-        call('fpc_rasterize_fwd', _p(self.pos_clip), _p(self.pos_idx), N, V, T, H, W, _p(self.rast), None,
+        call('pose_mvp_fwd', 'fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, F, C, _p(self.mvp), s); n += 1
+        call('blend_fwd', 'fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
+        call('project_fwd', 'fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
+        call('rasterize_fwd', 'fpc_rasterize_fwd', _p(self.pos_clip), _p(self.pos_idx), N, V, T, H, W, _p(self.rast), None,
              _p(self.scratch), self.scratch.numel(), s); n += 4
         if cfg.shading == 'vcol':
-            call('fpc_interpolate_fwd', _p(self.attr), 1, V, Ch, _p(self.rast), _p(self.attr_idx), N, T, H, W, _p(self.colour), s); n += 1
+            call('interpolate_fwd', 'fpc_interpolate_fwd', _p(self.attr), 1, V, Ch, _p(self.rast), _p(self.attr_idx), N, T, H, W, _p(self.colour), s); n += 1
         else:
-            call('fpc_interpolate_fwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), N, T, H, W, _p(self.texc), s); n += 1
-            call('fpc_texture_linear_fwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), N, H, W, _p(self.colour), s); n += 1
+            call('interpolate_fwd', 'fpc_interpolate_fwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), N, T, H, W, _p(self.texc), s); n += 1
+            call('texture_fwd', 'fpc_texture_linear_fwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), N, H, W, _p(self.colour), s); n += 1
         final = self.colour
         if cfg.antialias:
-            call('fpc_antialias_fwd', _p(self.colour), _p(self.rast), _p(self.pos_clip), _p(self.pos_idx), _p(self.tri_opp),
+            call('antialias_fwd', 'fpc_antialias_fwd', _p(self.colour), _p(self.rast), _p(self.pos_clip), _p(self.pos_idx), _p(self.tri_opp),
                  N, V, T, H, W, Ch, _p(self.colour_aa), s); n += 1
             final = self.colour_aa
         if not with_loss:
             comp = torch.where(self.rast[..., 3:] > 0, final, torch.tensor(cfg.bg, device=self.device))
             return comp
         assert self.ref is not None, 'call set_reference() first'
-        call('fpc_image_loss_fwd_bwd', _p(final), _p(self.rast), _p(self.ref), N, H, W, Ch, cfg.bg, 1.0 / self.C_total,
+        call('image_loss', 'fpc_image_loss_fwd_bwd', _p(final), _p(self.rast), _p(self.ref), N, H, W, Ch, cfg.bg, 1.0 / self.C_total,
              _p(self.loss), _p(self.d_colour), None, _p(self.scratch), self.scratch.numel(), s); n += 2
         return n
 
     def backward(self):
-        cfg, s, call = self.cfg, self._stream(), _lib.call
+        cfg, s, call = self.cfg, self._stream(), self._timed
         F, V, T, B, C, H, W, N, Ch = self.F, self.V, self.T, self.B, self.C, self.H, self.W, self.N, self.Ch
         n = 0
         g_colour = self.d_colour
         if cfg.antialias:
-            call('fpc_antialias_bwd', _p(self.colour), _p(self.rast), _p(self.pos_clip), _p(self.pos_idx), _p(self.tri_opp),
+            call('antialias_bwd', 'fpc_antialias_bwd', _p(self.colour), _p(self.rast), _p(self.pos_clip), _p(self.pos_idx), _p(self.tri_opp),
                  _p(self.d_colour), N, V, T, H, W, Ch, _p(self.g_colour_pre), _p(self.g_pos_aa), s); n += 2
             g_colour = self.g_colour_pre
         if cfg.shading == 'vcol':
-            call('fpc_interpolate_bwd', _p(self.attr), 1, V, Ch, _p(self.rast), _p(self.attr_idx), _p(g_colour), N, T, H, W,
+            call('interpolate_bwd', 'fpc_interpolate_bwd', _p(self.attr), 1, V, Ch, _p(self.rast), _p(self.attr_idx), _p(g_colour), N, T, H, W,
                  _p(self.g_attr), _p(self.g_rast), s); n += 2
         else:
-            call('fpc_texture_linear_bwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), _p(g_colour),
+            call('texture_bwd', 'fpc_texture_linear_bwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), _p(g_colour),
                  N, H, W, None, _p(self.g_texc), s); n += 1
-            call('fpc_interpolate_bwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), _p(self.g_texc),
+            call('interpolate_bwd', 'fpc_interpolate_bwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), _p(self.g_texc),
                  N, T, H, W, _p(self.g_attr), _p(self.g_rast), s); n += 2
-        call('fpc_rasterize_bwd', _p(self.pos_clip), _p(self.pos_idx), _p(self.rast), _p(self.g_rast), N, V, T, H, W,
+        call('rasterize_bwd', 'fpc_rasterize_bwd', _p(self.pos_clip), _p(self.pos_idx), _p(self.rast), _p(self.g_rast), N, V, T, H, W,
              _p(self.g_pos), s); n += 2
         if cfg.antialias:
             self.g_pos.add_(self.g_pos_aa); n += 1
-        call('fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
+        call('project_bwd', 'fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
              _p(self.scratch), self.scratch.numel(), s); n += 2
-        call('fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
-        call('fpc_pose_mvp_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.d_mvp), F, C,
+        call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
+        call('pose_mvp_bwd', 'fpc_pose_mvp_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.d_mvp), F, C,
              _p(self.d_t), _p(self.d_q), s); n += 1
         return n
 
     def optimizer_step(self):
-        cfg, s, call = self.cfg, self._stream(), _lib.call
+        cfg, s, call = self.cfg, self._stream(), self._timed
         F, B = self.F, self.B
         n = 0
         if cfg.cam_slice is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             torch.distributed.all_reduce(self.grads)   # the only exchange of the camera-split mode: (B+7) F floats
         nw = F * B
-        adam = lambda off, cnt, lr: call('fpc_adam_step', ctypes.c_void_p(self.params.data_ptr() + 4 * off),
+        adam = lambda off, cnt, lr: call('adam', 'fpc_adam_step', ctypes.c_void_p(self.params.data_ptr() + 4 * off),
                                          ctypes.c_void_p(self.grads.data_ptr() + 4 * off),
                                          ctypes.c_void_p(self.adam_m.data_ptr() + 4 * off),
                                          ctypes.c_void_p(self.adam_v.data_ptr() + 4 * off), cnt, lr, cfg.beta1, cfg.beta2,
@@ -236,8 +266,8 @@ class FitSession:
         if cfg.optimize_pose:
             adam(nw, F * 3, cfg.lr_t); n += 1
             adam(nw + F * 3, F * 4, cfg.lr_q); n += 1
-            call('fpc_quat_renorm', _p(self.q), F, 1 if cfg.quat_norm == 'frobenius' else 0, s); n += 1
-        call('fpc_adam_advance', _p(self.step_count), s); n += 1
+            call('adam', 'fpc_quat_renorm', _p(self.q), F, 1 if cfg.quat_norm == 'frobenius' else 0, s); n += 1
+        call('adam', 'fpc_adam_advance', _p(self.step_count), s); n += 1
         return n
 
     def iteration(self):

@@ -1,0 +1,213 @@
+"""GPU parity tests: every op of the drop-in (fpc_diffrend_b200.ops -> C-ABI -> CUDA kernels) against the
+CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): tri_id bit-exact wherever there is no depth tie; images and
+barycentrics 1e-5 abs; gradients 1e-4 relative (to the largest gradient magnitude of the tensor)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import clip_positions
+from oracle import golden as G
+
+pytestmark = pytest.mark.gpu
+
+ABS_FWD = 1e-5
+REL_GRAD = 1e-4
+
+
+@pytest.fixture(scope='module')
+def dr():
+    import fpc_diffrend_b200.ops as ops
+    assert torch.cuda.is_available()
+    return ops
+
+
+def cu(a, dtype=None):
+    t = torch.as_tensor(a)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def rel_err(a, ref):
+    return np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+def _scene(rig, H, W, w=None):
+    pc = clip_positions(rig, w=w)
+    rast, db, sec = G.rasterize_fwd(pc, rig.pos_idx, (H, W), with_second=True)
+    return pc, rast, db, sec
+
+
+def _check_rast(out, out_db, rast, db, sec):
+    ids, ids_ref = out[..., 3], rast[..., 3]
+    # depth near-tie mask: runner-up within 4 ulp of the winner (north-star: "wherever there is no depth tie")
+    tie = (sec - rast[..., 2]) <= 4 * np.spacing(np.abs(rast[..., 2]).astype(np.float32))
+    mism = (ids != ids_ref)
+    assert (mism & ~tie).sum() == 0, 'tri_id differs on %d non-tie pixels' % (mism & ~tie).sum()
+    ok = ~mism
+    assert np.abs(out[..., :3] - rast[..., :3])[ok].max() <= ABS_FWD
+    if out_db is not None:
+        assert rel_err(out_db[ok], db[ok]) < 1e-5
+    return int(mism.sum())
+
+
+@pytest.mark.parametrize('rigname,H,W', [('tiny_rig', 128, 128), ('small_rig3', 152, 200), ('small_rig3', 64, 64), ('tiny_rig', 77, 203)])
+def test_rasterize_fwd(dr, request, rigname, H, W):
+    rig = request.getfixturevalue(rigname)
+    pc, rast, db, sec = _scene(rig, H, W, w=np.linspace(0, 0.5, rig.B))
+    ctx = dr.RasterizeGLContext(device='cuda')
+    out, out_db = dr.rasterize(ctx, cu(pc), cu(rig.pos_idx), resolution=(H, W))
+    assert out.shape == (pc.shape[0], H, W, 4) and out_db.shape == out.shape
+    n_mism = _check_rast(out.cpu().numpy(), out_db.cpu().numpy(), rast, db, sec)
+    assert n_mism == 0          # same fp32 op order on both sides: even ties agree
+    # bit-exactness of the float outputs is not required, but the id plane must be integers and bg zero
+    bg = out[..., 3] == 0
+    assert (out[bg] == 0).all() and (out_db[bg] == 0).all()
+    # second call reuses the context scratch and is deterministic
+    out2, _ = dr.rasterize(ctx, cu(pc), cu(rig.pos_idx), resolution=(H, W))
+    assert torch.equal(out, out2)
+
+
+def test_rasterize_edge_cases(dr):
+    ctx = dr.RasterizeCudaContext()
+    # (a) watertight shared diagonal, (b) exact depth tie -> lower index, (c) large triangle (> 2x2 bins),
+    # (d) triangle behind the camera / outside the depth range / degenerate dropped, (e) off-screen vertices
+    quad = np.array([[[-0.5, -0.5, 0, 1], [0.5, -0.5, 0, 1], [0.5, 0.5, 0, 1], [-0.5, 0.5, 0, 1]]], np.float32)
+    tri = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    big = np.array([[[-3, -3, 0.2, 1], [3, -3, 0.2, 1], [0, 3.5, 0.2, 1], [0.9, 0.9, -0.3, 1], [0.95, 0.9, -0.3, 1], [0.9, 0.97, -0.3, 1],
+                     [0, 0, 0, -1], [1, 0, 0, 1], [0, 1, 0, 1], [0, 0, 1.5, 1], [1, 0, 1.5, 1], [0, 1, 1.5, 1]]], np.float32)
+    tri_big = np.array([[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10, 11], [3, 3, 4]], np.int32)
+    cases = [(quad, tri, (16, 16)), (np.concatenate([quad, quad], 1), np.concatenate([tri + 4, tri]), (16, 16)),
+             (big, tri_big, (300, 260)), (quad * np.array([40, 40, 1, 1], np.float32), tri, (130, 70))]
+    for pos, t, res in cases:
+        rast, db, sec = G.rasterize_fwd(pos, t, res, with_second=True)
+        out, out_db = dr.rasterize(ctx, cu(pos), cu(t), resolution=res)
+        assert np.array_equal(out[..., 3].cpu().numpy(), rast[..., 3])
+        assert np.abs(out.cpu().numpy() - rast).max() <= ABS_FWD
+        assert rel_err(out_db.cpu().numpy(), db) < 1e-5 or np.abs(db).max() == 0
+
+
+def test_rasterize_bwd(dr, small_rig3):
+    rig, H, W = small_rig3, 152, 200
+    pc, rast, db, sec = _scene(rig, H, W)
+    dy = np.random.default_rng(1).normal(size=rast.shape).astype(np.float32)
+    ref = G.rasterize_bwd(pc, rig.pos_idx, rast, dy)
+    ctx = dr.RasterizeCudaContext()
+    pos = cu(pc).requires_grad_(True)
+    out, _ = dr.rasterize(ctx, pos, cu(rig.pos_idx), resolution=(H, W))
+    assert np.array_equal(out[..., 3].detach().cpu().numpy(), rast[..., 3])
+    out.backward(cu(dy))
+    g = pos.grad.cpu().numpy()
+    assert rel_err(g, ref) < REL_GRAD
+    assert np.abs(g[..., 2]).max() == 0
+
+
+@pytest.mark.parametrize('A,bc', [(2, True), (3, True), (1, False), (6, False)])
+def test_interpolate(dr, small_rig3, A, bc):
+    rig, H, W = small_rig3, 152, 200
+    pc, rast, _, _ = _scene(rig, H, W)
+    N = rast.shape[0]
+    rng = np.random.default_rng(2)
+    if A == 2:
+        attr, idx = rig.uv[None], rig.uv_idx
+    else:
+        attr, idx = rng.normal(size=(1 if bc else N, rig.V, A)).astype(np.float32), rig.pos_idx
+    ref = G.interpolate_fwd(attr, rast, idx)
+    dy = rng.normal(size=ref.shape).astype(np.float32)
+    ga_ref, gr_ref = G.interpolate_bwd(attr, rast, idx, dy)
+    at, ra = cu(attr).requires_grad_(True), cu(rast).requires_grad_(True)
+    out, out_da = dr.interpolate(at, ra, cu(idx))
+    assert out_da.shape == (N, H, W, 0)
+    assert np.abs(out.detach().cpu().numpy() - ref).max() <= ABS_FWD
+    out.backward(cu(dy))
+    assert rel_err(at.grad.cpu().numpy(), ga_ref) < REL_GRAD
+    assert rel_err(ra.grad.cpu().numpy(), gr_ref) < REL_GRAD
+
+
+@pytest.mark.parametrize('C,Nt', [(1, 1), (3, 1), (2, 2), (4, 1)])
+def test_texture(dr, C, Nt):
+    rng = np.random.default_rng(4)
+    N, H, W, Ht, Wt = 2, 33, 47, 16, 32
+    tex = rng.random((Nt, Ht, Wt, C)).astype(np.float32)
+    uv = rng.uniform(-1.5, 2.5, size=(N, H, W, 2)).astype(np.float32)
+    uv[0, 0, 0] = (0.0, 0.0)
+    ref = G.texture_linear_fwd(tex, uv)
+    dy = rng.normal(size=ref.shape).astype(np.float32)
+    gt_ref, guv_ref = G.texture_linear_bwd(tex, uv, dy)
+    tt, tu = cu(tex).requires_grad_(True), cu(uv).requires_grad_(True)
+    out = dr.texture(tt, tu, filter_mode='linear')
+    assert np.abs(out.detach().cpu().numpy() - ref).max() <= ABS_FWD
+    out.backward(cu(dy))
+    assert rel_err(tt.grad.cpu().numpy(), gt_ref) < REL_GRAD
+    assert rel_err(tu.grad.cpu().numpy(), guv_ref) < REL_GRAD
+
+
+def test_topology(dr, tiny_rig):
+    ref = G.topology_build(tiny_rig.pos_idx)
+    h = dr.antialias_construct_topology_hash(cu(tiny_rig.pos_idx))
+    assert np.array_equal(h.tri_opp.cpu().numpy(), ref)
+    open_mesh = np.array([[0, 1, 2], [0, 2, 3], [2, 1, 4]], np.int32)
+    h2 = dr.antialias_construct_topology_hash(cu(open_mesh))
+    assert np.array_equal(h2.tri_opp.cpu().numpy(), G.topology_build(open_mesh))
+
+
+@pytest.mark.parametrize('C', [1, 3])
+def test_antialias(dr, small_rig3, C):
+    rig, H, W = small_rig3, 152, 200
+    pc, rast, _, _ = _scene(rig, H, W, w=np.linspace(0, 0.4, rig.B))
+    rng = np.random.default_rng(6)
+    col = rng.random(rast.shape[:3] + (C,)).astype(np.float32)
+    opp = G.topology_build(rig.pos_idx)
+    ref = G.antialias_fwd(col, rast, pc, rig.pos_idx, opp)
+    dy = rng.normal(size=ref.shape).astype(np.float32)
+    gc_ref, gp_ref = G.antialias_bwd(col, rast, pc, rig.pos_idx, dy, opp)
+    tc, tp = cu(col).requires_grad_(True), cu(pc).requires_grad_(True)
+    out = dr.antialias(tc, cu(rast), tp, cu(rig.pos_idx))
+    assert (np.abs(ref - col).max(-1) > 0).sum() > 50
+    assert np.abs(out.detach().cpu().numpy() - ref).max() <= ABS_FWD
+    out.backward(cu(dy))
+    assert np.abs(tc.grad.cpu().numpy() - gc_ref).max() <= 1e-5
+    assert rel_err(tp.grad.cpu().numpy(), gp_ref) < REL_GRAD
+
+
+def test_render_chain_like_reference(dr, tiny_rig):
+    """The reference's render() (fit.py:134-162) written against the drop-in, vs the oracle's render()."""
+    rig, H, W = tiny_rig, 128, 128
+    pc = clip_positions(rig)
+    verts = torch.tensor(rig.v_base).reshape(-1, 3)
+    mvp = G.mvp_chain(torch.tensor(rig.P[0]), torch.tensor(rig.A[0]), torch.zeros(3), torch.tensor([0., 0, 0, 1]))
+    opp = torch.tensor(G.topology_build(rig.pos_idx))
+    ref = G.render(mvp, verts, torch.tensor(rig.pos_idx), (H, W), uv=torch.tensor(rig.uv), uv_idx=torch.tensor(rig.uv_idx),
+                   tex=torch.tensor(rig.tex), tri_opp=opp).numpy()
+    glctx = dr.RasterizeGLContext(device='cuda')
+    pos_clip = cu(pc)
+    rast_out, rast_out_db = dr.rasterize(glctx, pos_clip, cu(rig.pos_idx), resolution=(H, W))
+    texc, _ = dr.interpolate(cu(rig.uv)[None, ...], rast_out, cu(rig.uv_idx))
+    colour = dr.texture(cu(rig.tex)[None, ...], texc, filter_mode='linear')
+    colour = dr.antialias(colour, rast_out, pos_clip, cu(rig.pos_idx))
+    colour = torch.where(rast_out[..., 3:] > 0, colour, torch.tensor(45.0 / 255.0).cuda())
+    assert np.abs(colour[0].cpu().numpy() - ref).max() <= ABS_FWD
+
+
+def test_full_size_properties(dr):
+    """BASELINE config 2 size (20k vertices / 40k triangles, 1024^2): one view against the oracle, and
+    size-independent properties on all 9 views (determinism, id range, interpolation of constants = mask)."""
+    from fpc_diffrend_b200 import rig as rigmod
+    rig = rigmod.make_rig(n_vertices=20000, n_shapes=4, n_cams=9, width=1024, height=1024, tex_size=64, seed=0)
+    pc = clip_positions(rig)
+    ctx = dr.RasterizeCudaContext()
+    out, _ = dr.rasterize(ctx, cu(pc), cu(rig.pos_idx), resolution=(1024, 1024))
+    out2, _ = dr.rasterize(ctx, cu(pc), cu(rig.pos_idx), resolution=(1024, 1024))
+    assert torch.equal(out, out2)
+    ids = out[..., 3]
+    assert ids.min() == 0 and ids.max() <= rig.T and torch.equal(ids, ids.round())
+    cov = (ids > 0).float().mean(dim=(1, 2))
+    assert (cov > 0.2).all() and (cov < 0.4).all()
+    ones = torch.ones(1, rig.V, 1, device='cuda')
+    m, _ = dr.interpolate(ones, out, cu(rig.pos_idx))
+    assert torch.allclose(m[..., 0], (ids > 0).float(), atol=1e-6)
+    rast, db, sec = G.rasterize_fwd(pc[4:5], rig.pos_idx, (1024, 1024), with_second=True)
+    n_mism = _check_rast(out[4:5].cpu().numpy(), None, rast, db, sec)
+    assert n_mism == 0

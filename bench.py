@@ -92,6 +92,8 @@ def algorithmic_bytes(wl, F, Vt):
         'interpolate_fwd': (16 + 4 * A) * px + 12 * T + 4 * A * Va,
         'interpolate_bwd': (4 * A + 16 + 16) * px + 12 * T + 8 * A * Va,
         'image_loss': (4 * Ch + 4 * Ch + 4 + 4 * Ch) * px,
+        # fused render+loss+gradient kernel as built: reference frame read + geometry + gradient accumulate
+        'render_loss_fused': 4 * Ch * px + geo + 12 * T + 4 * A * Va + 2 * 16 * N * V,
         'adam': 28 * F * (B + 7),
         'pose_mvp_fwd': 64 * 3 * N,
         'pose_mvp_bwd': 64 * 3 * N,
@@ -341,6 +343,12 @@ def run_ours(args, wl):
     roofline = {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[top],
                 'avg_ms_per_launch': stage_ms[top], 'share_of_step': stage_ms[top] / total_stage}
+    if top == 'render_loss_fused':
+        # context: the op-boundary chain this kernel replaces would move SURVEY §8(d)'s fused-path model of 56+20C B/px
+        Ch = 3 if wl['shading'] == 'vcol' else 1
+        model = (56 + 20 * Ch) * F * wl['C'] * wl['H'] * wl['W']
+        roofline['note'] = ('kernel is issue-bound, not HBM-bound: its compulsory traffic is only the reference frame, geometry and '
+                            'gradients; SURVEY fused-path model (56+20C B/px) would be %.1f GB/s' % (model / (stage_ms[top] * 1e-3) / 1e9))
     stages = {k: {'ms': round(v, 4), 'share': round(v / total_stage, 4),
                   'GBps_algorithmic': round(alg[k] / (v * 1e-3) / 1e9, 1) if k in alg and v > 0 else None}
               for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}

@@ -10,78 +10,11 @@
 //             covered pixel; after a barrier the CTA shades its 4096 pixels straight from the keys and
 //             writes rast / rast_db — the key buffer never touches HBM.
 // Semantics (bit-identical to oracle/golden.c): DESIGN.md "Rasterizer semantics".
-#include "common.cuh"
+#include "raster_core.cuh"
+
+using namespace fpc;
 
 namespace {
-
-constexpr int BIN = 64;              // bin edge in pixels
-constexpr int BIN_LOG2 = 6;
-constexpr int FINE_THREADS = 256;
-constexpr float SNAP_LIMIT = 16777216.0f;
-constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
-
-struct RasterParams {
-    const float* pos;
-    const int32_t* tri;
-    int N, V, T, H, W;
-    int BW, BH, NB;
-    float xs, xo, ys, yo;            // pixel -> NDC
-    float sxs, sys;                  // NDC -> 1/16 px:  8*W, 8*H
-    int* bin_count;                  // [N*NB]
-    int* bin_cursor;                 // [N*NB]
-    int* large_count;                // [N]
-    int* bin_offset;                 // [N*NB]
-    int* tri_info;                   // [N*T]
-    int* pairs;                      // [N*4T]
-    int* large_list;                 // [N*T]
-};
-
-struct SnappedTri {
-    int x0, y0, x1, y1, x2, y2;      // 1/16 px, oriented to positive area
-    int pxa, pxb, pya, pyb;          // candidate pixel range clamped to the image
-};
-
-__device__ __forceinline__ bool snap_vertex(const float4& p, float sxs, float sys, int& sx, int& sy)
-{
-    if (!(p.w > 0.f)) return false;
-    float rw = xdiv(1.0f, p.w);
-    float xf = xadd(xmul(xmul(p.x, rw), sxs), sxs);
-    float yf = xadd(xmul(xmul(p.y, rw), sys), sys);
-    if (!(fabsf(xf) < SNAP_LIMIT) || !(fabsf(yf) < SNAP_LIMIT)) return false;
-    sx = __float2int_rn(xf);
-    sy = __float2int_rn(yf);
-    return true;
-}
-
-// Returns false when the triangle produces no fragments at all.
-__device__ __forceinline__ bool setup_triangle(const float4& p0, const float4& p1, const float4& p2,
-                                               const RasterParams& rp, SnappedTri& s)
-{
-    if (!snap_vertex(p0, rp.sxs, rp.sys, s.x0, s.y0) || !snap_vertex(p1, rp.sxs, rp.sys, s.x1, s.y1) ||
-        !snap_vertex(p2, rp.sxs, rp.sys, s.x2, s.y2))
-        return false;
-    long long area = (long long)(s.x1 - s.x0) * (s.y2 - s.y0) - (long long)(s.x2 - s.x0) * (s.y1 - s.y0);
-    if (area == 0) return false;
-    if (area < 0) { int tx = s.x1, ty = s.y1; s.x1 = s.x2; s.y1 = s.y2; s.x2 = tx; s.y2 = ty; }
-    int minx = min(s.x0, min(s.x1, s.x2)), maxx = max(s.x0, max(s.x1, s.x2));
-    int miny = min(s.y0, min(s.y1, s.y2)), maxy = max(s.y0, max(s.y1, s.y2));
-    s.pxa = max((minx - 8 + 15) >> 4, 0);
-    s.pxb = min((maxx - 8) >> 4, rp.W - 1);
-    s.pya = max((miny - 8 + 15) >> 4, 0);
-    s.pyb = min((maxy - 8) >> 4, rp.H - 1);
-    return s.pxa <= s.pxb && s.pya <= s.pyb;
-}
-
-__device__ __forceinline__ bool load_triangle(const RasterParams& rp, int n, int t, float4& p0, float4& p1, float4& p2)
-{
-    int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
-    if ((unsigned)i0 >= (unsigned)rp.V || (unsigned)i1 >= (unsigned)rp.V || (unsigned)i2 >= (unsigned)rp.V) return false;
-    const float* P = rp.pos + (size_t)n * rp.V * 4;
-    p0 = ldg4(P + 4 * (size_t)i0);
-    p1 = ldg4(P + 4 * (size_t)i1);
-    p2 = ldg4(P + 4 * (size_t)i2);
-    return true;
-}
 
 // tri_info: bits 0..9 bx0, 10..19 by0, 20 (nbx-1), 21 (nby-1), 22..23 class (0 none, 1 small, 2 large)
 __global__ void __launch_bounds__(256) k_setup(RasterParams rp)
@@ -94,7 +27,7 @@ __global__ void __launch_bounds__(256) k_setup(RasterParams rp)
     int info = 0;
     if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
         int bx0 = s.pxa >> BIN_LOG2, bx1 = s.pxb >> BIN_LOG2, by0 = s.pya >> BIN_LOG2, by1 = s.pyb >> BIN_LOG2;
-        if (bx1 - bx0 > 1 || by1 - by0 > 1) {
+        if (!is_small(s)) {
             int slot = atomicAdd(rp.large_count + n, 1);
             rp.large_list[(size_t)n * rp.T + slot] = t;
             info = 2 << 22;
@@ -153,102 +86,14 @@ __global__ void __launch_bounds__(256) k_fill(RasterParams rp)
         }
 }
 
-__device__ __forceinline__ unsigned depth_key(float zw)
-{
-    unsigned b = __float_as_uint(zw);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-
-struct EdgeEval {
-    long long e0, e1, e2;            // edge functions (+ fill-rule bias) at the first pixel of the walk
-    long long ax0, ax1, ax2;         // step per +1 px in x
-    long long ay0, ay1, ay2;         // step per +1 px in y
-};
-
-__device__ __forceinline__ long long edge_bias(long long dx, long long dy)
-{
-    return (dy > 0 || (dy == 0 && dx < 0)) ? 0 : -1;
-}
-
-__device__ __forceinline__ void edge_setup(const SnappedTri& s, int px, int py, EdgeEval& e)
-{
-    long long sx = 16 * px + 8, sy = 16 * py + 8;
-    long long ex0 = s.x1 - s.x0, ey0 = s.y1 - s.y0;
-    long long ex1 = s.x2 - s.x1, ey1 = s.y2 - s.y1;
-    long long ex2 = s.x0 - s.x2, ey2 = s.y0 - s.y2;
-    e.e0 = ex0 * (sy - s.y0) - ey0 * (sx - s.x0) + edge_bias(ex0, ey0);
-    e.e1 = ex1 * (sy - s.y1) - ey1 * (sx - s.x1) + edge_bias(ex1, ey1);
-    e.e2 = ex2 * (sy - s.y2) - ey2 * (sx - s.x2) + edge_bias(ex2, ey2);
-    e.ax0 = -16 * ey0; e.ax1 = -16 * ey1; e.ax2 = -16 * ey2;
-    e.ay0 = 16 * ex0;  e.ay1 = 16 * ex1;  e.ay2 = 16 * ex2;
-}
-
-__device__ __forceinline__ void emit_fragment(unsigned long long* keys, const RasterParams& rp, const float4& p0,
-                                              const float4& p1, const float4& p2, int t, int px, int py, int lx, int ly)
-{
-    float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
-    Shade sh = shade_pixel(p0, p1, p2, fx, fy);
-    if (!(sh.zw >= -1.f && sh.zw <= 1.f)) return;
-    unsigned long long key = ((unsigned long long)depth_key(sh.zw) << 32) | (unsigned)t;
-    atomicMin(keys + ly * BIN + lx, key);
-}
-
 __global__ void __launch_bounds__(FINE_THREADS) k_fine(RasterParams rp, float* __restrict__ rast, float* __restrict__ rast_db)
 {
-    __shared__ unsigned long long keys[BIN * BIN];
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+    WarpStage* stage = reinterpret_cast<WarpStage*>(smem + sizeof(unsigned long long) * BIN * BIN);
     const int bin = blockIdx.x, n = blockIdx.y;
-    const int bx = bin % rp.BW, by = bin / rp.BW;
-    const int ox = bx * BIN, oy = by * BIN;                   // bin origin in pixels
-    const int lim_x = min(ox + BIN, rp.W) - 1, lim_y = min(oy + BIN, rp.H) - 1;
-    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
-    const int nlarge = rp.large_count[n];
-
-    for (int i = threadIdx.x; i < BIN * BIN; i += FINE_THREADS) keys[i] = KEY_EMPTY;
-    __syncthreads();
-
-    // ---- small triangles: one thread per triangle of the bin list ----
-    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
-    for (int i = threadIdx.x; i < count; i += FINE_THREADS) {
-        int t = list[i];
-        float4 p0, p1, p2;
-        SnappedTri s;
-        if (!load_triangle(rp, n, t, p0, p1, p2) || !setup_triangle(p0, p1, p2, rp, s)) continue;
-        int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
-        if (xa > xb || ya > yb) continue;
-        EdgeEval e;
-        edge_setup(s, xa, ya, e);
-        for (int py = ya; py <= yb; py++) {
-            long long r0 = e.e0, r1 = e.e1, r2 = e.e2;
-            for (int px = xa; px <= xb; px++) {
-                if ((r0 | r1 | r2) >= 0) emit_fragment(keys, rp, p0, p1, p2, t, px, py, px - ox, py - oy);
-                r0 += e.ax0; r1 += e.ax1; r2 += e.ax2;
-            }
-            e.e0 += e.ay0; e.e1 += e.ay1; e.e2 += e.ay2;
-        }
-    }
-
-    // ---- large triangles: the whole CTA cooperates on each one (16 pixels per thread) ----
-    const int* llist = rp.large_list + (size_t)n * rp.T;
-    for (int i = 0; i < nlarge; i++) {
-        int t = llist[i];
-        float4 p0, p1, p2;
-        SnappedTri s;
-        if (!load_triangle(rp, n, t, p0, p1, p2) || !setup_triangle(p0, p1, p2, rp, s)) continue;
-        int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
-        if (xa > xb || ya > yb) continue;
-        EdgeEval e;
-        edge_setup(s, ox, oy, e);
-        for (int idx = threadIdx.x; idx < BIN * BIN; idx += FINE_THREADS) {
-            int lx = idx & (BIN - 1), ly = idx >> BIN_LOG2;
-            int px = ox + lx, py = oy + ly;
-            if (px < xa || px > xb || py < ya || py > yb) continue;
-            long long r0 = e.e0 + lx * e.ax0 + ly * e.ay0;
-            long long r1 = e.e1 + lx * e.ax1 + ly * e.ay1;
-            long long r2 = e.e2 + lx * e.ax2 + ly * e.ay2;
-            if ((r0 | r1 | r2) >= 0) emit_fragment(keys, rp, p0, p1, p2, t, px, py, lx, ly);
-        }
-    }
-    __syncthreads();
+    const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
+    raster_bin(rp, n, bin, keys, stage);
 
     // ---- shade: (u, v, z/w, id+1) and the barycentric pixel differentials ----
     const float* P = rp.pos + (size_t)n * rp.V * 4;
@@ -321,10 +166,9 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const float* __restrict__ po
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct ScratchLayout {
-    size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, total;
-};
+}  // namespace
+
+namespace fpc {
 
 ScratchLayout raster_layout(int N, int T, int NB)
 {
@@ -342,7 +186,40 @@ ScratchLayout raster_layout(int N, int T, int NB)
     return L;
 }
 
-}  // namespace
+int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
+                         void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp)
+{
+    FPC_CHECK_ARG(pos && tri, "%s: pos and tri must be non-null", who);
+    FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "%s: N, V, T, H, W must be positive (got %d %d %d %d %d)", who, N, V, T, H, W);
+    FPC_CHECK_ARG(T < (1 << 24), "%s: at most 2^24-1 triangles (got %d)", who, T);
+    FPC_CHECK_ARG(H <= 32768 && W <= 32768 && N <= 65535, "%s: resolution <= 32768^2 and N <= 65535 (got %dx%d, N=%d)", who, H, W, N);
+    rp.pos = pos; rp.tri = tri; rp.N = N; rp.V = V; rp.T = T; rp.H = H; rp.W = W;
+    rp.BW = fpc_div_up(W, BIN); rp.BH = fpc_div_up(H, BIN); rp.NB = rp.BW * rp.BH;
+    ScratchLayout L = raster_layout(N, T, rp.NB);
+    FPC_CHECK_ARG(scratch && scratch_bytes >= L.total, "%s: scratch too small (%zu < %zu bytes)", who, scratch_bytes, L.total);
+    rp.xs = 2.0f / (float)W; rp.xo = 1.0f / (float)W - 1.0f;
+    rp.ys = 2.0f / (float)H; rp.yo = 1.0f / (float)H - 1.0f;
+    rp.sxs = 8.0f * (float)W; rp.sys = 8.0f * (float)H;
+    char* s = (char*)scratch;
+    rp.bin_count = (int*)(s + L.off_count);
+    rp.bin_cursor = (int*)(s + L.off_cursor);
+    rp.large_count = (int*)(s + L.off_large_count);
+    rp.bin_offset = (int*)(s + L.off_offset);
+    rp.tri_info = (int*)(s + L.off_info);
+    rp.pairs = (int*)(s + L.off_pairs);
+    rp.large_list = (int*)(s + L.off_large);
+    FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
+    long long nt = (long long)N * T;
+    k_setup<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);
+    FPC_LAUNCH_CHECK();
+    k_scan<<<N, 256, 0, stream>>>(rp);
+    FPC_LAUNCH_CHECK();
+    k_fill<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+}  // namespace fpc
 
 extern "C" size_t fpc_rasterize_scratch_bytes(int N, int T, int H, int W)
 {
@@ -355,36 +232,17 @@ extern "C" int fpc_rasterize_fwd(const float* pos, const int32_t* tri, int N, in
                                  float* rast, float* rast_db, void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    FPC_CHECK_ARG(pos && tri && rast, "rasterize_fwd: pos, tri and rast must be non-null");
-    FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "rasterize_fwd: N, V, T, H, W must be positive (got %d %d %d %d %d)", N, V, T, H, W);
-    FPC_CHECK_ARG(T < (1 << 24), "rasterize_fwd: at most 2^24-1 triangles (got %d)", T);
-    FPC_CHECK_ARG(H <= 65536 && W <= 65536 && N <= 65535, "rasterize_fwd: resolution <= 65536^2 and N <= 65535 (got %dx%d, N=%d)", H, W, N);
+    FPC_CHECK_ARG(rast, "rasterize_fwd: rast must be non-null");
     RasterParams rp;
-    rp.pos = pos; rp.tri = tri; rp.N = N; rp.V = V; rp.T = T; rp.H = H; rp.W = W;
-    rp.BW = fpc_div_up(W, BIN); rp.BH = fpc_div_up(H, BIN); rp.NB = rp.BW * rp.BH;
-    ScratchLayout L = raster_layout(N, T, rp.NB);
-    FPC_CHECK_ARG(scratch && scratch_bytes >= L.total, "rasterize_fwd: scratch too small (%zu < %zu bytes)", scratch_bytes, L.total);
-    rp.xs = 2.0f / (float)W; rp.xo = 1.0f / (float)W - 1.0f;
-    rp.ys = 2.0f / (float)H; rp.yo = 1.0f / (float)H - 1.0f;
-    rp.sxs = 8.0f * (float)W; rp.sys = 8.0f * (float)H;
-    char* s = (char*)scratch;
-    rp.bin_count = (int*)(s + L.off_count);
-    rp.bin_cursor = (int*)(s + L.off_cursor);
-    rp.large_count = (int*)(s + L.off_large_count);
-    rp.bin_offset = (int*)(s + L.off_offset);
-    rp.tri_info = (int*)(s + L.off_info);
-    rp.pairs = (int*)(s + L.off_pairs);
-    rp.large_list = (int*)(s + L.off_large);
-
-    FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
-    long long nt = (long long)N * T;
-    k_setup<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);
-    FPC_LAUNCH_CHECK();
-    k_scan<<<N, 256, 0, stream>>>(rp);
-    FPC_LAUNCH_CHECK();
-    k_fill<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);
-    FPC_LAUNCH_CHECK();
-    k_fine<<<dim3(rp.NB, N), FINE_THREADS, 0, stream>>>(rp, rast, rast_db);
+    int st = raster_bin_triangles("rasterize_fwd", pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp);
+    if (st != FPC_OK) return st;
+    const size_t smem = sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FPC_CUDA(cudaFuncSetAttribute(k_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_fine<<<dim3(rp.NB, N), FINE_THREADS, smem, stream>>>(rp, rast, rast_db);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

@@ -1,0 +1,275 @@
+// Rasterizer core shared by the stand-alone rasterize op (raster.cu) and the fused fit kernel (fused.cu).
+//
+// Binning (k_setup / k_scan / k_fill, raster.cu) produces, per (instance, 64x64-px bin), a list of SMALL
+// triangles (snapped bbox <= 128 px in both axes and <= 2x2 bins: int32 edge math is exact) and, per instance,
+// a list of LARGE triangles (everything else, int64 edge math, whole CTA cooperates on each).
+//
+// raster_bin(): one CTA resolves visibility of its bin into a 64x64 shared-memory array of 64-bit keys
+//   key = order_preserving(depth) << 32 | triangle_id         (atomicMin == LESS test, lower id wins ties)
+// Small triangles are processed warp by warp, 32 at a time: each lane sets up one triangle and stages it in
+// shared memory, then the warp walks the (triangle, bbox-row) work items of the batch with a balanced
+// lane <-> item mapping (prefix sum + binary search), so lanes stay busy whatever the triangle sizes are.
+//
+// Semantics are bit-identical to oracle/golden.c (DESIGN.md "Rasterizer semantics").
+#pragma once
+#include "common.cuh"
+
+namespace fpc {
+
+constexpr int BIN = 64;              // bin edge in pixels
+constexpr int BIN_LOG2 = 6;
+constexpr int FINE_THREADS = 256;
+constexpr int FINE_WARPS = FINE_THREADS / 32;
+constexpr float SNAP_LIMIT = 16777216.0f;
+constexpr int SMALL_EXTENT = 2048;   // 128 px in 1/16-px units
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+struct RasterParams {
+    const float* pos;
+    const int32_t* tri;
+    int N, V, T, H, W;
+    int BW, BH, NB;
+    float xs, xo, ys, yo;            // pixel -> NDC
+    float sxs, sys;                  // NDC -> 1/16 px:  8*W, 8*H
+    int* bin_count;                  // [N*NB]
+    int* bin_cursor;                 // [N*NB]
+    int* large_count;                // [N]
+    int* bin_offset;                 // [N*NB]
+    int* tri_info;                   // [N*T]
+    int* pairs;                      // [N*4T]
+    int* large_list;                 // [N*T]
+};
+
+struct SnappedTri {
+    int x0, y0, x1, y1, x2, y2;      // 1/16 px, ORIGINAL vertex order
+    bool flip;                       // true when the original order has negative area
+    int minx, maxx, miny, maxy;      // unclamped bbox, 1/16 px
+    int pxa, pxb, pya, pyb;          // candidate pixel range clamped to the image
+};
+
+__device__ __forceinline__ bool snap_vertex(const float4& p, float sxs, float sys, int& sx, int& sy)
+{
+    if (!(p.w > 0.f)) return false;
+    float rw = xdiv(1.0f, p.w);
+    float xf = xadd(xmul(xmul(p.x, rw), sxs), sxs);
+    float yf = xadd(xmul(xmul(p.y, rw), sys), sys);
+    if (!(fabsf(xf) < SNAP_LIMIT) || !(fabsf(yf) < SNAP_LIMIT)) return false;
+    sx = __float2int_rn(xf);
+    sy = __float2int_rn(yf);
+    return true;
+}
+
+// Returns false when the triangle produces no fragments at all.
+__device__ __forceinline__ bool setup_triangle(const float4& p0, const float4& p1, const float4& p2,
+                                               const RasterParams& rp, SnappedTri& s)
+{
+    if (!snap_vertex(p0, rp.sxs, rp.sys, s.x0, s.y0) || !snap_vertex(p1, rp.sxs, rp.sys, s.x1, s.y1) ||
+        !snap_vertex(p2, rp.sxs, rp.sys, s.x2, s.y2))
+        return false;
+    long long area = (long long)(s.x1 - s.x0) * (s.y2 - s.y0) - (long long)(s.x2 - s.x0) * (s.y1 - s.y0);
+    if (area == 0) return false;
+    s.flip = area < 0;
+    s.minx = min(s.x0, min(s.x1, s.x2)); s.maxx = max(s.x0, max(s.x1, s.x2));
+    s.miny = min(s.y0, min(s.y1, s.y2)); s.maxy = max(s.y0, max(s.y1, s.y2));
+    s.pxa = max((s.minx - 8 + 15) >> 4, 0);
+    s.pxb = min((s.maxx - 8) >> 4, rp.W - 1);
+    s.pya = max((s.miny - 8 + 15) >> 4, 0);
+    s.pyb = min((s.maxy - 8) >> 4, rp.H - 1);
+    return s.pxa <= s.pxb && s.pya <= s.pyb;
+}
+
+__device__ __forceinline__ bool is_small(const SnappedTri& s)
+{
+    return (s.maxx - s.minx) <= SMALL_EXTENT && (s.maxy - s.miny) <= SMALL_EXTENT &&
+           ((s.pxb >> BIN_LOG2) - (s.pxa >> BIN_LOG2)) <= 1 && ((s.pyb >> BIN_LOG2) - (s.pya >> BIN_LOG2)) <= 1;
+}
+
+__device__ __forceinline__ bool load_triangle(const RasterParams& rp, int n, int t, float4& p0, float4& p1, float4& p2)
+{
+    int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+    if ((unsigned)i0 >= (unsigned)rp.V || (unsigned)i1 >= (unsigned)rp.V || (unsigned)i2 >= (unsigned)rp.V) return false;
+    const float* P = rp.pos + (size_t)n * rp.V * 4;
+    p0 = ldg4(P + 4 * (size_t)i0);
+    p1 = ldg4(P + 4 * (size_t)i1);
+    p2 = ldg4(P + 4 * (size_t)i2);
+    return true;
+}
+
+// ---- depth plane (oracle/golden.c: depth_plane / plane_eval) ---------------------------------------------
+struct Plane { float zref, dzdx, dzdy; };
+
+__device__ __forceinline__ Plane depth_plane(const float4& p0, const float4& p1, const float4& p2, const SnappedTri& s)
+{
+    float zv0 = xdiv(p0.z, p0.w), zv1 = xdiv(p1.z, p1.w), zv2 = xdiv(p2.z, p2.w);
+    double X1 = (double)(s.x1 - s.x0), Y1 = (double)(s.y1 - s.y0), X2 = (double)(s.x2 - s.x0), Y2 = (double)(s.y2 - s.y0);
+    double A = __dsub_rn(__dmul_rn(X1, Y2), __dmul_rn(X2, Y1));
+    double dz1 = __dsub_rn((double)zv1, (double)zv0), dz2 = __dsub_rn((double)zv2, (double)zv0);
+    double gx = __ddiv_rn(__dsub_rn(__dmul_rn(dz1, Y2), __dmul_rn(dz2, Y1)), A);
+    double gy = __ddiv_rn(__dsub_rn(__dmul_rn(dz2, X1), __dmul_rn(dz1, X2)), A);
+    double rx = (double)(16 * s.pxa + 8 - s.x0), ry = (double)(16 * s.pya + 8 - s.y0);
+    Plane pl;
+    pl.zref = __double2float_rn(__dadd_rn(__dadd_rn((double)zv0, __dmul_rn(gx, rx)), __dmul_rn(gy, ry)));
+    pl.dzdx = __double2float_rn(__dmul_rn(gx, 16.0));
+    pl.dzdy = __double2float_rn(__dmul_rn(gy, 16.0));
+    return pl;
+}
+
+__device__ __forceinline__ float plane_eval(float zref, float dzdx, float dzdy, int dx, int dy)
+{
+    return __fmaf_rn(dzdx, (float)dx, __fmaf_rn(dzdy, (float)dy, zref));
+}
+
+__device__ __forceinline__ unsigned depth_key(float zw)
+{
+    unsigned b = __float_as_uint(zw);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ void emit_fragment(unsigned long long* keys, float zd, int t, int lx, int ly)
+{
+    if (!(zd >= -1.f && zd <= 1.f)) return;
+    unsigned long long key = ((unsigned long long)depth_key(zd) << 32) | (unsigned)t;
+    atomicMin(keys + ly * BIN + lx, key);
+}
+
+// ---- fill rule -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int edge_bias(int dx, int dy) { return (dy > 0 || (dy == 0 && dx < 0)) ? 0 : -1; }
+__device__ __forceinline__ long long edge_bias64(long long dx, long long dy) { return (dy > 0 || (dy == 0 && dx < 0)) ? 0 : -1; }
+
+// per-warp staging area for a batch of 32 small triangles (structure of arrays: lane-contiguous)
+struct WarpStage {
+    int e[3][32];        // edge functions (+bias) at the first pixel (xa, ya) of the bin-clipped bbox
+    int ax[3][32];       // step per +1 px in x
+    int ay[3][32];       // step per +1 px in y
+    int xy[32];          // xa | ya << 16          (absolute pixel coordinates)
+    int wn[32];          // row width | rows << 16
+    int off[32];         // (xa - pxa) | (ya - pya) << 16   offsets from the plane's reference pixel
+    float zref[32], dzdx[32], dzdy[32];
+    int tri[32];
+    int prefix[32];      // inclusive prefix sum of rows
+};
+
+// Resolve the visibility of bin (bx,by) of instance n into keys[BIN*BIN] (shared memory, initialised here).
+// `stage` is FINE_WARPS WarpStage records in shared memory.  All FINE_THREADS threads must call this.
+__device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bin, unsigned long long* keys, WarpStage* stage)
+{
+    const int bx = bin % rp.BW, by = bin / rp.BW;
+    const int ox = bx * BIN, oy = by * BIN;
+    const int lim_x = min(ox + BIN, rp.W) - 1, lim_y = min(oy + BIN, rp.H) - 1;
+    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
+    const int nlarge = rp.large_count[n];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int i = threadIdx.x; i < BIN * BIN; i += FINE_THREADS) keys[i] = KEY_EMPTY;
+    __syncthreads();
+
+    // ---- small triangles ----
+    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
+    WarpStage& st = stage[warp];
+    for (int base = warp * 32; base < count; base += FINE_THREADS) {
+        int i = base + lane;
+        int rows = 0;
+        if (i < count) {
+            int t = list[i];
+            float4 p0, p1, p2;
+            SnappedTri s;
+            if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
+                int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
+                if (xa <= xb && ya <= yb) {
+                    rows = yb - ya + 1;
+                    // oriented vertex order (positive area): swap 1 <-> 2 when flipped
+                    int ax1 = s.flip ? s.x2 : s.x1, ay1 = s.flip ? s.y2 : s.y1;
+                    int ax2 = s.flip ? s.x1 : s.x2, ay2 = s.flip ? s.y1 : s.y2;
+                    int sx = 16 * xa + 8, sy = 16 * ya + 8;
+                    int ex0 = ax1 - s.x0, ey0 = ay1 - s.y0;
+                    int ex1 = ax2 - ax1, ey1 = ay2 - ay1;
+                    int ex2 = s.x0 - ax2, ey2 = s.y0 - ay2;
+                    st.e[0][lane] = ex0 * (sy - s.y0) - ey0 * (sx - s.x0) + edge_bias(ex0, ey0);
+                    st.e[1][lane] = ex1 * (sy - ay1) - ey1 * (sx - ax1) + edge_bias(ex1, ey1);
+                    st.e[2][lane] = ex2 * (sy - ay2) - ey2 * (sx - ax2) + edge_bias(ex2, ey2);
+                    st.ax[0][lane] = -16 * ey0; st.ax[1][lane] = -16 * ey1; st.ax[2][lane] = -16 * ey2;
+                    st.ay[0][lane] = 16 * ex0;  st.ay[1][lane] = 16 * ex1;  st.ay[2][lane] = 16 * ex2;
+                    st.xy[lane] = xa | (ya << 16);
+                    st.wn[lane] = (xb - xa + 1) | (rows << 16);
+                    st.off[lane] = (xa - s.pxa) | ((ya - s.pya) << 16);
+                    Plane pl = depth_plane(p0, p1, p2, s);
+                    st.zref[lane] = pl.zref; st.dzdx[lane] = pl.dzdx; st.dzdy[lane] = pl.dzdy;
+                    st.tri[lane] = t;
+                }
+            }
+        }
+        int incl = rows;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        st.prefix[lane] = incl;
+        int total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        for (int k = lane; k < total; k += 32) {
+            int j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (st.prefix[j + step - 1] <= k) j += step;
+            int wn = st.wn[j];
+            int r = k - (st.prefix[j] - (wn >> 16));
+            int wd = wn & 0xffff;
+            int e0 = st.e[0][j] + r * st.ay[0][j], e1 = st.e[1][j] + r * st.ay[1][j], e2 = st.e[2][j] + r * st.ay[2][j];
+            int a0 = st.ax[0][j], a1 = st.ax[1][j], a2 = st.ax[2][j];
+            int xy = st.xy[j], off = st.off[j];
+            int lx = (xy & 0xffff) - ox, ly = (int)((unsigned)xy >> 16) + r - oy;
+            int dx = off & 0xffff, dy = (off >> 16) + r;
+            float zref = st.zref[j], dzdx = st.dzdx[j], dzdy = st.dzdy[j];
+            int t = st.tri[j];
+            float zrow = __fmaf_rn(dzdy, (float)dy, zref);
+            for (int x = 0; x < wd; x++) {
+                if ((e0 | e1 | e2) >= 0) emit_fragment(keys, __fmaf_rn(dzdx, (float)(dx + x), zrow), t, lx + x, ly);
+                e0 += a0; e1 += a1; e2 += a2;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- large triangles: the whole CTA cooperates on each one (16 pixels per thread), int64 edge math ----
+    const int* llist = rp.large_list + (size_t)n * rp.T;
+    for (int i = 0; i < nlarge; i++) {
+        int t = llist[i];
+        float4 p0, p1, p2;
+        SnappedTri s;
+        if (!load_triangle(rp, n, t, p0, p1, p2) || !setup_triangle(p0, p1, p2, rp, s)) continue;
+        int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
+        if (xa > xb || ya > yb) continue;
+        long long ax1 = s.flip ? s.x2 : s.x1, ay1 = s.flip ? s.y2 : s.y1;
+        long long ax2 = s.flip ? s.x1 : s.x2, ay2 = s.flip ? s.y1 : s.y2;
+        long long sx = 16 * ox + 8, sy = 16 * oy + 8;
+        long long ex0 = ax1 - s.x0, ey0 = ay1 - s.y0, ex1 = ax2 - ax1, ey1 = ay2 - ay1, ex2 = s.x0 - ax2, ey2 = s.y0 - ay2;
+        long long b0 = ex0 * (sy - s.y0) - ey0 * (sx - s.x0) + edge_bias64(ex0, ey0);
+        long long b1 = ex1 * (sy - ay1) - ey1 * (sx - ax1) + edge_bias64(ex1, ey1);
+        long long b2 = ex2 * (sy - ay2) - ey2 * (sx - ax2) + edge_bias64(ex2, ey2);
+        Plane pl = depth_plane(p0, p1, p2, s);
+        for (int idx = threadIdx.x; idx < BIN * BIN; idx += FINE_THREADS) {
+            int lx = idx & (BIN - 1), ly = idx >> BIN_LOG2;
+            int px = ox + lx, py = oy + ly;
+            if (px < xa || px > xb || py < ya || py > yb) continue;
+            long long r0 = b0 - 16 * ey0 * lx + 16 * ex0 * ly;
+            long long r1 = b1 - 16 * ey1 * lx + 16 * ex1 * ly;
+            long long r2 = b2 - 16 * ey2 * lx + 16 * ex2 * ly;
+            if ((r0 | r1 | r2) >= 0) emit_fragment(keys, plane_eval(pl.zref, pl.dzdx, pl.dzdy, px - s.pxa, py - s.pya), t, lx, ly);
+        }
+    }
+    __syncthreads();
+}
+
+// Host side: scratch layout + the three binning launches.
+struct ScratchLayout {
+    size_t zero_bytes;               // leading region that must be zeroed each call
+    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, total;
+};
+
+ScratchLayout raster_layout(int N, int T, int NB);
+// Validates, fills rp and enqueues memset + k_setup + k_scan + k_fill.  Returns an fpc_status.
+int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
+                         void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp);
+
+}  // namespace fpc

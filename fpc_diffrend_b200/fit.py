@@ -45,6 +45,8 @@ class FitConfig:
     quat_norm: str = 'row'                # 'row' (default) or 'frobenius' (reference quirk)
     optimize_pose: bool = True
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
+    fused: bool = True                    # antialias off: one fused render+loss+gradient kernel (csrc/fused.cu)
+    ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
 
 
 def _p(t):
@@ -115,15 +117,21 @@ class FitSession:
         self.mvp = torch.empty(self.N, 16, **f32)
         self.verts = torch.empty(F, V * 3, **f32)
         self.pos_clip = torch.empty(self.N, V, 4, **f32)
-        self.rast = torch.empty(self.N, H, W, 4, **f32)
-        self.colour = torch.empty(self.N, H, W, Ch, **f32)
-        self.d_colour = torch.empty(self.N, H, W, Ch, **f32)
-        self.g_rast = torch.empty(self.N, H, W, 4, **f32)
+        self.use_fused = bool(cfg.fused and not cfg.antialias)
+        if cfg.ref_dtype not in ('f32', 'u8'):
+            raise ValueError("ref_dtype must be 'f32' or 'u8'")
+        if cfg.ref_dtype == 'u8' and not self.use_fused:
+            raise ValueError("ref_dtype='u8' needs the fused path (antialias=False, fused=True)")
         self.g_pos = torch.empty(self.N, V, 4, **f32)
-        self.g_attr = torch.empty_like(self.attr)
+        if not self.use_fused:
+            self.rast = torch.empty(self.N, H, W, 4, **f32)
+            self.colour = torch.empty(self.N, H, W, Ch, **f32)
+            self.d_colour = torch.empty(self.N, H, W, Ch, **f32)
+            self.g_rast = torch.empty(self.N, H, W, 4, **f32)
+            self.g_attr = torch.empty_like(self.attr)
         self.d_verts = torch.empty(F, V * 3, **f32)
         self.d_mvp = torch.empty(self.N, 16, **f32)
-        if cfg.shading == 'texture':
+        if cfg.shading == 'texture' and not self.use_fused:
             self.texc = torch.empty(self.N, H, W, 2, **f32)
             self.g_texc = torch.empty(self.N, H, W, 2, **f32)
         if cfg.antialias:
@@ -136,7 +144,8 @@ class FitSession:
         self.ref = None
 
         L = _lib.load()
-        nbytes = max(L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_blend_bwd_scratch_bytes(V * 3, B, F),
+        nbytes = max(L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_render_loss_fused_scratch_bytes(self.N, T, H, W),
+                     L.fpc_blend_bwd_scratch_bytes(V * 3, B, F),
                      L.fpc_project_bwd_scratch_bytes(F, C, V), L.fpc_image_loss_scratch_bytes(self.N, H, W, Ch))
         self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         self.graph = None
@@ -151,8 +160,12 @@ class FitSession:
     def set_reference(self, frames):
         """frames [F, C_local, H, W, Ch] float32 grey levels on the 0..255 scale (already clipped / flipped as
         fit.py:531-533 does); device tensor or host array (copied once, frames stay resident on device)."""
-        ref = torch.as_tensor(frames, dtype=torch.float32).to(self.device, non_blocking=True)
+        ref = torch.as_tensor(frames).to(self.device, non_blocking=True)
         assert tuple(ref.shape) == (self.F, self.C, self.H, self.W, self.Ch), (tuple(ref.shape), (self.F, self.C, self.H, self.W, self.Ch))
+        if self.cfg.ref_dtype == 'u8':
+            ref = ref if ref.dtype == torch.uint8 else ref.round().clamp(0, 255).to(torch.uint8)
+        else:
+            ref = ref.to(torch.float32)
         self.ref = ref.reshape(self.N, self.H, self.W, self.Ch).contiguous()
 
     def iteration_from_host(self, frames_host, loss_host=None):
@@ -161,7 +174,8 @@ class FitSession:
         one), read the loss back.  Returns the loss as a float (this synchronises the stream)."""
         src = frames_host.reshape(self.N, self.H, self.W, self.Ch)
         if self.ref is None:
-            self.ref = torch.empty(self.N, self.H, self.W, self.Ch, dtype=torch.float32, device=self.device)
+            dt = torch.uint8 if self.cfg.ref_dtype == 'u8' else torch.float32
+            self.ref = torch.empty(self.N, self.H, self.W, self.Ch, dtype=dt, device=self.device)
         self.ref.copy_(src, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
@@ -202,6 +216,8 @@ class FitSession:
         call('pose_mvp_fwd', 'fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, F, C, _p(self.mvp), s); n += 1
         call('blend_fwd', 'fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
         call('project_fwd', 'fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
+        if self.use_fused:
+            return n + self._fused(True) if with_loss else self._fused(False)
         call('rasterize_fwd', 'fpc_rasterize_fwd', _p(self.pos_clip), _p(self.pos_idx), N, V, T, H, W, _p(self.rast), None,
              _p(self.scratch), self.scratch.numel(), s); n += 4
         if cfg.shading == 'vcol':
@@ -222,10 +238,33 @@ class FitSession:
              _p(self.loss), _p(self.d_colour), None, _p(self.scratch), self.scratch.numel(), s); n += 2
         return n
 
+    def _fused(self, with_loss):
+        """render + loss + d loss / d pos_clip in one kernel (csrc/fused.cu); with_loss=False renders images instead."""
+        cfg, s = self.cfg, self._stream()
+        V, T, H, W, N, Ch = self.V, self.T, self.H, self.W, self.N, self.Ch
+        tex = self.tex
+        Ht, Wt = (tex.shape[1], tex.shape[2]) if tex is not None else (0, 0)
+        if not with_loss:
+            # forward only: composited image out, loss against a dummy reference is discarded
+            img = torch.empty(N, H, W, Ch, dtype=torch.float32, device=self.device)
+            dummy = torch.zeros(N, H, W, Ch, dtype=torch.float32, device=self.device)
+            _lib.call('fpc_render_loss_fused', _p(self.pos_clip), _p(self.pos_idx), _p(self.attr), _p(self.attr_idx), self.attr.shape[1],
+                      self.attr.shape[2], _p(tex), Ht, Wt, _p(dummy), 0, N, V, T, H, W, Ch, cfg.bg, 1.0, _p(self.loss), None, None,
+                      _p(img), _p(self.scratch), self.scratch.numel(), s)
+            return img
+        assert self.ref is not None, 'call set_reference() first'
+        self._timed('render_loss_fused', 'fpc_render_loss_fused', _p(self.pos_clip), _p(self.pos_idx), _p(self.attr), _p(self.attr_idx),
+                    self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
+                    N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, _p(self.loss), _p(self.g_pos), None, None,
+                    _p(self.scratch), self.scratch.numel(), s)
+        return 6
+
     def backward(self):
         cfg, s, call = self.cfg, self._stream(), self._timed
         F, V, T, B, C, H, W, N, Ch = self.F, self.V, self.T, self.B, self.C, self.H, self.W, self.N, self.Ch
         n = 0
+        if self.use_fused:
+            return self._backward_geometry()
         g_colour = self.d_colour
         if cfg.antialias:
             call('antialias_bwd', 'fpc_antialias_bwd', _p(self.colour), _p(self.rast), _p(self.pos_clip), _p(self.pos_idx), _p(self.tri_opp),
@@ -243,6 +282,13 @@ class FitSession:
              _p(self.g_pos), s); n += 2
         if cfg.antialias:
             self.g_pos.add_(self.g_pos_aa); n += 1
+        return n + self._backward_geometry()
+
+    def _backward_geometry(self):
+        """d pos_clip -> d verts, d mvp -> d w (D^T), d t, d q."""
+        s, call = self._stream(), self._timed
+        F, V, B, C = self.F, self.V, self.B, self.C
+        n = 0
         call('project_bwd', 'fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
              _p(self.scratch), self.scratch.numel(), s); n += 2
         call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2

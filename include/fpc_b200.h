@@ -131,9 +131,25 @@ int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, const float* 
                            float bg, float scale, float* loss, float* d_colour, float* comp,
                            void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
+/* ---- fused render + loss + gradient (no antialias): rasterize -> interpolate -> [texture] -> background ->
+ *      image loss -> backward to clip-space positions, in one kernel per (64x64-px bin, view).  Replaces the chain
+ *      fit.py:151-158,161,579 and its part of loss.backward() (fit.py:611) when antialias is off.
+ * attr [Va,A] + attr_tri [T,3]: vertex colours (tex == NULL, A == C) or uv (tex [Ht,Wt,C] given, A == 2);
+ * ref [N,H,W,C] float32 (ref_is_u8 == 0) or uint8 (ref_is_u8 == 1) grey levels on the 0..255 scale; C in {1,3}.
+ *   loss [1]            = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2                     (overwritten)
+ *   grad_pos [N,V,4]    = d loss / d pos (x, y, w; z = 0), overwritten; NULL = forward only
+ *   rast_out [N,H,W,4], colour_out [N,H,W,C] (composited image): optional outputs, NULL to skip the HBM writes. */
+size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W);
+int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* attr, const int32_t* attr_tri, int Va, int A,
+                          const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
+                          int N, int V, int T, int H, int W, int C, float bg, float scale,
+                          float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                          void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
 /* ---- Adam (replaces torch.optim.Adam + LambdaLR + quaternion renorm, fit.py:493-505,610-618) ---------------
- * p, g, m, v [n]; state [2] device floats: state[0] = step count (incremented here), state[1] unused.
- * lr_eff = lr * lr_ramp^(step/max_iter) with step counted before the increment (LambdaLR semantics).
+ * p, g, m, v [n]; step_count [1]: device float holding the number of optimiser steps taken so far
+ * (advanced by fpc_adam_advance after all parameter groups of an iteration have been stepped).
+ * lr_eff = lr * lr_ramp^(step_count/max_iter)  (LambdaLR semantics), Adam's t = step_count + 1.
  * torch.optim.Adam update rule with bias correction, betas (b1,b2), eps, no weight decay / amsgrad. */
 int fpc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                   float lr_ramp, float max_iter, const float* step_count, fpc_stream_t stream);

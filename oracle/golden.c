@@ -21,8 +21,12 @@
  *     evaluated as separate IEEE fp32 mul / add (no FMA contraction: compile with -ffp-contract=off);
  *   - coverage: pixel centre (16*px+8, 16*py+8) against integer edge functions, shared edges owned by
  *     exactly one side (rule in edge_bias());  no back-face culling;  zero-area triangles dropped;
- *   - visibility: smallest z/w wins (LESS), ties keep the lower triangle index;  z/w is the fp32
- *     value of the shading formula below, fragments with z/w outside [-1,1] are discarded;
+ *   - visibility: smallest depth wins (LESS), ties keep the lower triangle index;  the depth of a fragment
+ *     is the triangle's screen-space z/w PLANE (z/w is affine in window space; upstream's CUDA rasterizer
+ *     also depth-tests on a per-triangle plane equation) evaluated as in depth_plane() / plane_eval():
+ *     per-vertex z/w in fp32, plane set-up in fp64 on the snapped vertices, per-fragment evaluation with two
+ *     fp32 FMAs;  fragments whose plane depth is outside [-1,1] are discarded.  The z/w written to
+ *     rast[...,2] is the fp32 value of the shading formula (what upstream's shader pass writes);
  *   - triangles with any w <= 0 or a window coordinate beyond +-2^20 px are dropped (no clipper yet;
  *     the fit never produces them: cameras look at the head from ~170 units, zn = 0.01).
  *
@@ -61,6 +65,33 @@ static int snap_vertex(f4 p, int W, int H, int32_t* sx, int32_t* sy)
 static inline int64_t edge_bias(int64_t dx, int64_t dy)
 {
     return (dy > 0 || (dy == 0 && dx < 0)) ? 0 : -1;
+}
+
+/* Depth plane of a triangle.  (x_i,y_i): snapped vertices in ORIGINAL order, (pxa,pya): first candidate pixel
+ * of the triangle's image-clamped bbox (the plane's reference point).  All fp64 products of the snapped
+ * integer coordinates are exact; every fp64 op is separate (no contraction). */
+typedef struct { float zref, dzdx, dzdy; } plane_t;
+
+static inline plane_t depth_plane(f4 p0, f4 p1, f4 p2, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
+                                  int32_t x2, int32_t y2, int pxa, int pya)
+{
+    float zv0 = p0.z / p0.w, zv1 = p1.z / p1.w, zv2 = p2.z / p2.w;
+    double X1 = (double)(x1 - x0), Y1 = (double)(y1 - y0), X2 = (double)(x2 - x0), Y2 = (double)(y2 - y0);
+    double A = X1 * Y2 - X2 * Y1;
+    double dz1 = (double)zv1 - (double)zv0, dz2 = (double)zv2 - (double)zv0;
+    double gx = (dz1 * Y2 - dz2 * Y1) / A;                 /* d(z/w) per sub-pixel unit in x */
+    double gy = (dz2 * X1 - dz1 * X2) / A;
+    double rx = (double)(16 * pxa + 8 - x0), ry = (double)(16 * pya + 8 - y0);
+    plane_t pl;
+    pl.zref = (float)(((double)zv0 + gx * rx) + gy * ry);
+    pl.dzdx = (float)(gx * 16.0);
+    pl.dzdy = (float)(gy * 16.0);
+    return pl;
+}
+
+static inline float plane_eval(plane_t pl, int dx, int dy)
+{
+    return fmaf(pl.dzdx, (float)dx, fmaf(pl.dzdy, (float)dy, pl.zref));
 }
 
 typedef struct { float u, v, zw; float db[4]; } shade_t;
@@ -102,7 +133,8 @@ static inline int shade_pixel(f4 p0, f4 p1, f4 p2, int px, int py, int W, int H,
 }
 
 /* rast [N,H,W,4] = (u, v, z/w, tri_id+1), rast_db [N,H,W,4] or NULL,
- * second_zw [N,H,W] or NULL: z/w of the runner-up fragment (2.0 if none) so tests can mask depth near-ties. */
+ * second_zw [N,H,W,2] or NULL: plane depth of the winning and of the runner-up fragment (2.0 if none) so tests
+ * can mask depth near-ties. */
 void gold_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                         float* rast, float* rast_db, float* second_zw)
 {
@@ -123,6 +155,7 @@ void gold_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int 
                 !snap_vertex(p2, W, H, &x2, &y2)) continue;
             int64_t area = (int64_t)(x1 - x0) * (y2 - y0) - (int64_t)(x2 - x0) * (y1 - y0);
             if (area == 0) continue;
+            const int32_t qx1 = x1, qy1 = y1, qx2 = x2, qy2 = y2;   /* original order, for the depth plane */
             if (area < 0) { int32_t tx = x1, ty = y1; x1 = x2; y1 = y2; x2 = tx; y2 = ty; }
             int32_t minx = x0 < x1 ? (x0 < x2 ? x0 : x2) : (x1 < x2 ? x1 : x2);
             int32_t maxx = x0 > x1 ? (x0 > x2 ? x0 : x2) : (x1 > x2 ? x1 : x2);
@@ -141,6 +174,7 @@ void gold_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int 
             int32_t ox[3] = { x0, x1, x2 }, oy[3] = { y0, y1, y2 };
             int64_t bias[3];
             for (int e = 0; e < 3; e++) bias[e] = edge_bias(ex[e], ey[e]);
+            plane_t pl = depth_plane(p0, p1, p2, x0, y0, qx1, qy1, qx2, qy2, pxa, pya);
             for (int py = pya; py <= pyb; py++) {
                 for (int px = pxa; px <= pxb; px++) {
                     int64_t sx = 16 * px + 8, sy = 16 * py + 8;
@@ -150,11 +184,11 @@ void gold_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int 
                         if (E < 0) { inside = 0; break; }
                     }
                     if (!inside) continue;
-                    shade_t s;
-                    if (!shade_pixel(p0, p1, p2, px, py, W, H, &s, 0)) continue;
+                    float zd = plane_eval(pl, px - pxa, py - pya);
+                    if (!(zd >= -1.0f && zd <= 1.0f)) continue;
                     size_t pi = (size_t)py * W + px;
-                    if (s.zw < depth[pi]) { depth2[pi] = depth[pi]; depth[pi] = s.zw; id[pi] = t; }
-                    else if (s.zw < depth2[pi]) depth2[pi] = s.zw;
+                    if (zd < depth[pi]) { depth2[pi] = depth[pi]; depth[pi] = zd; id[pi] = t; }
+                    else if (zd < depth2[pi]) depth2[pi] = zd;
                 }
             }
         }
@@ -163,7 +197,7 @@ void gold_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int 
                 size_t pi = (size_t)py * W + px;
                 float* o = rast + ((size_t)n * npx + pi) * 4;
                 float* odb = rast_db ? rast_db + ((size_t)n * npx + pi) * 4 : NULL;
-                if (second_zw) second_zw[(size_t)n * npx + pi] = depth2[pi];
+                if (second_zw) { second_zw[((size_t)n * npx + pi) * 2] = depth[pi]; second_zw[((size_t)n * npx + pi) * 2 + 1] = depth2[pi]; }
                 int t = id[pi];
                 if (t < 0) {
                     o[0] = o[1] = o[2] = o[3] = 0.0f;

@@ -71,7 +71,7 @@ def rasterize_fwd(pos, tri, resolution, with_db=True, with_second=False):
     H, W = resolution
     rast, prast = _out((N, H, W, 4))
     db, pdb = _out((N, H, W, 4)) if with_db else (None, None)
-    sec, psec = _out((N, H, W)) if with_second else (None, None)
+    sec, psec = _out((N, H, W, 2)) if with_second else (None, None)
     lib().gold_rasterize_fwd(ppos, ptri, N, V, tri.shape[0], H, W, prast, pdb, psec)
     return rast, db, sec
 

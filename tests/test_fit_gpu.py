@@ -49,8 +49,9 @@ def oracle_render_loss(rig, pos_clip, ref, shading, use_aa, H, W, opp, n_cams_to
     return G.image_loss(ref, img) / n_cams_total
 
 
-@pytest.mark.parametrize('shading,use_aa', [('vcol', False), ('texture', True), ('vcol', True)])
-def test_iteration_gradients(small_rig3, shading, use_aa):
+@pytest.mark.parametrize('shading,use_aa,fused', [('vcol', False, True), ('vcol', False, False), ('texture', False, True),
+                                                  ('texture', True, False), ('vcol', True, False)])
+def test_iteration_gradients(small_rig3, shading, use_aa, fused):
     """Every link of one fit iteration against the oracle ON IDENTICAL INPUT BITS.
 
     The chain is not continuous in its inputs (a 1-ulp change of a clip-space coordinate can move a snapped
@@ -62,10 +63,11 @@ def test_iteration_gradients(small_rig3, shading, use_aa):
     from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
     rig, H, W, F = small_rig3, 152, 200, 2
     C = rig.P.shape[0]
-    cfg = FitConfig(resolution=(H, W), shading=shading, antialias=use_aa)
+    cfg = FitConfig(resolution=(H, W), shading=shading, antialias=use_aa, fused=fused)
     w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
     ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, cfg)
     s = FitSession(rig, F, cfg)
+    assert s.use_fused == (fused and not use_aa)
     s.set_reference(ref)
     rng = np.random.default_rng(0)
     w0 = (0.05 * rng.random((F, rig.B))).astype(np.float32)

@@ -43,7 +43,7 @@ def _scene(rig, H, W, w=None):
 def _check_rast(out, out_db, rast, db, sec):
     ids, ids_ref = out[..., 3], rast[..., 3]
     # depth near-tie mask: runner-up within 4 ulp of the winner (north-star: "wherever there is no depth tie")
-    tie = (sec - rast[..., 2]) <= 4 * np.spacing(np.abs(rast[..., 2]).astype(np.float32))
+    tie = (sec[..., 1] - sec[..., 0]) <= 4 * np.spacing(np.abs(sec[..., 0]).astype(np.float32))
     mism = (ids != ids_ref)
     assert (mism & ~tie).sum() == 0, 'tri_id differs on %d non-tie pixels' % (mism & ~tie).sum()
     ok = ~mism
@@ -189,6 +189,56 @@ def test_render_chain_like_reference(dr, tiny_rig):
     colour = dr.antialias(colour, rast_out, pos_clip, cu(rig.pos_idx))
     colour = torch.where(rast_out[..., 3:] > 0, colour, torch.tensor(45.0 / 255.0).cuda())
     assert np.abs(colour[0].cpu().numpy() - ref).max() <= ABS_FWD
+
+
+@pytest.mark.parametrize('textured,C,u8', [(False, 3, False), (False, 1, True), (True, 1, False), (True, 3, True)])
+def test_fused_render_loss(dr, small_rig3, textured, C, u8):
+    """fpc_render_loss_fused (rasterize+interpolate+[texture]+bg+loss+backward in one kernel) vs the oracle chain."""
+    import ctypes
+    from fpc_diffrend_b200 import _lib
+    rig, H, W = small_rig3, 152, 200
+    pc, rast, _, _ = _scene(rig, H, W, w=np.linspace(0, 0.3, rig.B))
+    N, V, T = pc.shape[0], rig.V, rig.T
+    rng = np.random.default_rng(8)
+    if textured:
+        attr, idx = rig.uv, rig.uv_idx
+        tex = rng.random((24, 40, C)).astype(np.float32) * 0.5
+    else:
+        attr, idx = (rng.random((rig.V, C)) * 0.5).astype(np.float32), rig.pos_idx
+        tex = None
+    ref = rng.uniform(0, 140, size=(N, H, W, C)).astype(np.float32)
+    if u8:
+        ref = np.round(ref)
+    scale = 1.0 / 3.0
+    # oracle chain with autograd
+    tp = torch.tensor(pc, requires_grad=True)
+    r_o, _ = G.rasterize(tp, torch.tensor(rig.pos_idx), (H, W))
+    a_o = G.interpolate(torch.tensor(attr)[None], r_o, torch.tensor(idx))
+    col_o = G.texture(torch.tensor(tex)[None], a_o) if textured else a_o
+    comp_o = torch.where(r_o[..., 3:] > 0, col_o, torch.tensor(G.BG))
+    loss_o = scale * sum(G.image_loss(torch.tensor(ref[n]), comp_o[n]) for n in range(N))
+    loss_o.backward()
+    # kernel
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    d_pos, d_tri, d_attr, d_idx = cu(pc), cu(rig.pos_idx), cu(attr), cu(idx)
+    d_tex = cu(tex) if textured else None
+    d_ref = cu(ref.astype(np.uint8)) if u8 else cu(ref)
+    loss = torch.zeros(1, device='cuda')
+    g_pos = torch.full((N, V, 4), 7.0, device='cuda')
+    rast_out = torch.empty(N, H, W, 4, device='cuda')
+    col_out = torch.empty(N, H, W, C, device='cuda')
+    nbytes = _lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W)
+    scratch = torch.empty(int(nbytes), dtype=torch.uint8, device='cuda')
+    _lib.call('fpc_render_loss_fused', P(d_pos), P(d_tri), P(d_attr), P(d_idx), attr.shape[0], attr.shape[1], P(d_tex),
+              tex.shape[0] if textured else 0, tex.shape[1] if textured else 0, P(d_ref), 1 if u8 else 0, N, V, T, H, W, C,
+              G.BG, scale, P(loss), P(g_pos), P(rast_out), P(col_out), P(scratch), scratch.numel(),
+              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(rast_out[..., 3].cpu().numpy(), rast[..., 3])
+    assert np.abs(rast_out.cpu().numpy() - rast).max() <= ABS_FWD
+    assert np.abs(col_out.cpu().numpy() - comp_o.detach().numpy()).max() <= ABS_FWD
+    assert abs(float(loss) - float(loss_o.detach())) / float(loss_o.detach()) < 1e-5
+    assert rel_err(g_pos.cpu().numpy(), tp.grad.numpy()) < REL_GRAD
 
 
 def test_full_size_properties(dr):

@@ -43,7 +43,8 @@ def test_raster_depth_order_and_tie_break():
     ids = rast[0, ..., 3]
     assert set(np.unique(ids[ids > 0])) == {5.0, 6.0}
     np.testing.assert_allclose(rast[0, ..., 2][ids > 0], -0.5)
-    np.testing.assert_allclose(sec[0][ids > 0], 0.0)
+    np.testing.assert_allclose(sec[0][..., 0][ids > 0], -0.5)      # winner / runner-up plane depths
+    np.testing.assert_allclose(sec[0][..., 1][ids > 0], 0.0)
     # exact depth tie: the lower triangle index wins (in-order LESS)
     P2 = np.concatenate([pos, pos], axis=1)
     T2 = np.concatenate([tri + 4, tri])           # triangles 0,1 use the second copy, 2,3 the first

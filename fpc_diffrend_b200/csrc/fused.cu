@@ -7,9 +7,11 @@
 //
 // Per CTA:  (1) raster_bin(): visibility keys in shared memory (raster_core.cuh);
 //           (2) pixel-parallel shading, loss and (d u, d v) per pixel -> shared memory;
-//           (3) triangle-parallel gradient pass over the same balanced (triangle,row) work items: every lane sums
-//               the position gradient of its row in registers, rows of one triangle are combined with a segmented
-//               warp-shuffle reduction, and each visible (triangle, bin) pair issues 9 float REDs to grad_pos.
+//               The barycentric numerators are affine in the pixel position, so the position gradient of a triangle
+//               needs only nine moments of d loss / d a_k over its visible pixels; runs of pixels of the same
+//               triangle inside a warp are combined with a segmented warp-shuffle reduction and each run issues
+//               9 float REDs into a per-(view,triangle) moment buffer;
+//           (3) k_tri_grad (one thread per (view, triangle)) turns the moments into d loss / d pos.
 #include "raster_core.cuh"
 
 using namespace fpc;
@@ -30,36 +32,8 @@ struct FusedParams {
     float* rast_out;         // [N,H,W,4] or null
     float* colour_out;       // [N,H,W,C] or null (composited image)
     double* loss_partial;    // [N*NB]
+    float* moments;          // [N*T*9] zeroed by the host function
 };
-
-// second use of the per-warp staging memory (gradient pass)
-struct GradStage {
-    float px[3][32], py[3][32], pw[3][32];
-    int xy[32], wn[32], tri[32], vidx[3][32], prefix[32];
-};
-static_assert(sizeof(GradStage) <= sizeof(WarpStage), "GradStage must fit in the WarpStage memory");
-
-struct PosGrad { float v[9]; };   // (x,y,w) of vertex 0, 1, 2
-
-// d pos of one pixel from (gu, gv) = d loss / d (u, v)   (same formula as k_raster_bwd / gold_rasterize_bwd)
-__device__ __forceinline__ void pixel_pos_grad(float gu, float gv, float fx, float fy, float q0x, float q0y, float q0w,
-                                               float q1x, float q1y, float q1w, float q2x, float q2y, float q2w, PosGrad& a)
-{
-    float p0x = q0x - fx * q0w, p0y = q0y - fy * q0w;
-    float p1x = q1x - fx * q1w, p1y = q1y - fy * q1w;
-    float p2x = q2x - fx * q2w, p2y = q2y - fy * q2w;
-    float a0 = p1x * p2y - p1y * p2x, a1 = p2x * p0y - p2y * p0x, a2 = p0x * p1y - p0y * p1x;
-    float iw = 1.f / (a0 + a1 + a2);
-    float u = a0 * iw, v = a1 * iw;
-    float gbb = gu * u + gv * v;
-    float g0 = iw * (gu - gbb), g1 = iw * (gv - gbb), g2 = -iw * gbb;
-    float g0x = -g1 * p2y + g2 * p1y, g0y = g1 * p2x - g2 * p1x;
-    float g1x = g0 * p2y - g2 * p0y, g1y = -g0 * p2x + g2 * p0x;
-    float g2x = -g0 * p1y + g1 * p0y, g2y = g0 * p1x - g1 * p0x;
-    a.v[0] += g0x; a.v[1] += g0y; a.v[2] += -fx * g0x - fy * g0y;
-    a.v[3] += g1x; a.v[4] += g1y; a.v[5] += -fx * g1x - fy * g1y;
-    a.v[6] += g2x; a.v[7] += g2y; a.v[8] += -fx * g2x - fy * g2y;
-}
 
 __device__ __forceinline__ void red_vertex(float* G, int vi, float gx, float gy, float gw)
 {
@@ -68,14 +42,50 @@ __device__ __forceinline__ void red_vertex(float* G, int vi, float gx, float gy,
     if (gw != 0.f) atomicAdd(G + 4 * (size_t)vi + 3, gw);
 }
 
+// The barycentric numerators are affine in the pixel position:  a_k(px) = C_k + A_k fx + B_k fy  with
+//   C0 = x1 y2 - y1 x2, A0 = y1 w2 - w1 y2, B0 = w1 x2 - x1 w2   (and cyclic),
+// so d loss / d pos of a triangle needs only nine sums over its visible pixels, m = (S_k, SX_k, SY_k) with
+// g_k = d loss / d a_k at the pixel and (lx, ly) the pixel offset from the triangle's anchor pixel (fx0, fy0).
+// Same result as summing k_raster_bwd's per-pixel formula (oracle: gold_rasterize_bwd).
+__device__ __forceinline__ void triangle_pos_grad(const float* m, float fx0, float fy0, float xs, float ys,
+                                                  const float4& q0, const float4& q1, const float4& q2, float* G,
+                                                  int i0, int i1, int i2)
+{
+    const float S0 = m[0], S1 = m[1], S2 = m[2];
+    const float X0 = xs * m[3], X1 = xs * m[4], X2 = xs * m[5];     // sum g_k (fx - fx0)
+    const float Y0 = ys * m[6], Y1 = ys * m[7], Y2 = ys * m[8];     // sum g_k (fy - fy0)
+    // vertex positions relative to the anchor: p_m = (x_m - fx0 w_m, y_m - fy0 w_m)
+    float p0x = q0.x - fx0 * q0.w, p0y = q0.y - fy0 * q0.w;
+    float p1x = q1.x - fx0 * q1.w, p1y = q1.y - fy0 * q1.w;
+    float p2x = q2.x - fx0 * q2.w, p2y = q2.y - fy0 * q2.w;
+    // sum_px g_k p_my(px) = S_k p_my - w_m Y_k ;  sum_px g_k p_mx(px) = S_k p_mx - w_m X_k
+#define SY_(k, pmy, wm) (S##k * (pmy) - (wm) * Y##k)
+#define SX_(k, pmx, wm) (S##k * (pmx) - (wm) * X##k)
+    float g0x = -SY_(1, p2y, q2.w) + SY_(2, p1y, q1.w);
+    float g0y = SX_(1, p2x, q2.w) - SX_(2, p1x, q1.w);
+    float g1x = SY_(0, p2y, q2.w) - SY_(2, p0y, q0.w);
+    float g1y = -SX_(0, p2x, q2.w) + SX_(2, p0x, q0.w);
+    float g2x = -SY_(0, p1y, q1.w) + SY_(1, p0y, q0.w);
+    float g2y = SX_(0, p1x, q1.w) - SX_(1, p0x, q0.w);
+#undef SY_
+#undef SX_
+    // d loss / d A_k = sum g_k fx, d loss / d B_k = sum g_k fy
+    float dA0 = fx0 * S0 + X0, dA1 = fx0 * S1 + X1, dA2 = fx0 * S2 + X2;
+    float dB0 = fy0 * S0 + Y0, dB1 = fy0 * S1 + Y1, dB2 = fy0 * S2 + Y2;
+    float g0w = q2.y * dA1 - q2.x * dB1 - q1.y * dA2 + q1.x * dB2;
+    float g1w = -q2.y * dA0 + q2.x * dB0 + q0.y * dA2 - q0.x * dB2;
+    float g2w = q1.y * dA0 - q1.x * dB0 - q0.y * dA1 + q0.x * dB1;
+    red_vertex(G, i0, g0x, g0y, g0w);
+    red_vertex(G, i1, g1x, g1y, g1w);
+    red_vertex(G, i2, g2x, g2y, g2w);
+}
+
 template <int C, bool TEX>
-__global__ void __launch_bounds__(FINE_THREADS) k_fused(RasterParams rp, FusedParams fp)
+__global__ void __launch_bounds__(FINE_THREADS, 3) k_fused(RasterParams rp, FusedParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
     WarpStage* stage = reinterpret_cast<WarpStage*>(smem + sizeof(unsigned long long) * BIN * BIN);
-    float2* guv = reinterpret_cast<float2*>(smem + sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS);
-    float* acc_all = reinterpret_cast<float*>(guv + BIN * BIN);          // [FINE_WARPS][9][32]
     __shared__ double red[FINE_WARPS];
 
     const int bin = blockIdx.x, n = blockIdx.y;
@@ -90,15 +100,22 @@ __global__ void __launch_bounds__(FINE_THREADS) k_fused(RasterParams rp, FusedPa
     for (int idx = threadIdx.x; idx < BIN * BIN; idx += FINE_THREADS) {
         int lx = idx & (BIN - 1), ly = idx >> BIN_LOG2;
         int px = ox + lx, py = oy + ly;
-        float2 g = make_float2(0.f, 0.f);
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        unsigned long long key = keys[idx];
         if (px < rp.W && py < rp.H) {
             size_t pi = ((size_t)n * rp.H + py) * rp.W + px;
-            unsigned long long key = keys[idx];
+            // reference pixel first: its HBM latency overlaps the dependent gather chain below
+            float refv[C];
+#pragma unroll
+            for (int c = 0; c < C; c++)
+                refv[c] = fp.ref_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(fp.ref) + pi * C + c)
+                                    : __ldg(reinterpret_cast<const float*>(fp.ref) + pi * C + c);
             float col[C];
             float4 rout = make_float4(0.f, 0.f, 0.f, 0.f);
             bool fg = key != KEY_EMPTY;
             float a0c[TEX ? 2 : C], a1c[TEX ? 2 : C], a2c[TEX ? 2 : C];
             float dudc[C], dvdc[C];      // TEX: d colour_c / d texU, d texV
+            float su = 0.f, sv = 0.f, siw = 0.f;
             if (fg) {
                 int t = (int)(key & 0xFFFFFFFFu);
                 int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
@@ -106,6 +123,7 @@ __global__ void __launch_bounds__(FINE_THREADS) k_fused(RasterParams rp, FusedPa
                 float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
                 Shade sh = shade_pixel(p0, p1, p2, fx, fy);
                 float u = clamp01(sh.u), v = clamp01(sh.v);
+                su = sh.u; sv = sh.v; siw = sh.iw;
                 rout = make_float4(u, v, fminf(fmaxf(sh.zw, -1.f), 1.f), (float)(t + 1));
                 int j0 = __ldg(fp.attr_tri + 3 * t), j1 = __ldg(fp.attr_tri + 3 * t + 1), j2 = __ldg(fp.attr_tri + 3 * t + 2);
                 bool ok = (unsigned)j0 < (unsigned)fp.Va && (unsigned)j1 < (unsigned)fp.Va && (unsigned)j2 < (unsigned)fp.Va;
@@ -152,23 +170,27 @@ __global__ void __launch_bounds__(FINE_THREADS) k_fused(RasterParams rp, FusedPa
             float gc[C];
 #pragma unroll
             for (int c = 0; c < C; c++) {
-                float r = fp.ref_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(fp.ref) + pi * C + c)
-                                    : __ldg(reinterpret_cast<const float*>(fp.ref) + pi * C + c);
-                float e = r - 255.f * col[c];
+                float e = refv[c] - 255.f * col[c];
                 loss_acc += (double)(e * e);
                 gc[c] = (-510.f * fp.k) * e;
             }
             if (fg) {
+                float gu = 0.f, gv = 0.f;
                 if (TEX) {
                     float gU = 0.f, gV = 0.f;
 #pragma unroll
                     for (int c = 0; c < C; c++) { gU += gc[c] * dudc[c]; gV += gc[c] * dvdc[c]; }
-                    g.x = gU * (a0c[0] - a2c[0]) + gV * (a0c[1] - a2c[1]);
-                    g.y = gU * (a1c[0] - a2c[0]) + gV * (a1c[1] - a2c[1]);
+                    gu = gU * (a0c[0] - a2c[0]) + gV * (a0c[1] - a2c[1]);
+                    gv = gU * (a1c[0] - a2c[0]) + gV * (a1c[1] - a2c[1]);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < C; c++) { g.x += gc[c] * (a0c[c] - a2c[c]); g.y += gc[c] * (a1c[c] - a2c[c]); }
+                    for (int c = 0; c < C; c++) { gu += gc[c] * (a0c[c] - a2c[c]); gv += gc[c] * (a1c[c] - a2c[c]); }
                 }
+                // d loss / d a_k  (u = a0/at, v = a1/at, unclamped barycentrics as in the op-level backward)
+                float gbb = gu * su + gv * sv;
+                g2 = -siw * gbb;
+                g0 = siw * gu + g2;
+                g1 = siw * gv + g2;
             }
             if (fp.rast_out) reinterpret_cast<float4*>(fp.rast_out)[pi] = rout;
             if (fp.colour_out) {
@@ -176,7 +198,40 @@ __global__ void __launch_bounds__(FINE_THREADS) k_fused(RasterParams rp, FusedPa
                 for (int c = 0; c < C; c++) fp.colour_out[pi * C + c] = col[c];
             }
         }
-        guv[idx] = g;
+        // ---- moments of (g0, g1, g2) per triangle: combine runs of equal triangle id inside the warp, then RED ----
+        if (fp.moments) {
+            unsigned tid = (unsigned)(key & 0xFFFFFFFFu);                 // 0xFFFFFFFF on background
+            bool live = (g0 != 0.f || g1 != 0.f || g2 != 0.f);
+            if (__any_sync(0xffffffffu, live)) {
+                float m[9];
+                float flx = 0.f, fly = 0.f;
+                if (live) {
+                    int an = __ldg(rp.tri_anchor + (size_t)n * rp.T + tid);
+                    flx = (float)(px - (an & 0xffff));
+                    fly = (float)(py - (int)((unsigned)an >> 16));
+                }
+                m[0] = g0; m[1] = g1; m[2] = g2;
+                m[3] = g0 * flx; m[4] = g1 * flx; m[5] = g2 * flx;
+                m[6] = g0 * fly; m[7] = g1 * fly; m[8] = g2 * fly;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    unsigned to = __shfl_down_sync(0xffffffffu, tid, d);
+                    bool take = (lane + d < 32) && (to == tid);
+#pragma unroll
+                    for (int c = 0; c < 9; c++) {
+                        float o = __shfl_down_sync(0xffffffffu, m[c], d);
+                        if (take) m[c] += o;
+                    }
+                }
+                unsigned tp = __shfl_up_sync(0xffffffffu, tid, 1);
+                if (tid != 0xFFFFFFFFu && (lane == 0 || tp != tid)) {
+                    float* M = fp.moments + ((size_t)n * rp.T + tid) * 9;
+#pragma unroll
+                    for (int c = 0; c < 9; c++)
+                        if (m[c] != 0.f) atomicAdd(M + c, m[c]);
+                }
+            }
+        }
     }
     for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
     if (lane == 0) red[warp] = loss_acc;
@@ -186,138 +241,26 @@ __global__ void __launch_bounds__(FINE_THREADS) k_fused(RasterParams rp, FusedPa
         for (int w = 0; w < FINE_WARPS; w++) s += red[w];
         fp.loss_partial[(size_t)n * rp.NB + bin] = s;
     }
-    if (!fp.grad_pos) return;
+}
 
-    // ---- (3) gradient pass: small triangles, warp-balanced (triangle,row) items ----
-    const int lim_x = min(ox + BIN, rp.W) - 1, lim_y = min(oy + BIN, rp.H) - 1;
-    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
-    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
-    GradStage& st = *reinterpret_cast<GradStage*>(&stage[warp]);
-    float* acc = acc_all + warp * 9 * 32;
-    float* G = fp.grad_pos + (size_t)n * rp.V * 4;
-    for (int base = warp * 32; base < count; base += FINE_THREADS) {
-        int i = base + lane;
-        int rows = 0;
-        if (i < count) {
-            int t = list[i];
-            float4 p0, p1, p2;
-            SnappedTri s;
-            if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
-                int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
-                if (xa <= xb && ya <= yb) {
-                    rows = yb - ya + 1;
-                    st.px[0][lane] = p0.x; st.py[0][lane] = p0.y; st.pw[0][lane] = p0.w;
-                    st.px[1][lane] = p1.x; st.py[1][lane] = p1.y; st.pw[1][lane] = p1.w;
-                    st.px[2][lane] = p2.x; st.py[2][lane] = p2.y; st.pw[2][lane] = p2.w;
-                    st.xy[lane] = xa | (ya << 16);
-                    st.wn[lane] = (xb - xa + 1) | (rows << 16);
-                    st.tri[lane] = t;
-                    st.vidx[0][lane] = __ldg(rp.tri + 3 * t); st.vidx[1][lane] = __ldg(rp.tri + 3 * t + 1); st.vidx[2][lane] = __ldg(rp.tri + 3 * t + 2);
-                }
-            }
-        }
+// one thread per (view, triangle): moments -> d loss / d pos (9 float REDs per visible triangle)
+__global__ void __launch_bounds__(256) k_tri_grad(RasterParams rp, const float* __restrict__ moments, float* __restrict__ grad_pos)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)rp.N * rp.T) return;
+    const float* M = moments + gid * 9;
+    float m[9];
+    bool any = false;
 #pragma unroll
-        for (int c = 0; c < 9; c++) acc[c * 32 + lane] = 0.f;
-        int incl = rows;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += y;
-        }
-        st.prefix[lane] = incl;
-        int total = __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
-        for (int k0 = 0; k0 < total; k0 += 32) {
-            int k = k0 + lane;
-            int j = -1;
-            PosGrad a;
-#pragma unroll
-            for (int c = 0; c < 9; c++) a.v[c] = 0.f;
-            if (k < total) {
-                j = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1)
-                    if (st.prefix[j + step - 1] <= k) j += step;
-                int wn = st.wn[j];
-                int r = k - (st.prefix[j] - (wn >> 16));
-                int wd = wn & 0xffff;
-                int xy = st.xy[j];
-                int x0 = xy & 0xffff, yy = (int)((unsigned)xy >> 16) + r;
-                int t = st.tri[j];
-                int kidx = (yy - oy) * BIN + (x0 - ox);
-                float fy = pixel_ndc(yy, rp.ys, rp.yo);
-                bool loaded = false;
-                float q0x = 0, q0y = 0, q0w = 0, q1x = 0, q1y = 0, q1w = 0, q2x = 0, q2y = 0, q2w = 0;
-                for (int x = 0; x < wd; x++) {
-                    if ((int)(keys[kidx + x] & 0xFFFFFFFFu) != t || keys[kidx + x] == KEY_EMPTY) continue;
-                    float2 g = guv[kidx + x];
-                    if (g.x == 0.f && g.y == 0.f) continue;
-                    if (!loaded) {
-                        q0x = st.px[0][j]; q0y = st.py[0][j]; q0w = st.pw[0][j];
-                        q1x = st.px[1][j]; q1y = st.py[1][j]; q1w = st.pw[1][j];
-                        q2x = st.px[2][j]; q2y = st.py[2][j]; q2w = st.pw[2][j];
-                        loaded = true;
-                    }
-                    pixel_pos_grad(g.x, g.y, pixel_ndc(x0 + x, rp.xs, rp.xo), fy, q0x, q0y, q0w, q1x, q1y, q1w, q2x, q2y, q2w, a);
-                }
-            }
-            // segmented reduction over runs of equal j (items of one triangle are consecutive lanes)
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int jo = __shfl_down_sync(0xffffffffu, j, d);
-                bool take = (lane + d < 32) && (jo == j) && (j >= 0);
-#pragma unroll
-                for (int c = 0; c < 9; c++) {
-                    float o = __shfl_down_sync(0xffffffffu, a.v[c], d);
-                    if (take) a.v[c] += o;
-                }
-            }
-            int jp = __shfl_up_sync(0xffffffffu, j, 1);
-            if (j >= 0 && (lane == 0 || jp != j)) {
-#pragma unroll
-                for (int c = 0; c < 9; c++) acc[c * 32 + j] += a.v[c];
-            }
-            __syncwarp();
-        }
-        if (rows > 0) {
-            red_vertex(G, st.vidx[0][lane], acc[0 * 32 + lane], acc[1 * 32 + lane], acc[2 * 32 + lane]);
-            red_vertex(G, st.vidx[1][lane], acc[3 * 32 + lane], acc[4 * 32 + lane], acc[5 * 32 + lane]);
-            red_vertex(G, st.vidx[2][lane], acc[6 * 32 + lane], acc[7 * 32 + lane], acc[8 * 32 + lane]);
-        }
-        __syncwarp();
-    }
-
-    // ---- gradient pass: large triangles (rare), whole CTA per triangle ----
-    const int nlarge = rp.large_count[n];
-    const int* llist = rp.large_list + (size_t)n * rp.T;
-    for (int i = 0; i < nlarge; i++) {
-        int t = llist[i];
-        float4 p0, p1, p2;
-        SnappedTri s;
-        if (!load_triangle(rp, n, t, p0, p1, p2) || !setup_triangle(p0, p1, p2, rp, s)) continue;
-        int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
-        if (xa > xb || ya > yb) continue;
-        PosGrad a;
-#pragma unroll
-        for (int c = 0; c < 9; c++) a.v[c] = 0.f;
-        for (int idx = threadIdx.x; idx < BIN * BIN; idx += FINE_THREADS) {
-            unsigned long long key = keys[idx];
-            if (key == KEY_EMPTY || (int)(key & 0xFFFFFFFFu) != t) continue;
-            float2 g = guv[idx];
-            if (g.x == 0.f && g.y == 0.f) continue;
-            int px = ox + (idx & (BIN - 1)), py = oy + (idx >> BIN_LOG2);
-            pixel_pos_grad(g.x, g.y, pixel_ndc(px, rp.xs, rp.xo), pixel_ndc(py, rp.ys, rp.yo), p0.x, p0.y, p0.w, p1.x, p1.y, p1.w,
-                           p2.x, p2.y, p2.w, a);
-        }
-#pragma unroll
-        for (int c = 0; c < 9; c++)
-            for (int o = 16; o > 0; o >>= 1) a.v[c] += __shfl_xor_sync(0xffffffffu, a.v[c], o);
-        if (lane == 0) {
-            red_vertex(G, __ldg(rp.tri + 3 * t), a.v[0], a.v[1], a.v[2]);
-            red_vertex(G, __ldg(rp.tri + 3 * t + 1), a.v[3], a.v[4], a.v[5]);
-            red_vertex(G, __ldg(rp.tri + 3 * t + 2), a.v[6], a.v[7], a.v[8]);
-        }
-    }
+    for (int c = 0; c < 9; c++) { m[c] = M[c]; any = any || (m[c] != 0.f); }
+    if (!any) return;
+    int n = (int)(gid / rp.T), t = (int)(gid - (long long)n * rp.T);
+    int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+    const float* P = rp.pos + (size_t)n * rp.V * 4;
+    float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
+    int an = rp.tri_anchor[gid];
+    float fx0 = pixel_ndc(an & 0xffff, rp.xs, rp.xo), fy0 = pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo);
+    triangle_pos_grad(m, fx0, fy0, rp.xs, rp.ys, p0, p1, p2, grad_pos + (size_t)n * rp.V * 4, i0, i1, i2);
 }
 
 __global__ void __launch_bounds__(256) k_fused_loss_reduce(const double* __restrict__ partial, int n, float k, float* __restrict__ loss)
@@ -334,8 +277,7 @@ __global__ void __launch_bounds__(256) k_fused_loss_reduce(const double* __restr
     if (threadIdx.x == 0) loss[0] = (float)(red[0] * (double)k);
 }
 
-constexpr size_t FUSED_SMEM = sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS + sizeof(float2) * BIN * BIN +
-                              sizeof(float) * FINE_WARPS * 9 * 32;
+constexpr size_t FUSED_SMEM = sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS;
 
 template <int C, bool TEX>
 int launch_fused(const RasterParams& rp, const FusedParams& fp, cudaStream_t stream)
@@ -358,7 +300,7 @@ extern "C" size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W
 {
     if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return 256;
     int NB = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
-    return align256(raster_layout(N, T, NB).total) + align256((size_t)N * NB * sizeof(double));
+    return align256(raster_layout(N, T, NB).total) + align256((size_t)N * NB * sizeof(double)) + align256((size_t)N * T * 9 * sizeof(float));
 }
 
 extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* attr, const int32_t* attr_tri, int Va, int A,
@@ -382,10 +324,19 @@ extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const
     fp.ref = ref; fp.ref_u8 = ref_is_u8; fp.C = C; fp.bg = bg; fp.k = scale / ((float)H * (float)W * (float)C);
     fp.grad_pos = grad_pos; fp.rast_out = rast_out; fp.colour_out = colour_out;
     fp.loss_partial = (double*)((char*)scratch + align256(raster_layout(N, T, rp.NB).total));
-    if (grad_pos) FPC_CUDA(cudaMemsetAsync(grad_pos, 0, (size_t)N * V * 4 * sizeof(float), stream));
+    fp.moments = nullptr;
+    if (grad_pos) {
+        fp.moments = (float*)((char*)fp.loss_partial + align256((size_t)N * rp.NB * sizeof(double)));
+        FPC_CUDA(cudaMemsetAsync(fp.moments, 0, (size_t)N * T * 9 * sizeof(float), stream));
+        FPC_CUDA(cudaMemsetAsync(grad_pos, 0, (size_t)N * V * 4 * sizeof(float), stream));
+    }
     if (tex) st = (C == 1) ? launch_fused<1, true>(rp, fp, stream) : launch_fused<3, true>(rp, fp, stream);
     else st = (C == 1) ? launch_fused<1, false>(rp, fp, stream) : launch_fused<3, false>(rp, fp, stream);
     if (st != FPC_OK) return st;
+    if (grad_pos) {
+        k_tri_grad<<<fpc_div_up((long long)N * T, 256), 256, 0, stream>>>(rp, fp.moments, grad_pos);
+        FPC_LAUNCH_CHECK();
+    }
     k_fused_loss_reduce<<<1, 256, 0, stream>>>(fp.loss_partial, N * rp.NB, fp.k, loss);
     FPC_LAUNCH_CHECK();
     return FPC_OK;

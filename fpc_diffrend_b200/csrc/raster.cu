@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) k_setup(RasterParams rp)
     SnappedTri s;
     int info = 0;
     if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
+        rp.tri_anchor[gid] = s.pxa | (s.pya << 16);
         int bx0 = s.pxa >> BIN_LOG2, bx1 = s.pxb >> BIN_LOG2, by0 = s.pya >> BIN_LOG2, by1 = s.pyb >> BIN_LOG2;
         if (!is_small(s)) {
             int slot = atomicAdd(rp.large_count + n, 1);
@@ -182,6 +183,7 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_info = o;        o += align_up((size_t)N * T * 4);
     L.off_pairs = o;       o += align_up((size_t)N * T * 16);
     L.off_large = o;       o += align_up((size_t)N * T * 4);
+    L.off_anchor = o;      o += align_up((size_t)N * T * 4);
     L.total = o;
     return L;
 }
@@ -208,6 +210,7 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.tri_info = (int*)(s + L.off_info);
     rp.pairs = (int*)(s + L.off_pairs);
     rp.large_list = (int*)(s + L.off_large);
+    rp.tri_anchor = (int*)(s + L.off_anchor);
     FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
     long long nt = (long long)N * T;
     k_setup<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);

@@ -38,6 +38,7 @@ struct RasterParams {
     int* tri_info;                   // [N*T]
     int* pairs;                      // [N*4T]
     int* large_list;                 // [N*T]
+    int* tri_anchor;                 // [N*T]  pxa | pya << 16: first pixel of the image-clamped bbox (moment origin)
 };
 
 struct SnappedTri {
@@ -129,7 +130,8 @@ __device__ __forceinline__ void emit_fragment(unsigned long long* keys, float zd
 {
     if (!(zd >= -1.f && zd <= 1.f)) return;
     unsigned long long key = ((unsigned long long)depth_key(zd) << 32) | (unsigned)t;
-    atomicMin(keys + ly * BIN + lx, key);
+    // 64-bit shared atomicMin is a CAS loop: skip it for fragments that already lose against the stored key
+    if (key < keys[ly * BIN + lx]) atomicMin(keys + ly * BIN + lx, key);
 }
 
 // ---- fill rule -------------------------------------------------------------------------------------------
@@ -264,7 +266,7 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
 // Host side: scratch layout + the three binning launches.
 struct ScratchLayout {
     size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, total;
+    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, total;
 };
 
 ScratchLayout raster_layout(int N, int T, int NB);

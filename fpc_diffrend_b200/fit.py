@@ -169,9 +169,9 @@ class FitSession:
         self.ref = ref.reshape(self.N, self.H, self.W, self.Ch).contiguous()
 
     def iteration_from_host(self, frames_host, loss_host=None):
-        """The call a user of the drop-in makes per step with HOST buffers: upload this step's reference frames
-        (pinned host memory -> the resident device buffer), run one iteration (the captured graph when there is
-        one), read the loss back.  Returns the loss as a float (this synchronises the stream)."""
+        """One step with HOST buffers, unpipelined: upload this step's reference frames (pinned host memory -> the
+        resident device buffer), run one iteration (the captured graph when there is one), read the loss back.
+        Returns the loss as a float (this synchronises the stream).  See fit_stream() for the pipelined form."""
         src = frames_host.reshape(self.N, self.H, self.W, self.Ch)
         if self.ref is None:
             dt = torch.uint8 if self.cfg.ref_dtype == 'u8' else torch.float32
@@ -186,6 +186,64 @@ class FitSession:
         loss_host.copy_(self.loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host)
+
+    def fit_stream(self, frames_iter, use_graph=True):
+        """Pipelined fit over a stream of HOST reference-frame batches (role of the reference's in-loop frame read,
+        fit.py:529-533, but double-buffered): yields the loss of every step.
+
+        frames_iter yields pinned host tensors [F, C, H, W, Ch] (uint8 when ref_dtype == 'u8', else float32).
+        While step k runs on the compute stream, the frames of step k+1 are uploaded on a copy stream into the
+        other of two resident device buffers; one CUDA graph per buffer is captured on first use.  Every step's
+        loss is read back (4 bytes, device -> pinned host) before it is yielded."""
+        dt = torch.uint8 if self.cfg.ref_dtype == 'u8' else torch.float32
+        shape = (self.N, self.H, self.W, self.Ch)
+        if getattr(self, '_stream_bufs', None) is None:
+            self._stream_bufs = [torch.empty(shape, dtype=dt, device=self.device) for _ in range(2)]
+            self._stream_graphs = [None, None]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        bufs, graphs, cs = self._stream_bufs, self._stream_graphs, self._copy_stream
+        compute = torch.cuda.current_stream()
+        uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [None, None]
+
+        def upload(slot, frames):
+            if consumed[slot] is not None:
+                cs.wait_event(consumed[slot])          # the step that last read this buffer has finished
+            with torch.cuda.stream(cs):
+                bufs[slot].copy_(frames.reshape(shape), non_blocking=True)
+                uploaded[slot].record(cs)
+
+        it = iter(frames_iter)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        upload(0, nxt)
+        k = 0
+        while nxt is not None:
+            slot = k & 1
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            if nxt is not None:
+                upload(slot ^ 1, nxt)                  # overlaps with the compute of step k
+            compute.wait_event(uploaded[slot])
+            self.ref = bufs[slot]
+            if use_graph:
+                if graphs[slot] is None:
+                    graphs[slot] = self._capture_current()
+                graphs[slot].replay()
+            else:
+                self.iteration()
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            consumed[slot] = ev
+            self._loss_host.copy_(self.loss, non_blocking=True)
+            compute.synchronize()
+            yield float(self._loss_host)
+            k += 1
 
     def set_parameters(self, w=None, t=None, q=None):
         if w is not None:
@@ -324,17 +382,23 @@ class FitSession:
         return n
 
     # ---- CUDA graph ----------------------------------------------------------------------------------
+    def _capture_current(self):
+        """Capture one iteration (reading the current self.ref buffer) into a CUDA graph.  Capturing does not
+        execute: parameters and optimiser state are untouched."""
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.iteration()
+        return g
+
     def capture(self):
-        """Capture one iteration into a CUDA graph (after a warm-up iteration on a side stream)."""
+        """Run one eager warm-up iteration on a side stream, then capture one iteration into self.graph."""
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self.iteration()
         torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize(self.device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.iteration()
+        self.graph = self._capture_current()
         return self.graph
 
     def replay(self):

@@ -186,3 +186,24 @@ def test_graph_replay_matches_eager(tiny_rig):
     assert float(b.step_count) == 5.0 and float(a.step_count) == 5.0
     # float atomics in the gradient scatter make the two runs differ by rounding only
     assert torch.allclose(a.w, b.w, atol=1e-5) and torch.allclose(a.t, b.t, atol=1e-6)
+
+
+def test_fit_stream_matches_resident(tiny_rig):
+    """Pipelined host-buffer API (double-buffered uploads, one graph per buffer) == resident-frame iterations."""
+    from fpc_diffrend_b200 import rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, F = tiny_rig, 2
+    cfg = FitConfig(resolution=(128, 128), shading='vcol', antialias=False, lr_base=1e-2, max_iter=100, ref_dtype='u8')
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=3)
+    ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, cfg).round().clamp(0, 255).to(torch.uint8)
+    a, b = FitSession(rig, F, cfg), FitSession(rig, F, cfg)
+    a.set_reference(ref)
+    la = []
+    for _ in range(6):
+        a.iteration()
+        la.append(float(a.loss))
+    host = ref.cpu().pin_memory()
+    lb = list(b.fit_stream((host for _ in range(6))))
+    assert len(lb) == 6 and float(b.step_count) == 6.0
+    np.testing.assert_allclose(lb, la, rtol=1e-4)
+    assert torch.allclose(a.w, b.w, atol=1e-5)

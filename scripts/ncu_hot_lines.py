@@ -35,3 +35,21 @@ for kn in kernels[:1]:
         st = sorted(v[4].items(), key=lambda kv: -kv[1])[:3]
         print('%-14s %4d smp=%5.1f%% inst=%5.1f%% thr/inst=%4.1f %-38s| %s' % (k[1], k[2], 100 * v[1] / ts, 100 * v[2] / ti, v[3] / max(v[2], 1),
               ','.join('%s:%d' % (a.replace('stall_', ''), b) for a, b in st), v[0]))
+
+# ---- per-file / per-line-range phase totals (optional 3rd arg: file:lo-hi,file:lo-hi,...) ----
+if len(sys.argv) > 3:
+    for kn in kernels[:1]:
+        items = [(k, v) for k, v in out.items() if k[0] == kn]
+        ts = sum(v[1] for _, v in items) or 1
+        ti = sum(v[2] for _, v in items) or 1
+        for spec in sys.argv[3].split(','):
+            f, rng = spec.split(':')
+            lo, hi = map(int, rng.split('-'))
+            sel = [v for k, v in items if k[1] == f and lo <= k[2] <= hi]
+            st = {}
+            for v in sel:
+                for a, b in v[4].items():
+                    st[a] = st.get(a, 0) + b
+            top3 = sorted(st.items(), key=lambda kv: -kv[1])[:4]
+            print('%-28s smp=%5.1f%% inst=%5.1f%%  %s' % (spec, 100 * sum(v[1] for v in sel) / ts, 100 * sum(v[2] for v in sel) / ti,
+                  ','.join('%s:%d' % (a.replace('stall_', ''), b) for a, b in top3)))

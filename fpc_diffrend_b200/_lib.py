@@ -7,7 +7,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libfpc_b200.so')
+# FPC_B200_LIB selects another build of the SAME library (kernel-variant experiments, scripts/exp_variants.py)
+LIB_PATH = os.environ.get('FPC_B200_LIB') or os.path.join(_HERE, 'libfpc_b200.so')
 HEADER_PATH = os.path.join(_HERE, '..', 'include', 'fpc_b200.h')
 
 _lib = None
@@ -43,6 +44,10 @@ SIGNATURES = {
     'fpc_project_fwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),
     'fpc_project_bwd_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_project_bwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    'fpc_geometry_fused_supported': (_I, [_I, _I, _I, _I]),
+    'fpc_geometry_fwd': (_I, [_P] * 9 + [_I] * 4 + [_P] * 4),
+    'fpc_geometry_bwd_scratch_bytes': (_Z, [_I, _I, _I, _I]),
+    'fpc_geometry_bwd': (_I, [_P] * 11 + [_I] * 4 + [_P] * 6 + [_Z, _P]),
     'fpc_image_loss_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'fpc_image_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _Z, _P]),
     'fpc_render_loss_fused_scratch_bytes': (_Z, [_I, _I, _I, _I]),
@@ -50,6 +55,7 @@ SIGNATURES = {
     'fpc_adam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P]),
     'fpc_adam_advance': (_I, [_P, _P]),
     'fpc_quat_renorm': (_I, [_P, _I, _I, _P]),
+    'fpc_adam_fused': (_I, [_P] * 4 + [_I] * 3 + [_F] * 8 + [_I, _P, _P]),
 }
 
 

@@ -29,11 +29,11 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(src, verbose):
-    obj = src[:-3] + '.o'
+def _compile(src, verbose, defines=(), tag=''):
+    obj = src[:-3] + tag + '.o'
     if not _stale(obj, [src] + _deps()):
         return obj
-    cmd = [NVCC] + ARCH_FLAGS + CFLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+    cmd = [NVCC] + ARCH_FLAGS + CFLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -42,22 +42,25 @@ def _compile(src, verbose):
     return obj
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=''):
+    """Compile csrc/*.cu and link the library.  `defines` / `tag` build a kernel-variant copy
+    libfpc_b200<tag>.so (experiments only; the product is the untagged library)."""
     srcs = sources()
+    lib = LIB if not tag else LIB[:-3] + tag + '.so'
     if force:
         for s in srcs:
-            o = s[:-3] + '.o'
+            o = s[:-3] + tag + '.o'
             if os.path.exists(o):
                 os.remove(o)
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
-    if force or _stale(LIB, objs):
-        cmd = [NVCC] + ARCH_FLAGS + ['-shared', '-o', LIB] + objs + ['-lcudart']
+        objs = list(ex.map(lambda s: _compile(s, verbose, defines, tag), srcs))
+    if force or _stale(lib, objs):
+        cmd = [NVCC] + ARCH_FLAGS + ['-shared', '-o', lib] + objs + ['-lcudart']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError('link failed')
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':

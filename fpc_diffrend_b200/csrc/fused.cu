@@ -80,8 +80,12 @@ __device__ __forceinline__ void triangle_pos_grad(const float* m, float fx0, flo
     red_vertex(G, i2, g2x, g2y, g2w);
 }
 
+#ifndef FPC_FUSED_MINBLOCKS
+#define FPC_FUSED_MINBLOCKS 8
+#endif
+
 template <int C, bool TEX>
-__global__ void __launch_bounds__(FINE_THREADS, 3) k_fused(RasterParams rp, FusedParams fp)
+__global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(RasterParams rp, FusedParams fp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
@@ -92,7 +96,39 @@ __global__ void __launch_bounds__(FINE_THREADS, 3) k_fused(RasterParams rp, Fuse
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    // ---- (0) the tile of the reference frame starts its way into shared memory now (cp.async), so its HBM / L2
+    //          latency is hidden behind the rasterization phase ----
+    unsigned char* sref = smem + sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS;
+    const int esz = fp.ref_u8 ? 1 : 4;
+    const int pitch = BIN * C * esz;                          // bytes per tile row (multiple of 16)
+    {
+        const unsigned char* rbase = reinterpret_cast<const unsigned char*>(fp.ref);
+        const int rows = min(BIN, rp.H - oy);
+        const size_t row_bytes = (size_t)rp.W * C * esz;
+        const bool fast = (ox + BIN <= rp.W) && (row_bytes % 16 == 0) && ((reinterpret_cast<size_t>(rbase) & 15) == 0);
+        if (fast) {
+            const int cpr = pitch >> 4;
+            for (int i = threadIdx.x; i < rows * cpr; i += FINE_THREADS) {
+                int r = i / cpr, ch = i - r * cpr;
+                const unsigned char* src = rbase + ((size_t)n * rp.H + oy + r) * row_bytes + (size_t)ox * C * esz + ch * 16;
+                unsigned dst = (unsigned)__cvta_generic_to_shared(sref + r * pitch + ch * 16);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+        } else {
+            const int wpx = min(BIN, rp.W - ox);
+            for (int i = threadIdx.x; i < rows * wpx * C; i += FINE_THREADS) {
+                int r = i / (wpx * C), e = i - r * (wpx * C);
+                size_t gi = (((size_t)n * rp.H + oy + r) * rp.W + ox) * C + e;
+                if (fp.ref_u8) sref[r * pitch + e] = __ldg(rbase + gi);
+                else reinterpret_cast<float*>(sref + r * pitch)[e] = __ldg(reinterpret_cast<const float*>(rbase) + gi);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
     raster_bin(rp, n, bin, keys, stage);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
 
     // ---- (2) shade + loss + (d u, d v) per pixel ----
     const float* P = rp.pos + (size_t)n * rp.V * 4;
@@ -101,15 +137,15 @@ __global__ void __launch_bounds__(FINE_THREADS, 3) k_fused(RasterParams rp, Fuse
         int lx = idx & (BIN - 1), ly = idx >> BIN_LOG2;
         int px = ox + lx, py = oy + ly;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        int an = 0;
         unsigned long long key = keys[idx];
         if (px < rp.W && py < rp.H) {
             size_t pi = ((size_t)n * rp.H + py) * rp.W + px;
-            // reference pixel first: its HBM latency overlaps the dependent gather chain below
             float refv[C];
 #pragma unroll
             for (int c = 0; c < C; c++)
-                refv[c] = fp.ref_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(fp.ref) + pi * C + c)
-                                    : __ldg(reinterpret_cast<const float*>(fp.ref) + pi * C + c);
+                refv[c] = fp.ref_u8 ? (float)sref[ly * pitch + lx * C + c]
+                                    : reinterpret_cast<const float*>(sref + ly * pitch)[lx * C + c];
             float col[C];
             float4 rout = make_float4(0.f, 0.f, 0.f, 0.f);
             bool fg = key != KEY_EMPTY;
@@ -119,13 +155,15 @@ __global__ void __launch_bounds__(FINE_THREADS, 3) k_fused(RasterParams rp, Fuse
             if (fg) {
                 int t = (int)(key & 0xFFFFFFFFu);
                 int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+                if (fp.moments) an = __ldg(rp.tri_anchor + (size_t)n * rp.T + t);     // early: consumed by the moments below
                 float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
                 float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
                 Shade sh = shade_pixel(p0, p1, p2, fx, fy);
                 float u = clamp01(sh.u), v = clamp01(sh.v);
                 su = sh.u; sv = sh.v; siw = sh.iw;
                 rout = make_float4(u, v, fminf(fmaxf(sh.zw, -1.f), 1.f), (float)(t + 1));
-                int j0 = __ldg(fp.attr_tri + 3 * t), j1 = __ldg(fp.attr_tri + 3 * t + 1), j2 = __ldg(fp.attr_tri + 3 * t + 2);
+                int j0 = i0, j1 = i1, j2 = i2;
+                if (fp.attr_tri != rp.tri) { j0 = __ldg(fp.attr_tri + 3 * t); j1 = __ldg(fp.attr_tri + 3 * t + 1); j2 = __ldg(fp.attr_tri + 3 * t + 2); }
                 bool ok = (unsigned)j0 < (unsigned)fp.Va && (unsigned)j1 < (unsigned)fp.Va && (unsigned)j2 < (unsigned)fp.Va;
                 constexpr int AA = TEX ? 2 : C;
                 float b2 = 1.f - u - v;
@@ -206,15 +244,22 @@ __global__ void __launch_bounds__(FINE_THREADS, 3) k_fused(RasterParams rp, Fuse
                 float m[9];
                 float flx = 0.f, fly = 0.f;
                 if (live) {
-                    int an = __ldg(rp.tri_anchor + (size_t)n * rp.T + tid);
                     flx = (float)(px - (an & 0xffff));
                     fly = (float)(py - (int)((unsigned)an >> 16));
                 }
                 m[0] = g0; m[1] = g1; m[2] = g2;
                 m[3] = g0 * flx; m[4] = g1 * flx; m[5] = g2 * flx;
                 m[6] = g0 * fly; m[7] = g1 * fly; m[8] = g2 * fly;
+                // longest run of one triangle in this warp: shuffle steps with d >= that length combine nothing
+                unsigned tprev = __shfl_up_sync(0xffffffffu, tid, 1);
+                const bool head = (lane == 0) || (tprev != tid);
+                const unsigned hm = __ballot_sync(0xffffffffu, head);
+                const unsigned above = (lane == 31) ? 0u : (hm & (0xFFFFFFFEu << lane));
+                const unsigned len = (head && tid != 0xFFFFFFFFu) ? (unsigned)((above ? __ffs(above) - 1 : 32) - lane) : 0u;
+                const unsigned maxlen = __reduce_max_sync(0xffffffffu, len);
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
+                    if ((unsigned)d >= maxlen) break;
                     unsigned to = __shfl_down_sync(0xffffffffu, tid, d);
                     bool take = (lane + d < 32) && (to == tid);
 #pragma unroll
@@ -223,8 +268,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 3) k_fused(RasterParams rp, Fuse
                         if (take) m[c] += o;
                     }
                 }
-                unsigned tp = __shfl_up_sync(0xffffffffu, tid, 1);
-                if (tid != 0xFFFFFFFFu && (lane == 0 || tp != tid)) {
+                if (tid != 0xFFFFFFFFu && head) {
                     float* M = fp.moments + ((size_t)n * rp.T + tid) * 9;
 #pragma unroll
                     for (int c = 0; c < 9; c++)
@@ -277,17 +321,18 @@ __global__ void __launch_bounds__(256) k_fused_loss_reduce(const double* __restr
     if (threadIdx.x == 0) loss[0] = (float)(red[0] * (double)k);
 }
 
-constexpr size_t FUSED_SMEM = sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS;
+// keys + per-warp triangle staging + the reference-frame tile (u8 or f32, C channels)
+__host__ size_t fused_smem(int C, int ref_u8) { return sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS + (size_t)BIN * BIN * C * (ref_u8 ? 1 : 4); }
 
 template <int C, bool TEX>
 int launch_fused(const RasterParams& rp, const FusedParams& fp, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        FPC_CUDA(cudaFuncSetAttribute(k_fused<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM));
+        FPC_CUDA(cudaFuncSetAttribute(k_fused<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(C, 0)));
         attr_set = true;
     }
-    k_fused<C, TEX><<<dim3(rp.NB, rp.N), FINE_THREADS, FUSED_SMEM, stream>>>(rp, fp);
+    k_fused<C, TEX><<<dim3(rp.NB, rp.N), FINE_THREADS, fused_smem(C, fp.ref_u8), stream>>>(rp, fp);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }
@@ -317,19 +362,18 @@ extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const
     else FPC_CHECK_ARG(A == C, "render_loss_fused: vertex-colour shading needs A == C (got A=%d, C=%d)", A, C);
     FPC_CHECK_ARG(scratch_bytes >= fpc_render_loss_fused_scratch_bytes(N, T, H, W), "render_loss_fused: scratch too small");
     RasterParams rp;
-    int st = raster_bin_triangles("render_loss_fused", pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp);
+    const int NB0 = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
+    double* loss_partial = (double*)((char*)scratch + align256(raster_layout(N, T, NB0).total));
+    float* moments = grad_pos ? (float*)((char*)loss_partial + align256((size_t)N * NB0 * sizeof(double))) : nullptr;
+    // k_setup clears the moment and gradient accumulators on its way (no separate memsets)
+    int st = raster_bin_triangles("render_loss_fused", pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, moments, grad_pos);
     if (st != FPC_OK) return st;
     FusedParams fp;
     fp.attr = attr; fp.attr_tri = attr_tri; fp.Va = Va; fp.A = A; fp.tex = tex; fp.Ht = Ht; fp.Wt = Wt;
     fp.ref = ref; fp.ref_u8 = ref_is_u8; fp.C = C; fp.bg = bg; fp.k = scale / ((float)H * (float)W * (float)C);
     fp.grad_pos = grad_pos; fp.rast_out = rast_out; fp.colour_out = colour_out;
-    fp.loss_partial = (double*)((char*)scratch + align256(raster_layout(N, T, rp.NB).total));
-    fp.moments = nullptr;
-    if (grad_pos) {
-        fp.moments = (float*)((char*)fp.loss_partial + align256((size_t)N * rp.NB * sizeof(double)));
-        FPC_CUDA(cudaMemsetAsync(fp.moments, 0, (size_t)N * T * 9 * sizeof(float), stream));
-        FPC_CUDA(cudaMemsetAsync(grad_pos, 0, (size_t)N * V * 4 * sizeof(float), stream));
-    }
+    fp.loss_partial = loss_partial;
+    fp.moments = moments;
     if (tex) st = (C == 1) ? launch_fused<1, true>(rp, fp, stream) : launch_fused<3, true>(rp, fp, stream);
     else st = (C == 1) ? launch_fused<1, false>(rp, fp, stream) : launch_fused<3, false>(rp, fp, stream);
     if (st != FPC_OK) return st;

@@ -1,0 +1,405 @@
+// Fused geometry stages of the fit iteration for small frame batches (one pass over D per direction):
+//
+//   fpc_geometry_fwd : pose -> MVP chain (fit.py:546-553)  +  blend V = base + D w (fit.py:103-129)
+//                      +  clip transform [V 1] mvp^T (camera.py:11-23)                       -> ONE kernel
+//   fpc_geometry_bwd : d pos_clip -> d V (transform_clip bwd) -> d w = D^T d V (blend bwd), d mvp -> d t, d q
+//                      (pose bwd)                                                            -> TWO kernels
+//   fpc_adam_fused   : Adam + LambdaLR for the packed [w | t | q] vector, quaternion renorm and the step
+//                      counter advance (fit.py:493-505,610-618)                              -> ONE kernel
+//
+// A warp owns one vertex at a time: its three rows of D are 3B contiguous floats (HBM/L2-bound float4 stream,
+// the only large operand), reduced with warp shuffles; lanes 0..C-1 then act as the cameras of that vertex.
+// Everything is deterministic: per-warp partials are combined in a fixed order (no float atomics).
+#include "pose.cuh"
+
+namespace {
+
+constexpr int GEO_THREADS = 256;
+constexpr int GEO_WARPS = GEO_THREADS / 32;
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+// row loader: the 3B floats of vertex v as K float4 per lane (flat index i = lane + 32 k)
+template <int K>
+__device__ __forceinline__ void load_rows(const float* __restrict__ D, int v, int B, int n4, int lane, float4 (&d)[K])
+{
+    const float4* row4 = reinterpret_cast<const float4*>(D + (size_t)v * 3 * B);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        int i = lane + 32 * k;
+        d[k] = (i < n4) ? __ldg(row4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int K>   // K = ceil(3B/4 / 32): float4 of D per lane and vertex
+__global__ void __launch_bounds__(GEO_THREADS) k_geom_fwd(const float* __restrict__ P, const float* __restrict__ A,
+                                                          const float* __restrict__ t, const float* __restrict__ q,
+                                                          const float* __restrict__ t_cam, const float* __restrict__ q_cam,
+                                                          const float* __restrict__ D, const float* __restrict__ base,
+                                                          const float* __restrict__ w, int V, int B, int F, int C,
+                                                          float* __restrict__ mvp_out, float* __restrict__ verts,
+                                                          float* __restrict__ pos_clip)
+{
+    extern __shared__ float sm[];
+    float* s_mvp = sm;                 // [C][16]
+    float* s_w = sm + C * 16;          // [B]
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * GEO_WARPS + (threadIdx.x >> 5), nw = gridDim.x * GEO_WARPS;
+    const int n4 = (3 * B) >> 2;       // B % 4 == 0 (checked by the host function)
+    // the first vertex's rows are requested before the (serial, latency-bound) pose chain below
+    float4 cur[K];
+    if (gw < V) load_rows<K>(D, gw, B, n4, lane, cur);
+    for (int c = threadIdx.x; c < C; c += GEO_THREADS) {
+        M4 m = frame_camera_mvp(P, A, t, q, t_cam, q_cam, f, c);
+#pragma unroll
+        for (int i = 0; i < 16; i++) s_mvp[16 * c + i] = m.m[i >> 2][i & 3];
+        if (blockIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) mvp_out[((size_t)f * C + c) * 16 + i] = m.m[i >> 2][i & 3];
+        }
+    }
+    for (int i = threadIdx.x; i < B; i += GEO_THREADS) s_w[i] = w[(size_t)f * B + i];
+    __syncthreads();
+
+    for (int v = gw; v < V; v += nw) {
+        float4 nxt[K];
+        if (v + nw < V) load_rows<K>(D, v + nw, B, n4, lane, nxt);     // in flight while this vertex is reduced
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            int e = 4 * (lane + 32 * k);
+            if (e < 3 * B) {
+                int r = (e >= B) + (e >= 2 * B);
+                const float* ww = s_w + (e - r * B);
+                float s = cur[k].x * ww[0] + cur[k].y * ww[1] + cur[k].z * ww[2] + cur[k].w * ww[3];
+                a0 += (r == 0) ? s : 0.f;
+                a1 += (r == 1) ? s : 0.f;
+                a2 += (r == 2) ? s : 0.f;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        const float x = __ldg(base + 3 * (size_t)v) + a0, y = __ldg(base + 3 * (size_t)v + 1) + a1, z = __ldg(base + 3 * (size_t)v + 2) + a2;
+        if (lane == 0) {
+            float* o = verts + ((size_t)f * V + v) * 3;
+            o[0] = x; o[1] = y; o[2] = z;
+        }
+        for (int c = lane; c < C; c += 32) {
+            const float* m = s_mvp + 16 * c;
+            float4 o;      // same op order as k_project_fwd (project.cu)
+            o.x = m[0] * x + m[1] * y + m[2] * z + m[3];
+            o.y = m[4] * x + m[5] * y + m[6] * z + m[7];
+            o.z = m[8] * x + m[9] * y + m[10] * z + m[11];
+            o.w = m[12] * x + m[13] * y + m[14] * z + m[15];
+            reinterpret_cast<float4*>(pos_clip)[((size_t)f * C + c) * V + v] = o;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) cur[k] = nxt[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward, stage 1: per-CTA partials of d w [F,B] and d mvp [F*C,16]
+// ---------------------------------------------------------------------------------------------------------
+template <int K>   // K = ceil(3B/4 / 32): float4 accumulators per lane
+__global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restrict__ D, const float* __restrict__ verts,
+                                                          const float* __restrict__ mvp, const float* __restrict__ g_pos,
+                                                          const float* __restrict__ d_verts_add, int V, int B, int F, int C,
+                                                          float* __restrict__ d_verts, float* __restrict__ part_w,
+                                                          float* __restrict__ part_mvp)
+{
+    extern __shared__ float sm[];
+    float* s_mvp = sm;                                  // [C][16]
+    float* s_w = s_mvp + C * 16;                        // [GEO_WARPS][3B]
+    float* s_m = s_w + GEO_WARPS * 3 * B;               // [GEO_WARPS][C][16]
+    const int f = blockIdx.y;
+    for (int i = threadIdx.x; i < C * 16; i += GEO_THREADS) s_mvp[i] = mvp[(size_t)f * C * 16 + i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * GEO_WARPS + warp, nw = gridDim.x * GEO_WARPS;
+    const int n4 = (3 * B) >> 2;
+    float4 acc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float am[16];                                       // d mvp of camera `lane` (cameras beyond 32: see host check)
+#pragma unroll
+    for (int i = 0; i < 16; i++) am[i] = 0.f;
+
+    float4 cur[K];
+    if (gw < V) load_rows<K>(D, gw, B, n4, lane, cur);
+    for (int v = gw; v < V; v += nw) {
+        float4 nxt[K];
+        if (v + nw < V) load_rows<K>(D, v + nw, B, n4, lane, nxt);     // in flight while this vertex is processed
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        if (lane < C) {
+            float4 g = ldg4(g_pos + (((size_t)f * C + lane) * V + v) * 4);
+            const float* m = s_mvp + 16 * lane;
+            gx = m[0] * g.x + m[4] * g.y + m[8] * g.z + m[12] * g.w;
+            gy = m[1] * g.x + m[5] * g.y + m[9] * g.z + m[13] * g.w;
+            gz = m[2] * g.x + m[6] * g.y + m[10] * g.z + m[14] * g.w;
+            const float* p = verts + ((size_t)f * V + v) * 3;
+            float vh[4] = {__ldg(p), __ldg(p + 1), __ldg(p + 2), 1.f};
+            float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) am[4 * i + j] += gg[i] * vh[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            gz += __shfl_xor_sync(0xffffffffu, gz, o);
+        }
+        if (d_verts_add) {
+            const float* e = d_verts_add + ((size_t)f * V + v) * 3;
+            gx += __ldg(e); gy += __ldg(e + 1); gz += __ldg(e + 2);
+        }
+        if (d_verts && lane == 0) {
+            float* o = d_verts + ((size_t)f * V + v) * 3;
+            o[0] = gx; o[1] = gy; o[2] = gz;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            int e = 4 * (lane + 32 * k);
+            int r = (e >= B) + (e >= 2 * B);
+            float gv = (r == 0) ? gx : ((r == 1) ? gy : gz);       // rows beyond 3B were loaded as zeros
+            acc[k].x += cur[k].x * gv; acc[k].y += cur[k].y * gv; acc[k].z += cur[k].z * gv; acc[k].w += cur[k].w * gv;
+            cur[k] = nxt[k];
+        }
+    }
+    // per-warp partials -> shared memory, then a fixed-order sum over warps (and over the 3 rows of a vertex)
+    float4* mine = reinterpret_cast<float4*>(s_w + (size_t)warp * 3 * B);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        int i = lane + 32 * k;
+        if (i < n4) mine[i] = acc[k];
+    }
+    if (lane < C) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s_m[((size_t)warp * C + lane) * 16 + i] = am[i];
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += GEO_THREADS) {
+        float s = 0.f;
+        for (int wv = 0; wv < GEO_WARPS; wv++) {
+            const float* r = s_w + (size_t)wv * 3 * B;
+            s += r[b] + r[B + b] + r[2 * B + b];
+        }
+        part_w[((size_t)blockIdx.x * F + f) * B + b] = s;
+    }
+    for (int i = threadIdx.x; i < C * 16; i += GEO_THREADS) {
+        float s = 0.f;
+        for (int wv = 0; wv < GEO_WARPS; wv++) s += s_m[(size_t)wv * C * 16 + i];
+        part_mvp[((size_t)blockIdx.x * F + f) * C * 16 + i] = s;
+    }
+}
+
+// backward, stage 2: CTA (f, j) sums the d w partials of columns [32 j, 32 j + 32) — 32 warps take every 32nd block,
+// then a fixed-order sum over the warps (deterministic); CTA (f, 0) also sums d mvp and runs the pose backward.
+constexpr int RED_THREADS = 1024;
+
+__global__ void __launch_bounds__(RED_THREADS) k_geom_bwd_reduce(const float* __restrict__ part_w, const float* __restrict__ part_mvp,
+                                                                 int nblk, const float* __restrict__ P, const float* __restrict__ A,
+                                                                 const float* __restrict__ t, const float* __restrict__ q,
+                                                                 const float* __restrict__ t_cam, const float* __restrict__ q_cam,
+                                                                 int B, int F, int C, float* __restrict__ d_w,
+                                                                 float* __restrict__ d_mvp, float* __restrict__ d_t, float* __restrict__ d_q)
+{
+    extern __shared__ float s_dm[];                     // [C][16]
+    __shared__ float red[32][33];
+    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y * 32 + lane;
+    float s = 0.f;
+    if (b < B)
+        for (int k = warp; k < nblk; k += 32) s += part_w[((size_t)k * F + f) * B + b];
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && b < B) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k++) tot += red[k][lane];
+        d_w[(size_t)f * B + b] = tot;
+    }
+    if (blockIdx.y != 0) return;
+    __syncthreads();
+    // d mvp: C*16 values x nblk partials; thread (slice = tid / 16 within groups of 16 values)
+    const int nval = C * 16;
+    for (int base = 0; base < nval; base += 32) {
+        int i = base + lane;
+        float a = 0.f;
+        if (i < nval)
+            for (int k = warp; k < nblk; k += 32) a += part_mvp[((size_t)k * F + f) * nval + i];
+        red[warp][lane] = a;
+        __syncthreads();
+        if (warp == 0 && i < nval) {
+            float tot = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; k++) tot += red[k][lane];
+            s_dm[i] = tot;
+            if (d_mvp) d_mvp[(size_t)f * nval + i] = tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pose_backward_frame(P, A, t, q, t_cam, q_cam, s_dm, f, C, d_t, d_q);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Adam for the packed parameter vector [w (F*B) | t (F*3) | q (F*4)], single CTA (n is small: F*(B+7))
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_adam_fused(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                     float* __restrict__ v, int nw, int F, int pose, float lr_w, float lr_t, float lr_q,
+                                                     float b1, float b2, float eps, float lr_ramp, float max_iter, int quat_mode,
+                                                     float* __restrict__ step_count)
+{
+    __shared__ float red[32];
+    const float step0 = step_count[0];
+    const float tstep = step0 + 1.f;
+    const float ramp = powf(lr_ramp, step0 / max_iter);
+    const float bc1 = 1.f - powf(b1, tstep), bc2 = 1.f - powf(b2, tstep);
+    const int n = nw + (pose ? 7 * F : 0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float lr = (i < nw) ? lr_w : ((i < nw + 3 * F) ? lr_t : lr_q);
+        float gi = g[i];
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) / sqrtf(bc2) + eps;      // torch.optim.Adam op order (k_adam, loss_adam.cu)
+        p[i] -= (lr * ramp / bc1) * (mi / denom);
+    }
+    __syncthreads();
+    if (pose) {
+        float* qq = p + nw + 3 * F;
+        if (quat_mode == 0) {
+            for (int i = threadIdx.x; i < F; i += blockDim.x) {
+                float x = qq[4 * i], y = qq[4 * i + 1], z = qq[4 * i + 2], w = qq[4 * i + 3];
+                float s = 1.f / sqrtf(x * x + y * y + z * z + w * w);
+                qq[4 * i] = x * s; qq[4 * i + 1] = y * s; qq[4 * i + 2] = z * s; qq[4 * i + 3] = w * s;
+            }
+        } else {
+            float s = 0.f;
+            for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) s += qq[i] * qq[i];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+            __syncthreads();
+            float tot = 0.f;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) tot += red[k];
+            float inv = 1.f / sqrtf(tot);
+            for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) qq[i] *= inv;
+        }
+    }
+    if (threadIdx.x == 0) step_count[0] = tstep;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int geom_blocks(int V)
+{
+    int want = fpc_div_up(V, GEO_WARPS);
+    return want < 296 ? want : 296;           // 2 CTAs per SM on 148 SMs; each warp strides over the vertices
+}
+
+template <int K>
+int launch_bwd(dim3 grid, size_t smem, cudaStream_t stream, const float* D, const float* verts, const float* mvp, const float* g_pos,
+               const float* d_verts_add, int V, int B, int F, int C, float* d_verts, float* part_w, float* part_mvp)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        FPC_CUDA(cudaFuncSetAttribute(k_geom_bwd<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    k_geom_bwd<K><<<grid, GEO_THREADS, smem, stream>>>(D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+}  // namespace
+
+extern "C" int fpc_geometry_fused_supported(int V, int B, int F, int C)
+{
+    return V > 0 && B > 0 && (B & 3) == 0 && B <= 1024 && F > 0 && F <= 65535 && C > 0 && C <= 32;
+}
+
+extern "C" int fpc_geometry_fwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
+                                const float* D, const float* base, const float* w, int V, int B, int F, int C,
+                                float* mvp, float* verts, float* pos_clip, fpc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FPC_CHECK_ARG(P && A && t && q && D && base && w && mvp && verts && pos_clip, "geometry_fwd: null pointer argument");
+    FPC_CHECK_ARG((t_cam == nullptr) == (q_cam == nullptr), "geometry_fwd: t_cam and q_cam must both be given or both be NULL");
+    FPC_CHECK_ARG(fpc_geometry_fused_supported(V, B, F, C),
+                  "geometry_fwd: needs B %% 4 == 0, B <= 1024, F <= 65535, C <= 32 (got V=%d B=%d F=%d C=%d); use blend_fwd + project_fwd", V, B, F, C);
+    size_t smem = (size_t)(C * 16 + B) * sizeof(float);
+    dim3 grid(geom_blocks(V), F);
+    const int K = fpc_div_up((3 * B) >> 2, 32);
+#define FPC_FWD_CASE(k) case k: k_geom_fwd<k><<<grid, GEO_THREADS, smem, stream>>>(P, A, t, q, t_cam, q_cam, D, base, w, V, B, F, C, mvp, verts, pos_clip); break
+    switch (K <= 8 ? K : (K <= 12 ? 12 : (K <= 16 ? 16 : 24))) {
+        FPC_FWD_CASE(1); FPC_FWD_CASE(2); FPC_FWD_CASE(3); FPC_FWD_CASE(4); FPC_FWD_CASE(5); FPC_FWD_CASE(6);
+        FPC_FWD_CASE(7); FPC_FWD_CASE(8); FPC_FWD_CASE(12); FPC_FWD_CASE(16); FPC_FWD_CASE(24);
+    }
+#undef FPC_FWD_CASE
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+extern "C" size_t fpc_geometry_bwd_scratch_bytes(int V, int B, int F, int C)
+{
+    if (V <= 0 || B <= 0 || F <= 0 || C <= 0) return 256;
+    int nblk = geom_blocks(V);
+    return align256((size_t)nblk * F * B * sizeof(float)) + align256((size_t)nblk * F * C * 16 * sizeof(float));
+}
+
+extern "C" int fpc_geometry_bwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
+                                const float* D, const float* verts, const float* mvp, const float* g_pos, const float* d_verts_add,
+                                int V, int B, int F, int C, float* d_w, float* d_t, float* d_q, float* d_verts, float* d_mvp,
+                                void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FPC_CHECK_ARG(P && A && t && q && D && verts && mvp && g_pos && d_w && d_t && d_q, "geometry_bwd: null pointer argument");
+    FPC_CHECK_ARG((t_cam == nullptr) == (q_cam == nullptr), "geometry_bwd: t_cam and q_cam must both be given or both be NULL");
+    FPC_CHECK_ARG(fpc_geometry_fused_supported(V, B, F, C),
+                  "geometry_bwd: needs B %% 4 == 0, B <= 1024, F <= 65535, C <= 32 (got V=%d B=%d F=%d C=%d); use project_bwd + blend_bwd + pose_mvp_bwd", V, B, F, C);
+    FPC_CHECK_ARG(scratch && scratch_bytes >= fpc_geometry_bwd_scratch_bytes(V, B, F, C), "geometry_bwd: scratch too small");
+    const int nblk = geom_blocks(V);
+    float* part_w = (float*)scratch;
+    float* part_mvp = (float*)((char*)scratch + align256((size_t)nblk * F * B * sizeof(float)));
+    size_t smem = (size_t)(C * 16 + GEO_WARPS * 3 * B + GEO_WARPS * C * 16) * sizeof(float);
+    dim3 grid(nblk, F);
+    const int K = fpc_div_up((3 * B) >> 2, 32);
+    int st;
+#define FPC_BWD_CASE(k) case k: st = launch_bwd<k>(grid, smem, stream, D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp); break
+    switch (K <= 8 ? K : (K <= 12 ? 12 : (K <= 16 ? 16 : 24))) {
+        FPC_BWD_CASE(1); FPC_BWD_CASE(2); FPC_BWD_CASE(3); FPC_BWD_CASE(4); FPC_BWD_CASE(5); FPC_BWD_CASE(6);
+        FPC_BWD_CASE(7); FPC_BWD_CASE(8); FPC_BWD_CASE(12); FPC_BWD_CASE(16); FPC_BWD_CASE(24);
+        default: st = FPC_ERR_UNSUPPORTED; fpc_set_error("geometry_bwd: unsupported B=%d", B);
+    }
+#undef FPC_BWD_CASE
+    if (st != FPC_OK) return st;
+    k_geom_bwd_reduce<<<dim3(F, fpc_div_up(B, 32)), RED_THREADS, (size_t)C * 16 * sizeof(float), stream>>>(part_w, part_mvp, nblk, P, A, t, q, t_cam, q_cam,
+                                                                                 B, F, C, d_w, d_mvp, d_t, d_q);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+extern "C" int fpc_adam_fused(float* params, const float* grads, float* m, float* v, int B, int F, int optimize_pose,
+                              float lr_w, float lr_t, float lr_q, float b1, float b2, float eps, float lr_ramp, float max_iter,
+                              int quat_mode, float* step_count, fpc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FPC_CHECK_ARG(params && grads && m && v && step_count, "adam_fused: null pointer argument");
+    FPC_CHECK_ARG(B > 0 && F > 0 && max_iter > 0.f && lr_ramp > 0.f, "adam_fused: B, F, max_iter and lr_ramp must be positive");
+    FPC_CHECK_ARG((long long)F * (B + 7) <= (1 << 22), "adam_fused: packed parameter vector too long for the single-CTA kernel (%lld)", (long long)F * (B + 7));
+    FPC_CHECK_ARG(quat_mode == 0 || quat_mode == 1, "adam_fused: quat_mode must be 0 (per row) or 1 (Frobenius)");
+    k_adam_fused<<<1, 1024, 0, stream>>>(params, grads, m, v, F * B, F, optimize_pose ? 1 : 0, lr_w, lr_t, lr_q, b1, b2, eps, lr_ramp,
+                                         max_iter, quat_mode, step_count);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}

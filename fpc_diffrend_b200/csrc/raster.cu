@@ -17,28 +17,62 @@ using namespace fpc;
 namespace {
 
 // tri_info: bits 0..9 bx0, 10..19 by0, 20 (nbx-1), 21 (nby-1), 22..23 class (0 none, 1 small, 2 large)
-__global__ void __launch_bounds__(256) k_setup(RasterParams rp)
+//
+// k_setup / k_fill run one CTA per chunk of BIN_TPB triangles of ONE instance (grid.y = instance).  When the bin
+// grid fits in shared memory (HIST) the CTA first histograms its triangles there and then touches each global
+// counter once, so the hot counters (a head covers only ~1/4 of the bins) see ~10x fewer global atomics.
+constexpr int BIN_TPB = 1024;
+constexpr int HIST_MAX_BINS = 8192;
+
+template <bool HIST>
+__global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
 {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)rp.N * rp.T) return;
-    int n = (int)(gid / rp.T), t = (int)(gid - (long long)n * rp.T);
-    float4 p0, p1, p2;
-    SnappedTri s;
-    int info = 0;
-    if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
-        rp.tri_anchor[gid] = s.pxa | (s.pya << 16);
-        int bx0 = s.pxa >> BIN_LOG2, bx1 = s.pxb >> BIN_LOG2, by0 = s.pya >> BIN_LOG2, by1 = s.pyb >> BIN_LOG2;
-        if (!is_small(s)) {
-            int slot = atomicAdd(rp.large_count + n, 1);
-            rp.large_list[(size_t)n * rp.T + slot] = t;
-            info = 2 << 22;
-        } else {
-            info = bx0 | (by0 << 10) | ((bx1 - bx0) << 20) | ((by1 - by0) << 21) | (1 << 22);
-            for (int by = by0; by <= by1; by++)
-                for (int bx = bx0; bx <= bx1; bx++) atomicAdd(rp.bin_count + (size_t)n * rp.NB + by * rp.BW + bx, 1);
+    extern __shared__ int hist[];
+    const int n = blockIdx.y;
+    const int t = blockIdx.x * BIN_TPB + threadIdx.x;
+    if (HIST) {
+        for (int b = threadIdx.x; b < rp.NB; b += BIN_TPB) hist[b] = 0;
+        __syncthreads();
+    }
+    if (t < rp.T) {
+        const size_t gid = (size_t)n * rp.T + t;
+        float4 p0, p1, p2;
+        SnappedTri s;
+        int info = 0;
+        if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
+            rp.tri_anchor[gid] = s.pxa | (s.pya << 16);
+            int bx0 = s.pxa >> BIN_LOG2, bx1 = s.pxb >> BIN_LOG2, by0 = s.pya >> BIN_LOG2, by1 = s.pyb >> BIN_LOG2;
+            if (!is_small(s)) {
+                int slot = atomicAdd(rp.large_count + n, 1);
+                rp.large_list[(size_t)n * rp.T + slot] = t;
+                info = 2 << 22;
+            } else {
+                info = bx0 | (by0 << 10) | ((bx1 - bx0) << 20) | ((by1 - by0) << 21) | (1 << 22);
+                for (int by = by0; by <= by1; by++)
+                    for (int bx = bx0; bx <= bx1; bx++) {
+                        if (HIST) atomicAdd(hist + by * rp.BW + bx, 1);
+                        else atomicAdd(rp.bin_count + (size_t)n * rp.NB + by * rp.BW + bx, 1);
+                    }
+            }
+        }
+        rp.tri_info[gid] = info;
+        // buffers the consumer of the bins accumulates into (fused.cu): cleared here instead of by separate memsets
+        if (rp.clear_tri9) {
+            float* m = rp.clear_tri9 + gid * 9;
+#pragma unroll
+            for (int c = 0; c < 9; c++) m[c] = 0.f;
         }
     }
-    rp.tri_info[gid] = info;
+    if (rp.clear_vtx4)
+        for (int v = t; v < rp.V; v += gridDim.x * BIN_TPB)
+            reinterpret_cast<float4*>(rp.clear_vtx4)[(size_t)n * rp.V + v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HIST) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < rp.NB; b += BIN_TPB) {
+            int c = hist[b];
+            if (c) atomicAdd(rp.bin_count + (size_t)n * rp.NB + b, c);
+        }
+    }
 }
 
 // one CTA per instance; NB is small (256 at 1024^2, 1024 at 2048^2)
@@ -71,20 +105,48 @@ __global__ void __launch_bounds__(256) k_scan(RasterParams rp)
     }
 }
 
-__global__ void __launch_bounds__(256) k_fill(RasterParams rp)
+template <bool HIST>
+__global__ void __launch_bounds__(BIN_TPB) k_fill(RasterParams rp)
 {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)rp.N * rp.T) return;
-    int info = rp.tri_info[gid];
-    if ((info >> 22) != 1) return;
-    int n = (int)(gid / rp.T), t = (int)(gid - (long long)n * rp.T);
-    int bx0 = info & 1023, by0 = (info >> 10) & 1023, nbx = (info >> 20) & 1, nby = (info >> 21) & 1;
-    for (int by = by0; by <= by0 + nby; by++)
-        for (int bx = bx0; bx <= bx0 + nbx; bx++) {
-            size_t b = (size_t)n * rp.NB + by * rp.BW + bx;
-            int slot = atomicAdd(rp.bin_cursor + b, 1);
-            rp.pairs[(size_t)n * 4 * rp.T + rp.bin_offset[b] + slot] = t;
-        }
+    extern __shared__ int hist[];
+    const int n = blockIdx.y;
+    const int t = blockIdx.x * BIN_TPB + threadIdx.x;
+    if (HIST) {
+        for (int b = threadIdx.x; b < rp.NB; b += BIN_TPB) hist[b] = 0;
+        __syncthreads();
+    }
+    int info = (t < rp.T) ? rp.tri_info[(size_t)n * rp.T + t] : 0;
+    const bool small = (info >> 22) == 1;
+    const int bx0 = info & 1023, by0 = (info >> 10) & 1023, nbx = (info >> 20) & 1, nby = (info >> 21) & 1;
+    int* pairs = rp.pairs + (size_t)n * 4 * rp.T;
+    const int* offset = rp.bin_offset + (size_t)n * rp.NB;
+    int* cursor = rp.bin_cursor + (size_t)n * rp.NB;
+    if (!HIST) {
+        if (small)
+            for (int by = by0; by <= by0 + nby; by++)
+                for (int bx = bx0; bx <= bx0 + nbx; bx++) {
+                    int b = by * rp.BW + bx;
+                    pairs[offset[b] + atomicAdd(cursor + b, 1)] = t;
+                }
+        return;
+    }
+    int rank[4] = {0, 0, 0, 0};
+    if (small) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if ((k & 1) <= nbx && (k >> 1) <= nby) rank[k] = atomicAdd(hist + (by0 + (k >> 1)) * rp.BW + bx0 + (k & 1), 1);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < rp.NB; b += BIN_TPB) {
+        int c = hist[b];
+        if (c) hist[b] = offset[b] + atomicAdd(cursor + b, c);      // count -> first slot of this CTA's entries
+    }
+    __syncthreads();
+    if (small) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if ((k & 1) <= nbx && (k >> 1) <= nby) pairs[hist[(by0 + (k >> 1)) * rp.BW + bx0 + (k & 1)] + rank[k]] = t;
+    }
 }
 
 __global__ void __launch_bounds__(FINE_THREADS) k_fine(RasterParams rp, float* __restrict__ rast, float* __restrict__ rast_db)
@@ -189,7 +251,8 @@ ScratchLayout raster_layout(int N, int T, int NB)
 }
 
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
-                         void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp)
+                         void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
+                         float* clear_tri9, float* clear_vtx4)
 {
     FPC_CHECK_ARG(pos && tri, "%s: pos and tri must be non-null", who);
     FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "%s: N, V, T, H, W must be positive (got %d %d %d %d %d)", who, N, V, T, H, W);
@@ -212,12 +275,22 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.large_list = (int*)(s + L.off_large);
     rp.tri_anchor = (int*)(s + L.off_anchor);
     FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
-    long long nt = (long long)N * T;
-    k_setup<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);
-    FPC_LAUNCH_CHECK();
-    k_scan<<<N, 256, 0, stream>>>(rp);
-    FPC_LAUNCH_CHECK();
-    k_fill<<<fpc_div_up(nt, 256), 256, 0, stream>>>(rp);
+    rp.clear_tri9 = clear_tri9; rp.clear_vtx4 = clear_vtx4;
+    dim3 grid(fpc_div_up(T, BIN_TPB), N);
+    if (rp.NB <= HIST_MAX_BINS) {
+        size_t hb = (size_t)rp.NB * sizeof(int);
+        k_setup<true><<<grid, BIN_TPB, hb, stream>>>(rp);
+        FPC_LAUNCH_CHECK();
+        k_scan<<<N, 256, 0, stream>>>(rp);
+        FPC_LAUNCH_CHECK();
+        k_fill<true><<<grid, BIN_TPB, hb, stream>>>(rp);
+    } else {
+        k_setup<false><<<grid, BIN_TPB, 0, stream>>>(rp);
+        FPC_LAUNCH_CHECK();
+        k_scan<<<N, 256, 0, stream>>>(rp);
+        FPC_LAUNCH_CHECK();
+        k_fill<false><<<grid, BIN_TPB, 0, stream>>>(rp);
+    }
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

@@ -16,9 +16,21 @@
 
 namespace fpc {
 
-constexpr int BIN = 64;              // bin edge in pixels
-constexpr int BIN_LOG2 = 6;
-constexpr int FINE_THREADS = 256;
+// Tuning knobs (scripts/exp_variants.py builds variants; measured on B200 at config 2, see profiles/):
+// 32x32-px bins with 128-thread CTAs and 64 registers/thread put 8 independent CTAs on an SM, which hides the
+// raster -> shade barrier and the gather latency of the shading phase better than 64x64 bins / 256 threads.
+#ifndef FPC_BIN_LOG2
+#define FPC_BIN_LOG2 5
+#endif
+#ifndef FPC_FINE_THREADS
+#define FPC_FINE_THREADS 128
+#endif
+#ifndef FPC_DYN_BATCH
+#define FPC_DYN_BATCH 1
+#endif
+constexpr int BIN_LOG2 = FPC_BIN_LOG2;
+constexpr int BIN = 1 << BIN_LOG2;   // bin edge in pixels
+constexpr int FINE_THREADS = FPC_FINE_THREADS;
 constexpr int FINE_WARPS = FINE_THREADS / 32;
 constexpr float SNAP_LIMIT = 16777216.0f;
 constexpr int SMALL_EXTENT = 2048;   // 128 px in 1/16-px units
@@ -39,6 +51,8 @@ struct RasterParams {
     int* pairs;                      // [N*4T]
     int* large_list;                 // [N*T]
     int* tri_anchor;                 // [N*T]  pxa | pya << 16: first pixel of the image-clamped bbox (moment origin)
+    float* clear_tri9;               // nullable: [N*T*9] zeroed by k_setup (moment accumulators of fused.cu)
+    float* clear_vtx4;               // nullable: [N*V*4] zeroed by k_setup (position-gradient accumulator)
 };
 
 struct SnappedTri {
@@ -162,13 +176,25 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
     const int nlarge = rp.large_count[n];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+#if FPC_DYN_BATCH
+    __shared__ int next_batch;       // warps claim batches of 32 triangles dynamically (balances uneven batches)
+    if (threadIdx.x == 0) next_batch = 0;
+#endif
     for (int i = threadIdx.x; i < BIN * BIN; i += FINE_THREADS) keys[i] = KEY_EMPTY;
     __syncthreads();
 
     // ---- small triangles ----
     const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
     WarpStage& st = stage[warp];
+#if FPC_DYN_BATCH
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&next_batch, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+#else
     for (int base = warp * 32; base < count; base += FINE_THREADS) {
+#endif
         int i = base + lane;
         int rows = 0;
         if (i < count) {
@@ -271,7 +297,9 @@ struct ScratchLayout {
 
 ScratchLayout raster_layout(int N, int T, int NB);
 // Validates, fills rp and enqueues memset + k_setup + k_scan + k_fill.  Returns an fpc_status.
+// clear_tri9 [N*T*9] / clear_vtx4 [N*V*4] (nullable) are zero-filled by k_setup on the way.
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
-                         void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp);
+                         void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
+                         float* clear_tri9 = nullptr, float* clear_vtx4 = nullptr);
 
 }  // namespace fpc

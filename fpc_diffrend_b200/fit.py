@@ -47,6 +47,8 @@ class FitConfig:
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
     fused: bool = True                    # antialias off: one fused render+loss+gradient kernel (csrc/fused.cu)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
+    fused_geometry: bool = None           # pose+blend+project in one kernel per direction (csrc/geometry.cu); None = auto
+                                          # (small frame batches: D is re-read per frame there, the GEMM path is not)
 
 
 def _p(t):
@@ -144,7 +146,11 @@ class FitSession:
         self.ref = None
 
         L = _lib.load()
-        nbytes = max(L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_render_loss_fused_scratch_bytes(self.N, T, H, W),
+        fg = cfg.fused_geometry
+        if fg is None:
+            fg = F <= 4
+        self.use_geom_fused = bool(fg and L.fpc_geometry_fused_supported(V, B, F, C))
+        nbytes = max(L.fpc_geometry_bwd_scratch_bytes(V, B, F, C), L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_render_loss_fused_scratch_bytes(self.N, T, H, W),
                      L.fpc_blend_bwd_scratch_bytes(V * 3, B, F),
                      L.fpc_project_bwd_scratch_bytes(F, C, V), L.fpc_image_loss_scratch_bytes(self.N, H, W, Ch))
         self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
@@ -271,9 +277,13 @@ class FitSession:
         cfg, s, call = self.cfg, self._stream(), self._timed
         F, V, T, B, C, H, W, N, Ch = self.F, self.V, self.T, self.B, self.C, self.H, self.W, self.N, self.Ch
         n = 0
-        call('pose_mvp_fwd', 'fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, F, C, _p(self.mvp), s); n += 1
-        call('blend_fwd', 'fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
-        call('project_fwd', 'fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
+        if self.use_geom_fused:
+            call('geometry_fwd', 'fpc_geometry_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.D), _p(self.v_base),
+                 _p(self.w), V, B, F, C, _p(self.mvp), _p(self.verts), _p(self.pos_clip), s); n += 1
+        else:
+            call('pose_mvp_fwd', 'fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, F, C, _p(self.mvp), s); n += 1
+            call('blend_fwd', 'fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
+            call('project_fwd', 'fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
         if self.use_fused:
             return n + self._fused(True) if with_loss else self._fused(False)
         call('rasterize_fwd', 'fpc_rasterize_fwd', _p(self.pos_clip), _p(self.pos_idx), N, V, T, H, W, _p(self.rast), None,
@@ -347,6 +357,11 @@ class FitSession:
         s, call = self._stream(), self._timed
         F, V, B, C = self.F, self.V, self.B, self.C
         n = 0
+        if self.use_geom_fused:
+            call('geometry_bwd', 'fpc_geometry_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.D), _p(self.verts),
+                 _p(self.mvp), _p(self.g_pos), None, self.V, B, F, C, _p(self.d_w), _p(self.d_t), _p(self.d_q), None, None,
+                 _p(self.scratch), self.scratch.numel(), s)
+            return 2
         call('project_bwd', 'fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
              _p(self.scratch), self.scratch.numel(), s); n += 2
         call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
@@ -361,6 +376,11 @@ class FitSession:
         if cfg.cam_slice is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             torch.distributed.all_reduce(self.grads)   # the only exchange of the camera-split mode: (B+7) F floats
         nw = F * B
+        if F * (B + 7) <= (1 << 22):
+            call('adam', 'fpc_adam_fused', _p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), B, F, 1 if cfg.optimize_pose else 0,
+                 cfg.lr_base, cfg.lr_t, cfg.lr_q, cfg.beta1, cfg.beta2, cfg.eps, cfg.lr_ramp, float(cfg.max_iter),
+                 1 if cfg.quat_norm == 'frobenius' else 0, _p(self.step_count), s)
+            return n + 1
         adam = lambda off, cnt, lr: call('adam', 'fpc_adam_step', ctypes.c_void_p(self.params.data_ptr() + 4 * off),
                                          ctypes.c_void_p(self.grads.data_ptr() + 4 * off),
                                          ctypes.c_void_p(self.adam_m.data_ptr() + 4 * off),

@@ -122,6 +122,27 @@ size_t fpc_project_bwd_scratch_bytes(int F, int C, int V);
 int fpc_project_bwd(const float* verts, const float* mvp, const float* d_pos_clip, int F, int C, int V,
                     float* d_verts, float* d_mvp, void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
+/* ---- fused geometry stages (small frame batches): one pass over D per direction -----------------------------
+ * Same mathematics as fpc_pose_mvp_fwd + fpc_blend_fwd + fpc_project_fwd (forward) and fpc_project_bwd +
+ * fpc_blend_bwd + fpc_pose_mvp_bwd (backward), i.e. reference fit.py:546-553, fit.py:103-129, camera.py:11-23 and
+ * their part of loss.backward() (fit.py:611), fused so that D [3V,B] is streamed exactly once per direction and
+ * every frame's C cameras are handled by the lanes of the warp that owns the vertex.  Deterministic.
+ * Requirements (fpc_geometry_fused_supported() != 0): B % 4 == 0, B <= 1024, C <= 32, F <= 65535.  D is re-read for
+ * every frame, so for large frame batches the GEMM path (fpc_blend_fwd / fpc_blend_bwd) is the better choice. */
+int fpc_geometry_fused_supported(int V, int B, int F, int C);
+/* -> mvp [F*C,16], verts [F,V,3], pos_clip [F*C,V,4] (all overwritten) */
+int fpc_geometry_fwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
+                     const float* D, const float* base, const float* w, int V, int B, int F, int C,
+                     float* mvp, float* verts, float* pos_clip, fpc_stream_t stream);
+/* g_pos [F*C,V,4] = d loss / d pos_clip; d_verts_add [F,V,3] or NULL: extra gradient on the blended vertices
+ * (mesh regularisers, fit.py:580-582) added before the D^T contraction.
+ * -> d_w [F,B], d_t [F,3], d_q [F,4] (overwritten); optional outputs d_verts [F,V,3], d_mvp [F*C,16] (NULL to skip). */
+size_t fpc_geometry_bwd_scratch_bytes(int V, int B, int F, int C);
+int fpc_geometry_bwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
+                     const float* D, const float* verts, const float* mvp, const float* g_pos, const float* d_verts_add,
+                     int V, int B, int F, int C, float* d_w, float* d_t, float* d_q, float* d_verts, float* d_mvp,
+                     void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
 /* ---- background composite + image loss (replaces fit.py:161 and the first term of fit.py:579) --------------
  * colour [N,H,W,C], rast [N,H,W,4], ref [N,H,W,C] (grey levels, 0..255 scale):
  *   comp = rast.w > 0 ? colour : bg;   loss = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2
@@ -158,6 +179,12 @@ int fpc_adam_advance(float* step_count, fpc_stream_t stream);
 /* q [n,4] /= norm.  mode 0: per-row norm (default of this build);  mode 1: Frobenius norm of the whole tensor
  * (the reference's quirk, fit.py:616-618). */
 int fpc_quat_renorm(float* q, int n, int mode, fpc_stream_t stream);
+/* One launch for the packed parameter vector params = [w (F*B) | t (F*3) | q (F*4)] (grads, m, v alike):
+ * fpc_adam_step for the three groups (learning rates lr_w, lr_t, lr_q; pose groups skipped when optimize_pose == 0),
+ * fpc_quat_renorm (quat_mode as there) and fpc_adam_advance.  step_count [1] is read and then incremented. */
+int fpc_adam_fused(float* params, const float* grads, float* m, float* v, int B, int F, int optimize_pose,
+                   float lr_w, float lr_t, float lr_q, float b1, float b2, float eps, float lr_ramp, float max_iter,
+                   int quat_mode, float* step_count, fpc_stream_t stream);
 
 #ifdef __cplusplus
 }

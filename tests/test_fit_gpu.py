@@ -49,9 +49,10 @@ def oracle_render_loss(rig, pos_clip, ref, shading, use_aa, H, W, opp, n_cams_to
     return G.image_loss(ref, img) / n_cams_total
 
 
-@pytest.mark.parametrize('shading,use_aa,fused', [('vcol', False, True), ('vcol', False, False), ('texture', False, True),
-                                                  ('texture', True, False), ('vcol', True, False)])
-def test_iteration_gradients(small_rig3, shading, use_aa, fused):
+@pytest.mark.parametrize('shading,use_aa,fused,geom', [('vcol', False, True, True), ('vcol', False, True, False),
+                                                       ('vcol', False, False, True), ('texture', False, True, True),
+                                                       ('texture', True, False, False), ('vcol', True, False, True)])
+def test_iteration_gradients(small_rig3, shading, use_aa, fused, geom):
     """Every link of one fit iteration against the oracle ON IDENTICAL INPUT BITS.
 
     The chain is not continuous in its inputs (a 1-ulp change of a clip-space coordinate can move a snapped
@@ -63,11 +64,12 @@ def test_iteration_gradients(small_rig3, shading, use_aa, fused):
     from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
     rig, H, W, F = small_rig3, 152, 200, 2
     C = rig.P.shape[0]
-    cfg = FitConfig(resolution=(H, W), shading=shading, antialias=use_aa, fused=fused)
+    # geom: pose+blend+project fused into one kernel per direction (csrc/geometry.cu) vs the separate kernels
+    cfg = FitConfig(resolution=(H, W), shading=shading, antialias=use_aa, fused=fused, fused_geometry=geom)
     w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
     ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, cfg)
     s = FitSession(rig, F, cfg)
-    assert s.use_fused == (fused and not use_aa)
+    assert s.use_fused == (fused and not use_aa) and s.use_geom_fused == geom
     s.set_reference(ref)
     rng = np.random.default_rng(0)
     w0 = (0.05 * rng.random((F, rig.B))).astype(np.float32)

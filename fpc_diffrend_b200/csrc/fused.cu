@@ -12,6 +12,7 @@
 //               triangle inside a warp are combined with a segmented warp-shuffle reduction and each run issues
 //               9 float REDs into a per-(view,triangle) moment buffer;
 //           (3) k_tri_grad (one thread per (view, triangle)) turns the moments into d loss / d pos.
+#include "antialias.cuh"
 #include "raster_core.cuh"
 
 using namespace fpc;
@@ -78,6 +79,49 @@ __device__ __forceinline__ void triangle_pos_grad(const float* m, float fx0, flo
     red_vertex(G, i0, g0x, g0y, g0w);
     red_vertex(G, i1, g1x, g1y, g1w);
     red_vertex(G, i2, g2x, g2y, g2w);
+}
+
+// Moments of (g0, g1, g2) = d loss / d (a0, a1, a2) per triangle: runs of equal triangle id inside the warp are combined
+// with a segmented shuffle reduction, then the head lane of each run issues <= 9 float REDs into M [T,9] (this view's
+// moment buffer).  tid = 0xFFFFFFFF on background; `an` = packed anchor pixel of the triangle (valid when live).
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void accumulate_moments(float* __restrict__ M, unsigned tid, bool live, float g0, float g1, float g2,
+                                                   int px, int py, int an, int lane)
+{
+    if (!__any_sync(0xffffffffu, live)) return;
+    float m[9];
+    float flx = 0.f, fly = 0.f;
+    if (live) {
+        flx = (float)(px - (an & 0xffff));
+        fly = (float)(py - (int)((unsigned)an >> 16));
+    }
+    m[0] = g0; m[1] = g1; m[2] = g2;
+    m[3] = g0 * flx; m[4] = g1 * flx; m[5] = g2 * flx;
+    m[6] = g0 * fly; m[7] = g1 * fly; m[8] = g2 * fly;
+    // longest run of one triangle in this warp: shuffle steps with d >= that length combine nothing
+    unsigned tprev = __shfl_up_sync(0xffffffffu, tid, 1);
+    const bool head = (lane == 0) || (tprev != tid);
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    const unsigned above = (lane == 31) ? 0u : (hm & (0xFFFFFFFEu << lane));
+    const unsigned len = (head && tid != 0xFFFFFFFFu) ? (unsigned)((above ? __ffs(above) - 1 : 32) - lane) : 0u;
+    const unsigned maxlen = __reduce_max_sync(0xffffffffu, len);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        if ((unsigned)d >= maxlen) break;
+        unsigned to = __shfl_down_sync(0xffffffffu, tid, d);
+        bool take = (lane + d < 32) && (to == tid);
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            float o = __shfl_down_sync(0xffffffffu, m[c], d);
+            if (take) m[c] += o;
+        }
+    }
+    if (tid != 0xFFFFFFFFu && head) {
+        float* Mt = M + (size_t)tid * 9;
+#pragma unroll
+        for (int c = 0; c < 9; c++)
+            if (m[c] != 0.f) atomicAdd(Mt + c, m[c]);
+    }
 }
 
 #ifndef FPC_FUSED_MINBLOCKS
@@ -237,45 +281,9 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             }
         }
         // ---- moments of (g0, g1, g2) per triangle: combine runs of equal triangle id inside the warp, then RED ----
-        if (fp.moments) {
-            unsigned tid = (unsigned)(key & 0xFFFFFFFFu);                 // 0xFFFFFFFF on background
-            bool live = (g0 != 0.f || g1 != 0.f || g2 != 0.f);
-            if (__any_sync(0xffffffffu, live)) {
-                float m[9];
-                float flx = 0.f, fly = 0.f;
-                if (live) {
-                    flx = (float)(px - (an & 0xffff));
-                    fly = (float)(py - (int)((unsigned)an >> 16));
-                }
-                m[0] = g0; m[1] = g1; m[2] = g2;
-                m[3] = g0 * flx; m[4] = g1 * flx; m[5] = g2 * flx;
-                m[6] = g0 * fly; m[7] = g1 * fly; m[8] = g2 * fly;
-                // longest run of one triangle in this warp: shuffle steps with d >= that length combine nothing
-                unsigned tprev = __shfl_up_sync(0xffffffffu, tid, 1);
-                const bool head = (lane == 0) || (tprev != tid);
-                const unsigned hm = __ballot_sync(0xffffffffu, head);
-                const unsigned above = (lane == 31) ? 0u : (hm & (0xFFFFFFFEu << lane));
-                const unsigned len = (head && tid != 0xFFFFFFFFu) ? (unsigned)((above ? __ffs(above) - 1 : 32) - lane) : 0u;
-                const unsigned maxlen = __reduce_max_sync(0xffffffffu, len);
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    if ((unsigned)d >= maxlen) break;
-                    unsigned to = __shfl_down_sync(0xffffffffu, tid, d);
-                    bool take = (lane + d < 32) && (to == tid);
-#pragma unroll
-                    for (int c = 0; c < 9; c++) {
-                        float o = __shfl_down_sync(0xffffffffu, m[c], d);
-                        if (take) m[c] += o;
-                    }
-                }
-                if (tid != 0xFFFFFFFFu && head) {
-                    float* M = fp.moments + ((size_t)n * rp.T + tid) * 9;
-#pragma unroll
-                    for (int c = 0; c < 9; c++)
-                        if (m[c] != 0.f) atomicAdd(M + c, m[c]);
-                }
-            }
-        }
+        if (fp.moments)
+            accumulate_moments(fp.moments + (size_t)n * rp.T * 9, (unsigned)(key & 0xFFFFFFFFu), (g0 != 0.f || g1 != 0.f || g2 != 0.f),
+                               g0, g1, g2, px, py, an, lane);
     }
     for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
     if (lane == 0) red[warp] = loss_acc;
@@ -341,6 +349,25 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
+#include "fused_aa.cuh"
+
+namespace {
+
+template <int C, bool TEX>
+int launch_fused_aa(const RasterParams& rp, const FusedParams& fp, const int32_t* tri_opp, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        FPC_CUDA(cudaFuncSetAttribute(k_fused_aa<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aa_smem_layout(C, 4).total));
+        attr_set = true;
+    }
+    k_fused_aa<C, TEX><<<dim3(rp.NB, rp.N), FINE_THREADS, aa_smem_layout(C, fp.ref_u8 ? 1 : 4).total, stream>>>(rp, fp, tri_opp);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+}  // namespace
+
 extern "C" size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W)
 {
     if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return 256;
@@ -348,25 +375,25 @@ extern "C" size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W
     return align256(raster_layout(N, T, NB).total) + align256((size_t)N * NB * sizeof(double)) + align256((size_t)N * T * 9 * sizeof(float));
 }
 
-extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* attr, const int32_t* attr_tri, int Va, int A,
-                                     const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
-                                     int N, int V, int T, int H, int W, int C, float bg, float scale,
-                                     float* loss, float* grad_pos, float* rast_out, float* colour_out,
-                                     void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
+static int render_loss_fused_impl(const char* who, const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
+                                  const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
+                                  int N, int V, int T, int H, int W, int C, float bg, float scale,
+                                  float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                                  void* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    FPC_CHECK_ARG(attr && attr_tri && ref && loss, "render_loss_fused: attr, attr_tri, ref and loss must be non-null");
-    FPC_CHECK_ARG(C == 1 || C == 3, "render_loss_fused: C must be 1 or 3 (got %d)", C);
-    FPC_CHECK_ARG(Va > 0, "render_loss_fused: Va must be positive");
-    if (tex) FPC_CHECK_ARG(A == 2 && Ht > 0 && Wt > 0, "render_loss_fused: textured shading needs A == 2 (uv) and a non-empty texture");
-    else FPC_CHECK_ARG(A == C, "render_loss_fused: vertex-colour shading needs A == C (got A=%d, C=%d)", A, C);
-    FPC_CHECK_ARG(scratch_bytes >= fpc_render_loss_fused_scratch_bytes(N, T, H, W), "render_loss_fused: scratch too small");
+    FPC_CHECK_ARG(attr && attr_tri && ref && loss, "%s: attr, attr_tri, ref and loss must be non-null", who);
+    FPC_CHECK_ARG(C == 1 || C == 3, "%s: C must be 1 or 3 (got %d)", who, C);
+    FPC_CHECK_ARG(Va > 0, "%s: Va must be positive", who);
+    if (tex) FPC_CHECK_ARG(A == 2 && Ht > 0 && Wt > 0, "%s: textured shading needs A == 2 (uv) and a non-empty texture", who);
+    else FPC_CHECK_ARG(A == C, "%s: vertex-colour shading needs A == C (got A=%d, C=%d)", who, A, C);
+    FPC_CHECK_ARG(scratch_bytes >= fpc_render_loss_fused_scratch_bytes(N, T, H, W), "%s: scratch too small", who);
     RasterParams rp;
     const int NB0 = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
     double* loss_partial = (double*)((char*)scratch + align256(raster_layout(N, T, NB0).total));
     float* moments = grad_pos ? (float*)((char*)loss_partial + align256((size_t)N * NB0 * sizeof(double))) : nullptr;
-    // k_setup clears the moment and gradient accumulators on its way (no separate memsets)
-    int st = raster_bin_triangles("render_loss_fused", pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, moments, grad_pos);
+    // k_setup clears the moment and gradient accumulators on its way (no separate memsets); with antialias the bins are
+    // widened by the 2-px halo the fused kernel resolves around its bin
+    int st = raster_bin_triangles(who, pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, moments, grad_pos, tri_opp ? AA_HALO : 0);
     if (st != FPC_OK) return st;
     FusedParams fp;
     fp.attr = attr; fp.attr_tri = attr_tri; fp.Va = Va; fp.A = A; fp.tex = tex; fp.Ht = Ht; fp.Wt = Wt;
@@ -374,8 +401,13 @@ extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const
     fp.grad_pos = grad_pos; fp.rast_out = rast_out; fp.colour_out = colour_out;
     fp.loss_partial = loss_partial;
     fp.moments = moments;
-    if (tex) st = (C == 1) ? launch_fused<1, true>(rp, fp, stream) : launch_fused<3, true>(rp, fp, stream);
-    else st = (C == 1) ? launch_fused<1, false>(rp, fp, stream) : launch_fused<3, false>(rp, fp, stream);
+    if (tri_opp) {
+        if (tex) st = (C == 1) ? launch_fused_aa<1, true>(rp, fp, tri_opp, stream) : launch_fused_aa<3, true>(rp, fp, tri_opp, stream);
+        else st = (C == 1) ? launch_fused_aa<1, false>(rp, fp, tri_opp, stream) : launch_fused_aa<3, false>(rp, fp, tri_opp, stream);
+    } else {
+        if (tex) st = (C == 1) ? launch_fused<1, true>(rp, fp, stream) : launch_fused<3, true>(rp, fp, stream);
+        else st = (C == 1) ? launch_fused<1, false>(rp, fp, stream) : launch_fused<3, false>(rp, fp, stream);
+    }
     if (st != FPC_OK) return st;
     if (grad_pos) {
         k_tri_grad<<<fpc_div_up((long long)N * T, 256), 256, 0, stream>>>(rp, fp.moments, grad_pos);
@@ -384,4 +416,25 @@ extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const
     k_fused_loss_reduce<<<1, 256, 0, stream>>>(fp.loss_partial, N * rp.NB, fp.k, loss);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
+}
+
+extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* attr, const int32_t* attr_tri, int Va, int A,
+                                     const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
+                                     int N, int V, int T, int H, int W, int C, float bg, float scale,
+                                     float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                                     void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
+{
+    return render_loss_fused_impl("render_loss_fused", pos, tri, nullptr, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
+                                  bg, scale, loss, grad_pos, rast_out, colour_out, scratch, scratch_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
+                                        const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
+                                        const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
+                                        float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                                        void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
+{
+    FPC_CHECK_ARG(tri_opp, "render_loss_fused_aa: tri_opp must be non-null (fpc_topology_build)");
+    return render_loss_fused_impl("render_loss_fused_aa", pos, tri, tri_opp, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
+                                  bg, scale, loss, grad_pos, rast_out, colour_out, scratch, scratch_bytes, (cudaStream_t)stream_);
 }

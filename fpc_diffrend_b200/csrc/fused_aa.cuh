@@ -1,0 +1,388 @@
+// Fused render + ANTIALIAS + loss + gradient kernel (included by fused.cu):
+//   rasterize -> interpolate -> [bilinear texture] -> antialias -> background composite -> image loss
+//   -> d loss / d colour -> antialias bwd -> [texture bwd] -> interpolate bwd -> rasterize bwd -> d loss / d pos_clip
+// i.e. reference fit.py:151-161,579 and their part of loss.backward() (fit.py:611) in ONE kernel per (32x32-px bin, view).
+//
+// Antialiasing couples a pixel to its 4-neighbourhood (forward) and to the 4-neighbourhoods of those (backward), so a
+// CTA resolves visibility and colour for its bin widened by a 2-px halo (36x36 tile; triangles are binned against the
+// widened bins, RasterParams::halo) and keeps everything per-pixel in shared memory:
+//   (1) raster_tile<36>: (depth,id) keys;
+//   (2) shade every tile pixel: colour and z/w (kept in the key slot); for the bin's own pixels also the 3C
+//       coefficients of the linear map  d loss/d colour -> d loss/d (a0,a1,a2)  (barycentric numerators);
+//   (3) pixel pairs (p,right) / (p,up) with different triangle ids are compacted into a work list and analysed
+//       densely (aa_analyze, the op-level code, bit-identical decisions) -> per-pixel alpha of its two own pairs;
+//   (4) ring-1 region (34x34): antialiased colour, loss (own pixels only) and d loss / d out;
+//   (5) own pixels: d loss / d colour gathered from the 4 pairs (no atomics), mapped to the triangle moments
+//       (as k_fused) and the silhouette position gradient of the two own pairs (sparse REDs into grad_pos).
+// Each pair is owned by its lower/left pixel, each pixel by exactly one bin: nothing is counted twice.
+#pragma once
+
+namespace {
+
+constexpr int AA_HALO = 2;
+constexpr int AA_TW = BIN + 2 * AA_HALO;       // tile edge
+constexpr int AA_NT = AA_TW * AA_TW;
+constexpr int AA_R1 = BIN + 2;                 // ring-1 region edge (pixels whose d loss / d out is needed)
+constexpr int AA_REF_MARGIN = 4;               // reference tile starts 4 px left of the bin: 4-byte aligned for every C / dtype
+constexpr int AA_REF_W = BIN + 2 * AA_REF_MARGIN;
+
+struct AASmem {
+    size_t keys, region0, col, alpha_r, alpha_u, info, coef, ref, total;
+};
+
+__host__ __device__ inline size_t aa_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// region0 is time-shared: WarpStage records (phase 1), pair work list (phase 3), d loss / d out (phases 4-5)
+__host__ __device__ inline AASmem aa_smem_layout(int C, int esz)
+{
+    AASmem L;
+    size_t o = 0;
+    L.keys = o; o += sizeof(unsigned long long) * AA_NT;
+    size_t r0 = sizeof(WarpStage) * FINE_WARPS;
+    size_t lst = sizeof(unsigned short) * 2 * AA_NT;
+    size_t gc = sizeof(float) * AA_R1 * AA_R1 * C;
+    if (lst > r0) r0 = lst;
+    if (gc > r0) r0 = gc;
+    L.region0 = o; o += aa_align16(r0);
+    L.col = o; o += aa_align16(sizeof(float) * AA_NT * C);
+    L.alpha_r = o; o += aa_align16(sizeof(float) * AA_NT);
+    L.alpha_u = o; o += aa_align16(sizeof(float) * AA_NT);
+    L.info = o; o += aa_align16(AA_NT);
+    L.coef = o; o += aa_align16(sizeof(float) * BIN * BIN * 3 * C);
+    L.ref = o; o += aa_align16((size_t)AA_R1 * AA_REF_W * C * esz);
+    L.total = o;
+    return L;
+}
+
+// bilinear, wrap (texture.cu: tex_index); same op order as k_fused
+template <int C>
+__device__ __forceinline__ void tex_bilinear(const FusedParams& fp, float au, float av, float (&col)[C], float (&dudc)[C], float (&dvdc)[C])
+{
+    float tu = au - floorf(au), tv = av - floorf(av);
+    float x = xsub(xmul(tu, (float)fp.Wt), 0.5f), y = xsub(xmul(tv, (float)fp.Ht), 0.5f);
+    float x0f = floorf(x), y0f = floorf(y);
+    int ix0 = (int)x0f, iy0 = (int)y0f, ix1 = ix0 + 1, iy1 = iy0 + 1;
+    float wx = x - x0f, wy = y - y0f;
+    if (ix0 < 0) ix0 += fp.Wt;
+    if (iy0 < 0) iy0 += fp.Ht;
+    if (ix1 >= fp.Wt) ix1 -= fp.Wt;
+    if (iy1 >= fp.Ht) iy1 -= fp.Ht;
+    size_t i00 = (size_t)iy0 * fp.Wt + ix0, i10 = (size_t)iy0 * fp.Wt + ix1;
+    size_t i01 = (size_t)iy1 * fp.Wt + ix0, i11 = (size_t)iy1 * fp.Wt + ix1;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        float t00 = __ldg(fp.tex + i00 * C + c), t10 = __ldg(fp.tex + i10 * C + c);
+        float t01 = __ldg(fp.tex + i01 * C + c), t11 = __ldg(fp.tex + i11 * C + c);
+        float a = t00 + (t10 - t00) * wx, b = t01 + (t11 - t01) * wx;
+        col[c] = a + (b - a) * wy;
+        dudc[c] = (float)fp.Wt * ((t10 - t00) * (1.f - wy) + (t11 - t01) * wy);
+        dvdc[c] = (float)fp.Ht * ((t01 - t00) * (1.f - wx) + (t11 - t10) * wx);
+    }
+}
+
+template <int C, bool TEX>
+__global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, FusedParams fp, const int32_t* __restrict__ tri_opp)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int esz = fp.ref_u8 ? 1 : 4;
+    const AASmem L = aa_smem_layout(C, esz);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
+    WarpStage* stage = reinterpret_cast<WarpStage*>(smem + L.region0);
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + L.region0);
+    float* s_gc = reinterpret_cast<float*>(smem + L.region0);
+    float* s_col = reinterpret_cast<float*>(smem + L.col);
+    float* s_ar = reinterpret_cast<float*>(smem + L.alpha_r);
+    float* s_au = reinterpret_cast<float*>(smem + L.alpha_u);
+    unsigned char* s_info = smem + L.info;
+    float* s_coef = reinterpret_cast<float*>(smem + L.coef);
+    unsigned char* s_ref = smem + L.ref;
+    __shared__ double red[FINE_WARPS];
+    __shared__ int s_nlist;
+
+    const int bin = blockIdx.x, n = blockIdx.y;
+    const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
+    const int tx0 = ox - AA_HALO, ty0 = oy - AA_HALO;           // tile origin (may be negative)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ref_pitch = AA_REF_W * C * esz;                   // bytes per reference tile row (multiple of 4)
+
+    // ---- (0) reference tile (rows oy-1 .. oy+32, columns ox-4 .. ox+35) on its way into shared memory ----
+    {
+        const unsigned char* rbase = reinterpret_cast<const unsigned char*>(fp.ref);
+        const long long row_bytes = (long long)rp.W * C * esz;
+        const bool fast = (row_bytes % 4 == 0) && ((reinterpret_cast<size_t>(rbase) & 3) == 0);
+        if (fast) {
+            const int gpr = ref_pitch >> 2;                     // 4-byte granules per tile row
+            const long long x_off = (long long)(ox - AA_REF_MARGIN) * C * esz;
+            for (int i = threadIdx.x; i < AA_R1 * gpr; i += FINE_THREADS) {
+                int r = i / gpr, g = i - r * gpr;
+                int py = oy - 1 + r;
+                long long b0 = x_off + 4 * g;
+                if (py < 0 || py >= rp.H || b0 < 0 || b0 + 4 > row_bytes) continue;
+                const unsigned char* src = rbase + ((size_t)n * rp.H + py) * (size_t)row_bytes + b0;
+                unsigned dst = (unsigned)__cvta_generic_to_shared(s_ref + r * ref_pitch + 4 * g);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+            }
+        } else {
+            for (int i = threadIdx.x; i < AA_R1 * AA_REF_W * C; i += FINE_THREADS) {
+                int r = i / (AA_REF_W * C), e = i - r * (AA_REF_W * C);
+                int py = oy - 1 + r, px = ox - AA_REF_MARGIN + e / C;
+                if (py < 0 || py >= rp.H || px < 0 || px >= rp.W) continue;
+                size_t gi = (((size_t)n * rp.H + py) * rp.W + px) * C + (e % C);
+                if (fp.ref_u8) s_ref[r * ref_pitch + e] = __ldg(rbase + gi);
+                else reinterpret_cast<float*>(s_ref + r * ref_pitch)[e] = __ldg(reinterpret_cast<const float*>(rbase) + gi);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    // ---- (1) visibility of the widened tile ----
+    raster_tile<AA_TW>(rp, n, bin, tx0, ty0, keys, stage);
+
+    // colour a background pixel hands to the antialias op: texture at uv = (0,0) or 0 (interpolate)
+    float bgcol[C];
+    if (TEX) {
+        float du[C], dv[C];
+        tex_bilinear<C>(fp, 0.f, 0.f, bgcol, du, dv);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; c++) bgcol[c] = 0.f;
+    }
+
+    // ---- (2) shade every tile pixel; the key slot becomes (z/w bits << 32 | id + 1) ----
+    const float* P = rp.pos + (size_t)n * rp.V * 4;
+    for (int idx = threadIdx.x; idx < AA_NT; idx += FINE_THREADS) {
+        const int tx = idx % AA_TW, ty = idx / AA_TW;
+        const int px = tx0 + tx, py = ty0 + ty;
+        const unsigned long long key = keys[idx];
+        const bool inner = tx >= AA_HALO && tx < AA_HALO + BIN && ty >= AA_HALO && ty < AA_HALO + BIN;
+        float col[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) col[c] = bgcol[c];
+        unsigned long long slot = 0ull;
+        float K[3 * C];
+#pragma unroll
+        for (int c = 0; c < 3 * C; c++) K[c] = 0.f;
+        float4 rout = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (key != KEY_EMPTY) {       // only in-image pixels receive fragments
+            int t = (int)(key & 0xFFFFFFFFu);
+            int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+            float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
+            float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
+            Shade sh = shade_pixel(p0, p1, p2, fx, fy);
+            float u = clamp01(sh.u), v = clamp01(sh.v);
+            float zw = fminf(fmaxf(sh.zw, -1.f), 1.f);
+            rout = make_float4(u, v, zw, (float)(t + 1));
+            slot = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned)(t + 1);
+            int j0 = i0, j1 = i1, j2 = i2;
+            if (fp.attr_tri != rp.tri) { j0 = __ldg(fp.attr_tri + 3 * t); j1 = __ldg(fp.attr_tri + 3 * t + 1); j2 = __ldg(fp.attr_tri + 3 * t + 2); }
+            bool ok = (unsigned)j0 < (unsigned)fp.Va && (unsigned)j1 < (unsigned)fp.Va && (unsigned)j2 < (unsigned)fp.Va;
+            constexpr int AA = TEX ? 2 : C;
+            float b2 = 1.f - u - v;
+            float a0c[AA], a1c[AA], a2c[AA], at[AA];
+#pragma unroll
+            for (int c = 0; c < AA; c++) {
+                a0c[c] = ok ? __ldg(fp.attr + (size_t)j0 * AA + c) : 0.f;
+                a1c[c] = ok ? __ldg(fp.attr + (size_t)j1 * AA + c) : 0.f;
+                a2c[c] = ok ? __ldg(fp.attr + (size_t)j2 * AA + c) : 0.f;
+                at[c] = u * a0c[c] + v * a1c[c] + b2 * a2c[c];
+            }
+            float ku[C], kv[C];        // d colour_c / d u, d colour_c / d v
+            if (TEX) {
+                float dudc[C], dvdc[C];
+                tex_bilinear<C>(fp, at[0], at[1], col, dudc, dvdc);
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    ku[c] = dudc[c] * (a0c[0] - a2c[0]) + dvdc[c] * (a0c[1] - a2c[1]);
+                    kv[c] = dudc[c] * (a1c[0] - a2c[0]) + dvdc[c] * (a1c[1] - a2c[1]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    col[c] = at[c];
+                    ku[c] = a0c[c] - a2c[c];
+                    kv[c] = a1c[c] - a2c[c];
+                }
+            }
+            // d loss / d a_k = sum_c g_c K[k][c]   (u = a0/at, v = a1/at, unclamped barycentrics as in the op-level backward)
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                float k2 = -sh.iw * (ku[c] * sh.u + kv[c] * sh.v);
+                K[2 * C + c] = k2;
+                K[0 * C + c] = sh.iw * ku[c] + k2;
+                K[1 * C + c] = sh.iw * kv[c] + k2;
+            }
+        }
+        keys[idx] = slot;
+#pragma unroll
+        for (int c = 0; c < C; c++) s_col[idx * C + c] = col[c];
+        s_ar[idx] = 0.f; s_au[idx] = 0.f; s_info[idx] = 0;
+        if (inner) {
+            const int ii = (ty - AA_HALO) * BIN + (tx - AA_HALO);
+#pragma unroll
+            for (int c = 0; c < 3 * C; c++) s_coef[ii * 3 * C + c] = K[c];
+            if (fp.rast_out && px < rp.W && py < rp.H) reinterpret_cast<float4*>(fp.rast_out)[((size_t)n * rp.H + py) * rp.W + px] = rout;
+        }
+    }
+    if (threadIdx.x == 0) s_nlist = 0;
+    __syncthreads();
+
+    // ---- (3a) work list of pixel pairs with different triangle ids (both pixels inside the tile and the image) ----
+    for (int base = 0; base < AA_NT; base += FINE_THREADS) {
+        const int idx = base + threadIdx.x;
+        bool cr = false, cu = false;
+        if (idx < AA_NT) {
+            const int tx = idx % AA_TW, ty = idx / AA_TW;
+            const int px = tx0 + tx, py = ty0 + ty;
+            if (px >= 0 && py >= 0 && px < rp.W && py < rp.H) {
+                unsigned id = (unsigned)keys[idx];
+                cr = (tx + 1 < AA_TW) && (px + 1 < rp.W) && ((unsigned)keys[idx + 1] != id);
+                cu = (ty + 1 < AA_TW) && (py + 1 < rp.H) && ((unsigned)keys[idx + AA_TW] != id);
+            }
+        }
+        const unsigned mr = __ballot_sync(0xffffffffu, cr), mu = __ballot_sync(0xffffffffu, cu);
+        const int cnt = __popc(mr) + __popc(mu);
+        int wbase = 0;
+        if (lane == 0 && cnt) wbase = atomicAdd(&s_nlist, cnt);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (cr) s_list[wbase + __popc(mr & below)] = (unsigned short)idx;
+        if (cu) s_list[wbase + __popc(mr) + __popc(mu & below)] = (unsigned short)(idx | 0x8000);
+    }
+    __syncthreads();
+
+    // ---- (3b) analyse the pairs densely ----
+    AAParams ap;
+    ap.rast = nullptr; ap.pos = rp.pos; ap.tri = rp.tri; ap.tri_opp = tri_opp;
+    ap.N = rp.N; ap.V = rp.V; ap.T = rp.T; ap.H = rp.H; ap.W = rp.W; ap.C = C;
+    ap.xh = 0.5f * (float)rp.W; ap.yh = 0.5f * (float)rp.H;
+    const int nlist = s_nlist;
+    for (int i = threadIdx.x; i < nlist; i += FINE_THREADS) {
+        const unsigned e = s_list[i];
+        const int idx = e & 0x7fff, d = e >> 15;
+        const int tx = idx % AA_TW, ty = idx / AA_TW;
+        const int px = tx0 + tx, py = ty0 + ty;
+        const unsigned long long k0 = keys[idx], k1 = keys[idx + (d ? AA_TW : 1)];
+        float2 z0 = make_float2(__uint_as_float((unsigned)(k0 >> 32)), (float)(unsigned)k0);
+        float2 z1 = make_float2(__uint_as_float((unsigned)(k1 >> 32)), (float)(unsigned)k1);
+        AAPair a = aa_analyze(ap, n, px, py, d, z0, z1);
+        if (a.valid) {
+            const int front1 = (a.px != px || a.py != py) ? 1 : 0;
+            const unsigned bits = 8u | (unsigned)a.di | ((unsigned)front1 << 2);
+            if (d) { s_au[idx] = a.alpha; atomicOr(reinterpret_cast<unsigned*>(s_info + (idx & ~3)), (bits << 4) << (8 * (idx & 3))); }
+            else { s_ar[idx] = a.alpha; atomicOr(reinterpret_cast<unsigned*>(s_info + (idx & ~3)), bits << (8 * (idx & 3))); }
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    // ---- (4) ring-1 region: antialiased colour, loss (own pixels), d loss / d out ----
+    double loss_acc = 0.0;
+    for (int r = threadIdx.x; r < AA_R1 * AA_R1; r += FINE_THREADS) {
+        const int rx = r % AA_R1, ry = r / AA_R1;
+        const int tx = rx + 1, ty = ry + 1, idx = ty * AA_TW + tx;
+        const int px = tx0 + tx, py = ty0 + ty;
+        const bool in_img = px >= 0 && py >= 0 && px < rp.W && py < rp.H;
+        const bool inner = rx >= 1 && rx <= BIN && ry >= 1 && ry <= BIN;
+        const bool fg = in_img && ((unsigned)keys[idx] != 0u);
+        float gcv[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) gcv[c] = 0.f;
+        if (in_img) {
+            const float a0 = s_ar[idx], a1 = s_ar[idx - 1], a2 = s_au[idx], a3 = s_au[idx - AA_TW];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                float comp = fp.bg;
+                if (fg) {
+                    const float cc = s_col[idx * C + c];
+                    float o = cc;
+                    if (a0 > 0.f) o += a0 * (s_col[(idx + 1) * C + c] - cc);
+                    if (a1 < 0.f) o += a1 * (cc - s_col[(idx - 1) * C + c]);
+                    if (a2 > 0.f) o += a2 * (s_col[(idx + AA_TW) * C + c] - cc);
+                    if (a3 < 0.f) o += a3 * (cc - s_col[(idx - AA_TW) * C + c]);
+                    comp = o;
+                }
+                const int rb = ry * ref_pitch + ((rx + AA_REF_MARGIN - 1) * C + c) * esz;
+                const float refv = fp.ref_u8 ? (float)s_ref[rb] : *reinterpret_cast<const float*>(s_ref + rb);
+                const float e = refv - 255.f * comp;
+                if (inner) {
+                    loss_acc += (double)(e * e);
+                    if (fp.colour_out) fp.colour_out[(((size_t)n * rp.H + py) * rp.W + px) * C + c] = comp;
+                }
+                if (fg) gcv[c] = (-510.f * fp.k) * e;
+            }
+        }
+        // region0 still holds the work list for other threads of phase 3b? no: a barrier separates the phases
+#pragma unroll
+        for (int c = 0; c < C; c++) s_gc[r * C + c] = gcv[c];
+    }
+    __syncthreads();
+
+    // ---- (5) own pixels: d loss / d colour (gather over the 4 pairs), triangle moments, silhouette position gradient ----
+    for (int ii = threadIdx.x; ii < BIN * BIN; ii += FINE_THREADS) {
+        const int ix = ii & (BIN - 1), iy = ii >> BIN_LOG2;
+        const int tx = ix + AA_HALO, ty = iy + AA_HALO, idx = ty * AA_TW + tx;
+        const int r = (iy + 1) * AA_R1 + (ix + 1);
+        const int px = ox + ix, py = oy + iy;
+        const bool in_img = px < rp.W && py < rp.H;
+        const unsigned long long key = keys[idx];
+        const unsigned idp1 = (unsigned)key;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (in_img) {
+            const float a0 = s_ar[idx], a1 = s_ar[idx - 1], a2 = s_au[idx], a3 = s_au[idx - AA_TW];
+            // destination pixel (ring-1 index) of every pair: pix0 when alpha > 0, else pix1
+            const int d0 = (a0 > 0.f) ? r : r + 1, d1 = (a1 > 0.f) ? r - 1 : r;
+            const int d2 = (a2 > 0.f) ? r : r + AA_R1, d3 = (a3 > 0.f) ? r - AA_R1 : r;
+            const unsigned info = s_info[idx];
+            float ddr = 0.f, ddu = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                float g = s_gc[r * C + c];
+                if (a0 != 0.f) g -= a0 * s_gc[d0 * C + c];
+                if (a1 != 0.f) g += a1 * s_gc[d1 * C + c];
+                if (a2 != 0.f) g -= a2 * s_gc[d2 * C + c];
+                if (a3 != 0.f) g += a3 * s_gc[d3 * C + c];
+                if (idp1) {
+                    g0 += g * s_coef[ii * 3 * C + 0 * C + c];
+                    g1 += g * s_coef[ii * 3 * C + 1 * C + c];
+                    g2 += g * s_coef[ii * 3 * C + 2 * C + c];
+                }
+                const float cc = s_col[idx * C + c];
+                if (info & 8u) ddr += s_gc[d0 * C + c] * (s_col[(idx + 1) * C + c] - cc);
+                if (info & 0x80u) ddu += s_gc[d2 * C + c] * (s_col[(idx + AA_TW) * C + c] - cc);
+            }
+            if (fp.moments) {
+                if ((info & 8u) && ddr != 0.f) {
+                    AAPair a;
+                    const int f1 = (info >> 2) & 1;
+                    a.valid = true; a.di = info & 3; a.alpha = a0; a.px = px + f1; a.py = py;
+                    a.tri = (int)(unsigned)keys[idx + f1] - 1;
+                    aa_pos_grad(ap, n, a, 0, ddr, fp.grad_pos);
+                }
+                if ((info & 0x80u) && ddu != 0.f) {
+                    AAPair a;
+                    const int f1 = (info >> 6) & 1;
+                    a.valid = true; a.di = (info >> 4) & 3; a.alpha = a2; a.px = px; a.py = py + f1;
+                    a.tri = (int)(unsigned)keys[idx + f1 * AA_TW] - 1;
+                    aa_pos_grad(ap, n, a, 1, ddu, fp.grad_pos);
+                }
+            }
+        }
+        if (fp.moments) {
+            int an = 0;
+            const unsigned tid = idp1 - 1u;                               // 0xFFFFFFFF on background
+            const bool live = (g0 != 0.f || g1 != 0.f || g2 != 0.f);
+            if (live) an = __ldg(rp.tri_anchor + (size_t)n * rp.T + tid);
+            accumulate_moments(fp.moments + (size_t)n * rp.T * 9, tid, live, g0, g1, g2, px, py, an, lane);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+    if (lane == 0) red[warp] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < FINE_WARPS; w++) s += red[w];
+        fp.loss_partial[(size_t)n * rp.NB + bin] = s;
+    }
+}
+
+}  // namespace

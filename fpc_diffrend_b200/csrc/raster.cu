@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
         int info = 0;
         if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
             rp.tri_anchor[gid] = s.pxa | (s.pya << 16);
-            int bx0 = s.pxa >> BIN_LOG2, bx1 = s.pxb >> BIN_LOG2, by0 = s.pya >> BIN_LOG2, by1 = s.pyb >> BIN_LOG2;
-            if (!is_small(s)) {
+            const BinRange br = bin_range(s, rp);
+            const int bx0 = br.bx0, bx1 = br.bx1, by0 = br.by0, by1 = br.by1;
+            if (!is_small(s, br)) {
                 int slot = atomicAdd(rp.large_count + n, 1);
                 rp.large_list[(size_t)n * rp.T + slot] = t;
                 info = 2 << 22;
@@ -252,14 +253,14 @@ ScratchLayout raster_layout(int N, int T, int NB)
 
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                          void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
-                         float* clear_tri9, float* clear_vtx4)
+                         float* clear_tri9, float* clear_vtx4, int halo)
 {
     FPC_CHECK_ARG(pos && tri, "%s: pos and tri must be non-null", who);
     FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "%s: N, V, T, H, W must be positive (got %d %d %d %d %d)", who, N, V, T, H, W);
     FPC_CHECK_ARG(T < (1 << 24), "%s: at most 2^24-1 triangles (got %d)", who, T);
     FPC_CHECK_ARG(H <= 32768 && W <= 32768 && N <= 65535, "%s: resolution <= 32768^2 and N <= 65535 (got %dx%d, N=%d)", who, H, W, N);
     rp.pos = pos; rp.tri = tri; rp.N = N; rp.V = V; rp.T = T; rp.H = H; rp.W = W;
-    rp.BW = fpc_div_up(W, BIN); rp.BH = fpc_div_up(H, BIN); rp.NB = rp.BW * rp.BH;
+    rp.BW = fpc_div_up(W, BIN); rp.BH = fpc_div_up(H, BIN); rp.NB = rp.BW * rp.BH; rp.halo = halo;
     ScratchLayout L = raster_layout(N, T, rp.NB);
     FPC_CHECK_ARG(scratch && scratch_bytes >= L.total, "%s: scratch too small (%zu < %zu bytes)", who, scratch_bytes, L.total);
     rp.xs = 2.0f / (float)W; rp.xo = 1.0f / (float)W - 1.0f;

@@ -41,6 +41,7 @@ struct RasterParams {
     const int32_t* tri;
     int N, V, T, H, W;
     int BW, BH, NB;
+    int halo;                        // bins are widened by `halo` px on every side when triangles are binned (fused_aa.cu)
     float xs, xo, ys, yo;            // pixel -> NDC
     float sxs, sys;                  // NDC -> 1/16 px:  8*W, 8*H
     int* bin_count;                  // [N*NB]
@@ -93,10 +94,22 @@ __device__ __forceinline__ bool setup_triangle(const float4& p0, const float4& p
     return s.pxa <= s.pxb && s.pya <= s.pyb;
 }
 
-__device__ __forceinline__ bool is_small(const SnappedTri& s)
+// Bins whose (halo-widened) pixel window overlaps the triangle's candidate pixel range.
+struct BinRange { int bx0, bx1, by0, by1; };
+
+__device__ __forceinline__ BinRange bin_range(const SnappedTri& s, const RasterParams& rp)
 {
-    return (s.maxx - s.minx) <= SMALL_EXTENT && (s.maxy - s.miny) <= SMALL_EXTENT &&
-           ((s.pxb >> BIN_LOG2) - (s.pxa >> BIN_LOG2)) <= 1 && ((s.pyb >> BIN_LOG2) - (s.pya >> BIN_LOG2)) <= 1;
+    BinRange r;
+    r.bx0 = max(s.pxa - rp.halo, 0) >> BIN_LOG2;
+    r.bx1 = min((s.pxb + rp.halo) >> BIN_LOG2, rp.BW - 1);
+    r.by0 = max(s.pya - rp.halo, 0) >> BIN_LOG2;
+    r.by1 = min((s.pyb + rp.halo) >> BIN_LOG2, rp.BH - 1);
+    return r;
+}
+
+__device__ __forceinline__ bool is_small(const SnappedTri& s, const BinRange& r)
+{
+    return (s.maxx - s.minx) <= SMALL_EXTENT && (s.maxy - s.miny) <= SMALL_EXTENT && (r.bx1 - r.bx0) <= 1 && (r.by1 - r.by0) <= 1;
 }
 
 __device__ __forceinline__ bool load_triangle(const RasterParams& rp, int n, int t, float4& p0, float4& p1, float4& p2)
@@ -140,12 +153,13 @@ __device__ __forceinline__ unsigned depth_key(float zw)
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+template <int TW>
 __device__ __forceinline__ void emit_fragment(unsigned long long* keys, float zd, int t, int lx, int ly)
 {
     if (!(zd >= -1.f && zd <= 1.f)) return;
     unsigned long long key = ((unsigned long long)depth_key(zd) << 32) | (unsigned)t;
     // 64-bit shared atomicMin is a CAS loop: skip it for fragments that already lose against the stored key
-    if (key < keys[ly * BIN + lx]) atomicMin(keys + ly * BIN + lx, key);
+    if (key < keys[ly * TW + lx]) atomicMin(keys + ly * TW + lx, key);
 }
 
 // ---- fill rule -------------------------------------------------------------------------------------------
@@ -165,13 +179,15 @@ struct WarpStage {
     int prefix[32];      // inclusive prefix sum of rows
 };
 
-// Resolve the visibility of bin (bx,by) of instance n into keys[BIN*BIN] (shared memory, initialised here).
-// `stage` is FINE_WARPS WarpStage records in shared memory.  All FINE_THREADS threads must call this.
-__device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bin, unsigned long long* keys, WarpStage* stage)
+// Resolve the visibility of the TW x TW pixel tile with origin (ox, oy) — bin `bin` of instance n, widened by
+// rp.halo px on every side when TW == BIN + 2 halo (the origin may then be negative) — into keys[TW*TW] (shared
+// memory, initialised here).  `stage` is FINE_WARPS WarpStage records in shared memory.  All FINE_THREADS threads
+// must call this.
+template <int TW>
+__device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int bin, int ox, int oy, unsigned long long* keys, WarpStage* stage)
 {
-    const int bx = bin % rp.BW, by = bin / rp.BW;
-    const int ox = bx * BIN, oy = by * BIN;
-    const int lim_x = min(ox + BIN, rp.W) - 1, lim_y = min(oy + BIN, rp.H) - 1;
+    const int min_x = max(ox, 0), min_y = max(oy, 0);
+    const int lim_x = min(ox + TW, rp.W) - 1, lim_y = min(oy + TW, rp.H) - 1;
     const int count = rp.bin_count[(size_t)n * rp.NB + bin];
     const int nlarge = rp.large_count[n];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -180,7 +196,7 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
     __shared__ int next_batch;       // warps claim batches of 32 triangles dynamically (balances uneven batches)
     if (threadIdx.x == 0) next_batch = 0;
 #endif
-    for (int i = threadIdx.x; i < BIN * BIN; i += FINE_THREADS) keys[i] = KEY_EMPTY;
+    for (int i = threadIdx.x; i < TW * TW; i += FINE_THREADS) keys[i] = KEY_EMPTY;
     __syncthreads();
 
     // ---- small triangles ----
@@ -202,7 +218,7 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
             float4 p0, p1, p2;
             SnappedTri s;
             if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
-                int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
+                int xa = max(s.pxa, min_x), xb = min(s.pxb, lim_x), ya = max(s.pya, min_y), yb = min(s.pyb, lim_y);
                 if (xa <= xb && ya <= yb) {
                     rows = yb - ya + 1;
                     // oriented vertex order (positive area): swap 1 <-> 2 when flipped
@@ -252,7 +268,7 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
             int t = st.tri[j];
             float zrow = __fmaf_rn(dzdy, (float)dy, zref);
             for (int x = 0; x < wd; x++) {
-                if ((e0 | e1 | e2) >= 0) emit_fragment(keys, __fmaf_rn(dzdx, (float)(dx + x), zrow), t, lx + x, ly);
+                if ((e0 | e1 | e2) >= 0) emit_fragment<TW>(keys, __fmaf_rn(dzdx, (float)(dx + x), zrow), t, lx + x, ly);
                 e0 += a0; e1 += a1; e2 += a2;
             }
         }
@@ -266,7 +282,7 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
         float4 p0, p1, p2;
         SnappedTri s;
         if (!load_triangle(rp, n, t, p0, p1, p2) || !setup_triangle(p0, p1, p2, rp, s)) continue;
-        int xa = max(s.pxa, ox), xb = min(s.pxb, lim_x), ya = max(s.pya, oy), yb = min(s.pyb, lim_y);
+        int xa = max(s.pxa, min_x), xb = min(s.pxb, lim_x), ya = max(s.pya, min_y), yb = min(s.pyb, lim_y);
         if (xa > xb || ya > yb) continue;
         long long ax1 = s.flip ? s.x2 : s.x1, ay1 = s.flip ? s.y2 : s.y1;
         long long ax2 = s.flip ? s.x1 : s.x2, ay2 = s.flip ? s.y1 : s.y2;
@@ -276,17 +292,23 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
         long long b1 = ex1 * (sy - ay1) - ey1 * (sx - ax1) + edge_bias64(ex1, ey1);
         long long b2 = ex2 * (sy - ay2) - ey2 * (sx - ax2) + edge_bias64(ex2, ey2);
         Plane pl = depth_plane(p0, p1, p2, s);
-        for (int idx = threadIdx.x; idx < BIN * BIN; idx += FINE_THREADS) {
-            int lx = idx & (BIN - 1), ly = idx >> BIN_LOG2;
+        for (int idx = threadIdx.x; idx < TW * TW; idx += FINE_THREADS) {
+            int lx = idx % TW, ly = idx / TW;
             int px = ox + lx, py = oy + ly;
             if (px < xa || px > xb || py < ya || py > yb) continue;
             long long r0 = b0 - 16 * ey0 * lx + 16 * ex0 * ly;
             long long r1 = b1 - 16 * ey1 * lx + 16 * ex1 * ly;
             long long r2 = b2 - 16 * ey2 * lx + 16 * ex2 * ly;
-            if ((r0 | r1 | r2) >= 0) emit_fragment(keys, plane_eval(pl.zref, pl.dzdx, pl.dzdy, px - s.pxa, py - s.pya), t, lx, ly);
+            if ((r0 | r1 | r2) >= 0) emit_fragment<TW>(keys, plane_eval(pl.zref, pl.dzdx, pl.dzdy, px - s.pxa, py - s.pya), t, lx, ly);
         }
     }
     __syncthreads();
+}
+
+// the plain bin (no halo)
+__device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bin, unsigned long long* keys, WarpStage* stage)
+{
+    raster_tile<BIN>(rp, n, bin, (bin % rp.BW) * BIN, (bin / rp.BW) * BIN, keys, stage);
 }
 
 // Host side: scratch layout + the three binning launches.
@@ -300,6 +322,6 @@ ScratchLayout raster_layout(int N, int T, int NB);
 // clear_tri9 [N*T*9] / clear_vtx4 [N*V*4] (nullable) are zero-filled by k_setup on the way.
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                          void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
-                         float* clear_tri9 = nullptr, float* clear_vtx4 = nullptr);
+                         float* clear_tri9 = nullptr, float* clear_vtx4 = nullptr, int halo = 0);
 
 }  // namespace fpc

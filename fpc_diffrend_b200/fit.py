@@ -45,7 +45,7 @@ class FitConfig:
     quat_norm: str = 'row'                # 'row' (default) or 'frobenius' (reference quirk)
     optimize_pose: bool = True
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
-    fused: bool = True                    # antialias off: one fused render+loss+gradient kernel (csrc/fused.cu)
+    fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
     fused_geometry: bool = None           # pose+blend+project in one kernel per direction (csrc/geometry.cu); None = auto
                                           # (small frame batches: D is re-read per frame there, the GEMM path is not)
@@ -119,11 +119,11 @@ class FitSession:
         self.mvp = torch.empty(self.N, 16, **f32)
         self.verts = torch.empty(F, V * 3, **f32)
         self.pos_clip = torch.empty(self.N, V, 4, **f32)
-        self.use_fused = bool(cfg.fused and not cfg.antialias)
+        self.use_fused = bool(cfg.fused)
         if cfg.ref_dtype not in ('f32', 'u8'):
             raise ValueError("ref_dtype must be 'f32' or 'u8'")
         if cfg.ref_dtype == 'u8' and not self.use_fused:
-            raise ValueError("ref_dtype='u8' needs the fused path (antialias=False, fused=True)")
+            raise ValueError("ref_dtype='u8' needs the fused path (fused=True)")
         self.g_pos = torch.empty(self.N, V, 4, **f32)
         if not self.use_fused:
             self.rast = torch.empty(self.N, H, W, 4, **f32)
@@ -137,9 +137,10 @@ class FitSession:
             self.texc = torch.empty(self.N, H, W, 2, **f32)
             self.g_texc = torch.empty(self.N, H, W, 2, **f32)
         if cfg.antialias:
-            self.colour_aa = torch.empty(self.N, H, W, Ch, **f32)
-            self.g_colour_pre = torch.empty(self.N, H, W, Ch, **f32)
-            self.g_pos_aa = torch.empty(self.N, V, 4, **f32)
+            if not self.use_fused:
+                self.colour_aa = torch.empty(self.N, H, W, Ch, **f32)
+                self.g_colour_pre = torch.empty(self.N, H, W, Ch, **f32)
+                self.g_pos_aa = torch.empty(self.N, V, 4, **f32)
             self.tri_opp = torch.empty(T, 3, dtype=torch.int32, device=dev)
             sc = torch.empty(int(_lib.load().fpc_topology_scratch_bytes(T)), dtype=torch.uint8, device=dev)
             _lib.call('fpc_topology_build', _p(self.pos_idx), T, V, _p(self.tri_opp), _p(sc), sc.numel(), self._stream())
@@ -312,16 +313,19 @@ class FitSession:
         V, T, H, W, N, Ch = self.V, self.T, self.H, self.W, self.N, self.Ch
         tex = self.tex
         Ht, Wt = (tex.shape[1], tex.shape[2]) if tex is not None else (0, 0)
+        # with antialias: the variant that resolves a 2-px halo around every bin (csrc/fused_aa.cuh)
+        name = 'fpc_render_loss_fused_aa' if cfg.antialias else 'fpc_render_loss_fused'
+        head = (_p(self.pos_clip), _p(self.pos_idx)) + ((_p(self.tri_opp),) if cfg.antialias else ())
         if not with_loss:
             # forward only: composited image out, loss against a dummy reference is discarded
             img = torch.empty(N, H, W, Ch, dtype=torch.float32, device=self.device)
-            dummy = torch.zeros(N, H, W, Ch, dtype=torch.float32, device=self.device)
-            _lib.call('fpc_render_loss_fused', _p(self.pos_clip), _p(self.pos_idx), _p(self.attr), _p(self.attr_idx), self.attr.shape[1],
-                      self.attr.shape[2], _p(tex), Ht, Wt, _p(dummy), 0, N, V, T, H, W, Ch, cfg.bg, 1.0, _p(self.loss), None, None,
+            dummy = torch.zeros(N, H, W, Ch, dtype=torch.uint8, device=self.device)
+            _lib.call(name, *head, _p(self.attr), _p(self.attr_idx), self.attr.shape[1],
+                      self.attr.shape[2], _p(tex), Ht, Wt, _p(dummy), 1, N, V, T, H, W, Ch, cfg.bg, 1.0, _p(self.loss), None, None,
                       _p(img), _p(self.scratch), self.scratch.numel(), s)
             return img
         assert self.ref is not None, 'call set_reference() first'
-        self._timed('render_loss_fused', 'fpc_render_loss_fused', _p(self.pos_clip), _p(self.pos_idx), _p(self.attr), _p(self.attr_idx),
+        self._timed('render_loss_fused', name, *head, _p(self.attr), _p(self.attr_idx),
                     self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
                     N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, _p(self.loss), _p(self.g_pos), None, None,
                     _p(self.scratch), self.scratch.numel(), s)

@@ -167,6 +167,17 @@ int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* att
                           float* loss, float* grad_pos, float* rast_out, float* colour_out,
                           void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
+/* The same with dr.antialias (fit.py:160) between shading and the background composite: replaces the chain
+ * fit.py:151-161,579 and its part of loss.backward() (fit.py:611).  tri_opp [T,3] from fpc_topology_build.
+ * One kernel per (32x32-px bin, view) resolves the bin plus a 2-px halo in shared memory; the antialias forward and the
+ * colour gradient are atomics-free gathers, results equal fpc_antialias_fwd/bwd applied to the op-level chain.
+ * Same scratch size as fpc_render_loss_fused; colour_out is the antialiased, composited image. */
+int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
+                             const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
+                             const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
+                             float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                             void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
 /* ---- Adam (replaces torch.optim.Adam + LambdaLR + quaternion renorm, fit.py:493-505,610-618) ---------------
  * p, g, m, v [n]; step_count [1]: device float holding the number of optimiser steps taken so far
  * (advanced by fpc_adam_advance after all parameter groups of an iteration have been stepped).

@@ -51,7 +51,8 @@ def oracle_render_loss(rig, pos_clip, ref, shading, use_aa, H, W, opp, n_cams_to
 
 @pytest.mark.parametrize('shading,use_aa,fused,geom', [('vcol', False, True, True), ('vcol', False, True, False),
                                                        ('vcol', False, False, True), ('texture', False, True, True),
-                                                       ('texture', True, False, False), ('vcol', True, False, True)])
+                                                       ('texture', True, False, False), ('vcol', True, False, True),
+                                                       ('texture', True, True, True), ('vcol', True, True, False)])
 def test_iteration_gradients(small_rig3, shading, use_aa, fused, geom):
     """Every link of one fit iteration against the oracle ON IDENTICAL INPUT BITS.
 
@@ -69,7 +70,7 @@ def test_iteration_gradients(small_rig3, shading, use_aa, fused, geom):
     w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
     ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, cfg)
     s = FitSession(rig, F, cfg)
-    assert s.use_fused == (fused and not use_aa) and s.use_geom_fused == geom
+    assert s.use_fused == fused and s.use_geom_fused == geom
     s.set_reference(ref)
     rng = np.random.default_rng(0)
     w0 = (0.05 * rng.random((F, rig.B))).astype(np.float32)

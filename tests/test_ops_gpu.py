@@ -191,9 +191,11 @@ def test_render_chain_like_reference(dr, tiny_rig):
     assert np.abs(colour[0].cpu().numpy() - ref).max() <= ABS_FWD
 
 
+@pytest.mark.parametrize('aa', [False, True])
 @pytest.mark.parametrize('textured,C,u8', [(False, 3, False), (False, 1, True), (True, 1, False), (True, 3, True)])
-def test_fused_render_loss(dr, small_rig3, textured, C, u8):
-    """fpc_render_loss_fused (rasterize+interpolate+[texture]+bg+loss+backward in one kernel) vs the oracle chain."""
+def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
+    """fpc_render_loss_fused[_aa] (rasterize+interpolate+[texture]+[antialias]+bg+loss+backward in one kernel) vs the
+    oracle chain."""
     import ctypes
     from fpc_diffrend_b200 import _lib
     rig, H, W = small_rig3, 152, 200
@@ -215,6 +217,9 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8):
     r_o, _ = G.rasterize(tp, torch.tensor(rig.pos_idx), (H, W))
     a_o = G.interpolate(torch.tensor(attr)[None], r_o, torch.tensor(idx))
     col_o = G.texture(torch.tensor(tex)[None], a_o) if textured else a_o
+    if aa:
+        opp = G.topology_build(rig.pos_idx)
+        col_o = G.antialias(col_o, r_o, tp, torch.tensor(rig.pos_idx), torch.tensor(opp))
     comp_o = torch.where(r_o[..., 3:] > 0, col_o, torch.tensor(G.BG))
     loss_o = scale * sum(G.image_loss(torch.tensor(ref[n]), comp_o[n]) for n in range(N))
     loss_o.backward()
@@ -229,7 +234,8 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8):
     col_out = torch.empty(N, H, W, C, device='cuda')
     nbytes = _lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W)
     scratch = torch.empty(int(nbytes), dtype=torch.uint8, device='cuda')
-    _lib.call('fpc_render_loss_fused', P(d_pos), P(d_tri), P(d_attr), P(d_idx), attr.shape[0], attr.shape[1], P(d_tex),
+    head = (P(d_pos), P(d_tri)) + ((P(cu(opp)),) if aa else ())
+    _lib.call('fpc_render_loss_fused_aa' if aa else 'fpc_render_loss_fused', *head, P(d_attr), P(d_idx), attr.shape[0], attr.shape[1], P(d_tex),
               tex.shape[0] if textured else 0, tex.shape[1] if textured else 0, P(d_ref), 1 if u8 else 0, N, V, T, H, W, C,
               G.BG, scale, P(loss), P(g_pos), P(rast_out), P(col_out), P(scratch), scratch.numel(),
               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))

@@ -23,6 +23,7 @@ import torch
 
 from . import _lib
 from .ops import _check_device
+from .shard import allreduce_gradients
 
 BG = 45.0 / 255.0  # fit.py:161
 
@@ -377,8 +378,8 @@ class FitSession:
         cfg, s, call = self.cfg, self._stream(), self._timed
         F, B = self.F, self.B
         n = 0
-        if cfg.cam_slice is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(self.grads)   # the only exchange of the camera-split mode: (B+7) F floats
+        if cfg.cam_slice is not None:
+            allreduce_gradients(self.grads)            # the only exchange of the camera-split mode: (B+7) F floats
         nw = F * B
         if F * (B + 7) <= (1 << 22):
             call('adam', 'fpc_adam_fused', _p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), B, F, 1 if cfg.optimize_pose else 0,
@@ -435,12 +436,21 @@ class FitSession:
         return self.verts.clone()
 
 
-def synthesize_reference(rig, w_true, t_true, q_true, config, device=None):
+def synthesize_reference(rig, w_true, t_true, q_true, config, device=None, out_dtype=torch.float32, chunk=16):
     """Render reference frames from ground-truth parameters with the kernels themselves, x255, clipped to [0,140]
-    (fit.py:531) -> [F, C, H, W, Ch] float32 on device."""
+    (fit.py:531) -> [F, C_local, H, W, Ch] on device (float32, or rounded to uint8 grey levels like the camera TIFFs).
+    Frames are rendered `chunk` at a time so that long sequences need no float copy of the whole stack."""
     F = w_true.shape[0]
-    s = FitSession(rig, F, config, device)
-    s.set_parameters(w_true, t_true, q_true)
-    img = s.forward(with_loss=False)
-    ref = torch.clamp(img * 255.0, 0.0, 140.0)
-    return ref.reshape(F, s.C, s.H, s.W, s.Ch).contiguous()
+    out, sessions = None, {}
+    for a in range(0, F, chunk):
+        b = min(a + chunk, F)
+        s = sessions.get(b - a)
+        if s is None:
+            s = sessions[b - a] = FitSession(rig, b - a, config, device)
+        s.set_parameters(w_true[a:b], t_true[a:b], q_true[a:b])
+        img = s.forward(with_loss=False)
+        ref = torch.clamp(img * 255.0, 0.0, 140.0).reshape(b - a, s.C, s.H, s.W, s.Ch)
+        if out is None:
+            out = torch.empty((F, s.C, s.H, s.W, s.Ch), dtype=out_dtype, device=ref.device)
+        out[a:b] = ref.round().to(torch.uint8) if out_dtype == torch.uint8 else ref
+    return out

@@ -57,8 +57,8 @@ __device__ __forceinline__ AAPair aa_analyze(const AAParams& ap, int n, int px, 
     float4 o1 = (op1 < 0) ? p1 : ldg4(P + 4 * (size_t)op1);
     float4 o2 = (op2 < 0) ? p2 : ldg4(P + 4 * (size_t)op2);
     float xh = ap.xh, yh = ap.yh;
-    float w0 = xdiv(1.f, p0.w), w1 = xdiv(1.f, p1.w), w2 = xdiv(1.f, p2.w);
-    float ow0 = xdiv(1.f, o0.w), ow1 = xdiv(1.f, o1.w), ow2 = xdiv(1.f, o2.w);
+    float w0 = xrcp(p0.w), w1 = xrcp(p1.w), w2 = xrcp(p2.w);
+    float ow0 = xrcp(o0.w), ow1 = xrcp(o1.w), ow2 = xrcp(o2.w);
     float fx = xsub(xadd((float)px, 0.5f), xh), fy = xsub(xadd((float)py, 0.5f), yh);
     float x0 = xsub(xmul(xmul(p0.x, w0), xh), fx), y0 = xsub(xmul(xmul(p0.y, w0), yh), fy);
     float x1 = xsub(xmul(xmul(p1.x, w1), xh), fx), y1 = xsub(xmul(xmul(p1.y, w1), yh), fy);
@@ -104,7 +104,7 @@ __device__ __forceinline__ void aa_pos_grad(const AAParams& ap, int n, const AAP
     const float* P = ap.pos + (size_t)n * ap.V * 4;
     float4 p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
     float xh = ap.xh, yh = ap.yh;
-    float w1 = xdiv(1.f, p1.w), w2 = xdiv(1.f, p2.w);
+    float w1 = xrcp(p1.w), w2 = xrcp(p2.w);
     float fx = xsub(xadd((float)a.px, 0.5f), xh), fy = xsub(xadd((float)a.py, 0.5f), yh);
     float x1 = xsub(xmul(xmul(p1.x, w1), xh), fx), y1 = xsub(xmul(xmul(p1.y, w1), yh), fy);
     float x2 = xsub(xmul(xmul(p2.x, w2), xh), fx), y2 = xsub(xmul(xmul(p2.y, w2), yh), fy);

@@ -40,6 +40,8 @@ __device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+// correctly rounded 1/x: the same bits as xdiv(1, x) (and as 1.0f / x on the CPU), in fewer instructions
+__device__ __forceinline__ float xrcp(float x) { return __frcp_rn(x); }
 
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
 
@@ -50,6 +52,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 // Shading formula of SURVEY App. A.1 (perspective-correct barycentrics from clip-space vertices).
 struct Shade { float u, v, zw, iw; };
+struct ShadeLazy { float u, v, iw, zn, wn; };      // z/w = xdiv(zn, wn), left to the caller (fused kernel: only for rast_out)
 
 __device__ __forceinline__ Shade shade_pixel(const float4& p0, const float4& p1, const float4& p2,
                                              float fx, float fy)
@@ -61,7 +64,7 @@ __device__ __forceinline__ Shade shade_pixel(const float4& p0, const float4& p1,
     float a1 = xsub(xmul(p2x, p0y), xmul(p2y, p0x));
     float a2 = xsub(xmul(p0x, p1y), xmul(p0y, p1x));
     float at = xadd(xadd(a0, a1), a2);
-    float iw = xdiv(1.0f, at);
+    float iw = xrcp(at);
     Shade s;
     s.iw = iw;
     s.u = xmul(a0, iw);
@@ -69,6 +72,24 @@ __device__ __forceinline__ Shade shade_pixel(const float4& p0, const float4& p1,
     float z = xadd(xadd(xmul(p0.z, a0), xmul(p1.z, a1)), xmul(p2.z, a2));
     float w = xadd(xadd(xmul(p0.w, a0), xmul(p1.w, a1)), xmul(p2.w, a2));
     s.zw = xdiv(z, w);
+    return s;
+}
+
+__device__ __forceinline__ ShadeLazy shade_pixel_lazy(const float4& p0, const float4& p1, const float4& p2, float fx, float fy)
+{
+    float p0x = xsub(p0.x, xmul(fx, p0.w)), p0y = xsub(p0.y, xmul(fy, p0.w));
+    float p1x = xsub(p1.x, xmul(fx, p1.w)), p1y = xsub(p1.y, xmul(fy, p1.w));
+    float p2x = xsub(p2.x, xmul(fx, p2.w)), p2y = xsub(p2.y, xmul(fy, p2.w));
+    float a0 = xsub(xmul(p1x, p2y), xmul(p1y, p2x));
+    float a1 = xsub(xmul(p2x, p0y), xmul(p2y, p0x));
+    float a2 = xsub(xmul(p0x, p1y), xmul(p0y, p1x));
+    float at = xadd(xadd(a0, a1), a2);
+    ShadeLazy s;
+    s.iw = xrcp(at);
+    s.u = xmul(a0, s.iw);
+    s.v = xmul(a1, s.iw);
+    s.zn = xadd(xadd(xmul(p0.z, a0), xmul(p1.z, a1)), xmul(p2.z, a2));
+    s.wn = xadd(xadd(xmul(p0.w, a0), xmul(p1.w, a1)), xmul(p2.w, a2));
     return s;
 }
 

@@ -124,6 +124,74 @@ __device__ __forceinline__ void accumulate_moments(float* __restrict__ M, unsign
     }
 }
 
+// A bin no triangle touches: every pixel is background.  Its loss term sum (ref - 255 bg)^2 is streamed straight from
+// the reference frame (16-byte loads when the layout allows), optional image outputs are filled, nothing else runs.
+// Returns the CTA's partial loss in thread 0 via `red` (shared, FINE_WARPS doubles).
+template <int C>
+__device__ __forceinline__ void background_bin(const RasterParams& rp, const FusedParams& fp, int n, int bin, int ox, int oy, double* red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int esz = fp.ref_u8 ? 1 : 4;
+    const int rows = min(BIN, rp.H - oy), wpx = min(BIN, rp.W - ox);
+    const unsigned char* rbase = reinterpret_cast<const unsigned char*>(fp.ref);
+    const size_t row_bytes = (size_t)rp.W * C * esz;
+    const float b255 = 255.f * fp.bg;
+    double acc = 0.0;
+    const bool fast = (wpx == BIN) && (row_bytes % 16 == 0) && ((reinterpret_cast<size_t>(rbase) & 15) == 0);
+    if (fast) {
+        const int cpr = (BIN * C * esz) >> 4;                    // 16-byte chunks per tile row
+        for (int i = threadIdx.x; i < rows * cpr; i += FINE_THREADS) {
+            int r = i / cpr, ch = i - r * cpr;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(rbase + ((size_t)n * rp.H + oy + r) * row_bytes + (size_t)ox * C * esz + ch * 16));
+            const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+            float sacc = 0.f;
+            if (fp.ref_u8) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        float e = (float)((w4[k] >> (8 * b)) & 0xffu) - b255;
+                        sacc += e * e;
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float e = __uint_as_float(w4[k]) - b255;
+                    sacc += e * e;
+                }
+            }
+            acc += (double)sacc;
+        }
+    } else {
+        for (int i = threadIdx.x; i < rows * wpx * C; i += FINE_THREADS) {
+            int r = i / (wpx * C), e0 = i - r * (wpx * C);
+            size_t gi = (((size_t)n * rp.H + oy + r) * rp.W + ox) * C + e0;
+            float rv = fp.ref_u8 ? (float)__ldg(rbase + gi) : __ldg(reinterpret_cast<const float*>(rbase) + gi);
+            float e = rv - b255;
+            acc += (double)(e * e);
+        }
+    }
+    if (fp.rast_out || fp.colour_out) {
+        for (int i = threadIdx.x; i < rows * wpx; i += FINE_THREADS) {
+            int r = i / wpx, x = i - r * wpx;
+            size_t pi = ((size_t)n * rp.H + oy + r) * rp.W + ox + x;
+            if (fp.rast_out) reinterpret_cast<float4*>(fp.rast_out)[pi] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (fp.colour_out) {
+#pragma unroll
+                for (int c = 0; c < C; c++) fp.colour_out[pi * C + c] = fp.bg;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < FINE_WARPS; w++) t += red[w];
+        fp.loss_partial[(size_t)n * rp.NB + bin] = t;
+    }
+}
+
 #ifndef FPC_FUSED_MINBLOCKS
 #define FPC_FUSED_MINBLOCKS 8
 #endif
@@ -139,6 +207,11 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     const int bin = blockIdx.x, n = blockIdx.y;
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0) {      // ~2/3 of the bins of a head shot
+        background_bin<C>(rp, fp, n, bin, ox, oy, red);
+        return;
+    }
 
     // ---- (0) the tile of the reference frame starts its way into shared memory now (cp.async), so its HBM / L2
     //          latency is hidden behind the rasterization phase ----
@@ -192,6 +265,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
                                     : reinterpret_cast<const float*>(sref + ly * pitch)[lx * C + c];
             float col[C];
             float4 rout = make_float4(0.f, 0.f, 0.f, 0.f);
+            float zn = 0.f, wn = 1.f;
             bool fg = key != KEY_EMPTY;
             float a0c[TEX ? 2 : C], a1c[TEX ? 2 : C], a2c[TEX ? 2 : C];
             float dudc[C], dvdc[C];      // TEX: d colour_c / d texU, d texV
@@ -202,10 +276,11 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
                 if (fp.moments) an = __ldg(rp.tri_anchor + (size_t)n * rp.T + t);     // early: consumed by the moments below
                 float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
                 float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
-                Shade sh = shade_pixel(p0, p1, p2, fx, fy);
+                ShadeLazy sh = shade_pixel_lazy(p0, p1, p2, fx, fy);
                 float u = clamp01(sh.u), v = clamp01(sh.v);
                 su = sh.u; sv = sh.v; siw = sh.iw;
-                rout = make_float4(u, v, fminf(fmaxf(sh.zw, -1.f), 1.f), (float)(t + 1));
+                zn = sh.zn; wn = sh.wn;
+                rout = make_float4(u, v, 0.f, (float)(t + 1));
                 int j0 = i0, j1 = i1, j2 = i2;
                 if (fp.attr_tri != rp.tri) { j0 = __ldg(fp.attr_tri + 3 * t); j1 = __ldg(fp.attr_tri + 3 * t + 1); j2 = __ldg(fp.attr_tri + 3 * t + 2); }
                 bool ok = (unsigned)j0 < (unsigned)fp.Va && (unsigned)j1 < (unsigned)fp.Va && (unsigned)j2 < (unsigned)fp.Va;
@@ -274,7 +349,10 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
                 g0 = siw * gu + g2;
                 g1 = siw * gv + g2;
             }
-            if (fp.rast_out) reinterpret_cast<float4*>(fp.rast_out)[pi] = rout;
+            if (fp.rast_out) {
+                if (fg) rout.z = fminf(fmaxf(xdiv(zn, wn), -1.f), 1.f);      // the z/w division only when somebody looks at it
+                reinterpret_cast<float4*>(fp.rast_out)[pi] = rout;
+            }
             if (fp.colour_out) {
 #pragma unroll
                 for (int c = 0; c < C; c++) fp.colour_out[pi * C + c] = col[c];

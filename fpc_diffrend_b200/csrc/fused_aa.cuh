@@ -105,6 +105,12 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ref_pitch = AA_REF_W * C * esz;                   // bytes per reference tile row (multiple of 4)
 
+    // bins are widened by the halo when triangles are binned: an empty list means an all-background tile
+    if (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0) {
+        background_bin<C>(rp, fp, n, bin, ox, oy, red);
+        return;
+    }
+
     // ---- (0) reference tile (rows oy-1 .. oy+32, columns ox-4 .. ox+35) on its way into shared memory ----
     {
         const unsigned char* rbase = reinterpret_cast<const unsigned char*>(fp.ref);

@@ -63,21 +63,27 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geom_fwd(const float* __restric
     for (int i = threadIdx.x; i < B; i += GEO_THREADS) s_w[i] = w[(size_t)f * B + i];
     __syncthreads();
 
+    // a lane always meets the same columns of D: its activations live in registers for the whole vertex loop
+    float4 wr[K];
+    int rsel[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        int e = 4 * (lane + 32 * k);
+        rsel[k] = (e >= B) + (e >= 2 * B);
+        wr[k] = (e < 3 * B) ? *reinterpret_cast<const float4*>(s_w + (e - rsel[k] * B)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
     for (int v = gw; v < V; v += nw) {
         float4 nxt[K];
         if (v + nw < V) load_rows<K>(D, v + nw, B, n4, lane, nxt);     // in flight while this vertex is reduced
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            int e = 4 * (lane + 32 * k);
-            if (e < 3 * B) {
-                int r = (e >= B) + (e >= 2 * B);
-                const float* ww = s_w + (e - r * B);
-                float s = cur[k].x * ww[0] + cur[k].y * ww[1] + cur[k].z * ww[2] + cur[k].w * ww[3];
-                a0 += (r == 0) ? s : 0.f;
-                a1 += (r == 1) ? s : 0.f;
-                a2 += (r == 2) ? s : 0.f;
-            }
+            // rows beyond 3B were loaded as zeros (and carry zero activations)
+            float s = cur[k].x * wr[k].x + cur[k].y * wr[k].y + cur[k].z * wr[k].z + cur[k].w * wr[k].w;
+            a0 += (rsel[k] == 0) ? s : 0.f;
+            a1 += (rsel[k] == 1) ? s : 0.f;
+            a2 += (rsel[k] == 2) ? s : 0.f;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -202,8 +208,9 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restric
     }
 }
 
-// backward, stage 2: CTA (f, j) sums the d w partials of columns [32 j, 32 j + 32) — 32 warps take every 32nd block,
-// then a fixed-order sum over the warps (deterministic); CTA (f, 0) also sums d mvp and runs the pose backward.
+// backward, stage 2: CTA (f, j < nby) sums the d w partials of columns [32 j, 32 j + 32) — 32 warps take every 32nd block,
+// then a fixed-order sum over the warps (deterministic); CTA (f, nby) sums d mvp the same way and runs the pose backward
+// with one thread per camera (camera contributions are then added in index order).
 constexpr int RED_THREADS = 1024;
 
 __global__ void __launch_bounds__(RED_THREADS) k_geom_bwd_reduce(const float* __restrict__ part_w, const float* __restrict__ part_mvp,
@@ -213,42 +220,54 @@ __global__ void __launch_bounds__(RED_THREADS) k_geom_bwd_reduce(const float* __
                                                                  int B, int F, int C, float* __restrict__ d_w,
                                                                  float* __restrict__ d_mvp, float* __restrict__ d_t, float* __restrict__ d_q)
 {
-    extern __shared__ float s_dm[];                     // [C][16]
+    extern __shared__ float dyn[];                      // pose CTA: red2 [32][nval] | s_dm [nval] | s_cam [C][12]
     __shared__ float red[32][33];
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y * 32 + lane;
-    float s = 0.f;
-    if (b < B)
-        for (int k = warp; k < nblk; k += 32) s += part_w[((size_t)k * F + f) * B + b];
-    red[warp][lane] = s;
-    __syncthreads();
-    if (warp == 0 && b < B) {
-        float tot = 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; k++) tot += red[k][lane];
-        d_w[(size_t)f * B + b] = tot;
-    }
-    if (blockIdx.y != 0) return;
-    __syncthreads();
-    // d mvp: C*16 values x nblk partials; thread (slice = tid / 16 within groups of 16 values)
-    const int nval = C * 16;
-    for (int base = 0; base < nval; base += 32) {
-        int i = base + lane;
-        float a = 0.f;
-        if (i < nval)
-            for (int k = warp; k < nblk; k += 32) a += part_mvp[((size_t)k * F + f) * nval + i];
-        red[warp][lane] = a;
+    if (blockIdx.y < gridDim.y - 1) {
+        const int b = blockIdx.y * 32 + lane;
+        float s = 0.f;
+        if (b < B) {
+#pragma unroll 4
+            for (int k = warp; k < nblk; k += 32) s += part_w[((size_t)k * F + f) * B + b];
+        }
+        red[warp][lane] = s;
         __syncthreads();
-        if (warp == 0 && i < nval) {
+        if (warp == 0 && b < B) {
             float tot = 0.f;
 #pragma unroll
             for (int k = 0; k < 32; k++) tot += red[k][lane];
-            s_dm[i] = tot;
-            if (d_mvp) d_mvp[(size_t)f * nval + i] = tot;
+            d_w[(size_t)f * B + b] = tot;
         }
-        __syncthreads();
+        return;
     }
-    if (threadIdx.x == 0) pose_backward_frame(P, A, t, q, t_cam, q_cam, s_dm, f, C, d_t, d_q);
+    const int nval = C * 16;
+    float* red2 = dyn;
+    float* s_dm = dyn + 32 * nval;
+    float* s_cam = s_dm + nval;
+    for (int i = lane; i < nval; i += 32) {
+        float a = 0.f;
+#pragma unroll 4
+        for (int k = warp; k < nblk; k += 32) a += part_mvp[((size_t)k * F + f) * nval + i];
+        red2[warp * nval + i] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nval; i += RED_THREADS) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k++) tot += red2[k * nval + i];
+        s_dm[i] = tot;
+        if (d_mvp) d_mvp[(size_t)f * nval + i] = tot;
+    }
+    __syncthreads();
+    if (threadIdx.x < C) pose_backward_camera(P, A, t_cam, q_cam, s_dm + 16 * threadIdx.x, threadIdx.x, s_cam + 12 * threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float g[12] = {};
+        for (int c = 0; c < C; c++)
+#pragma unroll
+            for (int i = 0; i < 12; i++) g[i] += s_cam[12 * c + i];
+        pose_backward_finish(q, f, g, d_t, d_q);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -383,8 +402,13 @@ extern "C" int fpc_geometry_bwd(const float* P, const float* A, const float* t, 
     }
 #undef FPC_BWD_CASE
     if (st != FPC_OK) return st;
-    k_geom_bwd_reduce<<<dim3(F, fpc_div_up(B, 32)), RED_THREADS, (size_t)C * 16 * sizeof(float), stream>>>(part_w, part_mvp, nblk, P, A, t, q, t_cam, q_cam,
-                                                                                 B, F, C, d_w, d_mvp, d_t, d_q);
+    static bool red_attr_set = false;
+    if (!red_attr_set) {
+        FPC_CUDA(cudaFuncSetAttribute(k_geom_bwd_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (33 * 32 * 16 + 12 * 32) * (int)sizeof(float)));
+        red_attr_set = true;
+    }
+    k_geom_bwd_reduce<<<dim3(F, fpc_div_up(B, 32) + 1), RED_THREADS, (size_t)(33 * C * 16 + 12 * C) * sizeof(float), stream>>>(
+        part_w, part_mvp, nblk, P, A, t, q, t_cam, q_cam, B, F, C, d_w, d_mvp, d_t, d_q);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

@@ -64,53 +64,71 @@ __device__ __forceinline__ M4 frame_camera_mvp(const float* P, const float* A, c
     return mul(load_m4(P + 16 * c), mul(rigid(tf, qf), cam_base(A, t_cam, q_cam, c)));
 }
 
+// One camera's contribution to the gradient of the frame's rigid transform: out[0..8] = d R (row-major), out[9..11] = d t.
+// d_mvp_c = 16 floats (any address space).
+__device__ __forceinline__ void pose_backward_camera(const float* P, const float* A, const float* t_cam, const float* q_cam,
+                                                     const float* d_mvp_c, int c, float* out)
+{
+    M4 p = load_m4(P + 16 * c);
+    M4 b = cam_base(A, t_cam, q_cam, c);
+    M4 g;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) g.m[i][j] = d_mvp_c[4 * i + j];
+    // dRig = P^T g B^T ; only the top 3 rows are needed
+    M4 pg;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s += p.m[k][i] * g.m[k][j];
+            pg.m[i][j] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s += pg.m[i][k] * b.m[j][k];
+            out[3 * i + j] = s;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) s += pg.m[i][k] * b.m[3][k];
+        out[9 + i] = s;
+    }
+}
+
+// summed contributions (d R [9], d t [3]) -> d_t[f], d_q[f]
+__device__ __forceinline__ void pose_backward_finish(const float* q, int f, const float* g, float* d_t, float* d_q)
+{
+    float x = q[4 * f], y = q[4 * f + 1], z = q[4 * f + 2], w = q[4 * f + 3];
+    const float (*gR)[3] = reinterpret_cast<const float (*)[3]>(g);
+    d_t[3 * f] = g[9]; d_t[3 * f + 1] = g[10]; d_t[3 * f + 2] = g[11];
+    d_q[4 * f + 0] = 2.f * (gR[0][0] * x + gR[0][1] * y + gR[0][2] * z + gR[1][0] * y - gR[1][1] * x - gR[1][2] * w + gR[2][0] * z + gR[2][1] * w - gR[2][2] * x);
+    d_q[4 * f + 1] = 2.f * (-gR[0][0] * y + gR[0][1] * x + gR[0][2] * w + gR[1][0] * x + gR[1][1] * y + gR[1][2] * z - gR[2][0] * w + gR[2][1] * z - gR[2][2] * y);
+    d_q[4 * f + 2] = 2.f * (-gR[0][0] * z - gR[0][1] * w + gR[0][2] * x + gR[1][0] * w - gR[1][1] * z + gR[1][2] * y + gR[2][0] * x + gR[2][1] * y + gR[2][2] * z);
+    d_q[4 * f + 3] = 2.f * (gR[0][0] * w - gR[0][1] * z + gR[0][2] * y + gR[1][0] * z + gR[1][1] * w - gR[1][2] * x - gR[2][0] * y + gR[2][1] * x + gR[2][2] * w);
+}
+
 // d_mvp_f [C][16] (any address space) -> d_t[f], d_q[f]; cameras summed in index order (deterministic)
 __device__ __forceinline__ void pose_backward_frame(const float* P, const float* A, const float* t, const float* q,
                                                     const float* t_cam, const float* q_cam, const float* d_mvp_f,
                                                     int f, int C, float* d_t, float* d_q)
 {
-    float x = q[4 * f], y = q[4 * f + 1], z = q[4 * f + 2], w = q[4 * f + 3];
-    float gt[3] = {0.f, 0.f, 0.f};
-    float gR[3][3] = {};
+    (void)t;
+    float g[12] = {};
     for (int c = 0; c < C; c++) {
-        M4 p = load_m4(P + 16 * c);
-        M4 b = cam_base(A, t_cam, q_cam, c);
-        M4 g;
+        float o[12];
+        pose_backward_camera(P, A, t_cam, q_cam, d_mvp_f + 16 * c, c, o);
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) g.m[i][j] = d_mvp_f[16 * c + 4 * i + j];
-        // dRig = P^T g B^T ; only the top 3 rows are needed
-        M4 pg;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float s = 0.f;
-#pragma unroll
-                for (int k = 0; k < 4; k++) s += p.m[k][i] * g.m[k][j];
-                pg.m[i][j] = s;
-            }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                float s = 0.f;
-#pragma unroll
-                for (int k = 0; k < 4; k++) s += pg.m[i][k] * b.m[j][k];
-                gR[i][j] += s;
-            }
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; k++) s += pg.m[i][k] * b.m[3][k];
-            gt[i] += s;
-        }
+        for (int i = 0; i < 12; i++) g[i] += o[i];
     }
-    d_t[3 * f] = gt[0]; d_t[3 * f + 1] = gt[1]; d_t[3 * f + 2] = gt[2];
-    d_q[4 * f + 0] = 2.f * (gR[0][0] * x + gR[0][1] * y + gR[0][2] * z + gR[1][0] * y - gR[1][1] * x - gR[1][2] * w + gR[2][0] * z + gR[2][1] * w - gR[2][2] * x);
-    d_q[4 * f + 1] = 2.f * (-gR[0][0] * y + gR[0][1] * x + gR[0][2] * w + gR[1][0] * x + gR[1][1] * y + gR[1][2] * z - gR[2][0] * w + gR[2][1] * z - gR[2][2] * y);
-    d_q[4 * f + 2] = 2.f * (-gR[0][0] * z - gR[0][1] * w + gR[0][2] * x + gR[1][0] * w - gR[1][1] * z + gR[1][2] * y + gR[2][0] * x + gR[2][1] * y + gR[2][2] * z);
-    d_q[4 * f + 3] = 2.f * (gR[0][0] * w - gR[0][1] * z + gR[0][2] * y + gR[1][0] * z + gR[1][1] * w - gR[1][2] * x - gR[2][0] * y + gR[2][1] * x + gR[2][2] * w);
+    pose_backward_finish(q, f, g, d_t, d_q);
 }
 
 }  // namespace

@@ -57,12 +57,21 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
             }
         }
         rp.tri_info[gid] = info;
-        // buffers the consumer of the bins accumulates into (fused.cu): cleared here instead of by separate memsets
-        if (rp.clear_tri9) {
-            float* m = rp.clear_tri9 + gid * 9;
-#pragma unroll
-            for (int c = 0; c < 9; c++) m[c] = 0.f;
-        }
+    }
+    // buffers the consumer of the bins accumulates into (fused.cu): cleared here instead of by separate memsets.
+    // The CTA's chunk of the moment buffer is 9 * BIN_TPB contiguous floats (36-byte records: 16-byte aligned as a whole).
+    if (rp.clear_tri9) {
+        const int t0 = blockIdx.x * BIN_TPB;
+        const int nt = min(BIN_TPB, rp.T - t0);
+        float* m = rp.clear_tri9 + ((size_t)n * rp.T + t0) * 9;
+        const int nfl = nt * 9;
+        const int head = (int)(((16 - (reinterpret_cast<size_t>(m) & 15)) & 15) >> 2);      // floats up to 16-byte alignment
+        const int h = head < nfl ? head : nfl;
+        const int n4 = (nfl - h) >> 2;
+        if (threadIdx.x < h) m[threadIdx.x] = 0.f;
+        float4* m4 = reinterpret_cast<float4*>(m + h);
+        for (int i = threadIdx.x; i < n4; i += BIN_TPB) m4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = h + 4 * n4 + threadIdx.x; i < nfl; i += BIN_TPB) m[i] = 0.f;
     }
     if (rp.clear_vtx4)
         for (int v = t; v < rp.V; v += gridDim.x * BIN_TPB)
@@ -106,21 +115,62 @@ __global__ void __launch_bounds__(256) k_scan(RasterParams rp)
     }
 }
 
+// HIST variant: no k_scan launch — every CTA recomputes the exclusive scan of its instance's bin counters in shared
+// memory (NB <= 8192 ints: a few hundred cycles) and the first CTA of the instance publishes it for the fine kernels.
 template <bool HIST>
 __global__ void __launch_bounds__(BIN_TPB) k_fill(RasterParams rp)
 {
-    extern __shared__ int hist[];
+    extern __shared__ int hist[];            // HIST: hist [NB] | soff [NB]
+    __shared__ int warp_tot[32];
     const int n = blockIdx.y;
     const int t = blockIdx.x * BIN_TPB + threadIdx.x;
+    int* soff = hist + rp.NB;
     if (HIST) {
-        for (int b = threadIdx.x; b < rp.NB; b += BIN_TPB) hist[b] = 0;
+        const int per = (rp.NB + BIN_TPB - 1) / BIN_TPB;                 // consecutive bins per thread
+        const int b0 = threadIdx.x * per;
+        const int* cnt = rp.bin_count + (size_t)n * rp.NB;
+        int local = 0;
+        for (int k = 0; k < per; k++) {
+            int b = b0 + k;
+            int c = (b < rp.NB) ? cnt[b] : 0;
+            if (b < rp.NB) { hist[b] = 0; soff[b] = local; }
+            local += c;
+        }
+        int x = local;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane], xs = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, xs, d);
+                if (lane >= d) xs += y;
+            }
+            warp_tot[lane] = xs - w;                                     // exclusive over warps
+        }
+        __syncthreads();
+        const int base = warp_tot[warp] + x - local;                     // exclusive prefix of this thread's first bin
+        for (int k = 0; k < per; k++) {
+            int b = b0 + k;
+            if (b < rp.NB) {
+                int o = soff[b] + base;
+                soff[b] = o;
+                if (blockIdx.x == 0) rp.bin_offset[(size_t)n * rp.NB + b] = o;
+            }
+        }
         __syncthreads();
     }
     int info = (t < rp.T) ? rp.tri_info[(size_t)n * rp.T + t] : 0;
     const bool small = (info >> 22) == 1;
     const int bx0 = info & 1023, by0 = (info >> 10) & 1023, nbx = (info >> 20) & 1, nby = (info >> 21) & 1;
     int* pairs = rp.pairs + (size_t)n * 4 * rp.T;
-    const int* offset = rp.bin_offset + (size_t)n * rp.NB;
+    const int* offset = HIST ? soff : rp.bin_offset + (size_t)n * rp.NB;
     int* cursor = rp.bin_cursor + (size_t)n * rp.NB;
     if (!HIST) {
         if (small)
@@ -282,9 +332,12 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
         size_t hb = (size_t)rp.NB * sizeof(int);
         k_setup<true><<<grid, BIN_TPB, hb, stream>>>(rp);
         FPC_LAUNCH_CHECK();
-        k_scan<<<N, 256, 0, stream>>>(rp);
-        FPC_LAUNCH_CHECK();
-        k_fill<true><<<grid, BIN_TPB, hb, stream>>>(rp);
+        static bool fill_attr_set = false;
+        if (!fill_attr_set) {
+            FPC_CUDA(cudaFuncSetAttribute(k_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * HIST_MAX_BINS * (int)sizeof(int)));
+            fill_attr_set = true;
+        }
+        k_fill<true><<<grid, BIN_TPB, 2 * hb, stream>>>(rp);              // scans the bin counters itself
     } else {
         k_setup<false><<<grid, BIN_TPB, 0, stream>>>(rp);
         FPC_LAUNCH_CHECK();

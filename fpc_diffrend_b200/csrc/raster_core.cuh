@@ -66,7 +66,7 @@ struct SnappedTri {
 __device__ __forceinline__ bool snap_vertex(const float4& p, float sxs, float sys, int& sx, int& sy)
 {
     if (!(p.w > 0.f)) return false;
-    float rw = xdiv(1.0f, p.w);
+    float rw = xrcp(p.w);
     float xf = xadd(xmul(xmul(p.x, rw), sxs), sxs);
     float yf = xadd(xmul(xmul(p.y, rw), sys), sys);
     if (!(fabsf(xf) < SNAP_LIMIT) || !(fabsf(yf) < SNAP_LIMIT)) return false;

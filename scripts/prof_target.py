@@ -14,13 +14,10 @@ from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference  #
 workload = sys.argv[sys.argv.index('--workload') + 1] if '--workload' in sys.argv else 'config2'
 iters = int(sys.argv[sys.argv.index('--iters') + 1]) if '--iters' in sys.argv else 1
 wl = bench.WORKLOADS[workload]
-F = wl['F']
+F = int(sys.argv[sys.argv.index('--frames') + 1]) if '--frames' in sys.argv else wl['F']
 rig, w_all, t_all, q_all = bench.make_inputs(wl, F)
-ref_dtype = 'u8' if not wl['aa'] else 'f32'
-cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype=ref_dtype)
-ref = synthesize_reference(rig, w_all, t_all, q_all, cfg)
-if ref_dtype == 'u8':
-    ref = ref.round().clamp(0, 255).to(torch.uint8)
+cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype='u8')
+ref = synthesize_reference(rig, w_all, t_all, q_all, cfg, out_dtype=torch.uint8)
 sess = FitSession(rig, F, cfg)
 sess.set_reference(ref)
 for _ in range(3):

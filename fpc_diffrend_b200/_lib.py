@@ -39,6 +39,10 @@ SIGNATURES = {
     'fpc_blend_fwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     'fpc_blend_bwd_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_blend_bwd': (_I, [_P, _P, _I, _I, _I, _P, _P, _Z, _P]),
+    'fpc_blend_tc_supported': (_I, [_I, _I, _I]),
+    'fpc_blend_fwd_tc': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    'fpc_blend_bwd_tc_scratch_bytes': (_Z, [_I, _I, _I]),
+    'fpc_blend_bwd_tc': (_I, [_P, _P, _I, _I, _I, _P, _P, _Z, _P]),
     'fpc_pose_mvp_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     'fpc_pose_mvp_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     'fpc_project_fwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),

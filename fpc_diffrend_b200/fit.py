@@ -48,6 +48,7 @@ class FitConfig:
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
     fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
+    tc_blend: bool = None                 # frame batches: blend fwd/bwd as a TMA + tcgen05 3xTF32 GEMM (csrc/blend_tc.cu); None = auto
     fused_geometry: bool = None           # pose+blend+project in one kernel per direction (csrc/geometry.cu); None = auto
                                           # (small frame batches: D is re-read per frame there, the GEMM path is not)
 
@@ -152,7 +153,14 @@ class FitSession:
         if fg is None:
             fg = F <= 4
         self.use_geom_fused = bool(fg and L.fpc_geometry_fused_supported(V, B, F, C))
-        nbytes = max(L.fpc_geometry_bwd_scratch_bytes(V, B, F, C), L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_render_loss_fused_scratch_bytes(self.N, T, H, W),
+        tc = cfg.tc_blend
+        if tc is None:
+            tc = F >= 8
+        self.use_tc_blend = bool(tc and not self.use_geom_fused and L.fpc_blend_tc_supported(V * 3, B, F))
+        # the tensor-core backward wants both operands K-major: a transposed copy of D, made once
+        self.DT = self.D.t().contiguous() if self.use_tc_blend else None
+        nbytes = max(L.fpc_blend_bwd_tc_scratch_bytes(V * 3, B, F) if self.use_tc_blend else 0,
+                     L.fpc_geometry_bwd_scratch_bytes(V, B, F, C), L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_render_loss_fused_scratch_bytes(self.N, T, H, W),
                      L.fpc_blend_bwd_scratch_bytes(V * 3, B, F),
                      L.fpc_project_bwd_scratch_bytes(F, C, V), L.fpc_image_loss_scratch_bytes(self.N, H, W, Ch))
         self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
@@ -284,7 +292,10 @@ class FitSession:
                  _p(self.w), V, B, F, C, _p(self.mvp), _p(self.verts), _p(self.pos_clip), s); n += 1
         else:
             call('pose_mvp_fwd', 'fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, F, C, _p(self.mvp), s); n += 1
-            call('blend_fwd', 'fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
+            if self.use_tc_blend:
+                call('blend_fwd', 'fpc_blend_fwd_tc', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
+            else:
+                call('blend_fwd', 'fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
             call('project_fwd', 'fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
         if self.use_fused:
             return n + self._fused(True) if with_loss else self._fused(False)
@@ -369,7 +380,10 @@ class FitSession:
             return 2
         call('project_bwd', 'fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
              _p(self.scratch), self.scratch.numel(), s); n += 2
-        call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
+        if self.use_tc_blend:
+            call('blend_bwd', 'fpc_blend_bwd_tc', _p(self.DT), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
+        else:
+            call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
         call('pose_mvp_bwd', 'fpc_pose_mvp_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.d_mvp), F, C,
              _p(self.d_t), _p(self.d_q), s); n += 1
         return n

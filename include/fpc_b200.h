@@ -104,6 +104,17 @@ size_t fpc_blend_bwd_scratch_bytes(int R, int B, int F);
 int fpc_blend_bwd(const float* D, const float* d_verts, int R, int B, int F, float* d_w,
                   void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
+/* Tensor-core path for frame batches (north-star item 1): the same mathematics as fpc_blend_fwd / fpc_blend_bwd as one
+ * TMA + tcgen05 (kind::tf32, 3xTF32 hi/lo split: fp32-level accuracy) GEMM kernel with the accumulator in TMEM.
+ * fpc_blend_tc_supported() != 0 requires B % 4 == 0 and R % 4 == 0 (16-byte row pitches for TMA).
+ * The backward takes DT [B,R] = D^T (a transposed copy made once at set-up) so that both operands are K-major;
+ * it is a split-K GEMM over one wave of CTAs with a fixed-order second-stage sum (deterministic). */
+int fpc_blend_tc_supported(int R, int B, int F);
+int fpc_blend_fwd_tc(const float* D, const float* base, const float* w, int R, int B, int F, float* verts, fpc_stream_t stream);
+size_t fpc_blend_bwd_tc_scratch_bytes(int R, int B, int F);
+int fpc_blend_bwd_tc(const float* DT, const float* d_verts, int R, int B, int F, float* d_w,
+                     void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
 /* ---- pose + projection (replaces the MVP chain fit.py:546-553 with camera.rigid_grad camera.py:128-132 and
  *      roma.unitquat_to_rotmat, and camera.transform_clip camera.py:11-23) --------------------------------- */
 /* P [C,16], A [C,16] (= MV @ translate(0,170,0)), row-major 4x4; t [F,3], q [F,4] XYZW (not normalised);

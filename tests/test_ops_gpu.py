@@ -267,3 +267,45 @@ def test_full_size_properties(dr):
     rast, db, sec = G.rasterize_fwd(pc[4:5], rig.pos_idx, (1024, 1024), with_second=True)
     n_mism = _check_rast(out[4:5].cpu().numpy(), None, rast, db, sec)
     assert n_mism == 0
+
+
+@pytest.mark.parametrize('V,B,F', [(600, 8, 2), (20000, 200, 64), (1204, 36, 70), (333 * 4, 200, 9)])
+def test_blend_tensor_core(V, B, F):
+    """fpc_blend_fwd_tc / fpc_blend_bwd_tc (TMA + tcgen05 3xTF32 GEMM, TMEM accumulator) against a float64 reference:
+    the split must deliver fp32-level accuracy (plain TF32 would be ~1e-3 relative)."""
+    import ctypes
+    from fpc_diffrend_b200 import _lib
+    L = _lib.load()
+    R = 3 * V
+    assert L.fpc_blend_tc_supported(R, B, F)
+    g = torch.Generator().manual_seed(V + B + F)
+    D = (torch.randn(R, B, generator=g) * 0.5).float()
+    base = (torch.randn(R, generator=g) * 10).float()
+    w = torch.rand(F, B, generator=g).float()
+    dv = torch.randn(F, R, generator=g).float()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dD, dbase, dw_in, ddv = D.cuda(), base.cuda(), w.cuda(), dv.cuda()
+    verts = torch.full((F, R), float('nan'), device='cuda')
+    _lib.call('fpc_blend_fwd_tc', P(dD), P(dbase), P(dw_in), R, B, F, P(verts), s)
+    ref = base.double()[None] + w.double() @ D.double().t()
+    err = (verts.cpu().double() - ref).abs().max().item()
+    scale = (w.double().abs() @ D.double().abs().t()).max().item()
+    assert err <= 2e-6 * scale + 1e-6 * ref.abs().max().item(), (err, scale)
+    # the SIMT fp32 kernel is the like-for-like comparison
+    verts2 = torch.empty(F, R, device='cuda')
+    _lib.call('fpc_blend_fwd', P(dD), P(dbase), P(dw_in), R, B, F, P(verts2), s)
+    assert (verts - verts2).abs().max().item() <= 4e-6 * scale
+    # backward
+    DT = dD.t().contiguous()
+    nbytes = int(L.fpc_blend_bwd_tc_scratch_bytes(R, B, F))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    d_w = torch.full((F, B), float('nan'), device='cuda')
+    _lib.call('fpc_blend_bwd_tc', P(DT), P(ddv), R, B, F, P(d_w), P(scratch), nbytes, s)
+    ref_b = dv.double() @ D.double()
+    scale_b = (dv.double().abs() @ D.double().abs()).max().item()
+    err_b = (d_w.cpu().double() - ref_b).abs().max().item()
+    assert err_b <= 2e-6 * scale_b, (err_b, scale_b)
+    d_w2 = torch.full((F, B), float('nan'), device='cuda')
+    _lib.call('fpc_blend_bwd_tc', P(DT), P(ddv), R, B, F, P(d_w2), P(scratch), nbytes, s)
+    assert torch.equal(d_w, d_w2)          # deterministic

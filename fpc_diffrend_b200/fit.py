@@ -48,6 +48,12 @@ class FitConfig:
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
     fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
+    # mesh regularisers of the shipped loss (fit.py:578-582; main.py:37-40 ships 5000 / 0 / 0.05 / 0, and fit.py:580 passes
+    # 0.1 as the edge target).  Off by default: BASELINE's hot path is the image loss.
+    weight_laplacian: float = 0.0
+    weight_meshedge: float = 0.0
+    meshedge_target: float = 0.1
+    weight_normalconsistency: float = 0.0
     tc_blend: bool = None                 # frame batches: blend fwd/bwd as a TMA + tcgen05 3xTF32 GEMM (csrc/blend_tc.cu); None = auto
     fused_geometry: bool = None           # pose+blend+project in one kernel per direction (csrc/geometry.cu); None = auto
                                           # (small frame batches: D is re-read per frame there, the GEMM path is not)
@@ -147,6 +153,16 @@ class FitSession:
             sc = torch.empty(int(_lib.load().fpc_topology_scratch_bytes(T)), dtype=torch.uint8, device=dev)
             _lib.call('fpc_topology_build', _p(self.pos_idx), T, V, _p(self.tri_opp), _p(sc), sc.numel(), self._stream())
         self.ref = None
+        self.use_reg = any(x != 0.0 for x in (cfg.weight_laplacian, cfg.weight_meshedge, cfg.weight_normalconsistency))
+        if self.use_reg:
+            from .topology import build_topology
+            tp = build_topology(rig.pos_idx, V)
+            self.n_edges, self.n_quads = tp.E, tp.E2
+            self.nbr_off = torch.tensor(tp.nbr_off, dtype=torch.int32, device=dev)
+            self.nbr_idx = torch.tensor(tp.nbr_idx, dtype=torch.int32, device=dev)
+            self.edge_quads = torch.tensor(tp.edge_quads, dtype=torch.int32, device=dev).contiguous()
+            self.reg_terms = torch.zeros(F, 3, **f32)            # raw (laplacian, edge, normal-consistency) per frame
+            self.d_verts_reg = torch.empty(F, V * 3, **f32)
 
         L = _lib.load()
         fg = cfg.fused_geometry
@@ -160,6 +176,7 @@ class FitSession:
         # the tensor-core backward wants both operands K-major: a transposed copy of D, made once
         self.DT = self.D.t().contiguous() if self.use_tc_blend else None
         nbytes = max(L.fpc_blend_bwd_tc_scratch_bytes(V * 3, B, F) if self.use_tc_blend else 0,
+                     L.fpc_mesh_reg_scratch_bytes(F, V, self.n_quads) if self.use_reg else 0,
                      L.fpc_geometry_bwd_scratch_bytes(V, B, F, C), L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_render_loss_fused_scratch_bytes(self.N, T, H, W),
                      L.fpc_blend_bwd_scratch_bytes(V * 3, B, F),
                      L.fpc_project_bwd_scratch_bytes(F, C, V), L.fpc_image_loss_scratch_bytes(self.N, H, W, Ch))
@@ -374,12 +391,16 @@ class FitSession:
         F, V, B, C = self.F, self.V, self.B, self.C
         n = 0
         if self.use_geom_fused:
+            if self.use_reg:
+                n += self._mesh_reg(self.d_verts_reg, 0)
             call('geometry_bwd', 'fpc_geometry_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.D), _p(self.verts),
-                 _p(self.mvp), _p(self.g_pos), None, self.V, B, F, C, _p(self.d_w), _p(self.d_t), _p(self.d_q), None, None,
-                 _p(self.scratch), self.scratch.numel(), s)
-            return 2
+                 _p(self.mvp), _p(self.g_pos), _p(self.d_verts_reg) if self.use_reg else None, self.V, B, F, C,
+                 _p(self.d_w), _p(self.d_t), _p(self.d_q), None, None, _p(self.scratch), self.scratch.numel(), s)
+            return n + 2
         call('project_bwd', 'fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
              _p(self.scratch), self.scratch.numel(), s); n += 2
+        if self.use_reg:
+            n += self._mesh_reg(self.d_verts, 1)
         if self.use_tc_blend:
             call('blend_bwd', 'fpc_blend_bwd_tc', _p(self.DT), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
         else:
@@ -387,6 +408,16 @@ class FitSession:
         call('pose_mvp_bwd', 'fpc_pose_mvp_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.d_mvp), F, C,
              _p(self.d_t), _p(self.d_q), s); n += 1
         return n
+
+    def _mesh_reg(self, d_verts, accumulate):
+        """Mesh regularisers on the blended vertices (fit.py:578-582): adds their value to self.loss and their gradient
+        to / into d_verts [F,3V] before the D^T contraction."""
+        cfg = self.cfg
+        self._timed('mesh_reg', 'fpc_mesh_reg_fwd_bwd', _p(self.verts), self.F, self.V, _p(self.nbr_off), _p(self.nbr_idx), self.n_edges,
+                    _p(self.edge_quads), self.n_quads, cfg.weight_laplacian, cfg.weight_meshedge, cfg.meshedge_target,
+                    cfg.weight_normalconsistency, _p(self.loss), _p(self.reg_terms), _p(d_verts), accumulate,
+                    _p(self.scratch), self.scratch.numel(), self._stream())
+        return 3 + (2 if cfg.weight_normalconsistency != 0.0 else 0)
 
     def optimizer_step(self):
         cfg, s, call = self.cfg, self._stream(), self._timed

@@ -189,6 +189,21 @@ int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t
                              float* loss, float* grad_pos, float* rast_out, float* colour_out,
                              void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
+/* ---- mesh regularisers (replaces the pytorch3d terms of fit.py:578-582: weight_laplacian * laplacian(mesh)^2 +
+ *      weight_meshedge * mesh_edge_loss(mesh, target) + weight_normalconsistency * mesh_normal_consistency(mesh)) -------
+ * verts [F,V,3]; static topology (fpc_diffrend_b200/topology.py): neighbour CSR nbr_off [V+1] / nbr_idx [2E] over the E
+ * unique edges and edge_quads [E2,4] = (v0, v1, a, b) for every pair of faces sharing an edge (NULL allowed if w_nc == 0).
+ *   loss_accum [1] (nullable) += sum_f (w_lap lap_f^2 + w_edge edge_f + w_nc nc_f)
+ *   terms [F,3] (nullable)     = raw (lap_f, edge_f, nc_f)
+ *   d_verts [F,V,3]            = (accumulate ? += : =) gradient of that sum w.r.t. the vertices.
+ * The Laplacian and edge gradients are gathers over the CSR (deterministic); only the normal-consistency term (weight 0 in
+ * the shipped configuration, main.py:40) scatters with float REDs. */
+size_t fpc_mesh_reg_scratch_bytes(int F, int V, int E2);
+int fpc_mesh_reg_fwd_bwd(const float* verts, int F, int V, const int32_t* nbr_off, const int32_t* nbr_idx, int E,
+                         const int32_t* edge_quads, int E2, float w_lap, float w_edge, float edge_target, float w_nc,
+                         float* loss_accum, float* terms, float* d_verts, int accumulate,
+                         void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
 /* ---- Adam (replaces torch.optim.Adam + LambdaLR + quaternion renorm, fit.py:493-505,610-618) ---------------
  * p, g, m, v [n]; step_count [1]: device float holding the number of optimiser steps taken so far
  * (advanced by fpc_adam_advance after all parameter groups of an iteration have been stepped).

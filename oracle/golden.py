@@ -16,6 +16,9 @@ Restated reference code (file:line under /root/reference/src/torch):
   render()           fit.py:134-162 (background constant 45/255 at :161)
   image_loss()       fit.py:579 (first term)
   Adam + LambdaLR    fit.py:493-505,610-613 (torch.optim used directly)
+  mesh_regularisers() fit.py:578-582: pytorch3d.loss mesh_laplacian_smoothing(method='uniform') (squared by the
+                     reference), mesh_edge_loss, mesh_normal_consistency.  pytorch3d (unpinned, v0.7-era API) is not
+                     installed here: its published algorithms are restated below -> PARITY UNPINNED for these terms too.
 """
 import ctypes
 import os
@@ -325,3 +328,46 @@ def render(mvp, pos, pos_idx, resolution, *, uv=None, uv_idx=None, tex=None, vco
 def image_loss(ref, colour):
     """fit.py:579, first term: mean((ref - 255 colour)^2)."""
     return torch.mean((ref - colour * 255) ** 2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# mesh regularisers (fit.py:578-582), pytorch3d.loss semantics restated in plain torch (autograd gives the gradients)
+# ---------------------------------------------------------------------------------------------------------
+
+def mesh_laplacian_uniform(verts, edges):
+    """pytorch3d mesh_laplacian_smoothing(method='uniform') for one mesh: L = D^-1 A - I over the unique edges,
+    loss = (1/V) sum_i |(L v)_i|_2.  verts [V,3], edges [E,2] int64."""
+    V = verts.shape[0]
+    e0, e1 = edges[:, 0], edges[:, 1]
+    deg = torch.zeros(V, dtype=verts.dtype).index_add_(0, e0, torch.ones(e0.shape[0], dtype=verts.dtype))
+    deg = deg.index_add_(0, e1, torch.ones(e1.shape[0], dtype=verts.dtype))
+    nsum = torch.zeros_like(verts).index_add(0, e0, verts[e1]).index_add(0, e1, verts[e0])
+    inv = torch.where(deg > 0, 1.0 / deg.clamp(min=1), torch.zeros_like(deg))
+    lv = torch.where(deg[:, None] > 0, nsum * inv[:, None] - verts, torch.zeros_like(verts))
+    return lv.norm(dim=1).sum() / V
+
+
+def mesh_edge_loss(verts, edges, target_length=0.0):
+    """pytorch3d mesh_edge_loss: mean over unique edges of (|v0 - v1| - target)^2."""
+    d = (verts[edges[:, 0]] - verts[edges[:, 1]]).norm(dim=1, p=2)
+    return ((d - target_length) ** 2).sum() / edges.shape[0]
+
+
+def mesh_normal_consistency(verts, edge_quads):
+    """pytorch3d mesh_normal_consistency: faces (v0,v1,a), (v0,v1,b) sharing an edge,
+    n0 = (v1-v0) x (a-v0), n1 = (v1-v0) x (b-v0), loss = mean(1 - cos(n0, -n1))."""
+    if edge_quads.shape[0] == 0:
+        return verts.sum() * 0.0
+    v0, v1, a, b = (verts[edge_quads[:, k]] for k in range(4))
+    n0 = torch.cross(v1 - v0, a - v0, dim=1)
+    n1 = torch.cross(v1 - v0, b - v0, dim=1)
+    return (1.0 - torch.cosine_similarity(n0, -n1, dim=1)).sum() / edge_quads.shape[0]
+
+
+def mesh_regularisers(verts, edges, edge_quads, w_lap=5000.0, w_edge=0.0, edge_target=0.1, w_nc=0.0):
+    """The three mesh terms of fit.py:579-582 for one frame (weights: main.py:37-40; the reference passes 0.1 as the edge
+    target at fit.py:580).  Returns (total, (lap, edge, nc))."""
+    lap = mesh_laplacian_uniform(verts, edges)
+    edge = mesh_edge_loss(verts, edges, edge_target)
+    nc = mesh_normal_consistency(verts, edge_quads)
+    return w_lap * lap ** 2 + w_edge * edge + w_nc * nc, (lap, edge, nc)

@@ -117,6 +117,39 @@ def test_iteration_gradients(small_rig3, shading, use_aa, fused, geom):
     assert rel(s.d_q.cpu(), q.grad) < 1e-4
 
 
+@pytest.mark.parametrize('geom', [True, False])
+def test_iteration_with_mesh_regularisers(small_rig3, geom):
+    """Whole-iteration gradients with the shipped mesh terms on (fit.py:578-582): the GPU's d_w must equal the image-only
+    d_w plus D^T (d reg / d V) from the oracle's torch restatement, and the loss the sum of both."""
+    from fpc_diffrend_b200 import rig as rigmod, topology
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F = small_rig3, 152, 200, 2
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
+    kw = dict(resolution=(H, W), shading='vcol', fused_geometry=geom)
+    ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, FitConfig(**kw))
+    rng = np.random.default_rng(0)
+    w0 = (0.3 * rng.random((F, rig.B))).astype(np.float32)
+    out = {}
+    for name, reg in (('img', {}), ('reg', dict(weight_laplacian=5000.0, weight_meshedge=70.0, meshedge_target=0.05,
+                                                  weight_normalconsistency=400.0))):
+        s = FitSession(rig, F, FitConfig(**kw, **reg))
+        assert s.use_geom_fused == geom
+        s.set_reference(ref)
+        s.set_parameters(w=w0)
+        s.forward(); s.backward()
+        torch.cuda.synchronize()
+        out[name] = (float(s.loss), s.d_w.cpu().clone(), s.d_t.cpu().clone(), s.verts.cpu().clone())
+    tp = topology.build_topology(rig.pos_idx, rig.V)
+    verts = out['img'][3].reshape(F, -1, 3).clone().requires_grad_(True)
+    tot = sum(G.mesh_regularisers(verts[f], torch.tensor(tp.edges).long(), torch.tensor(tp.edge_quads).long(), 5000.0, 70.0, 0.05, 400.0)[0]
+              for f in range(F))
+    tot.backward()
+    d_w_reg = verts.grad.reshape(F, -1) @ torch.tensor(rig.D)            # D^T d V per frame
+    assert abs(out['reg'][0] - out['img'][0] - float(tot.detach())) <= 1e-5 * abs(out['reg'][0])
+    assert rel(out['reg'][1] - out['img'][1], d_w_reg) < 1e-4
+    assert rel(out['reg'][2], out['img'][2]) < 1e-5                        # the mesh terms do not see the pose (float REDs: not bitwise)
+
+
 def test_fitted_parameters_after_fixed_iterations(tiny_rig):
     """North-star: fitted activations after a fixed iteration count must match the reference path within tolerance.
     Deterministic all-frames schedule, 12 iterations, config 1 (1 camera 128x128, 1 frame)."""

@@ -234,7 +234,8 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
     col_out = torch.empty(N, H, W, C, device='cuda')
     nbytes = _lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W)
     scratch = torch.empty(int(nbytes), dtype=torch.uint8, device='cuda')
-    head = (P(d_pos), P(d_tri)) + ((P(cu(opp)),) if aa else ())
+    d_opp = cu(opp) if aa else None
+    head = (P(d_pos), P(d_tri)) + ((P(d_opp),) if aa else ())
     _lib.call('fpc_render_loss_fused_aa' if aa else 'fpc_render_loss_fused', *head, P(d_attr), P(d_idx), attr.shape[0], attr.shape[1], P(d_tex),
               tex.shape[0] if textured else 0, tex.shape[1] if textured else 0, P(d_ref), 1 if u8 else 0, N, V, T, H, W, C,
               G.BG, scale, P(loss), P(g_pos), P(rast_out), P(col_out), P(scratch), scratch.numel(),
@@ -309,3 +310,53 @@ def test_blend_tensor_core(V, B, F):
     d_w2 = torch.full((F, B), float('nan'), device='cuda')
     _lib.call('fpc_blend_bwd_tc', P(DT), P(ddv), R, B, F, P(d_w2), P(scratch), nbytes, s)
     assert torch.equal(d_w, d_w2)          # deterministic
+
+
+@pytest.mark.parametrize('weights', [(5000.0, 0.0, 0.1, 0.0), (5000.0, 70.0, 0.05, 400.0), (0.0, 3.0, 0.1, 0.0)])
+def test_mesh_regularisers(small_rig3, weights):
+    """fpc_mesh_reg_fwd_bwd vs the oracle's torch restatement of the pytorch3d terms of fit.py:578-582 (autograd)."""
+    import ctypes
+    from fpc_diffrend_b200 import _lib, topology
+    rig = small_rig3
+    w_lap, w_edge, target, w_nc = weights
+    tp = topology.build_topology(rig.pos_idx, rig.V)
+    F, V = 3, rig.V
+    rng = np.random.default_rng(4)
+    verts = (rig.v_base.reshape(1, V, 3) + rng.normal(size=(F, V, 3)) * 0.05).astype(np.float32)
+    # oracle
+    vt = torch.tensor(verts, requires_grad=True)
+    tot, terms_ref = 0.0, []
+    for f in range(F):
+        t, (lap, edge, nc) = G.mesh_regularisers(vt[f], torch.tensor(tp.edges).long(), torch.tensor(tp.edge_quads).long(), w_lap, w_edge, target, w_nc)
+        tot = tot + t
+        terms_ref.append([float(lap.detach()), float(edge.detach()), float(nc.detach())])
+    tot.backward()
+    # kernel
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    L = _lib.load()
+    nbytes = int(L.fpc_mesh_reg_scratch_bytes(F, V, tp.E2))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    loss = torch.full((1,), 2.5, device='cuda')
+    terms = torch.zeros(F, 3, device='cuda')
+    base_grad = torch.randn(F, V, 3, device='cuda')
+    d_in, d_off, d_idx, d_quads = cu(verts), cu(tp.nbr_off), cu(tp.nbr_idx), cu(tp.edge_quads)     # keep the device copies alive
+    for acc in (0, 1):
+        d_verts = base_grad.clone()
+        loss.fill_(2.5)
+        _lib.call('fpc_mesh_reg_fwd_bwd', P(d_in), F, V, P(d_off), P(d_idx), tp.E, P(d_quads), tp.E2,
+                  w_lap, w_edge, target, w_nc, P(loss), P(terms), P(d_verts), acc, P(scratch), nbytes,
+                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        if acc:      # += : compare the sum (subtracting base_grad back would only measure cancellation)
+            want = base_grad.cpu().numpy() + vt.grad.numpy()
+            assert np.abs(d_verts.cpu().numpy() - want).max() <= 2e-6 * np.abs(want).max() + 1e-4 * np.abs(vt.grad.numpy()).max()
+        else:
+            assert rel_err(d_verts.cpu().numpy(), vt.grad.numpy()) < REL_GRAD, rel_err(d_verts.cpu().numpy(), vt.grad.numpy())
+        assert abs(float(loss) - 2.5 - float(tot.detach())) <= 1e-5 * max(1.0, abs(float(tot.detach())))
+    t_ref = np.array(terms_ref)
+    t_got = terms.cpu().numpy()
+    assert np.abs(t_got[:, 0] - t_ref[:, 0]).max() <= 1e-5 * max(1.0, np.abs(t_ref[:, 0]).max())
+    if w_edge != 0.0:
+        assert np.abs(t_got[:, 1] - t_ref[:, 1]).max() <= 1e-5 * max(1.0, np.abs(t_ref[:, 1]).max())
+    if w_nc != 0.0:
+        assert np.abs(t_got[:, 2] - t_ref[:, 2]).max() <= 1e-5

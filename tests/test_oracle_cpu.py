@@ -216,3 +216,52 @@ def test_torch_stages(tiny_rig):
     assert torch.allclose(img[0, 0], torch.tensor(G.BG))            # corner pixel is background 45/255
     ref = torch.clamp(img * 255, 0, 140)
     assert float(G.image_loss(ref, img)) < 1e-6
+
+
+def test_mesh_topology_and_regularisers(small_rig3):
+    """Static topology of a closed genus-0 mesh (E = 3V - 6, every edge has two faces) and the torch restatement of the
+    pytorch3d mesh terms (fit.py:578-582): known values on simple shapes + float64 gradcheck."""
+    import torch
+    from fpc_diffrend_b200 import topology
+    from oracle import golden as G
+    rig = small_rig3
+    tp = topology.build_topology(rig.pos_idx, rig.V)
+    assert tp.E == 3 * rig.V - 6 and tp.E2 == tp.E and tp.nbr_off[-1] == 2 * tp.E
+    assert (tp.edges[:, 0] < tp.edges[:, 1]).all()
+    # neighbour lists = the reference's own builder (data.py:44-66) without its padding
+    ref_nb = [set() for _ in range(rig.V)]
+    for a, b, c in rig.pos_idx:
+        ref_nb[a].update((b, c)); ref_nb[b].update((a, c)); ref_nb[c].update((a, b))
+    for i in (0, 1, rig.V // 2, rig.V - 1):
+        assert set(tp.nbr_idx[tp.nbr_off[i]:tp.nbr_off[i + 1]].tolist()) == ref_nb[i]
+    # a flat regular patch has zero normal-consistency loss; a unit square's diagonal edge pair likewise
+    quad = torch.tensor([[0., 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], dtype=torch.float64)
+    tq = topology.build_topology(np.array([[0, 1, 2], [0, 2, 3]]), 4)
+    assert tq.E == 5 and tq.E2 == 1
+    assert abs(float(G.mesh_normal_consistency(quad, torch.tensor(tq.edge_quads).long()))) < 1e-12
+    folded = quad.clone(); folded[3, 2] = 1.0; folded[3, 1] = 0.0      # fold the second face by 90 degrees about... the diagonal changes
+    assert float(G.mesh_normal_consistency(folded, torch.tensor(tq.edge_quads).long())) > 0.1
+    # edge loss: all edges of the unit square + diagonal against their own mean
+    el = float(G.mesh_edge_loss(quad, torch.tensor(tq.edges).long(), 1.0))
+    assert abs(el - (2 ** 0.5 - 1) ** 2 / 5) < 1e-12
+    # uniform Laplacian of a regular polygon fan centre is 0; of a displaced centre it is the displacement / V
+    n = 6
+    ring = torch.tensor([[np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n), 0.0] for k in range(n)], dtype=torch.float64)
+    fan = torch.cat([torch.zeros(1, 3, dtype=torch.float64), ring])
+    tf = topology.build_topology(np.array([[0, 1 + k, 1 + (k + 1) % n] for k in range(n)]), n + 1)
+    lv0 = G.mesh_laplacian_uniform(fan, torch.tensor(tf.edges).long())
+    fan2 = fan.clone(); fan2[0, 2] = 0.5
+    lv1 = G.mesh_laplacian_uniform(fan2, torch.tensor(tf.edges).long())
+    rim = (fan[[2, 6, 0]].mean(0) - fan[1]).norm()          # every rim vertex: mean of its 3 neighbours minus itself
+    assert abs(float(lv0) - float(n * rim / (n + 1))) < 1e-12
+    assert float(lv1) > float(lv0)
+    # gradcheck of the combined term on the rig (float64)
+    v = torch.tensor(rig.v_base, dtype=torch.float64).reshape(-1, 3)[:rig.V].clone().requires_grad_(True)
+    e, q = torch.tensor(tp.edges).long(), torch.tensor(tp.edge_quads).long()
+    f = lambda x: G.mesh_regularisers(x, e, q, 5000.0, 70.0, 0.05, 400.0)[0]
+    tot = f(v); tot.backward()
+    rng = np.random.default_rng(0)
+    d = torch.tensor(rng.normal(size=v.shape))
+    h = 1e-6
+    fd = (f(v.detach() + h * d) - f(v.detach() - h * d)) / (2 * h)
+    assert abs(float(fd) - float((v.grad * d).sum())) <= 1e-6 * abs(float(fd)) + 1e-8

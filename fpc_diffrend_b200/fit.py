@@ -199,7 +199,12 @@ class FitSession:
             ref = ref if ref.dtype == torch.uint8 else ref.round().clamp(0, 255).to(torch.uint8)
         else:
             ref = ref.to(torch.float32)
-        self.ref = ref.reshape(self.N, self.H, self.W, self.Ch).contiguous()
+        ref = ref.reshape(self.N, self.H, self.W, self.Ch)
+        if self.ref is not None and self.ref.dtype == ref.dtype and self.ref.shape == ref.shape:
+            self.ref.copy_(ref)                       # same buffer: a captured graph keeps reading the right frames
+        else:
+            self.ref = ref.contiguous()
+            self.graph = None
 
     def iteration_from_host(self, frames_host, loss_host=None):
         """One step with HOST buffers, unpipelined: upload this step's reference frames (pinned host memory -> the

@@ -292,3 +292,48 @@ def test_camera_split_two_gpus(tmp_path):
     s.iteration()
     torch.cuda.synchronize()
     assert rel(got['grads'], s.grads.cpu()) < 1e-5
+
+
+def test_fit_take_from_disk(tmp_path):
+    """The callers / formats either side of the hot path: a synthetic take written in the reference's
+    on-disk layout (OBJ base + blendshape directory, calibration.json, <cam>/<cam>_NN.tif) is fitted by fit_take and the
+    results come back in the reference's output layout; the image loss of every frame batch must decrease."""
+    import json
+    import os
+    from fpc_diffrend_b200 import dataio, rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, synthesize_reference
+    from fpc_diffrend_b200.take import fit_take
+    from test_host_cpu import _write_take
+    H, W, F = 96, 128, 3
+    rig = rigmod.make_rig(n_vertices=400, n_shapes=6, n_cams=2, width=W, height=H, tex_size=32, seed=2)
+    cams = ['take_%s' % k for k in rig.calib.keys()]
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=3)
+    w_true = np.full((F, rig.B), 0.8, np.float32) * (1.0 + 0.25 * np.arange(F, dtype=np.float32)[:, None])
+    cfg = FitConfig(resolution=(H, W), shading='texture', antialias=True)
+    ref = synthesize_reference(rig, w_true, 0.0 * t_true, q_true * 0 + np.array([0, 0, 0, 1], np.float32), cfg, out_dtype=torch.uint8)
+    base, bdir, imdir, calib = _write_take(tmp_path, rig, ref.cpu().numpy(), cams)
+    from PIL import Image
+    texpath = str(tmp_path / 'tex.png')
+    Image.fromarray((np.flip(rig.tex, 0) * 255).astype(np.uint8)[..., 0]).save(texpath)
+    out_dir = tmp_path / 'out'
+    out_dir.mkdir()
+    fit_cfg = FitConfig(shading='texture', antialias=True, lr_base=5e-3, optimize_pose=False, lr_ramp=1.0, max_iter=400, weight_laplacian=1.0)
+    res0 = fit_take(base, bdir, imdir, calib, None, iters_per_frame=0, frame_batch=2, cams=cams, texpath=texpath, config=fit_cfg,
+                    blend_order='sorted', use_graph=False)
+    res1 = fit_take(base, bdir, imdir, calib, None, iters_per_frame=1, frame_batch=2, cams=cams, texpath=texpath, config=fit_cfg,
+                    blend_order='sorted', use_graph=False)
+    res = fit_take(base, bdir, imdir, calib, str(out_dir), iters_per_frame=150, frame_batch=2, cams=cams, texpath=texpath, config=fit_cfg,
+                   blend_order='sorted')
+    assert all(b < a for a, b in zip(res1['loss'], res['loss'])), (res1['loss'], res['loss'])
+    assert res['vertices'].shape == (F, rig.V * 3) and res['w'].shape == (F, rig.B) and len(res['loss']) == 2
+    # zero iterations return the base mesh; the fit moves the vertices (the image loss above is what it minimises — with two
+    # views the 3-D shape itself is not uniquely determined, so no claim about the distance to the ground truth is made)
+    assert np.allclose(res0['vertices'], rig.v_base[None], atol=1e-5)
+    assert np.abs(res['vertices'] - rig.v_base[None]).max() > 1e-2 and np.abs(res['w']).max() > 1e-2
+    d = out_dir / 'result'
+    assert sorted(os.listdir(d)) == ['0.obj', '1.obj', '2.obj', 'pose.json', 'texture.png']
+    back = dataio.MeshData(str(d / '2.obj'))
+    assert np.array_equal(back.vertices, res['vertices'][2]) and np.array_equal(back.faces, rig.pos_idx)
+    pose = json.load(open(d / 'pose.json'))
+    assert np.allclose(pose['rotation'], res['q']) and np.allclose(pose['translation'], res['t'])
+    assert "iters_per_frame: '150'" in open(out_dir / 'config.txt').read()

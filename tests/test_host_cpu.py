@@ -138,3 +138,67 @@ def test_ops_refuse_cpu_tensors():
         dr.rasterize(ctx, torch.zeros(3, 4), torch.zeros(1, 3, dtype=torch.int32), resolution=(8, 8), ranges=torch.zeros(1, 2))
     with pytest.raises(RuntimeError, match='linear'):
         dr.texture(torch.zeros(1, 4, 4, 1), torch.zeros(1, 4, 4, 2), filter_mode='nearest')
+
+
+# ---- on-disk formats ------------------------------------------------------------------
+
+def _write_take(tmp_path, rig, frames_u8, cams):
+    """A synthetic take laid out like the reference's data: base.obj, blendshapes/*.obj, calibration.json, <cam>/<cam>_NN.tif."""
+    import json
+    from fpc_diffrend_b200 import dataio
+    rigmod.write_obj(str(tmp_path / 'base.obj'), rig.v_base, rig.uv, rig.pos_idx, rig.uv_idx)
+    bdir = tmp_path / 'blendshapes'
+    bdir.mkdir()
+    for b in range(rig.B):
+        rigmod.write_obj(str(bdir / ('shape_%03d.obj' % b)), rig.v_base + rig.D[:, b], rig.uv, rig.pos_idx, rig.uv_idx)
+    with open(tmp_path / 'calibration.json', 'w') as f:
+        json.dump(rig.calib, f)
+    imdir = tmp_path / 'frames'
+    imdir.mkdir()
+    F = frames_u8.shape[0]
+    digits = 2 if F < 100 else 3
+    for ci, c in enumerate(cams):
+        (imdir / c).mkdir()
+        for fi in range(F):
+            dataio.write_frame(str(imdir / c / ('%s_%0*d.tif' % (c, digits, fi))), frames_u8[fi, ci])
+    return str(tmp_path / 'base.obj'), str(bdir), str(imdir), str(tmp_path / 'calibration.json')
+
+
+def test_take_formats_roundtrip(tmp_path):
+    import json
+    from fpc_diffrend_b200 import dataio
+    rig = rigmod.make_rig(n_vertices=200, n_shapes=5, n_cams=2, width=40, height=24, tex_size=8, seed=1)
+    cams = ['take_%s' % k for k in rig.calib.keys()]
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, size=(3, 2, 24, 40, 1), dtype=np.uint8)
+    base, bdir, imdir, calib = _write_take(tmp_path, rig, frames, cams)
+    m = dataio.MeshData(base)
+    assert np.array_equal(m.vertices, rig.v_base) and np.array_equal(m.faces, rig.pos_idx)
+    assert np.array_equal(m.fuv, rig.uv_idx) and np.array_equal(m.uv, rig.uv)
+    D, names = dataio.load_blendshape_dir(bdir, m.vertices, order='sorted')
+    assert names == ['shape_%03d.obj' % b for b in range(rig.B)]
+    assert D.shape == rig.D.shape and np.abs(D - rig.D).max() <= 2e-6          # (base + delta) - base in float32
+    got_cams = dataio.list_cameras(imdir)
+    assert sorted(got_cams) == sorted(cams)
+    assert dataio.assert_num_frames(cams, imdir) == (3, 2)
+    ref = dataio.load_reference_frames(imdir, cams, [0, 1, 2])
+    assert ref.dtype == np.uint8 and ref.shape == (3, 2, 24, 40, 1)
+    assert np.array_equal(ref, np.clip(frames, 0, 140))                         # clip [0,140]; flip undone by write_frame
+    calibs = json.load(open(calib))
+    assert dataio.calibration_for(calibs, cams[0]) == rig.calib[cams[0].split('_')[1]]
+    # writers
+    out = tmp_path / 'out'
+    out.mkdir()
+    meshes = np.stack([rig.v_base, rig.v_base + 1.0])
+    t = rng.normal(size=(2, 3)).astype(np.float32)
+    q = np.tile(np.array([0, 0, 0, 1], np.float32), (2, 1))
+    d = dataio.save_results(meshes, rig.uv, rig.tex, t, q, str(out), faces_lines=dataio.faces_lines_for(rig.pos_idx, rig.uv_idx))
+    back = dataio.MeshData(os.path.join(d, '1.obj'))
+    assert np.array_equal(back.vertices, meshes[1]) and np.array_equal(back.faces, rig.pos_idx) and np.array_equal(back.fuv, rig.uv_idx)
+    pose = json.load(open(os.path.join(d, 'pose.json')))
+    assert list(pose.keys()) == ['rotation', 'translation'] and np.allclose(pose['translation'], t)
+    from PIL import Image
+    png = np.array(Image.open(os.path.join(d, 'texture.png')))
+    assert np.array_equal(png, (np.flip(rig.tex, 0) * 255).astype(np.uint8)[..., 0])
+    dataio.write_config(str(out), {'max_iter': 5, 'mode': 'prior'})
+    assert open(out / 'config.txt').read() == "max_iter: '5'\nmode: 'prior'\n"

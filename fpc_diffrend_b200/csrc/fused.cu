@@ -83,21 +83,29 @@ __device__ __forceinline__ void triangle_pos_grad(const float* m, float fx0, flo
 
 // Moments of (g0, g1, g2) = d loss / d (a0, a1, a2) per triangle: runs of equal triangle id inside the warp are combined
 // with a segmented shuffle reduction, then the head lane of each run issues <= 9 float REDs into M [T,9] (this view's
-// moment buffer).  tid = 0xFFFFFFFF on background; `an` = packed anchor pixel of the triangle (valid when live).
-// Must be called by all 32 lanes.
+// moment buffer).  tid = 0xFFFFFFFF on background; `an` = packed anchor pixel of the triangle (valid on every foreground lane).
+// The 32 lanes of a warp hold consecutive pixels of ONE image row (BIN is a multiple of 32), so the y-moments of a run are
+// ly * sum(g_k): only six values travel through the shuffles.  Must be called by all 32 lanes.
+#ifndef FPC_MOM6
+#define FPC_MOM6 1
+#endif
+static_assert(BIN % 32 == 0, "a warp must cover pixels of a single row");
 __device__ __forceinline__ void accumulate_moments(float* __restrict__ M, unsigned tid, bool live, float g0, float g1, float g2,
                                                    int px, int py, int an, int lane)
 {
     if (!__any_sync(0xffffffffu, live)) return;
-    float m[9];
-    float flx = 0.f, fly = 0.f;
-    if (live) {
-        flx = (float)(px - (an & 0xffff));
-        fly = (float)(py - (int)((unsigned)an >> 16));
-    }
+#if FPC_MOM6
+    constexpr int NM = 6;
+#else
+    constexpr int NM = 9;
+#endif
+    float m[NM];
+    const float flx = live ? (float)(px - (an & 0xffff)) : 0.f;
     m[0] = g0; m[1] = g1; m[2] = g2;
     m[3] = g0 * flx; m[4] = g1 * flx; m[5] = g2 * flx;
-    m[6] = g0 * fly; m[7] = g1 * fly; m[8] = g2 * fly;
+#if !FPC_MOM6
+    { const float fly = live ? (float)(py - (int)((unsigned)an >> 16)) : 0.f; m[6] = g0 * fly; m[7] = g1 * fly; m[8] = g2 * fly; }
+#endif
     // longest run of one triangle in this warp: shuffle steps with d >= that length combine nothing
     unsigned tprev = __shfl_up_sync(0xffffffffu, tid, 1);
     const bool head = (lane == 0) || (tprev != tid);
@@ -111,16 +119,27 @@ __device__ __forceinline__ void accumulate_moments(float* __restrict__ M, unsign
         unsigned to = __shfl_down_sync(0xffffffffu, tid, d);
         bool take = (lane + d < 32) && (to == tid);
 #pragma unroll
-        for (int c = 0; c < 9; c++) {
+        for (int c = 0; c < NM; c++) {
             float o = __shfl_down_sync(0xffffffffu, m[c], d);
             if (take) m[c] += o;
         }
     }
     if (tid != 0xFFFFFFFFu && head) {
+        // the head lane's anchor is the run's (callers load `an` for every foreground pixel, live or not)
+        const float ly = (float)(py - (int)((unsigned)an >> 16));
         float* Mt = M + (size_t)tid * 9;
 #pragma unroll
-        for (int c = 0; c < 9; c++)
+        for (int c = 0; c < NM; c++)
             if (m[c] != 0.f) atomicAdd(Mt + c, m[c]);
+#if FPC_MOM6
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float v = m[c] * ly;
+            if (v != 0.f) atomicAdd(Mt + 6 + c, v);
+        }
+#else
+        (void)ly;
+#endif
     }
 }
 

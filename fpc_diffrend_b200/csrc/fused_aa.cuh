@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
             int an = 0;
             const unsigned tid = idp1 - 1u;                               // 0xFFFFFFFF on background
             const bool live = (g0 != 0.f || g1 != 0.f || g2 != 0.f);
-            if (live) an = __ldg(rp.tri_anchor + (size_t)n * rp.T + tid);
+            if (idp1) an = __ldg(rp.tri_anchor + (size_t)n * rp.T + tid);
             accumulate_moments(fp.moments + (size_t)n * rp.T * 9, tid, live, g0, g1, g2, px, py, an, lane);
         }
     }

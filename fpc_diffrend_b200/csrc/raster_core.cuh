@@ -28,6 +28,12 @@ namespace fpc {
 #ifndef FPC_DYN_BATCH
 #define FPC_DYN_BATCH 1
 #endif
+#ifndef FPC_WALK_MASK
+#define FPC_WALK_MASK 1      // row coverage as a bit mask, then only the covered span is depth-tested
+#endif
+#ifndef FPC_CAS_MANUAL
+#define FPC_CAS_MANUAL 0     // 1: CAS loop seeded by the early-out read — measured 40 % SLOWER than atomicMin on B200
+#endif
 constexpr int BIN_LOG2 = FPC_BIN_LOG2;
 constexpr int BIN = 1 << BIN_LOG2;   // bin edge in pixels
 constexpr int FINE_THREADS = FPC_FINE_THREADS;
@@ -153,6 +159,23 @@ __device__ __forceinline__ unsigned depth_key(float zw)
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+// depth test + visibility update of one fragment at key slot kp; the CAS loop starts from the value the early-out read
+__device__ __forceinline__ void emit_fragment_at(unsigned long long* kp, float zd, int t)
+{
+    if (!(zd >= -1.f && zd <= 1.f)) return;
+    const unsigned long long key = ((unsigned long long)depth_key(zd) << 32) | (unsigned)t;
+#if FPC_CAS_MANUAL
+    unsigned long long old = *kp;
+    while (key < old) {
+        const unsigned long long prev = atomicCAS(kp, old, key);
+        if (prev == old) break;
+        old = prev;
+    }
+#else
+    if (key < *kp) atomicMin(kp, key);
+#endif
+}
+
 template <int TW>
 __device__ __forceinline__ void emit_fragment(unsigned long long* keys, float zd, int t, int lx, int ly)
 {
@@ -267,10 +290,34 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
             float zref = st.zref[j], dzdx = st.dzdx[j], dzdy = st.dzdy[j];
             int t = st.tri[j];
             float zrow = __fmaf_rn(dzdy, (float)dy, zref);
-            for (int x = 0; x < wd; x++) {
-                if ((e0 | e1 | e2) >= 0) emit_fragment<TW>(keys, __fmaf_rn(dzdx, (float)(dx + x), zrow), t, lx + x, ly);
+#if FPC_WALK_MASK
+            // coverage of the row as a 32-bit mask (branch-free body), then only the covered span — contiguous, the row cuts
+            // a convex region — is depth-tested: lanes do not idle through the misses.  Pixels beyond 32 (halo tiles only)
+            // take the plain per-pixel loop.
+            const int wm = min(wd, 32);
+            unsigned m = 0;
+            for (int x = 0; x < wm; x++) {
+                m |= ((unsigned)~(e0 | e1 | e2) >> 31) << x;
                 e0 += a0; e1 += a1; e2 += a2;
             }
+            if (m) {
+                const int first = __ffs(m) - 1, cnt = __popc(m);
+                unsigned long long* kp = keys + ly * TW + lx + first;
+                float xf = (float)(dx + first);
+                for (int c = 0; c < cnt; c++, kp++, xf += 1.f) emit_fragment_at(kp, __fmaf_rn(dzdx, xf, zrow), t);
+            }
+            if (TW > 32) {
+                for (int x = 32; x < wd; x++) {
+                    if ((e0 | e1 | e2) >= 0) emit_fragment_at(keys + ly * TW + lx + x, __fmaf_rn(dzdx, (float)(dx + x), zrow), t);
+                    e0 += a0; e1 += a1; e2 += a2;
+                }
+            }
+#else
+            for (int x = 0; x < wd; x++) {
+                if ((e0 | e1 | e2) >= 0) emit_fragment_at(keys + ly * TW + lx + x, __fmaf_rn(dzdx, (float)(dx + x), zrow), t);
+                e0 += a0; e1 += a1; e2 += a2;
+            }
+#endif
         }
         __syncwarp();
     }

@@ -24,13 +24,12 @@ def one(workload):
     import bench
     from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
     wl = bench.WORKLOADS[workload]
-    F = wl['F']
+    F = int(os.environ.get('FPC_EXP_FRAMES', '0')) or min(wl['F'], 4)
     rig, w_all, t_all, q_all = bench.make_inputs(wl, F)
-    ref_dtype = 'u8' if not wl['aa'] else 'f32'
-    cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype=ref_dtype)
-    ref = synthesize_reference(rig, w_all, t_all, q_all, cfg)
-    if ref_dtype == 'u8':
-        ref = ref.round().clamp(0, 255).to(torch.uint8)
+    # zero learning rates: the geometry (and with it the work per iteration) stays the same for every variant
+    cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype='u8',
+                    lr_base=0.0, lr_t=0.0, lr_q=0.0)
+    ref = synthesize_reference(rig, w_all, t_all, q_all, cfg, out_dtype=torch.uint8)
     sess = FitSession(rig, F, cfg)
     sess.set_reference(ref)
     sess.iteration()

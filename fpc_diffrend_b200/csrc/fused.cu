@@ -22,6 +22,7 @@ namespace {
 struct FusedParams {
     const float* attr;       // [Va, A]  vertex colours (A == C) or uv (A == 2, textured)
     const int32_t* attr_tri; // [T,3]
+    const int4* attr_tri4;   // [T] 16-byte copy (k_setup) or null when attr_tri == tri
     int Va, A;
     const float* tex;        // [Ht,Wt,C] or null
     int Ht, Wt;
@@ -291,28 +292,38 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             float su = 0.f, sv = 0.f, siw = 0.f;
             if (fg) {
                 int t = (int)(key & 0xFFFFFFFFu);
-                int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+                const int4 ti = tri_indices(rp, t);
+                const int i0 = ti.x, i1 = ti.y, i2 = ti.z;
                 if (fp.moments) an = __ldg(rp.tri_anchor + (size_t)n * rp.T + t);     // early: consumed by the moments below
                 float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
                 float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
                 ShadeLazy sh = shade_pixel_lazy(p0, p1, p2, fx, fy);
+                zn = sh.zn; wn = sh.wn;
                 float u = clamp01(sh.u), v = clamp01(sh.v);
                 su = sh.u; sv = sh.v; siw = sh.iw;
-                zn = sh.zn; wn = sh.wn;
                 rout = make_float4(u, v, 0.f, (float)(t + 1));
                 int j0 = i0, j1 = i1, j2 = i2;
-                if (fp.attr_tri != rp.tri) { j0 = __ldg(fp.attr_tri + 3 * t); j1 = __ldg(fp.attr_tri + 3 * t + 1); j2 = __ldg(fp.attr_tri + 3 * t + 2); }
+                if (fp.attr_tri4) { const int4 tj = __ldg(fp.attr_tri4 + t); j0 = tj.x; j1 = tj.y; j2 = tj.z; }
                 bool ok = (unsigned)j0 < (unsigned)fp.Va && (unsigned)j1 < (unsigned)fp.Va && (unsigned)j2 < (unsigned)fp.Va;
                 constexpr int AA = TEX ? 2 : C;
                 float b2 = 1.f - u - v;
                 float at[AA];
+                if (TEX) {           // uv pairs: one 8-byte load per corner
+                    const float2 z2 = make_float2(0.f, 0.f);
+                    const float2 q0 = ok ? __ldg(reinterpret_cast<const float2*>(fp.attr) + j0) : z2;
+                    const float2 q1 = ok ? __ldg(reinterpret_cast<const float2*>(fp.attr) + j1) : z2;
+                    const float2 q2 = ok ? __ldg(reinterpret_cast<const float2*>(fp.attr) + j2) : z2;
+                    a0c[0] = q0.x; a0c[AA - 1] = q0.y; a1c[0] = q1.x; a1c[AA - 1] = q1.y; a2c[0] = q2.x; a2c[AA - 1] = q2.y;
+                } else {
 #pragma unroll
-                for (int c = 0; c < AA; c++) {
-                    a0c[c] = ok ? __ldg(fp.attr + (size_t)j0 * AA + c) : 0.f;
-                    a1c[c] = ok ? __ldg(fp.attr + (size_t)j1 * AA + c) : 0.f;
-                    a2c[c] = ok ? __ldg(fp.attr + (size_t)j2 * AA + c) : 0.f;
-                    at[c] = u * a0c[c] + v * a1c[c] + b2 * a2c[c];
+                    for (int c = 0; c < AA; c++) {
+                        a0c[c] = ok ? __ldg(fp.attr + (size_t)j0 * AA + c) : 0.f;
+                        a1c[c] = ok ? __ldg(fp.attr + (size_t)j1 * AA + c) : 0.f;
+                        a2c[c] = ok ? __ldg(fp.attr + (size_t)j2 * AA + c) : 0.f;
+                    }
                 }
+#pragma unroll
+                for (int c = 0; c < AA; c++) at[c] = u * a0c[c] + v * a1c[c] + b2 * a2c[c];
                 if (TEX) {
                     // bilinear, wrap (texture.cu: tex_index)
                     float tu = at[0] - floorf(at[0]), tv = at[1] - floorf(at[1]);
@@ -404,7 +415,8 @@ __global__ void __launch_bounds__(256) k_tri_grad(RasterParams rp, const float* 
     for (int c = 0; c < 9; c++) { m[c] = M[c]; any = any || (m[c] != 0.f); }
     if (!any) return;
     int n = (int)(gid / rp.T), t = (int)(gid - (long long)n * rp.T);
-    int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+    const int4 ti = tri_indices(rp, t);
+    const int i0 = ti.x, i1 = ti.y, i2 = ti.z;
     const float* P = rp.pos + (size_t)n * rp.V * 4;
     float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
     int an = rp.tri_anchor[gid];
@@ -469,7 +481,8 @@ extern "C" size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W
 {
     if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return 256;
     int NB = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
-    return align256(raster_layout(N, T, NB).total) + align256((size_t)N * NB * sizeof(double)) + align256((size_t)N * T * 9 * sizeof(float));
+    return align256(raster_layout(N, T, NB).total) + align256((size_t)N * NB * sizeof(double)) + align256((size_t)N * T * 9 * sizeof(float)) +
+           align256((size_t)T * sizeof(int4));
 }
 
 static int render_loss_fused_impl(const char* who, const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
@@ -487,13 +500,16 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     RasterParams rp;
     const int NB0 = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
     double* loss_partial = (double*)((char*)scratch + align256(raster_layout(N, T, NB0).total));
-    float* moments = grad_pos ? (float*)((char*)loss_partial + align256((size_t)N * NB0 * sizeof(double))) : nullptr;
+    float* moments_mem = (float*)((char*)loss_partial + align256((size_t)N * NB0 * sizeof(double)));
+    float* moments = grad_pos ? moments_mem : nullptr;
+    int4* attr_tri4 = (attr_tri != tri) ? (int4*)((char*)moments_mem + align256((size_t)N * T * 9 * sizeof(float))) : nullptr;
     // k_setup clears the moment and gradient accumulators on its way (no separate memsets); with antialias the bins are
     // widened by the 2-px halo the fused kernel resolves around its bin
-    int st = raster_bin_triangles(who, pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, moments, grad_pos, tri_opp ? AA_HALO : 0);
+    int st = raster_bin_triangles(who, pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, moments, grad_pos, tri_opp ? AA_HALO : 0,
+                                  attr_tri4 ? attr_tri : nullptr, attr_tri4, T);
     if (st != FPC_OK) return st;
     FusedParams fp;
-    fp.attr = attr; fp.attr_tri = attr_tri; fp.Va = Va; fp.A = A; fp.tex = tex; fp.Ht = Ht; fp.Wt = Wt;
+    fp.attr = attr; fp.attr_tri = attr_tri; fp.attr_tri4 = attr_tri4; fp.Va = Va; fp.A = A; fp.tex = tex; fp.Ht = Ht; fp.Wt = Wt;
     fp.ref = ref; fp.ref_u8 = ref_is_u8; fp.C = C; fp.bg = bg; fp.k = scale / ((float)H * (float)W * (float)C);
     fp.grad_pos = grad_pos; fp.rast_out = rast_out; fp.colour_out = colour_out;
     fp.loss_partial = loss_partial;

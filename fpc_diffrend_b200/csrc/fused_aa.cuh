@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
         float4 rout = make_float4(0.f, 0.f, 0.f, 0.f);
         if (key != KEY_EMPTY) {       // only in-image pixels receive fragments
             int t = (int)(key & 0xFFFFFFFFu);
-            int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+            const int4 ti = tri_indices(rp, t);
+            const int i0 = ti.x, i1 = ti.y, i2 = ti.z;
             float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
             float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
             Shade sh = shade_pixel(p0, p1, p2, fx, fy);
@@ -180,18 +181,27 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
             rout = make_float4(u, v, zw, (float)(t + 1));
             slot = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned)(t + 1);
             int j0 = i0, j1 = i1, j2 = i2;
-            if (fp.attr_tri != rp.tri) { j0 = __ldg(fp.attr_tri + 3 * t); j1 = __ldg(fp.attr_tri + 3 * t + 1); j2 = __ldg(fp.attr_tri + 3 * t + 2); }
+            if (fp.attr_tri4) { const int4 tj = __ldg(fp.attr_tri4 + t); j0 = tj.x; j1 = tj.y; j2 = tj.z; }
             bool ok = (unsigned)j0 < (unsigned)fp.Va && (unsigned)j1 < (unsigned)fp.Va && (unsigned)j2 < (unsigned)fp.Va;
             constexpr int AA = TEX ? 2 : C;
             float b2 = 1.f - u - v;
             float a0c[AA], a1c[AA], a2c[AA], at[AA];
+            if (TEX) {               // uv pairs: one 8-byte load per corner
+                const float2 z2 = make_float2(0.f, 0.f);
+                const float2 q0 = ok ? __ldg(reinterpret_cast<const float2*>(fp.attr) + j0) : z2;
+                const float2 q1 = ok ? __ldg(reinterpret_cast<const float2*>(fp.attr) + j1) : z2;
+                const float2 q2 = ok ? __ldg(reinterpret_cast<const float2*>(fp.attr) + j2) : z2;
+                a0c[0] = q0.x; a0c[AA - 1] = q0.y; a1c[0] = q1.x; a1c[AA - 1] = q1.y; a2c[0] = q2.x; a2c[AA - 1] = q2.y;
+            } else {
 #pragma unroll
-            for (int c = 0; c < AA; c++) {
-                a0c[c] = ok ? __ldg(fp.attr + (size_t)j0 * AA + c) : 0.f;
-                a1c[c] = ok ? __ldg(fp.attr + (size_t)j1 * AA + c) : 0.f;
-                a2c[c] = ok ? __ldg(fp.attr + (size_t)j2 * AA + c) : 0.f;
-                at[c] = u * a0c[c] + v * a1c[c] + b2 * a2c[c];
+                for (int c = 0; c < AA; c++) {
+                    a0c[c] = ok ? __ldg(fp.attr + (size_t)j0 * AA + c) : 0.f;
+                    a1c[c] = ok ? __ldg(fp.attr + (size_t)j1 * AA + c) : 0.f;
+                    a2c[c] = ok ? __ldg(fp.attr + (size_t)j2 * AA + c) : 0.f;
+                }
             }
+#pragma unroll
+            for (int c = 0; c < AA; c++) at[c] = u * a0c[c] + v * a1c[c] + b2 * a2c[c];
             float ku[C], kv[C];        // d colour_c / d u, d colour_c / d v
             if (TEX) {
                 float dudc[C], dvdc[C];

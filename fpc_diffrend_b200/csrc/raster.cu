@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
         float4 p0, p1, p2;
         SnappedTri s;
         int info = 0;
-        if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
+        if (load_triangle<false>(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
             rp.tri_anchor[gid] = s.pxa | (s.pya << 16);
             const BinRange br = bin_range(s, rp);
             const int bx0 = br.bx0, bx1 = br.bx1, by0 = br.by0, by1 = br.by1;
@@ -72,6 +72,12 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
         float4* m4 = reinterpret_cast<float4*>(m + h);
         for (int i = threadIdx.x; i < n4; i += BIN_TPB) m4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = h + 4 * n4 + threadIdx.x; i < nfl; i += BIN_TPB) m[i] = 0.f;
+    }
+    if (n == 0) {
+        // 16-byte copies of the index / attribute arrays the per-pixel phases gather from (one load instead of three)
+        if (t < rp.T) rp.tri4[t] = make_int4(__ldg(rp.tri + 3 * t), __ldg(rp.tri + 3 * t + 1), __ldg(rp.tri + 3 * t + 2), 0);
+        for (int i = t; i < rp.pad_i_n; i += gridDim.x * BIN_TPB)
+            rp.pad_i_dst[i] = make_int4(__ldg(rp.pad_i_src + 3 * i), __ldg(rp.pad_i_src + 3 * i + 1), __ldg(rp.pad_i_src + 3 * i + 2), 0);
     }
     if (rp.clear_vtx4)
         for (int v = t; v < rp.V; v += gridDim.x * BIN_TPB)
@@ -220,7 +226,8 @@ __global__ void __launch_bounds__(FINE_THREADS) k_fine(RasterParams rp, float* _
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f), odb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (key != KEY_EMPTY) {
             int t = (int)(key & 0xFFFFFFFFu);
-            int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+            const int4 ti = tri_indices(rp, t);
+            const int i0 = ti.x, i1 = ti.y, i2 = ti.z;
             float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
             float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
             Shade sh = shade_pixel(p0, p1, p2, fx, fy);
@@ -297,13 +304,14 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_pairs = o;       o += align_up((size_t)N * T * 16);
     L.off_large = o;       o += align_up((size_t)N * T * 4);
     L.off_anchor = o;      o += align_up((size_t)N * T * 4);
+    L.off_tri4 = o;        o += align_up((size_t)T * 16);
     L.total = o;
     return L;
 }
 
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                          void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
-                         float* clear_tri9, float* clear_vtx4, int halo)
+                         float* clear_tri9, float* clear_vtx4, int halo, const int32_t* pad_i_src, int4* pad_i_dst, int pad_i_n)
 {
     FPC_CHECK_ARG(pos && tri, "%s: pos and tri must be non-null", who);
     FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "%s: N, V, T, H, W must be positive (got %d %d %d %d %d)", who, N, V, T, H, W);
@@ -325,6 +333,8 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.pairs = (int*)(s + L.off_pairs);
     rp.large_list = (int*)(s + L.off_large);
     rp.tri_anchor = (int*)(s + L.off_anchor);
+    rp.tri4 = (int4*)(s + L.off_tri4);
+    rp.pad_i_src = pad_i_src; rp.pad_i_dst = pad_i_dst; rp.pad_i_n = pad_i_src ? pad_i_n : 0;
     FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
     rp.clear_tri9 = clear_tri9; rp.clear_vtx4 = clear_vtx4;
     dim3 grid(fpc_div_up(T, BIN_TPB), N);

@@ -58,6 +58,8 @@ struct RasterParams {
     int* pairs;                      // [N*4T]
     int* large_list;                 // [N*T]
     int* tri_anchor;                 // [N*T]  pxa | pya << 16: first pixel of the image-clamped bbox (moment origin)
+    int4* tri4;                      // [T] (i0, i1, i2, 0): 16-byte copy of tri written by k_setup, one load per triangle
+    const int32_t* pad_i_src; int4* pad_i_dst; int pad_i_n;          // nullable job for k_setup: int [n,3] -> int4 [n]
     float* clear_tri9;               // nullable: [N*T*9] zeroed by k_setup (moment accumulators of fused.cu)
     float* clear_vtx4;               // nullable: [N*V*4] zeroed by k_setup (position-gradient accumulator)
 };
@@ -118,9 +120,15 @@ __device__ __forceinline__ bool is_small(const SnappedTri& s, const BinRange& r)
     return (s.maxx - s.minx) <= SMALL_EXTENT && (s.maxy - s.miny) <= SMALL_EXTENT && (r.bx1 - r.bx0) <= 1 && (r.by1 - r.by0) <= 1;
 }
 
+// vertex indices of triangle t from the 16-byte copy (valid in every kernel that runs after k_setup)
+__device__ __forceinline__ int4 tri_indices(const RasterParams& rp, int t) { return __ldg(rp.tri4 + t); }
+
+template <bool PADDED = true>
 __device__ __forceinline__ bool load_triangle(const RasterParams& rp, int n, int t, float4& p0, float4& p1, float4& p2)
 {
-    int i0 = __ldg(rp.tri + 3 * t), i1 = __ldg(rp.tri + 3 * t + 1), i2 = __ldg(rp.tri + 3 * t + 2);
+    int i0, i1, i2;
+    if (PADDED) { const int4 q = tri_indices(rp, t); i0 = q.x; i1 = q.y; i2 = q.z; }
+    else { i0 = __ldg(rp.tri + 3 * t); i1 = __ldg(rp.tri + 3 * t + 1); i2 = __ldg(rp.tri + 3 * t + 2); }
     if ((unsigned)i0 >= (unsigned)rp.V || (unsigned)i1 >= (unsigned)rp.V || (unsigned)i2 >= (unsigned)rp.V) return false;
     const float* P = rp.pos + (size_t)n * rp.V * 4;
     p0 = ldg4(P + 4 * (size_t)i0);
@@ -361,7 +369,7 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
 // Host side: scratch layout + the three binning launches.
 struct ScratchLayout {
     size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, total;
+    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, total;
 };
 
 ScratchLayout raster_layout(int N, int T, int NB);
@@ -369,6 +377,7 @@ ScratchLayout raster_layout(int N, int T, int NB);
 // clear_tri9 [N*T*9] / clear_vtx4 [N*V*4] (nullable) are zero-filled by k_setup on the way.
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                          void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
-                         float* clear_tri9 = nullptr, float* clear_vtx4 = nullptr, int halo = 0);
+                         float* clear_tri9 = nullptr, float* clear_vtx4 = nullptr, int halo = 0,
+                         const int32_t* pad_i_src = nullptr, int4* pad_i_dst = nullptr, int pad_i_n = 0);
 
 }  // namespace fpc

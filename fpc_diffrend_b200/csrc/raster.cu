@@ -39,21 +39,41 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
         float4 p0, p1, p2;
         SnappedTri s;
         int info = 0;
-        if (load_triangle<false>(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
-            rp.tri_anchor[gid] = s.pxa | (s.pya << 16);
-            const BinRange br = bin_range(s, rp);
-            const int bx0 = br.bx0, bx1 = br.bx1, by0 = br.by0, by1 = br.by1;
-            if (!is_small(s, br)) {
-                int slot = atomicAdd(rp.large_count + n, 1);
-                rp.large_list[(size_t)n * rp.T + slot] = t;
-                info = 2 << 22;
-            } else {
-                info = bx0 | (by0 << 10) | ((bx1 - bx0) << 20) | ((by1 - by0) << 21) | (1 << 22);
-                for (int by = by0; by <= by1; by++)
-                    for (int bx = bx0; bx <= bx1; bx++) {
-                        if (HIST) atomicAdd(hist + by * rp.BW + bx, 1);
-                        else atomicAdd(rp.bin_count + (size_t)n * rp.NB + by * rp.BW + bx, 1);
+        if (load_triangle<false>(rp, n, t, p0, p1, p2)) {
+            if (p0.w > 0.f && p1.w > 0.f && p2.w > 0.f) {
+                if (setup_triangle(p0, p1, p2, rp, s)) {
+                    rp.tri_anchor[gid] = s.pxa | (s.pya << 16);
+                    const BinRange br = bin_range(s, rp);
+                    const int bx0 = br.bx0, bx1 = br.bx1, by0 = br.by0, by1 = br.by1;
+                    if (!is_small(s, br)) {
+                        int slot = atomicAdd(rp.large_count + n, 1);
+                        rp.large_list[(size_t)n * 2 * rp.T + slot] = t;
+                        info = 2 << 22;
+                    } else {
+                        info = bx0 | (by0 << 10) | ((bx1 - bx0) << 20) | ((by1 - by0) << 21) | (1 << 22);
+                        for (int by = by0; by <= by1; by++)
+                            for (int bx = bx0; bx <= bx1; bx++) {
+                                if (HIST) atomicAdd(hist + by * rp.BW + bx, 1);
+                                else atomicAdd(rp.bin_count + (size_t)n * rp.NB + by * rp.BW + bx, 1);
+                            }
                     }
+                }
+            } else {
+                // a vertex at w <= 0: clip against the near plane; the (at most two) pieces go to the instance's large list
+                // with explicit vertices and compete under the parent's id (rare path: the whole CTA walks them)
+                const float4 v[3] = {p0, p1, p2};
+                float4 c[4];
+                const int nc = clip_near(v, c);
+                bool anchored = false;
+                for (int k = 0; k + 2 < nc; k++) {
+                    if (!setup_triangle(c[0], c[k + 1], c[k + 2], rp, s)) continue;
+                    const int slot = atomicAdd(rp.clip_count, 1);
+                    if (slot >= rp.clip_cap) break;                    // pool exhausted: piece dropped (sized N*T/32 + 1024)
+                    rp.clip_verts[3 * (size_t)slot] = c[0]; rp.clip_verts[3 * (size_t)slot + 1] = c[k + 1]; rp.clip_verts[3 * (size_t)slot + 2] = c[k + 2];
+                    rp.clip_parent[slot] = t;
+                    rp.large_list[(size_t)n * 2 * rp.T + atomicAdd(rp.large_count + n, 1)] = rp.T + slot;
+                    if (!anchored) { rp.tri_anchor[gid] = s.pxa | (s.pya << 16); anchored = true; }
+                }
             }
         }
         rp.tri_info[gid] = info;
@@ -298,11 +318,15 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_count = o;       o += align_up((size_t)N * NB * 4);
     L.off_cursor = o;      o += align_up((size_t)N * NB * 4);
     L.off_large_count = o; o += align_up((size_t)N * 4);
+    L.off_clip_count = o;  o += align_up(4);
     L.zero_bytes = o;
     L.off_offset = o;      o += align_up((size_t)N * NB * 4);
     L.off_info = o;        o += align_up((size_t)N * T * 4);
     L.off_pairs = o;       o += align_up((size_t)N * T * 16);
-    L.off_large = o;       o += align_up((size_t)N * T * 4);
+    L.off_large = o;       o += align_up((size_t)N * T * 8);
+    L.clip_cap = (int)(((size_t)N * T) / 32 + 1024 < 0x3fffffff ? ((size_t)N * T) / 32 + 1024 : 0x3fffffff);
+    L.off_clip_verts = o;  o += align_up((size_t)L.clip_cap * 48);
+    L.off_clip_parent = o; o += align_up((size_t)L.clip_cap * 4);
     L.off_anchor = o;      o += align_up((size_t)N * T * 4);
     L.off_tri4 = o;        o += align_up((size_t)T * 16);
     L.total = o;
@@ -334,6 +358,10 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.large_list = (int*)(s + L.off_large);
     rp.tri_anchor = (int*)(s + L.off_anchor);
     rp.tri4 = (int4*)(s + L.off_tri4);
+    rp.clip_count = (int*)(s + L.off_clip_count);
+    rp.clip_verts = (float4*)(s + L.off_clip_verts);
+    rp.clip_parent = (int*)(s + L.off_clip_parent);
+    rp.clip_cap = L.clip_cap;
     rp.pad_i_src = pad_i_src; rp.pad_i_dst = pad_i_dst; rp.pad_i_n = pad_i_src ? pad_i_n : 0;
     FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
     rp.clear_tri9 = clear_tri9; rp.clear_vtx4 = clear_vtx4;

@@ -56,7 +56,11 @@ struct RasterParams {
     int* bin_offset;                 // [N*NB]
     int* tri_info;                   // [N*T]
     int* pairs;                      // [N*4T]
-    int* large_list;                 // [N*T]
+    int* large_list;                 // [N*2T]  triangle ids, or T + slot of a clipped piece (clip_* below)
+    float4* clip_verts;              // [clip_cap*3] vertices of the pieces of near-clipped triangles
+    int* clip_parent;                // [clip_cap]   id of the triangle a piece belongs to
+    int* clip_count;                 // [1]          pieces allocated so far (all instances share the pool)
+    int clip_cap;
     int* tri_anchor;                 // [N*T]  pxa | pya << 16: first pixel of the image-clamped bbox (moment origin)
     int4* tri4;                      // [T] (i0, i1, i2, 0): 16-byte copy of tri written by k_setup, one load per triangle
     const int32_t* pad_i_src; int4* pad_i_dst; int pad_i_n;          // nullable job for k_setup: int [n,3] -> int4 [n]
@@ -123,9 +127,41 @@ __device__ __forceinline__ bool is_small(const SnappedTri& s, const BinRange& r)
 // vertex indices of triangle t from the 16-byte copy (valid in every kernel that runs after k_setup)
 __device__ __forceinline__ int4 tri_indices(const RasterParams& rp, int t) { return __ldg(rp.tri4 + t); }
 
+// Near-plane clipper, the exact mirror of oracle/golden.c: clip_near() / clip_lerp().
+__device__ __forceinline__ float4 clip_lerp(const float4& a, float da, const float4& b, float db)
+{
+    const float t = xdiv(da, xsub(da, db));
+    return make_float4(xadd(a.x, xmul(t, xsub(b.x, a.x))), xadd(a.y, xmul(t, xsub(b.y, a.y))),
+                       xadd(a.z, xmul(t, xsub(b.z, a.z))), xadd(a.w, xmul(t, xsub(b.w, a.w))));
+}
+
+__device__ __forceinline__ int clip_near(const float4 (&v)[3], float4 (&out)[4])
+{
+    float d[3];
+    bool in[3];
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { d[i] = xadd(v[i].z, v[i].w); in[i] = d[i] >= 0.f; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int j = (i + 1) % 3;
+        if (in[i]) out[n++] = v[i];
+        if (in[i] != in[j]) out[n++] = in[i] ? clip_lerp(v[i], d[i], v[j], d[j]) : clip_lerp(v[j], d[j], v[i], d[i]);
+    }
+    return n;
+}
+
+// id under which the fragments of list entry t compete: the triangle itself, or the parent of a clipped piece
+__device__ __forceinline__ int entry_triangle_id(const RasterParams& rp, int t) { return t < rp.T ? t : rp.clip_parent[t - rp.T]; }
+
 template <bool PADDED = true>
 __device__ __forceinline__ bool load_triangle(const RasterParams& rp, int n, int t, float4& p0, float4& p1, float4& p2)
 {
+    if (PADDED && t >= rp.T) {        // a piece of a near-clipped triangle: explicit vertices
+        const float4* c = rp.clip_verts + 3 * (size_t)(t - rp.T);
+        p0 = c[0]; p1 = c[1]; p2 = c[2];
+        return true;
+    }
     int i0, i1, i2;
     if (PADDED) { const int4 q = tri_indices(rp, t); i0 = q.x; i1 = q.y; i2 = q.z; }
     else { i0 = __ldg(rp.tri + 3 * t); i1 = __ldg(rp.tri + 3 * t + 1); i2 = __ldg(rp.tri + 3 * t + 2); }
@@ -331,7 +367,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
     }
 
     // ---- large triangles: the whole CTA cooperates on each one (16 pixels per thread), int64 edge math ----
-    const int* llist = rp.large_list + (size_t)n * rp.T;
+    const int* llist = rp.large_list + (size_t)n * 2 * rp.T;
     for (int i = 0; i < nlarge; i++) {
         int t = llist[i];
         float4 p0, p1, p2;
@@ -347,6 +383,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
         long long b1 = ex1 * (sy - ay1) - ey1 * (sx - ax1) + edge_bias64(ex1, ey1);
         long long b2 = ex2 * (sy - ay2) - ey2 * (sx - ax2) + edge_bias64(ex2, ey2);
         Plane pl = depth_plane(p0, p1, p2, s);
+        const int tid = entry_triangle_id(rp, t);
         for (int idx = threadIdx.x; idx < TW * TW; idx += FINE_THREADS) {
             int lx = idx % TW, ly = idx / TW;
             int px = ox + lx, py = oy + ly;
@@ -354,7 +391,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
             long long r0 = b0 - 16 * ey0 * lx + 16 * ex0 * ly;
             long long r1 = b1 - 16 * ey1 * lx + 16 * ex1 * ly;
             long long r2 = b2 - 16 * ey2 * lx + 16 * ex2 * ly;
-            if ((r0 | r1 | r2) >= 0) emit_fragment<TW>(keys, plane_eval(pl.zref, pl.dzdx, pl.dzdy, px - s.pxa, py - s.pya), t, lx, ly);
+            if ((r0 | r1 | r2) >= 0) emit_fragment<TW>(keys, plane_eval(pl.zref, pl.dzdx, pl.dzdy, px - s.pxa, py - s.pya), tid, lx, ly);
         }
     }
     __syncthreads();
@@ -369,7 +406,8 @@ __device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bi
 // Host side: scratch layout + the three binning launches.
 struct ScratchLayout {
     size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, total;
+    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_clip_count, off_clip_verts, off_clip_parent, total;
+    int clip_cap;
 };
 
 ScratchLayout raster_layout(int N, int T, int NB);

@@ -27,8 +27,9 @@
  *     per-vertex z/w in fp32, plane set-up in fp64 on the snapped vertices, per-fragment evaluation with two
  *     fp32 FMAs;  fragments whose plane depth is outside [-1,1] are discarded.  The z/w written to
  *     rast[...,2] is the fp32 value of the shading formula (what upstream's shader pass writes);
- *   - triangles with any w <= 0 or a window coordinate beyond +-2^20 px are dropped (no clipper yet;
- *     the fit never produces them: cameras look at the head from ~170 units, zn = 0.01).
+ *   - triangles with a vertex at w <= 0 are clipped against the near plane z + w >= 0 (clip_near()); the pieces keep
+ *     the parent's id and are shaded with the parent's vertices.  A (sub-)triangle with a window coordinate beyond
+ *     +-2^20 px is dropped (no guard-band clipper).
  *
  * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
  */
@@ -135,6 +136,79 @@ static inline int shade_pixel(f4 p0, f4 p1, f4 p2, int px, int py, int W, int H,
 /* rast [N,H,W,4] = (u, v, z/w, tri_id+1), rast_db [N,H,W,4] or NULL,
  * second_zw [N,H,W,2] or NULL: plane depth of the winning and of the runner-up fragment (2.0 if none) so tests
  * can mask depth near-ties. */
+/* Coverage + depth test of one (sub-)triangle with vertices p0,p1,p2 on behalf of triangle id t. */
+static void raster_one(f4 p0, f4 p1, f4 p2, int t, int H, int W, float* depth, float* depth2, int32_t* id)
+{
+    int32_t x0, y0, x1, y1, x2, y2;
+    if (!snap_vertex(p0, W, H, &x0, &y0) || !snap_vertex(p1, W, H, &x1, &y1) ||
+        !snap_vertex(p2, W, H, &x2, &y2)) return;
+    int64_t area = (int64_t)(x1 - x0) * (y2 - y0) - (int64_t)(x2 - x0) * (y1 - y0);
+    if (area == 0) return;
+    const int32_t qx1 = x1, qy1 = y1, qx2 = x2, qy2 = y2;   /* original order, for the depth plane */
+    if (area < 0) { int32_t tx = x1, ty = y1; x1 = x2; y1 = y2; x2 = tx; y2 = ty; }
+    int32_t minx = x0 < x1 ? (x0 < x2 ? x0 : x2) : (x1 < x2 ? x1 : x2);
+    int32_t maxx = x0 > x1 ? (x0 > x2 ? x0 : x2) : (x1 > x2 ? x1 : x2);
+    int32_t miny = y0 < y1 ? (y0 < y2 ? y0 : y2) : (y1 < y2 ? y1 : y2);
+    int32_t maxy = y0 > y1 ? (y0 > y2 ? y0 : y2) : (y1 > y2 ? y1 : y2);
+    /* pixel px is a candidate iff minx <= 16*px+8 <= maxx */
+    int pxa = (minx - 8 + 15) >> 4, pxb = (maxx - 8) >> 4;
+    int pya = (miny - 8 + 15) >> 4, pyb = (maxy - 8) >> 4;
+    if (pxa < 0) pxa = 0;
+    if (pya < 0) pya = 0;
+    if (pxb > W - 1) pxb = W - 1;
+    if (pyb > H - 1) pyb = H - 1;
+    if (pxa > pxb || pya > pyb) return;
+    int64_t ex[3] = { x1 - x0, x2 - x1, x0 - x2 };
+    int64_t ey[3] = { y1 - y0, y2 - y1, y0 - y2 };
+    int32_t ox[3] = { x0, x1, x2 }, oy[3] = { y0, y1, y2 };
+    int64_t bias[3];
+    for (int e = 0; e < 3; e++) bias[e] = edge_bias(ex[e], ey[e]);
+    plane_t pl = depth_plane(p0, p1, p2, x0, y0, qx1, qy1, qx2, qy2, pxa, pya);
+    for (int py = pya; py <= pyb; py++) {
+        for (int px = pxa; px <= pxb; px++) {
+            int64_t sx = 16 * px + 8, sy = 16 * py + 8;
+            int inside = 1;
+            for (int e = 0; e < 3; e++) {
+                int64_t E = ex[e] * (sy - oy[e]) - ey[e] * (sx - ox[e]) + bias[e];
+                if (E < 0) { inside = 0; break; }
+            }
+            if (!inside) continue;
+            float zd = plane_eval(pl, px - pxa, py - pya);
+            if (!(zd >= -1.0f && zd <= 1.0f)) continue;
+            size_t pi = (size_t)py * W + px;
+            if (zd < depth[pi]) { depth2[pi] = depth[pi]; depth[pi] = zd; id[pi] = t; }
+            else if (zd < depth2[pi]) depth2[pi] = zd;
+        }
+    }
+}
+
+/* Near-plane clipper (triangles with a vertex at w <= 0 are clipped, the pieces keep the parent id).
+ * Sutherland-Hodgman against z + w >= 0; a crossing is always interpolated from the INSIDE vertex towards the outside
+ * one, t = d_in / (d_in - d_out), so both triangles sharing the edge produce the same point (watertight).  out[4]. */
+static inline f4 clip_lerp(f4 a, float da, f4 b, float db)
+{
+    float t = da / (da - db);
+    f4 r;
+    r.x = a.x + t * (b.x - a.x);
+    r.y = a.y + t * (b.y - a.y);
+    r.z = a.z + t * (b.z - a.z);
+    r.w = a.w + t * (b.w - a.w);
+    return r;
+}
+
+static int clip_near(const f4* v, f4* out)
+{
+    float d[3];
+    int in[3], n = 0;
+    for (int i = 0; i < 3; i++) { d[i] = v[i].z + v[i].w; in[i] = d[i] >= 0.0f; }
+    for (int i = 0; i < 3; i++) {
+        int j = (i + 1) % 3;
+        if (in[i]) out[n++] = v[i];
+        if (in[i] != in[j]) out[n++] = in[i] ? clip_lerp(v[i], d[i], v[j], d[j]) : clip_lerp(v[j], d[j], v[i], d[i]);
+    }
+    return n;
+}
+
 void gold_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                         float* rast, float* rast_db, float* second_zw)
 {
@@ -149,47 +223,14 @@ void gold_rasterize_fwd(const float* pos, const int32_t* tri, int N, int V, int 
         for (int t = 0; t < T; t++) {
             int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
             if (i0 < 0 || i0 >= V || i1 < 0 || i1 >= V || i2 < 0 || i2 >= V) continue;
-            f4 p0 = P[i0], p1 = P[i1], p2 = P[i2];
-            int32_t x0, y0, x1, y1, x2, y2;
-            if (!snap_vertex(p0, W, H, &x0, &y0) || !snap_vertex(p1, W, H, &x1, &y1) ||
-                !snap_vertex(p2, W, H, &x2, &y2)) continue;
-            int64_t area = (int64_t)(x1 - x0) * (y2 - y0) - (int64_t)(x2 - x0) * (y1 - y0);
-            if (area == 0) continue;
-            const int32_t qx1 = x1, qy1 = y1, qx2 = x2, qy2 = y2;   /* original order, for the depth plane */
-            if (area < 0) { int32_t tx = x1, ty = y1; x1 = x2; y1 = y2; x2 = tx; y2 = ty; }
-            int32_t minx = x0 < x1 ? (x0 < x2 ? x0 : x2) : (x1 < x2 ? x1 : x2);
-            int32_t maxx = x0 > x1 ? (x0 > x2 ? x0 : x2) : (x1 > x2 ? x1 : x2);
-            int32_t miny = y0 < y1 ? (y0 < y2 ? y0 : y2) : (y1 < y2 ? y1 : y2);
-            int32_t maxy = y0 > y1 ? (y0 > y2 ? y0 : y2) : (y1 > y2 ? y1 : y2);
-            /* pixel px is a candidate iff minx <= 16*px+8 <= maxx */
-            int pxa = (minx - 8 + 15) >> 4, pxb = (maxx - 8) >> 4;
-            int pya = (miny - 8 + 15) >> 4, pyb = (maxy - 8) >> 4;
-            if (pxa < 0) pxa = 0;
-            if (pya < 0) pya = 0;
-            if (pxb > W - 1) pxb = W - 1;
-            if (pyb > H - 1) pyb = H - 1;
-            if (pxa > pxb || pya > pyb) continue;
-            int64_t ex[3] = { x1 - x0, x2 - x1, x0 - x2 };
-            int64_t ey[3] = { y1 - y0, y2 - y1, y0 - y2 };
-            int32_t ox[3] = { x0, x1, x2 }, oy[3] = { y0, y1, y2 };
-            int64_t bias[3];
-            for (int e = 0; e < 3; e++) bias[e] = edge_bias(ex[e], ey[e]);
-            plane_t pl = depth_plane(p0, p1, p2, x0, y0, qx1, qy1, qx2, qy2, pxa, pya);
-            for (int py = pya; py <= pyb; py++) {
-                for (int px = pxa; px <= pxb; px++) {
-                    int64_t sx = 16 * px + 8, sy = 16 * py + 8;
-                    int inside = 1;
-                    for (int e = 0; e < 3; e++) {
-                        int64_t E = ex[e] * (sy - oy[e]) - ey[e] * (sx - ox[e]) + bias[e];
-                        if (E < 0) { inside = 0; break; }
-                    }
-                    if (!inside) continue;
-                    float zd = plane_eval(pl, px - pxa, py - pya);
-                    if (!(zd >= -1.0f && zd <= 1.0f)) continue;
-                    size_t pi = (size_t)py * W + px;
-                    if (zd < depth[pi]) { depth2[pi] = depth[pi]; depth[pi] = zd; id[pi] = t; }
-                    else if (zd < depth2[pi]) depth2[pi] = zd;
-                }
+            f4 v[3] = { P[i0], P[i1], P[i2] };
+            if (v[0].w > 0.0f && v[1].w > 0.0f && v[2].w > 0.0f) {
+                raster_one(v[0], v[1], v[2], t, H, W, depth, depth2, id);
+            } else {
+                f4 c[4];
+                int nc = clip_near(v, c);
+                if (nc >= 3) raster_one(c[0], c[1], c[2], t, H, W, depth, depth2, id);
+                if (nc == 4) raster_one(c[0], c[2], c[3], t, H, W, depth, depth2, id);
             }
         }
         for (int py = 0; py < H; py++) {

@@ -360,3 +360,41 @@ def test_mesh_regularisers(small_rig3, weights):
         assert np.abs(t_got[:, 1] - t_ref[:, 1]).max() <= 1e-5 * max(1.0, np.abs(t_ref[:, 1]).max())
     if w_nc != 0.0:
         assert np.abs(t_got[:, 2] - t_ref[:, 2]).max() <= 1e-5
+
+
+def test_rasterize_near_plane_clipper(dr, small_rig3):
+    """GPU clipper vs the golden one: the mesh is pushed towards the camera until its front surface lies behind the near plane; ids must
+    match bit for bit (same clip arithmetic on both sides), values within the forward tolerance — op-level and fused."""
+    import ctypes
+    from fpc_diffrend_b200 import _lib
+    from test_oracle_cpu import _push_depth, _push_towards_camera
+    rig, H, W = small_rig3, 152, 200
+    pc = clip_positions(rig, w=np.linspace(0, 0.3, rig.B))
+    near = _push_towards_camera(pc, _push_depth(pc, rig.pos_idx))
+    rast, db, sec = G.rasterize_fwd(near, rig.pos_idx, (H, W), with_second=True)
+    assert (rast[..., 3] > 0).mean() > 0.05
+    ctx = dr.RasterizeCudaContext()
+    out, out_db = dr.rasterize(ctx, cu(near), cu(rig.pos_idx), resolution=(H, W))
+    assert _check_rast(out.cpu().numpy(), out_db.cpu().numpy(), rast, db, sec) == 0
+    # fused kernel on the same scene: loss and position gradient through clipped triangles
+    N, V, T, C = near.shape[0], rig.V, rig.T, 3
+    rng = np.random.default_rng(5)
+    attr = (rng.random((V, C)) * 0.5).astype(np.float32)
+    ref = np.round(rng.uniform(0, 140, size=(N, H, W, C))).astype(np.float32)
+    tp = torch.tensor(near, requires_grad=True)
+    r_o, _ = G.rasterize(tp, torch.tensor(rig.pos_idx), (H, W))
+    col_o = G.interpolate(torch.tensor(attr)[None], r_o, torch.tensor(rig.pos_idx))
+    comp_o = torch.where(r_o[..., 3:] > 0, col_o, torch.tensor(G.BG))
+    loss_o = sum(G.image_loss(torch.tensor(ref[n]), comp_o[n]) for n in range(N))
+    loss_o.backward()
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    d_pos, d_tri, d_attr, d_ref = cu(near), cu(rig.pos_idx), cu(attr), cu(ref.astype(np.uint8))
+    loss = torch.zeros(1, device='cuda')
+    g_pos = torch.empty(N, V, 4, device='cuda')
+    nbytes = int(_lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    _lib.call('fpc_render_loss_fused', P(d_pos), P(d_tri), P(d_attr), P(d_tri), V, C, None, 0, 0, P(d_ref), 1, N, V, T, H, W, C,
+              G.BG, 1.0, P(loss), P(g_pos), None, None, P(scratch), nbytes, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_o.detach())) / float(loss_o.detach()) < 1e-5
+    assert rel_err(g_pos.cpu().numpy(), tp.grad.numpy()) < REL_GRAD

@@ -54,7 +54,7 @@ def test_raster_depth_order_and_tie_break():
 
 def test_raster_drops_behind_camera_and_depth_range():
     pos, tri = _quad()
-    behind = pos.copy(); behind[0, 1, 3] = -1.0      # vertex 1 belongs to triangle 0 only: it is dropped (no clipper yet)
+    behind = pos.copy(); behind[0, 1, 3] = -1.0      # vertex 1 belongs to triangle 0 only; with z = 0 the whole triangle lies beyond the near plane: nothing survives the clipper
     rast, _, _ = G.rasterize_fwd(behind, tri, (16, 16))
     assert (rast[0, ..., 3] == 2.0).sum() > 0 and (rast[0, ..., 3] == 1.0).sum() == 0
     outside = pos.copy(); outside[..., 2] = 1.5      # z/w beyond the far plane: discarded
@@ -265,3 +265,64 @@ def test_mesh_topology_and_regularisers(small_rig3):
     h = 1e-6
     fd = (f(v.detach() + h * d) - f(v.detach() - h * d)) / (2 * h)
     assert abs(float(fd) - float((v.grad * d).sum())) <= 1e-6 * abs(float(fd)) + 1e-8
+
+
+def _push_towards_camera(pc, s, zn=0.01, zf=200.0):
+    """Clip-space positions of the same geometry moved s units towards the camera (standard projection of camera.py:27-41:
+    w = -z_eye, z_clip = A z_eye + B): the near plane then cuts through the mesh and part of it lies behind the camera."""
+    A = -(zf + zn) / (zf - zn)
+    out = pc.copy()
+    out[..., 2] = pc[..., 2] + np.float32(A * s)
+    out[..., 3] = pc[..., 3] - np.float32(s)
+    return out
+
+
+def _push_depth(pc, tri):
+    """Push distance that puts the surface point seen at the image centre of view 0 exactly on the near plane (w = zn), so
+    that the clip line of the triangle around it runs through the middle of the image."""
+    rast, _, _ = G.rasterize_fwd(pc[:1], tri, (65, 65), with_db=False)
+    u, v, _, idp1 = rast[0, 32, 32]
+    assert idp1 > 0
+    w3 = pc[0, tri[int(idp1) - 1], 3].astype(np.float64)
+    return float(u * w3[0] + v * w3[1] + (1 - u - v) * w3[2]) - 0.01
+
+
+def test_raster_near_plane_clipper(small_rig3):
+    """Triangles with a vertex at w <= 0 are clipped against the near plane, the pieces keep the parent id and are shaded
+    with the parent's vertices.  Properties: (1) perspective-correct barycentrics reproduce the pixel
+    centre for every covered pixel, including pixels of clipped triangles; (2) the coverage of a clipped triangle equals
+    the union of its pre-clipped pieces rasterized as ordinary triangles."""
+    rig = small_rig3
+    H, W = 96, 128
+    pc = clip_positions(rig)
+    near = _push_towards_camera(pc, _push_depth(pc, rig.pos_idx))   # the near plane cuts the front of the head at the image centre
+    assert (near[..., 3] <= 0).any() and (near[..., 3] > 0).any()
+    rast, _, _ = G.rasterize_fwd(near, rig.pos_idx, (H, W), with_db=False)
+    ids = rast[..., 3].astype(np.int64) - 1
+    clipped_tri = (near[:, rig.pos_idx, 3] <= 0).any(axis=2) & (near[:, rig.pos_idx, 3] > 0).any(axis=2)       # [C,T]
+    seen_clipped = 0
+    for n in range(near.shape[0]):
+        ys, xs = np.nonzero(ids[n] >= 0)
+        t = ids[n][ys, xs]
+        seen_clipped += int(clipped_tri[n][t].sum())
+        p = near[n][rig.pos_idx[t]].astype(np.float64)             # [K,3,4]
+        u, v = rast[n, ys, xs, 0].astype(np.float64), rast[n, ys, xs, 1].astype(np.float64)
+        b = np.stack([u, v, 1 - u - v], axis=1)[..., None]
+        q = (b * p).sum(axis=1)
+        fx, fy = (2 * xs + 1) / W - 1, (2 * ys + 1) / H - 1
+        inner = (u > 1e-6) & (v > 1e-6) & (u + v < 1 - 1e-6)         # the clamps bend the relation on the boundary
+        assert np.abs(q[inner, 0] / q[inner, 3] - fx[inner]).max() < 2e-4
+        assert np.abs(q[inner, 1] / q[inner, 3] - fy[inner]).max() < 2e-4
+        assert (q[inner, 3] > 0).all()                               # only the part in front of the camera is drawn
+    assert seen_clipped > 50, seen_clipped                            # pixels of clipped triangles do show up
+    # (2) one triangle, clipped by hand in float32 with the golden's formula
+    v = np.array([[[-0.5, -0.5, 0.2, 1.0], [0.5, -0.5, 0.2, 1.0], [0.1, 0.9, -1.5, -0.5]]], np.float32)
+    r1, _, _ = G.rasterize_fwd(v, np.array([[0, 1, 2]], np.int32), (64, 64), with_db=False)
+    d = v[0, :, 2] + v[0, :, 3]
+    lerp = lambda a, da, b, db: (a + (np.float32(da) / (np.float32(da) - np.float32(db))) * (b - a)).astype(np.float32)
+    c12, c20 = lerp(v[0, 1], d[1], v[0, 2], d[2]), lerp(v[0, 0], d[0], v[0, 2], d[2])
+    pieces = np.stack([v[0, 0], v[0, 1], c12, c20])[None]
+    r2, _, _ = G.rasterize_fwd(pieces, np.array([[0, 1, 2], [0, 2, 3]], np.int32), (64, 64), with_db=False)
+    assert (r1[..., 3] > 0).sum() > 100
+    assert np.array_equal(r1[..., 3] > 0, r2[..., 3] > 0)
+    assert np.abs(r1[..., 2] - r2[..., 2]).max() < 1e-5

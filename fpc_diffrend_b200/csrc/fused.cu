@@ -147,7 +147,7 @@ __device__ __forceinline__ void accumulate_moments(float* __restrict__ M, unsign
 // A bin no triangle touches: every pixel is background.  Its loss term sum (ref - 255 bg)^2 is streamed straight from
 // the reference frame (16-byte loads when the layout allows), optional image outputs are filled, nothing else runs.
 // Returns the CTA's partial loss in thread 0 via `red` (shared, FINE_WARPS doubles).
-template <int C>
+template <int C, int NT = FINE_THREADS>
 __device__ __forceinline__ void background_bin(const RasterParams& rp, const FusedParams& fp, int n, int bin, int ox, int oy, double* red)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -160,7 +160,7 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
     const bool fast = (wpx == BIN) && (row_bytes % 16 == 0) && ((reinterpret_cast<size_t>(rbase) & 15) == 0);
     if (fast) {
         const int cpr = (BIN * C * esz) >> 4;                    // 16-byte chunks per tile row
-        for (int i = threadIdx.x; i < rows * cpr; i += FINE_THREADS) {
+        for (int i = threadIdx.x; i < rows * cpr; i += NT) {
             int r = i / cpr, ch = i - r * cpr;
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(rbase + ((size_t)n * rp.H + oy + r) * row_bytes + (size_t)ox * C * esz + ch * 16));
             const unsigned w4[4] = {v.x, v.y, v.z, v.w};
@@ -183,7 +183,7 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
             acc += (double)sacc;
         }
     } else {
-        for (int i = threadIdx.x; i < rows * wpx * C; i += FINE_THREADS) {
+        for (int i = threadIdx.x; i < rows * wpx * C; i += NT) {
             int r = i / (wpx * C), e0 = i - r * (wpx * C);
             size_t gi = (((size_t)n * rp.H + oy + r) * rp.W + ox) * C + e0;
             float rv = fp.ref_u8 ? (float)__ldg(rbase + gi) : __ldg(reinterpret_cast<const float*>(rbase) + gi);
@@ -192,7 +192,7 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
         }
     }
     if (fp.rast_out || fp.colour_out) {
-        for (int i = threadIdx.x; i < rows * wpx; i += FINE_THREADS) {
+        for (int i = threadIdx.x; i < rows * wpx; i += NT) {
             int r = i / wpx, x = i - r * wpx;
             size_t pi = ((size_t)n * rp.H + oy + r) * rp.W + ox + x;
             if (fp.rast_out) reinterpret_cast<float4*>(fp.rast_out)[pi] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -207,7 +207,7 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int w = 0; w < FINE_WARPS; w++) t += red[w];
+        for (int w = 0; w < NT / 32; w++) t += red[w];
         fp.loss_partial[(size_t)n * rp.NB + bin] = t;
     }
 }
@@ -470,7 +470,7 @@ int launch_fused_aa(const RasterParams& rp, const FusedParams& fp, const int32_t
         FPC_CUDA(cudaFuncSetAttribute(k_fused_aa<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aa_smem_layout(C, 4).total));
         attr_set = true;
     }
-    k_fused_aa<C, TEX><<<dim3(rp.NB, rp.N), FINE_THREADS, aa_smem_layout(C, fp.ref_u8 ? 1 : 4).total, stream>>>(rp, fp, tri_opp);
+    k_fused_aa<C, TEX><<<dim3(rp.NB, rp.N), AA_THREADS, aa_smem_layout(C, fp.ref_u8 ? 1 : 4).total, stream>>>(rp, fp, tri_opp);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

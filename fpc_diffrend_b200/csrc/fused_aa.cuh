@@ -19,6 +19,16 @@
 
 namespace {
 
+// CTA size of the antialias kernel: 256 threads (8 warps) share one tile's ~60 KB of shared memory, 3 CTAs per SM = 24
+// resident warps (128-thread CTAs: 4 x 4 = 16 warps at the same footprint per tile; measured slower, see profiles/)
+#ifndef FPC_AA_THREADS
+#define FPC_AA_THREADS 256
+#endif
+#ifndef FPC_AA_MINBLOCKS
+#define FPC_AA_MINBLOCKS 3
+#endif
+constexpr int AA_THREADS = FPC_AA_THREADS;
+constexpr int AA_WARPS = AA_THREADS / 32;
 constexpr int AA_HALO = 2;
 constexpr int AA_TW = BIN + 2 * AA_HALO;       // tile edge
 constexpr int AA_NT = AA_TW * AA_TW;
@@ -38,7 +48,7 @@ __host__ __device__ inline AASmem aa_smem_layout(int C, int esz)
     AASmem L;
     size_t o = 0;
     L.keys = o; o += sizeof(unsigned long long) * AA_NT;
-    size_t r0 = sizeof(WarpStage) * FINE_WARPS;
+    size_t r0 = sizeof(WarpStage) * AA_WARPS;
     size_t lst = sizeof(unsigned short) * 2 * AA_NT;
     size_t gc = sizeof(float) * AA_R1 * AA_R1 * C;
     if (lst > r0) r0 = lst;
@@ -81,7 +91,7 @@ __device__ __forceinline__ void tex_bilinear(const FusedParams& fp, float au, fl
 }
 
 template <int C, bool TEX>
-__global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, FusedParams fp, const int32_t* __restrict__ tri_opp)
+__global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(RasterParams rp, FusedParams fp, const int32_t* __restrict__ tri_opp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int esz = fp.ref_u8 ? 1 : 4;
@@ -96,7 +106,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
     unsigned char* s_info = smem + L.info;
     float* s_coef = reinterpret_cast<float*>(smem + L.coef);
     unsigned char* s_ref = smem + L.ref;
-    __shared__ double red[FINE_WARPS];
+    __shared__ double red[AA_WARPS];
     __shared__ int s_nlist;
 
     const int bin = blockIdx.x, n = blockIdx.y;
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
 
     // bins are widened by the halo when triangles are binned: an empty list means an all-background tile
     if (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0) {
-        background_bin<C>(rp, fp, n, bin, ox, oy, red);
+        background_bin<C, AA_THREADS>(rp, fp, n, bin, ox, oy, red);
         return;
     }
 
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
         if (fast) {
             const int gpr = ref_pitch >> 2;                     // 4-byte granules per tile row
             const long long x_off = (long long)(ox - AA_REF_MARGIN) * C * esz;
-            for (int i = threadIdx.x; i < AA_R1 * gpr; i += FINE_THREADS) {
+            for (int i = threadIdx.x; i < AA_R1 * gpr; i += AA_THREADS) {
                 int r = i / gpr, g = i - r * gpr;
                 int py = oy - 1 + r;
                 long long b0 = x_off + 4 * g;
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
             }
         } else {
-            for (int i = threadIdx.x; i < AA_R1 * AA_REF_W * C; i += FINE_THREADS) {
+            for (int i = threadIdx.x; i < AA_R1 * AA_REF_W * C; i += AA_THREADS) {
                 int r = i / (AA_REF_W * C), e = i - r * (AA_REF_W * C);
                 int py = oy - 1 + r, px = ox - AA_REF_MARGIN + e / C;
                 if (py < 0 || py >= rp.H || px < 0 || px >= rp.W) continue;
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
     }
 
     // ---- (1) visibility of the widened tile ----
-    raster_tile<AA_TW>(rp, n, bin, tx0, ty0, keys, stage);
+    raster_tile<AA_TW, AA_THREADS>(rp, n, bin, tx0, ty0, keys, stage);
 
     // colour a background pixel hands to the antialias op: texture at uv = (0,0) or 0 (interpolate)
     float bgcol[C];
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
 
     // ---- (2) shade every tile pixel; the key slot becomes (z/w bits << 32 | id + 1) ----
     const float* P = rp.pos + (size_t)n * rp.V * 4;
-    for (int idx = threadIdx.x; idx < AA_NT; idx += FINE_THREADS) {
+    for (int idx = threadIdx.x; idx < AA_NT; idx += AA_THREADS) {
         const int tx = idx % AA_TW, ty = idx / AA_TW;
         const int px = tx0 + tx, py = ty0 + ty;
         const unsigned long long key = keys[idx];
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
     __syncthreads();
 
     // ---- (3a) work list of pixel pairs with different triangle ids (both pixels inside the tile and the image) ----
-    for (int base = 0; base < AA_NT; base += FINE_THREADS) {
+    for (int base = 0; base < AA_NT; base += AA_THREADS) {
         const int idx = base + threadIdx.x;
         bool cr = false, cu = false;
         if (idx < AA_NT) {
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
     ap.N = rp.N; ap.V = rp.V; ap.T = rp.T; ap.H = rp.H; ap.W = rp.W; ap.C = C;
     ap.xh = 0.5f * (float)rp.W; ap.yh = 0.5f * (float)rp.H;
     const int nlist = s_nlist;
-    for (int i = threadIdx.x; i < nlist; i += FINE_THREADS) {
+    for (int i = threadIdx.x; i < nlist; i += AA_THREADS) {
         const unsigned e = s_list[i];
         const int idx = e & 0x7fff, d = e >> 15;
         const int tx = idx % AA_TW, ty = idx / AA_TW;
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
 
     // ---- (4) ring-1 region: antialiased colour, loss (own pixels), d loss / d out ----
     double loss_acc = 0.0;
-    for (int r = threadIdx.x; r < AA_R1 * AA_R1; r += FINE_THREADS) {
+    for (int r = threadIdx.x; r < AA_R1 * AA_R1; r += AA_THREADS) {
         const int rx = r % AA_R1, ry = r / AA_R1;
         const int tx = rx + 1, ty = ry + 1, idx = ty * AA_TW + tx;
         const int px = tx0 + tx, py = ty0 + ty;
@@ -334,7 +344,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
     __syncthreads();
 
     // ---- (5) own pixels: d loss / d colour (gather over the 4 pairs), triangle moments, silhouette position gradient ----
-    for (int ii = threadIdx.x; ii < BIN * BIN; ii += FINE_THREADS) {
+    for (int ii = threadIdx.x; ii < BIN * BIN; ii += AA_THREADS) {
         const int ix = ii & (BIN - 1), iy = ii >> BIN_LOG2;
         const int tx = ix + AA_HALO, ty = iy + AA_HALO, idx = ty * AA_TW + tx;
         const int r = (iy + 1) * AA_R1 + (ix + 1);
@@ -396,7 +406,7 @@ __global__ void __launch_bounds__(FINE_THREADS, 4) k_fused_aa(RasterParams rp, F
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
-        for (int w = 0; w < FINE_WARPS; w++) s += red[w];
+        for (int w = 0; w < AA_WARPS; w++) s += red[w];
         fp.loss_partial[(size_t)n * rp.NB + bin] = s;
     }
 }

@@ -248,9 +248,9 @@ struct WarpStage {
 
 // Resolve the visibility of the TW x TW pixel tile with origin (ox, oy) — bin `bin` of instance n, widened by
 // rp.halo px on every side when TW == BIN + 2 halo (the origin may then be negative) — into keys[TW*TW] (shared
-// memory, initialised here).  `stage` is FINE_WARPS WarpStage records in shared memory.  All FINE_THREADS threads
+// memory, initialised here).  `stage` is NT/32 WarpStage records in shared memory.  All NT threads of the CTA
 // must call this.
-template <int TW>
+template <int TW, int NT = FINE_THREADS>
 __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int bin, int ox, int oy, unsigned long long* keys, WarpStage* stage)
 {
     const int min_x = max(ox, 0), min_y = max(oy, 0);
@@ -263,7 +263,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
     __shared__ int next_batch;       // warps claim batches of 32 triangles dynamically (balances uneven batches)
     if (threadIdx.x == 0) next_batch = 0;
 #endif
-    for (int i = threadIdx.x; i < TW * TW; i += FINE_THREADS) keys[i] = KEY_EMPTY;
+    for (int i = threadIdx.x; i < TW * TW; i += NT) keys[i] = KEY_EMPTY;
     __syncthreads();
 
     // ---- small triangles ----
@@ -276,7 +276,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
 #else
-    for (int base = warp * 32; base < count; base += FINE_THREADS) {
+    for (int base = warp * 32; base < count; base += NT) {
 #endif
         int i = base + lane;
         int rows = 0;
@@ -384,7 +384,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
         long long b2 = ex2 * (sy - ay2) - ey2 * (sx - ax2) + edge_bias64(ex2, ey2);
         Plane pl = depth_plane(p0, p1, p2, s);
         const int tid = entry_triangle_id(rp, t);
-        for (int idx = threadIdx.x; idx < TW * TW; idx += FINE_THREADS) {
+        for (int idx = threadIdx.x; idx < TW * TW; idx += NT) {
             int lx = idx % TW, ly = idx / TW;
             int px = ox + lx, py = oy + ly;
             if (px < xa || px > xb || py < ya || py > yb) continue;

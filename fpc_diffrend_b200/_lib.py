@@ -45,6 +45,7 @@ SIGNATURES = {
     'fpc_blend_bwd_tc': (_I, [_P, _P, _I, _I, _I, _P, _P, _Z, _P]),
     'fpc_pose_mvp_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     'fpc_pose_mvp_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    'fpc_pose_cam_bwd': (_I, [_P] * 7 + [_I, _I, _P, _P, _P]),
     'fpc_project_fwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),
     'fpc_project_bwd_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_project_bwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),

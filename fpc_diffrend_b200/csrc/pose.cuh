@@ -103,6 +103,46 @@ __device__ __forceinline__ void pose_backward_camera(const float* P, const float
     }
 }
 
+// Contribution of (frame f, camera c) to the gradient of the CAMERA's rigid correction Rigid(t_cam_c, q_cam_c)
+// (fit.py:443-448 t_opt / q_opt):  mvp = P Rf Rc A  ->  d Rc = (P Rf)^T d_mvp A^T.  out[0..8] = d R, out[9..11] = d t.
+__device__ __forceinline__ void cam_pose_backward_one(const float* P, const float* A, const float* t, const float* q,
+                                                      const float* d_mvp_fc, int f, int c, float* out)
+{
+    float tf[3] = {t[3 * f], t[3 * f + 1], t[3 * f + 2]};
+    float qf[4] = {q[4 * f], q[4 * f + 1], q[4 * f + 2], q[4 * f + 3]};
+    M4 pr = mul(load_m4(P + 16 * c), rigid(tf, qf));
+    M4 a = load_m4(A + 16 * c);
+    M4 g;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) g.m[i][j] = d_mvp_fc[4 * i + j];
+    M4 pg;      // (P Rf)^T g
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s += pr.m[k][i] * g.m[k][j];
+            pg.m[i][j] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s += pg.m[i][k] * a.m[j][k];
+            out[3 * i + j] = s;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) s += pg.m[i][k] * a.m[3][k];
+        out[9 + i] = s;
+    }
+}
+
 // summed contributions (d R [9], d t [3]) -> d_t[f], d_q[f]
 __device__ __forceinline__ void pose_backward_finish(const float* q, int f, const float* g, float* d_t, float* d_q)
 {

@@ -29,6 +29,23 @@ __global__ void k_pose_mvp_bwd(const float* __restrict__ P, const float* __restr
     pose_backward_frame(P, A, t, q, t_cam, q_cam, d_mvp + (size_t)f * C * 16, f, C, d_t, d_q);
 }
 
+// one thread per camera, frames summed in index order (deterministic): gradient of the per-camera pose corrections
+__global__ void k_pose_cam_bwd(const float* __restrict__ P, const float* __restrict__ A, const float* __restrict__ t,
+                               const float* __restrict__ q, const float* __restrict__ q_cam, const float* __restrict__ d_mvp,
+                               int F, int C, float* __restrict__ d_t_cam, float* __restrict__ d_q_cam)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float g[12] = {};
+    for (int f = 0; f < F; f++) {
+        float o[12];
+        cam_pose_backward_one(P, A, t, q, d_mvp + ((size_t)f * C + c) * 16, f, c, o);
+#pragma unroll
+        for (int i = 0; i < 12; i++) g[i] += o[i];
+    }
+    pose_backward_finish(q_cam, c, g, d_t_cam, d_q_cam);
+}
+
 // pos_clip[f*C+c, v, :] = mvp[f*C+c] @ (verts[f,v], 1)
 __global__ void __launch_bounds__(256) k_project_fwd(const float* __restrict__ verts, const float* __restrict__ mvp,
                                                      int F, int C, int V, float* __restrict__ pos_clip)
@@ -134,6 +151,17 @@ extern "C" int fpc_pose_mvp_bwd(const float* P, const float* A, const float* t, 
     FPC_CHECK_ARG((t_cam == nullptr) == (q_cam == nullptr), "pose_mvp_bwd: t_cam and q_cam must both be given or both be NULL");
     FPC_CHECK_ARG(F > 0 && C > 0, "pose_mvp_bwd: F and C must be positive");
     k_pose_mvp_bwd<<<fpc_div_up(F, 64), 64, 0, stream>>>(P, A, t, q, t_cam, q_cam, d_mvp, F, C, d_t, d_q);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+extern "C" int fpc_pose_cam_bwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
+                                const float* d_mvp, int F, int C, float* d_t_cam, float* d_q_cam, fpc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FPC_CHECK_ARG(P && A && t && q && t_cam && q_cam && d_mvp && d_t_cam && d_q_cam, "pose_cam_bwd: null pointer argument");
+    FPC_CHECK_ARG(F > 0 && C > 0, "pose_cam_bwd: F and C must be positive");
+    k_pose_cam_bwd<<<fpc_div_up(C, 32), 32, 0, stream>>>(P, A, t, q, q_cam, d_mvp, F, C, d_t_cam, d_q_cam);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

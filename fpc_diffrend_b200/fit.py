@@ -45,6 +45,7 @@ class FitConfig:
     bg: float = BG
     quat_norm: str = 'row'                # 'row' (default) or 'frobenius' (reference quirk)
     optimize_pose: bool = True
+    optimize_cam_pose: bool = False       # per-camera pose corrections t_opt / q_opt (fit.py:443-448,498-499), shared by all frames
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
     fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
@@ -120,6 +121,16 @@ class FitSession:
         self.d_w = self.grads[:nw].view(F, B)
         self.d_t = self.grads[nw:nw + nt].view(F, 3)
         self.d_q = self.grads[nw + nt:].view(F, 4)
+        # shared parameters: per-camera pose corrections [t_cam (C*3) | q_cam (C*4)] of the LOCAL cameras
+        self.cam_params = torch.zeros(C * 7, **f32)
+        self.cam_grads = torch.zeros_like(self.cam_params)
+        self.cam_m = torch.zeros_like(self.cam_params)
+        self.cam_v = torch.zeros_like(self.cam_params)
+        self.t_cam = self.cam_params[:C * 3].view(C, 3)
+        self.q_cam = self.cam_params[C * 3:].view(C, 4)
+        self.q_cam[:, 3] = 1.0
+        self.d_t_cam = self.cam_grads[:C * 3].view(C, 3)
+        self.d_q_cam = self.cam_grads[C * 3:].view(C, 4)
         self.step_count = torch.zeros(1, **f32)
         self.loss = torch.zeros(1, **f32)
 
@@ -310,10 +321,10 @@ class FitSession:
         F, V, T, B, C, H, W, N, Ch = self.F, self.V, self.T, self.B, self.C, self.H, self.W, self.N, self.Ch
         n = 0
         if self.use_geom_fused:
-            call('geometry_fwd', 'fpc_geometry_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.D), _p(self.v_base),
+            call('geometry_fwd', 'fpc_geometry_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), *self._cam(), _p(self.D), _p(self.v_base),
                  _p(self.w), V, B, F, C, _p(self.mvp), _p(self.verts), _p(self.pos_clip), s); n += 1
         else:
-            call('pose_mvp_fwd', 'fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, F, C, _p(self.mvp), s); n += 1
+            call('pose_mvp_fwd', 'fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), *self._cam(), F, C, _p(self.mvp), s); n += 1
             if self.use_tc_blend:
                 call('blend_fwd', 'fpc_blend_fwd_tc', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
             else:
@@ -398,10 +409,11 @@ class FitSession:
         if self.use_geom_fused:
             if self.use_reg:
                 n += self._mesh_reg(self.d_verts_reg, 0)
-            call('geometry_bwd', 'fpc_geometry_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.D), _p(self.verts),
+            call('geometry_bwd', 'fpc_geometry_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), *self._cam(), _p(self.D), _p(self.verts),
                  _p(self.mvp), _p(self.g_pos), _p(self.d_verts_reg) if self.use_reg else None, self.V, B, F, C,
-                 _p(self.d_w), _p(self.d_t), _p(self.d_q), None, None, _p(self.scratch), self.scratch.numel(), s)
-            return n + 2
+                 _p(self.d_w), _p(self.d_t), _p(self.d_q), None, _p(self.d_mvp) if self.cfg.optimize_cam_pose else None,
+                 _p(self.scratch), self.scratch.numel(), s)
+            return n + 2 + self._cam_pose_bwd()
         call('project_bwd', 'fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
              _p(self.scratch), self.scratch.numel(), s); n += 2
         if self.use_reg:
@@ -410,9 +422,20 @@ class FitSession:
             call('blend_bwd', 'fpc_blend_bwd_tc', _p(self.DT), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
         else:
             call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
-        call('pose_mvp_bwd', 'fpc_pose_mvp_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), None, None, _p(self.d_mvp), F, C,
+        call('pose_mvp_bwd', 'fpc_pose_mvp_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), *self._cam(), _p(self.d_mvp), F, C,
              _p(self.d_t), _p(self.d_q), s); n += 1
-        return n
+        return n + self._cam_pose_bwd()
+
+    def _cam(self):
+        """(t_cam, q_cam) pointers of the local cameras, or (None, None) = identity when they are not optimised."""
+        return (_p(self.t_cam), _p(self.q_cam)) if self.cfg.optimize_cam_pose else (None, None)
+
+    def _cam_pose_bwd(self):
+        if not self.cfg.optimize_cam_pose:
+            return 0
+        self._timed('pose_cam_bwd', 'fpc_pose_cam_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), _p(self.t_cam), _p(self.q_cam),
+                    _p(self.d_mvp), self.F, self.C, _p(self.d_t_cam), _p(self.d_q_cam), self._stream())
+        return 1
 
     def _mesh_reg(self, d_verts, accumulate):
         """Mesh regularisers on the blended vertices (fit.py:578-582): adds their value to self.loss and their gradient
@@ -430,6 +453,18 @@ class FitSession:
         n = 0
         if cfg.cam_slice is not None:
             allreduce_gradients(self.grads)            # the only exchange of the camera-split mode: (B+7) F floats
+        if cfg.optimize_cam_pose:
+            # shared by all frames: under frame sharding every rank holds a partial sum (camera-split ranks own their cameras)
+            if cfg.cam_slice is None:
+                allreduce_gradients(self.cam_grads)
+            C = self.C
+            adam_c = lambda off, cnt, lr: call('adam', 'fpc_adam_step', ctypes.c_void_p(self.cam_params.data_ptr() + 4 * off),
+                                               ctypes.c_void_p(self.cam_grads.data_ptr() + 4 * off),
+                                               ctypes.c_void_p(self.cam_m.data_ptr() + 4 * off),
+                                               ctypes.c_void_p(self.cam_v.data_ptr() + 4 * off), cnt, lr, cfg.beta1, cfg.beta2,
+                                               cfg.eps, cfg.lr_ramp, float(cfg.max_iter), _p(self.step_count), s)
+            adam_c(0, C * 3, cfg.lr_t); adam_c(C * 3, C * 4, cfg.lr_q)
+            call('adam', 'fpc_quat_renorm', _p(self.q_cam), C, 1 if cfg.quat_norm == 'frobenius' else 0, s); n += 3
         nw = F * B
         if F * (B + 7) <= (1 << 22):
             call('adam', 'fpc_adam_fused', _p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), B, F, 1 if cfg.optimize_pose else 0,

@@ -126,6 +126,10 @@ int fpc_pose_mvp_fwd(const float* P, const float* A, const float* t, const float
 int fpc_pose_mvp_bwd(const float* P, const float* A, const float* t, const float* q,
                      const float* t_cam, const float* q_cam, const float* d_mvp, int F, int C,
                      float* d_t, float* d_q, fpc_stream_t stream);
+/* Gradient of the per-camera pose corrections (t_opt / q_opt of fit.py:443-448, optimiser groups fit.py:498-499):
+ * d_mvp [F*C,16] -> d_t_cam [C,3], d_q_cam [C,4] (overwritten), summed over the F frames in index order. */
+int fpc_pose_cam_bwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
+                     const float* d_mvp, int F, int C, float* d_t_cam, float* d_q_cam, fpc_stream_t stream);
 /* verts [F,V,3], mvp [F*C,16] -> pos_clip [F*C,V,4] */
 int fpc_project_fwd(const float* verts, const float* mvp, int F, int C, int V, float* pos_clip, fpc_stream_t stream);
 /* d_pos_clip [F*C,V,4] -> d_verts [F,V,3] (overwritten), d_mvp [F*C,16] (overwritten) */

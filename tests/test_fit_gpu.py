@@ -150,6 +150,46 @@ def test_iteration_with_mesh_regularisers(small_rig3, geom):
     assert rel(out['reg'][2], out['img'][2]) < 1e-5                        # the mesh terms do not see the pose (float REDs: not bitwise)
 
 
+@pytest.mark.parametrize('geom', [True, False])
+def test_camera_pose_correction_gradients(small_rig3, geom):
+    """Per-camera pose corrections t_opt / q_opt (fit.py:443-448): forward through the MVP chain and the gradient summed over
+    the frames, against torch autograd through the oracle's mvp_chain fed the GPU's d mvp."""
+    from fpc_diffrend_b200 import rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F = small_rig3, 152, 200, 2
+    C = rig.P.shape[0]
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
+    cfg = FitConfig(resolution=(H, W), shading='vcol', fused_geometry=geom, optimize_cam_pose=True)
+    ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, FitConfig(resolution=(H, W), shading='vcol'))
+    s = FitSession(rig, F, cfg)
+    s.set_reference(ref)
+    rng = np.random.default_rng(3)
+    tc = (0.2 * rng.normal(size=(C, 3))).astype(np.float32)
+    qc = rng.normal(size=(C, 4)).astype(np.float32) * 0.02 + np.array([0, 0, 0, 1], np.float32)
+    qc /= np.linalg.norm(qc, axis=1, keepdims=True)
+    t0 = (0.1 * rng.normal(size=(F, 3))).astype(np.float32)
+    s.set_parameters(w=(0.05 * rng.random((F, rig.B))).astype(np.float32), t=t0)
+    s.t_cam.copy_(torch.tensor(tc)); s.q_cam.copy_(torch.tensor(qc))
+    s.forward(); s.backward()
+    torch.cuda.synchronize()
+    tct, qct = torch.tensor(tc, requires_grad=True), torch.tensor(qc, requires_grad=True)
+    tf, qf = s.t.cpu().clone().requires_grad_(True), s.q.cpu().clone().requires_grad_(True)
+    d_mvp = s.d_mvp.cpu().reshape(F, C, 4, 4)
+    tot = 0.0
+    for f in range(F):
+        for c in range(C):
+            mvp = G.mvp_chain(torch.tensor(rig.P[c]), torch.tensor(rig.A[c]), tf[f], qf[f], tct[c], qct[c])
+            assert rel(s.mvp[f * C + c].cpu().reshape(4, 4), mvp.detach()) < 1e-6
+            tot = tot + (mvp * d_mvp[f, c]).sum()
+    tot.backward()
+    assert rel(s.d_t_cam.cpu(), tct.grad) < 1e-4 and rel(s.d_q_cam.cpu(), qct.grad) < 1e-4
+    assert rel(s.d_t.cpu(), tf.grad) < 1e-4 and rel(s.d_q.cpu(), qf.grad) < 1e-4
+    before = s.cam_params.clone()
+    s.optimizer_step()
+    torch.cuda.synchronize()
+    assert (s.cam_params != before).any() and torch.allclose(s.q_cam.norm(dim=1), torch.ones(C, device='cuda'), atol=1e-6)
+
+
 def test_fitted_parameters_after_fixed_iterations(tiny_rig):
     """North-star: fitted activations after a fixed iteration count must match the reference path within tolerance.
     Deterministic all-frames schedule, 12 iterations, config 1 (1 camera 128x128, 1 frame)."""

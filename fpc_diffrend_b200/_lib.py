@@ -56,8 +56,8 @@ SIGNATURES = {
     'fpc_image_loss_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'fpc_image_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _Z, _P]),
     'fpc_render_loss_fused_scratch_bytes': (_Z, [_I, _I, _I, _I]),
-    'fpc_render_loss_fused': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _Z, _P]),
-    'fpc_render_loss_fused_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_render_loss_fused': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_render_loss_fused_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'fpc_mesh_reg_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_mesh_reg_fwd_bwd': (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _F, _F, _F, _F, _P, _P, _P, _I, _P, _Z, _P]),
     'fpc_adam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P]),

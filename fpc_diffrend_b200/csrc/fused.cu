@@ -31,6 +31,7 @@ struct FusedParams {
     int C;
     float bg, k;             // k = scale / (H*W*C)
     float* grad_pos;         // [N,V,4]
+    float* grad_tex;         // [Ht,Wt,C] or null: d loss / d tex accumulated with REDs (cleared by the host function)
     float* rast_out;         // [N,H,W,4] or null
     float* colour_out;       // [N,H,W,C] or null (composited image)
     double* loss_partial;    // [N*NB]
@@ -141,6 +142,24 @@ __device__ __forceinline__ void accumulate_moments(float* __restrict__ M, unsign
 #else
         (void)ly;
 #endif
+    }
+}
+
+// d loss / d tex of one pixel: g_c times the four bilinear weights, RED into grad_tex [Ht,Wt,C] (texture.cu: k_tex_bwd).
+// ix / iy pack the two (already wrapped) texel columns / rows, 16 bits each (textures up to 65535 texels a side).
+template <int C>
+__device__ __forceinline__ void tex_grad_scatter(const FusedParams& fp, unsigned ix, unsigned iy, float wx, float wy, const float (&g)[C])
+{
+    const size_t r0 = (size_t)(iy & 0xffffu) * fp.Wt, r1 = (size_t)(iy >> 16) * fp.Wt;
+    const unsigned x0 = ix & 0xffffu, x1 = ix >> 16;
+    const float w00 = (1.f - wx) * (1.f - wy), w10 = wx * (1.f - wy), w01 = (1.f - wx) * wy, w11 = wx * wy;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (g[c] == 0.f) continue;
+        atomicAdd(fp.grad_tex + (r0 + x0) * C + c, g[c] * w00);
+        atomicAdd(fp.grad_tex + (r0 + x1) * C + c, g[c] * w10);
+        atomicAdd(fp.grad_tex + (r1 + x0) * C + c, g[c] * w01);
+        atomicAdd(fp.grad_tex + (r1 + x1) * C + c, g[c] * w11);
     }
 }
 
@@ -290,6 +309,8 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             float a0c[TEX ? 2 : C], a1c[TEX ? 2 : C], a2c[TEX ? 2 : C];
             float dudc[C], dvdc[C];      // TEX: d colour_c / d texU, d texV
             float su = 0.f, sv = 0.f, siw = 0.f;
+            unsigned tix = 0u, tiy = 0u;     // TEX: packed texel columns / rows (lo 16 bits = index 0, hi = index 1)
+            float twx = 0.f, twy = 0.f;
             if (fg) {
                 int t = (int)(key & 0xFFFFFFFFu);
                 const int4 ti = tri_indices(rp, t);
@@ -337,6 +358,8 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
                     if (iy1 >= fp.Ht) iy1 -= fp.Ht;
                     size_t i00 = (size_t)iy0 * fp.Wt + ix0, i10 = (size_t)iy0 * fp.Wt + ix1;
                     size_t i01 = (size_t)iy1 * fp.Wt + ix0, i11 = (size_t)iy1 * fp.Wt + ix1;
+                    tix = (unsigned)ix0 | ((unsigned)ix1 << 16); tiy = (unsigned)iy0 | ((unsigned)iy1 << 16);
+                    twx = wx; twy = wy;
 #pragma unroll
                     for (int c = 0; c < C; c++) {
                         float t00 = __ldg(fp.tex + i00 * C + c), t10 = __ldg(fp.tex + i10 * C + c);
@@ -363,6 +386,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             }
             if (fg) {
                 float gu = 0.f, gv = 0.f;
+                if (TEX && fp.grad_tex) tex_grad_scatter<C>(fp, tix, tiy, twx, twy, gc);
                 if (TEX) {
                     float gU = 0.f, gV = 0.f;
 #pragma unroll
@@ -467,10 +491,10 @@ int launch_fused_aa(const RasterParams& rp, const FusedParams& fp, const int32_t
 {
     static bool attr_set = false;
     if (!attr_set) {
-        FPC_CUDA(cudaFuncSetAttribute(k_fused_aa<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aa_smem_layout(C, 4).total));
+        FPC_CUDA(cudaFuncSetAttribute(k_fused_aa<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aa_smem_layout(C, 4, TEX).total));
         attr_set = true;
     }
-    k_fused_aa<C, TEX><<<dim3(rp.NB, rp.N), AA_THREADS, aa_smem_layout(C, fp.ref_u8 ? 1 : 4).total, stream>>>(rp, fp, tri_opp);
+    k_fused_aa<C, TEX><<<dim3(rp.NB, rp.N), AA_THREADS, aa_smem_layout(C, fp.ref_u8 ? 1 : 4, TEX && fp.grad_tex).total, stream>>>(rp, fp, tri_opp);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }
@@ -488,7 +512,7 @@ extern "C" size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W
 static int render_loss_fused_impl(const char* who, const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                   const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
                                   int N, int V, int T, int H, int W, int C, float bg, float scale,
-                                  float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                                  float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                                   void* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
     FPC_CHECK_ARG(attr && attr_tri && ref && loss, "%s: attr, attr_tri, ref and loss must be non-null", who);
@@ -497,6 +521,11 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     if (tex) FPC_CHECK_ARG(A == 2 && Ht > 0 && Wt > 0, "%s: textured shading needs A == 2 (uv) and a non-empty texture", who);
     else FPC_CHECK_ARG(A == C, "%s: vertex-colour shading needs A == C (got A=%d, C=%d)", who, A, C);
     FPC_CHECK_ARG(scratch_bytes >= fpc_render_loss_fused_scratch_bytes(N, T, H, W), "%s: scratch too small", who);
+    if (grad_tex) {
+        FPC_CHECK_ARG(tex && grad_pos, "%s: grad_tex needs textured shading and the backward pass (grad_pos)", who);
+        FPC_CHECK_ARG(Ht <= 65535 && Wt <= 65535, "%s: grad_tex supports textures up to 65535 texels a side", who);
+        FPC_CUDA(cudaMemsetAsync(grad_tex, 0, (size_t)Ht * Wt * C * sizeof(float), stream));
+    }
     RasterParams rp;
     const int NB0 = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
     double* loss_partial = (double*)((char*)scratch + align256(raster_layout(N, T, NB0).total));
@@ -511,7 +540,7 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     FusedParams fp;
     fp.attr = attr; fp.attr_tri = attr_tri; fp.attr_tri4 = attr_tri4; fp.Va = Va; fp.A = A; fp.tex = tex; fp.Ht = Ht; fp.Wt = Wt;
     fp.ref = ref; fp.ref_u8 = ref_is_u8; fp.C = C; fp.bg = bg; fp.k = scale / ((float)H * (float)W * (float)C);
-    fp.grad_pos = grad_pos; fp.rast_out = rast_out; fp.colour_out = colour_out;
+    fp.grad_pos = grad_pos; fp.grad_tex = grad_tex; fp.rast_out = rast_out; fp.colour_out = colour_out;
     fp.loss_partial = loss_partial;
     fp.moments = moments;
     if (tri_opp) {
@@ -534,20 +563,20 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
 extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* attr, const int32_t* attr_tri, int Va, int A,
                                      const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
                                      int N, int V, int T, int H, int W, int C, float bg, float scale,
-                                     float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                                     float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                                      void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     return render_loss_fused_impl("render_loss_fused", pos, tri, nullptr, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss, grad_pos, rast_out, colour_out, scratch, scratch_bytes, (cudaStream_t)stream_);
+                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, scratch, scratch_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                         const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
                                         const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
-                                        float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                                        float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                                         void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     FPC_CHECK_ARG(tri_opp, "render_loss_fused_aa: tri_opp must be non-null (fpc_topology_build)");
     return render_loss_fused_impl("render_loss_fused_aa", pos, tri, tri_opp, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss, grad_pos, rast_out, colour_out, scratch, scratch_bytes, (cudaStream_t)stream_);
+                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, scratch, scratch_bytes, (cudaStream_t)stream_);
 }

@@ -37,13 +37,14 @@ constexpr int AA_REF_MARGIN = 4;               // reference tile starts 4 px lef
 constexpr int AA_REF_W = BIN + 2 * AA_REF_MARGIN;
 
 struct AASmem {
-    size_t keys, region0, col, alpha_r, alpha_u, info, coef, ref, total;
+    size_t keys, region0, col, alpha_r, alpha_u, info, coef, ref, texc, total;
 };
 
 __host__ __device__ inline size_t aa_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // region0 is time-shared: WarpStage records (phase 1), pair work list (phase 3), d loss / d out (phases 4-5)
-__host__ __device__ inline AASmem aa_smem_layout(int C, int esz)
+// texgrad: also keep the texture coordinates of the bin's own pixels (phase 5 scatters d loss / d tex from them)
+__host__ __device__ inline AASmem aa_smem_layout(int C, int esz, bool texgrad = false)
 {
     AASmem L;
     size_t o = 0;
@@ -60,8 +61,25 @@ __host__ __device__ inline AASmem aa_smem_layout(int C, int esz)
     L.info = o; o += aa_align16(AA_NT);
     L.coef = o; o += aa_align16(sizeof(float) * BIN * BIN * 3 * C);
     L.ref = o; o += aa_align16((size_t)AA_R1 * AA_REF_W * C * esz);
+    L.texc = o; if (texgrad) o += sizeof(float2) * BIN * BIN;
     L.total = o;
     return L;
+}
+
+// texel columns / rows (wrapped, packed 16 + 16 bits) and weights of a bilinear lookup; same op order as tex_bilinear
+__device__ __forceinline__ void tex_coords(const FusedParams& fp, float au, float av, unsigned& ix, unsigned& iy, float& wx, float& wy)
+{
+    float tu = au - floorf(au), tv = av - floorf(av);
+    float x = xsub(xmul(tu, (float)fp.Wt), 0.5f), y = xsub(xmul(tv, (float)fp.Ht), 0.5f);
+    float x0f = floorf(x), y0f = floorf(y);
+    int ix0 = (int)x0f, iy0 = (int)y0f, ix1 = ix0 + 1, iy1 = iy0 + 1;
+    wx = x - x0f; wy = y - y0f;
+    if (ix0 < 0) ix0 += fp.Wt;
+    if (iy0 < 0) iy0 += fp.Ht;
+    if (ix1 >= fp.Wt) ix1 -= fp.Wt;
+    if (iy1 >= fp.Ht) iy1 -= fp.Ht;
+    ix = (unsigned)ix0 | ((unsigned)ix1 << 16);
+    iy = (unsigned)iy0 | ((unsigned)iy1 << 16);
 }
 
 // bilinear, wrap (texture.cu: tex_index); same op order as k_fused
@@ -95,7 +113,8 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int esz = fp.ref_u8 ? 1 : 4;
-    const AASmem L = aa_smem_layout(C, esz);
+    const bool texgrad = TEX && fp.grad_tex != nullptr;
+    const AASmem L = aa_smem_layout(C, esz, texgrad);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
     WarpStage* stage = reinterpret_cast<WarpStage*>(smem + L.region0);
     unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + L.region0);
@@ -106,6 +125,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     unsigned char* s_info = smem + L.info;
     float* s_coef = reinterpret_cast<float*>(smem + L.coef);
     unsigned char* s_ref = smem + L.ref;
+    float2* s_texc = reinterpret_cast<float2*>(smem + L.texc);
     __shared__ double red[AA_WARPS];
     __shared__ int s_nlist;
 
@@ -179,6 +199,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
 #pragma unroll
         for (int c = 0; c < 3 * C; c++) K[c] = 0.f;
         float4 rout = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 tcoord = make_float2(0.f, 0.f);      // background pixels sample the texture at uv = (0,0)
         if (key != KEY_EMPTY) {       // only in-image pixels receive fragments
             int t = (int)(key & 0xFFFFFFFFu);
             const int4 ti = tri_indices(rp, t);
@@ -216,6 +237,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
             if (TEX) {
                 float dudc[C], dvdc[C];
                 tex_bilinear<C>(fp, at[0], at[1], col, dudc, dvdc);
+                tcoord = make_float2(at[0], at[AA - 1]);
 #pragma unroll
                 for (int c = 0; c < C; c++) {
                     ku[c] = dudc[c] * (a0c[0] - a2c[0]) + dvdc[c] * (a0c[1] - a2c[1]);
@@ -246,6 +268,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
             const int ii = (ty - AA_HALO) * BIN + (tx - AA_HALO);
 #pragma unroll
             for (int c = 0; c < 3 * C; c++) s_coef[ii * 3 * C + c] = K[c];
+            if (texgrad) s_texc[ii] = tcoord;
             if (fp.rast_out && px < rp.W && py < rp.H) reinterpret_cast<float4*>(fp.rast_out)[((size_t)n * rp.H + py) * rp.W + px] = rout;
         }
     }
@@ -360,6 +383,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
             const int d2 = (a2 > 0.f) ? r : r + AA_R1, d3 = (a3 > 0.f) ? r - AA_R1 : r;
             const unsigned info = s_info[idx];
             float ddr = 0.f, ddu = 0.f;
+            float gpre[C];             // d loss / d colour before antialias
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 float g = s_gc[r * C + c];
@@ -367,6 +391,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 if (a1 != 0.f) g += a1 * s_gc[d1 * C + c];
                 if (a2 != 0.f) g -= a2 * s_gc[d2 * C + c];
                 if (a3 != 0.f) g += a3 * s_gc[d3 * C + c];
+                gpre[c] = g;
                 if (idp1) {
                     g0 += g * s_coef[ii * 3 * C + 0 * C + c];
                     g1 += g * s_coef[ii * 3 * C + 1 * C + c];
@@ -375,6 +400,14 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 const float cc = s_col[idx * C + c];
                 if (info & 8u) ddr += s_gc[d0 * C + c] * (s_col[(idx + 1) * C + c] - cc);
                 if (info & 0x80u) ddu += s_gc[d2 * C + c] * (s_col[(idx + AA_TW) * C + c] - cc);
+            }
+            if (texgrad) {
+                // background pixels too: their colour (texture at uv = 0) can blend into a neighbour
+                const float2 tc = s_texc[ii];
+                unsigned tix, tiy;
+                float twx, twy;
+                tex_coords(fp, tc.x, tc.y, tix, tiy, twx, twy);
+                tex_grad_scatter<C>(fp, tix, tiy, twx, twy, gpre);
             }
             if (fp.moments) {
                 if ((info & 8u) && ddr != 0.f) {

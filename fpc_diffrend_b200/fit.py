@@ -46,6 +46,8 @@ class FitConfig:
     quat_norm: str = 'row'                # 'row' (default) or 'frobenius' (reference quirk)
     optimize_pose: bool = True
     optimize_cam_pose: bool = False       # per-camera pose corrections t_opt / q_opt (fit.py:443-448,498-499), shared by all frames
+    optimize_texture: bool = False        # tex_opt (fit.py:439,502): the texture is a shared parameter, lr = lr_base * lr_tex_coef
+    lr_tex_coef: float = 0.5              # main.py:15
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
     fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
@@ -133,6 +135,12 @@ class FitSession:
         self.d_q_cam = self.cam_grads[C * 3:].view(C, 4)
         self.step_count = torch.zeros(1, **f32)
         self.loss = torch.zeros(1, **f32)
+        if cfg.optimize_texture:
+            if cfg.shading != 'texture':
+                raise ValueError("optimize_texture needs shading='texture'")
+            self.d_tex = torch.zeros_like(self.tex)
+            self.tex_m = torch.zeros_like(self.tex)
+            self.tex_v = torch.zeros_like(self.tex)
 
         # per-iteration buffers
         self.mvp = torch.empty(self.N, 16, **f32)
@@ -366,15 +374,16 @@ class FitSession:
             img = torch.empty(N, H, W, Ch, dtype=torch.float32, device=self.device)
             dummy = torch.zeros(N, H, W, Ch, dtype=torch.uint8, device=self.device)
             _lib.call(name, *head, _p(self.attr), _p(self.attr_idx), self.attr.shape[1],
-                      self.attr.shape[2], _p(tex), Ht, Wt, _p(dummy), 1, N, V, T, H, W, Ch, cfg.bg, 1.0, _p(self.loss), None, None,
+                      self.attr.shape[2], _p(tex), Ht, Wt, _p(dummy), 1, N, V, T, H, W, Ch, cfg.bg, 1.0, _p(self.loss), None, None, None,
                       _p(img), _p(self.scratch), self.scratch.numel(), s)
             return img
         assert self.ref is not None, 'call set_reference() first'
         self._timed('render_loss_fused', name, *head, _p(self.attr), _p(self.attr_idx),
                     self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
-                    N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, _p(self.loss), _p(self.g_pos), None, None,
+                    N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, _p(self.loss), _p(self.g_pos),
+                    _p(self.d_tex) if cfg.optimize_texture else None, None, None,
                     _p(self.scratch), self.scratch.numel(), s)
-        return 6
+        return 6 + (1 if cfg.optimize_texture else 0)
 
     def backward(self):
         cfg, s, call = self.cfg, self._stream(), self._timed
@@ -392,7 +401,7 @@ class FitSession:
                  _p(self.g_attr), _p(self.g_rast), s); n += 2
         else:
             call('texture_bwd', 'fpc_texture_linear_bwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), _p(g_colour),
-                 N, H, W, None, _p(self.g_texc), s); n += 1
+                 N, H, W, _p(self.d_tex) if cfg.optimize_texture else None, _p(self.g_texc), s); n += 1 + (1 if cfg.optimize_texture else 0)
             call('interpolate_bwd', 'fpc_interpolate_bwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), _p(self.g_texc),
                  N, T, H, W, _p(self.g_attr), _p(self.g_rast), s); n += 2
         call('rasterize_bwd', 'fpc_rasterize_bwd', _p(self.pos_clip), _p(self.pos_idx), _p(self.rast), _p(self.g_rast), N, V, T, H, W,
@@ -465,6 +474,11 @@ class FitSession:
                                                cfg.eps, cfg.lr_ramp, float(cfg.max_iter), _p(self.step_count), s)
             adam_c(0, C * 3, cfg.lr_t); adam_c(C * 3, C * 4, cfg.lr_q)
             call('adam', 'fpc_quat_renorm', _p(self.q_cam), C, 1 if cfg.quat_norm == 'frobenius' else 0, s); n += 3
+        if cfg.optimize_texture:
+            # shared by all frames and all cameras: every rank holds a partial sum in both sharding modes
+            allreduce_gradients(self.d_tex)
+            call('adam_tex', 'fpc_adam_step', _p(self.tex), _p(self.d_tex), _p(self.tex_m), _p(self.tex_v), self.tex.numel(),
+                 cfg.lr_base * cfg.lr_tex_coef, cfg.beta1, cfg.beta2, cfg.eps, cfg.lr_ramp, float(cfg.max_iter), _p(self.step_count), s); n += 1
         nw = F * B
         if F * (B + 7) <= (1 << 22):
             call('adam', 'fpc_adam_fused', _p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), B, F, 1 if cfg.optimize_pose else 0,

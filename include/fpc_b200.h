@@ -174,12 +174,14 @@ int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, const float* 
  * ref [N,H,W,C] float32 (ref_is_u8 == 0) or uint8 (ref_is_u8 == 1) grey levels on the 0..255 scale; C in {1,3}.
  *   loss [1]            = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2                     (overwritten)
  *   grad_pos [N,V,4]    = d loss / d pos (x, y, w; z = 0), overwritten; NULL = forward only
+ *   grad_tex [Ht,Wt,C]  = d loss / d tex (texture optimisation, tex_opt of fit.py:439,502), overwritten; NULL to skip
+ *                         (needs tex and grad_pos; 4C float REDs per covered pixel)
  *   rast_out [N,H,W,4], colour_out [N,H,W,C] (composited image): optional outputs, NULL to skip the HBM writes. */
 size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W);
 int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* attr, const int32_t* attr_tri, int Va, int A,
                           const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
                           int N, int V, int T, int H, int W, int C, float bg, float scale,
-                          float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                          float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                           void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
 /* The same with dr.antialias (fit.py:160) between shading and the background composite: replaces the chain
@@ -190,7 +192,7 @@ int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* att
 int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                              const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
                              const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
-                             float* loss, float* grad_pos, float* rast_out, float* colour_out,
+                             float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                              void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
 /* ---- mesh regularisers (replaces the pytorch3d terms of fit.py:578-582: weight_laplacian * laplacian(mesh)^2 +

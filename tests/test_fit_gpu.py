@@ -190,6 +190,76 @@ def test_camera_pose_correction_gradients(small_rig3, geom):
     assert (s.cam_params != before).any() and torch.allclose(s.q_cam.norm(dim=1), torch.ones(C, device='cuda'), atol=1e-6)
 
 
+@pytest.mark.parametrize('use_aa,fused', [(False, True), (True, True), (True, False)])
+def test_texture_optimisation(small_rig3, use_aa, fused):
+    """tex_opt (fit.py:439,502): the texture as a shared parameter.  d loss / d tex of one iteration against the oracle fed
+    the GPU's pos_clip bits, then a fixed number of texture-only Adam steps against torch.optim.Adam driven by the same
+    gradients' oracle, and the loss must fall."""
+    from fpc_diffrend_b200 import rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F = small_rig3, 152, 200, 2
+    C = rig.P.shape[0]
+    cfg = FitConfig(resolution=(H, W), shading='texture', antialias=use_aa, fused=fused, optimize_texture=True, optimize_pose=False,
+                    lr_base=2e-2, lr_tex_coef=0.5, max_iter=100)
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
+    ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, cfg)
+    s = FitSession(rig, F, cfg)
+    s.set_reference(ref)
+    s.set_parameters(w=w_true, t=t_true * 0.2, q=q_true)
+    tex0 = (0.7 * torch.tensor(rig.tex) + 0.1).reshape(s.tex.shape)
+    s.tex.copy_(tex0)
+    s.forward()
+    s.backward()
+    torch.cuda.synchronize()
+    opp = torch.tensor(G.topology_build(rig.pos_idx))
+    ref_cpu = ref.cpu()
+
+    def oracle_tex_grad(tex):
+        tex = tex.clone().requires_grad_(True)
+        total = 0.0
+        for n in range(F * C):
+            pc = s.pos_clip[n:n + 1].cpu()
+            rast, _ = G.rasterize(pc, torch.tensor(rig.pos_idx), (H, W))
+            texc = G.interpolate(torch.tensor(rig.uv)[None], rast, torch.tensor(rig.uv_idx))
+            col = G.texture(tex, texc)
+            if use_aa:
+                col = G.antialias(col, rast, pc, torch.tensor(rig.pos_idx), opp)
+            img = torch.where(rast[..., 3:] > 0, col, torch.tensor(G.BG))[0]
+            total = total + G.image_loss(ref_cpu[n // C, n % C], img) / C
+        total.backward()
+        return float(total.detach()), tex.grad
+
+    loss_ref, g_ref = oracle_tex_grad(tex0)
+    assert abs(float(s.loss) - loss_ref) / loss_ref < 1e-5
+    assert g_ref.abs().max() > 0
+    assert rel(s.d_tex.cpu(), g_ref) < 1e-4
+
+    # texture-only fit: the activations are restored before every step (the oracle below optimises the texture alone)
+    iters = 6
+    tex_o = tex0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([{'params': tex_o, 'lr': s.cfg.lr_base * s.cfg.lr_tex_coef}])
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda x: cfg.lr_ramp ** (float(x) / float(cfg.max_iter)))
+    losses = []
+    for _ in range(iters):
+        s.set_parameters(w=w_true, t=t_true * 0.2, q=q_true)
+        s.iteration()
+        losses.append(float(s.loss))
+        _, g = oracle_tex_grad(tex_o.detach())
+        opt.zero_grad()
+        tex_o.grad = g
+        opt.step()
+        sched.step()
+    assert losses[-1] < losses[0]
+    travel = s.cfg.lr_base * s.cfg.lr_tex_coef * iters
+    d = (s.tex.cpu() - tex_o.detach()).abs()
+    # texels whose gradient is rounding noise move by +-lr per step either way (Adam divides by sqrt(v)): tight on the texels
+    # with a real signal, loose elsewhere (same criterion as test_fitted_parameters_after_fixed_iterations)
+    well = g_ref.abs() > 1e-2 * g_ref.abs().max()
+    assert well.sum() > 50
+    assert d[well].max() < 2e-3 * travel + 1e-6, float(d[well].max())
+    assert d.max() <= 2.01 * travel
+
+
 def test_fitted_parameters_after_fixed_iterations(tiny_rig):
     """North-star: fitted activations after a fixed iteration count must match the reference path within tolerance.
     Deterministic all-frames schedule, 12 iterations, config 1 (1 camera 128x128, 1 frame)."""

@@ -216,7 +216,8 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
     tp = torch.tensor(pc, requires_grad=True)
     r_o, _ = G.rasterize(tp, torch.tensor(rig.pos_idx), (H, W))
     a_o = G.interpolate(torch.tensor(attr)[None], r_o, torch.tensor(idx))
-    col_o = G.texture(torch.tensor(tex)[None], a_o) if textured else a_o
+    tex_o = torch.tensor(tex, requires_grad=True) if textured else None
+    col_o = G.texture(tex_o[None], a_o) if textured else a_o
     if aa:
         opp = G.topology_build(rig.pos_idx)
         col_o = G.antialias(col_o, r_o, tp, torch.tensor(rig.pos_idx), torch.tensor(opp))
@@ -230,6 +231,7 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
     d_ref = cu(ref.astype(np.uint8)) if u8 else cu(ref)
     loss = torch.zeros(1, device='cuda')
     g_pos = torch.full((N, V, 4), 7.0, device='cuda')
+    g_tex = torch.full(tex.shape, 7.0, device='cuda') if textured else None
     rast_out = torch.empty(N, H, W, 4, device='cuda')
     col_out = torch.empty(N, H, W, C, device='cuda')
     nbytes = _lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W)
@@ -238,7 +240,7 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
     head = (P(d_pos), P(d_tri)) + ((P(d_opp),) if aa else ())
     _lib.call('fpc_render_loss_fused_aa' if aa else 'fpc_render_loss_fused', *head, P(d_attr), P(d_idx), attr.shape[0], attr.shape[1], P(d_tex),
               tex.shape[0] if textured else 0, tex.shape[1] if textured else 0, P(d_ref), 1 if u8 else 0, N, V, T, H, W, C,
-              G.BG, scale, P(loss), P(g_pos), P(rast_out), P(col_out), P(scratch), scratch.numel(),
+              G.BG, scale, P(loss), P(g_pos), P(g_tex), P(rast_out), P(col_out), P(scratch), scratch.numel(),
               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert np.array_equal(rast_out[..., 3].cpu().numpy(), rast[..., 3])
@@ -246,6 +248,9 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
     assert np.abs(col_out.cpu().numpy() - comp_o.detach().numpy()).max() <= ABS_FWD
     assert abs(float(loss) - float(loss_o.detach())) / float(loss_o.detach()) < 1e-5
     assert rel_err(g_pos.cpu().numpy(), tp.grad.numpy()) < REL_GRAD
+    if textured:
+        # d loss / d tex (texture optimisation, fit.py:439,502); with antialias the background pixels' texel (uv = 0) takes part
+        assert rel_err(g_tex.cpu().numpy(), tex_o.grad.numpy()) < REL_GRAD
 
 
 def test_full_size_properties(dr):
@@ -394,7 +399,7 @@ def test_rasterize_near_plane_clipper(dr, small_rig3):
     nbytes = int(_lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W))
     scratch = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
     _lib.call('fpc_render_loss_fused', P(d_pos), P(d_tri), P(d_attr), P(d_tri), V, C, None, 0, 0, P(d_ref), 1, N, V, T, H, W, C,
-              G.BG, 1.0, P(loss), P(g_pos), None, None, P(scratch), nbytes, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+              G.BG, 1.0, P(loss), P(g_pos), None, None, None, P(scratch), nbytes, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert abs(float(loss) - float(loss_o.detach())) / float(loss_o.detach()) < 1e-5
     assert rel_err(g_pos.cpu().numpy(), tp.grad.numpy()) < REL_GRAD

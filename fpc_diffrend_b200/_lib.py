@@ -37,6 +37,12 @@ SIGNATURES = {
     'fpc_antialias_fwd': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     'fpc_antialias_bwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'fpc_blend_fwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    'fpc_blend_fwd_ex': (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P]),
+    'fpc_basis_code_fwd': (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    'fpc_basis_grad': (_I, [_P, _P, _I, _I, _I, _F, _P, _P]),
+    'fpc_basis_code_bwd': (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P]),
+    'fpc_l2_reg_scratch_bytes': (_Z, [_L]),
+    'fpc_l2_reg_fwd_bwd': (_I, [_P, _I, _L, _F, _P, _P, _P, _F, _P, _P, _Z, _P]),
     'fpc_blend_bwd_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_blend_bwd': (_I, [_P, _P, _I, _I, _I, _P, _P, _Z, _P]),
     'fpc_blend_tc_supported': (_I, [_I, _I, _I]),
@@ -61,6 +67,7 @@ SIGNATURES = {
     'fpc_mesh_reg_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_mesh_reg_fwd_bwd': (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _F, _F, _F, _F, _P, _P, _P, _I, _P, _Z, _P]),
     'fpc_adam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P]),
+    'fpc_adam_step_from': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _F, _P]),
     'fpc_adam_advance': (_I, [_P, _P]),
     'fpc_quat_renorm': (_I, [_P, _I, _I, _P]),
     'fpc_adam_fused': (_I, [_P] * 4 + [_I] * 3 + [_F] * 8 + [_I, _P, _P]),

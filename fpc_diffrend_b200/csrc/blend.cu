@@ -11,8 +11,14 @@
 
 namespace {
 
+// init(r) of the *_ex entry: the value the product is added to -- verts itself (accumulate), base, or 0
+__device__ __forceinline__ float blend_init(const float* base, const float* verts, size_t vi, int r, int accumulate)
+{
+    return accumulate ? verts[vi] : (base ? __ldg(base + r) : 0.f);
+}
+
 __global__ void __launch_bounds__(256) k_blend_gemv(const float* __restrict__ D, const float* __restrict__ base,
-                                                    const float* __restrict__ w, int R, int B, float* __restrict__ verts)
+                                                    const float* __restrict__ w, int R, int B, float coef, int accumulate, float* verts)
 {
     extern __shared__ float sw[];
     for (int i = threadIdx.x; i < B; i += blockDim.x) sw[i] = w[i];
@@ -33,7 +39,7 @@ __global__ void __launch_bounds__(256) k_blend_gemv(const float* __restrict__ D,
             for (int i = lane; i < B; i += 32) acc += __ldg(row + i) * sw[i];
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) verts[r] = __ldg(base + r) + acc;
+        if (lane == 0) verts[r] = blend_init(base, verts, r, r, accumulate) + coef * acc;
     }
 }
 
@@ -41,7 +47,7 @@ constexpr int TM = 64, TN = 64, TK = 16;
 
 // C[f, r] = base[r] + sum_k D[r,k] * w[f,k];  tile: 64 rows (r) x 64 frames (f)
 __global__ void __launch_bounds__(256) k_blend_gemm(const float* __restrict__ D, const float* __restrict__ base,
-                                                    const float* __restrict__ w, int R, int B, int F, float* __restrict__ verts)
+                                                    const float* __restrict__ w, int R, int B, int F, float coef, int accumulate, float* verts)
 {
     __shared__ float sA[TK][TM + 1];   // D tile, k-major
     __shared__ float sB[TK][TN + 1];   // w tile, k-major
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(256) k_blend_gemm(const float* __restrict__ D,
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             int r = r0 + tx * 4 + i;
-            if (r < R) verts[(size_t)f * R + r] = __ldg(base + r) + acc[j][i];
+            if (r < R) verts[(size_t)f * R + r] = blend_init(base, verts, (size_t)f * R + r, r, accumulate) + coef * acc[j][i];
         }
     }
 }
@@ -131,21 +137,27 @@ constexpr int BWD_ROWS = 128;
 
 }  // namespace
 
-extern "C" int fpc_blend_fwd(const float* D, const float* base, const float* w, int R, int B, int F, float* verts,
-                             fpc_stream_t stream_)
+extern "C" int fpc_blend_fwd_ex(const float* D, const float* base, const float* w, int R, int B, int F, float coef, int accumulate,
+                                float* verts, fpc_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    FPC_CHECK_ARG(D && base && w && verts, "blend_fwd: null pointer argument");
+    FPC_CHECK_ARG(D && w && verts, "blend_fwd: null pointer argument");
     FPC_CHECK_ARG(R > 0 && B > 0 && F > 0, "blend_fwd: R, B, F must be positive (got %d %d %d)", R, B, F);
-    if (F == 1) {
-        FPC_CHECK_ARG((size_t)B * 4 <= 48 * 1024, "blend_fwd: B too large for the GEMV path (%d)", B);
+    if (F == 1 && (size_t)B * 4 <= 48 * 1024) {
         int grid = min(fpc_div_up(R, 8), 148 * 8);
-        k_blend_gemv<<<grid, 256, (size_t)B * 4, stream>>>(D, base, w, R, B, verts);
+        k_blend_gemv<<<grid, 256, (size_t)B * 4, stream>>>(D, base, w, R, B, coef, accumulate, verts);
     } else {
-        k_blend_gemm<<<dim3(fpc_div_up(R, TM), fpc_div_up(F, TN)), 256, 0, stream>>>(D, base, w, R, B, F, verts);
+        k_blend_gemm<<<dim3(fpc_div_up(R, TM), fpc_div_up(F, TN)), 256, 0, stream>>>(D, base, w, R, B, F, coef, accumulate, verts);
     }
     FPC_LAUNCH_CHECK();
     return FPC_OK;
+}
+
+extern "C" int fpc_blend_fwd(const float* D, const float* base, const float* w, int R, int B, int F, float* verts,
+                             fpc_stream_t stream_)
+{
+    FPC_CHECK_ARG(base, "blend_fwd: null pointer argument");
+    return fpc_blend_fwd_ex(D, base, w, R, B, F, 1.f, 0, verts, stream_);
 }
 
 extern "C" size_t fpc_blend_bwd_scratch_bytes(int R, int B, int F)

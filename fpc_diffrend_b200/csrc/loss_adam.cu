@@ -86,12 +86,13 @@ __global__ void __launch_bounds__(256) k_loss_reduce(const double* __restrict__ 
 
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                              float lr_ramp, float max_iter, const float* __restrict__ step_count)
+                                              float lr_ramp, float max_iter, const float* __restrict__ step_count, float start_step)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float step0 = __ldg(step_count);              // steps taken so far (LambdaLR epoch)
-    float tstep = step0 + 1.f;                    // Adam's t
+    if (step0 < start_step) return;               // group still locked (requires_grad False: torch skips it, state untouched)
+    float tstep = step0 - start_step + 1.f;       // Adam's t counts the updates of THIS group
     float lr_eff = lr * powf(lr_ramp, step0 / max_iter);
     float bc1 = 1.f - powf(b1, tstep), bc2 = 1.f - powf(b2, tstep);
     float gi = g[i];
@@ -158,15 +159,21 @@ extern "C" int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, co
     return FPC_OK;
 }
 
-extern "C" int fpc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                             float lr_ramp, float max_iter, const float* step_count, fpc_stream_t stream_)
+extern "C" int fpc_adam_step_from(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                                  float lr_ramp, float max_iter, const float* step_count, float start_step, fpc_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     FPC_CHECK_ARG(p && g && m && v && step_count, "adam_step: null pointer argument");
-    FPC_CHECK_ARG(n > 0 && max_iter > 0.f && lr_ramp > 0.f, "adam_step: n, max_iter and lr_ramp must be positive");
-    k_adam<<<fpc_div_up(n, 256), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, lr_ramp, max_iter, step_count);
+    FPC_CHECK_ARG(n > 0 && max_iter > 0.f && lr_ramp > 0.f && start_step >= 0.f, "adam_step: n, max_iter and lr_ramp must be positive, start_step >= 0");
+    k_adam<<<fpc_div_up(n, 256), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, lr_ramp, max_iter, step_count, start_step);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
+}
+
+extern "C" int fpc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                             float lr_ramp, float max_iter, const float* step_count, fpc_stream_t stream_)
+{
+    return fpc_adam_step_from(p, g, m, v, n, lr, b1, b2, eps, lr_ramp, max_iter, step_count, 0.f, stream_);
 }
 
 extern "C" int fpc_adam_advance(float* step_count, fpc_stream_t stream_)

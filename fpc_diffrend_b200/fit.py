@@ -16,7 +16,7 @@ Loss convention for a batch: sum over frames of the mean over that frame's camer
 single-view loss mean((ref - 255 colour)^2); per-frame gradients therefore do not depend on the batch size.
 """
 import ctypes
-from dataclasses import dataclass
+from dataclasses import dataclass, replace
 
 import numpy as np
 import torch
@@ -48,6 +48,16 @@ class FitConfig:
     optimize_cam_pose: bool = False       # per-camera pose corrections t_opt / q_opt (fit.py:443-448,498-499), shared by all frames
     optimize_texture: bool = False        # tex_opt (fit.py:439,502): the texture is a shared parameter, lr = lr_base * lr_tex_coef
     lr_tex_coef: float = 0.5              # main.py:15
+    # optimisation mode (fit.py:465-480): 'prior' V = base + D w_f;  'free' V = base + m3 m2 m1 e_f (blend_free, fit.py:47-62);
+    # 'combined' V = base + D w_f + combined_coefficient * m3 m2 m1 e_f (blend_combined, fit.py:66-99, coefficient fit.py:562)
+    mode: str = 'prior'
+    n_frames_total: int = None            # frames of the whole take = size of m1, m2 [Fn,Fn] and columns of m3 (default: this session's F)
+    combined_coefficient: float = 0.5
+    corrective_start: int = None          # first optimiser step that updates m1..m3; None = 0 ('free') or max_iter//2 + 2
+                                          # ('combined': requires_grad is switched on after the forward pass of the first
+                                          # iteration i > max_iter/2, fit.py:603-608, so that iteration still has no gradient)
+    regularize_correctives: bool = False  # combined: loss += mean((m3 m2 m1 e_f)^2)  (fit.py:584-589)
+    regularize_prior: bool = False        # prior: loss += mean(w_f^2)                 (fit.py:591-595)
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
     fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
@@ -67,9 +77,10 @@ def _p(t):
 
 
 class FitSession:
-    def __init__(self, rig, n_frames, config=None, device=None):
+    def __init__(self, rig, n_frames, config=None, device=None, frame_ids=None):
         """rig: an object with v_base [3V], pos_idx [T,3], uv, uv_idx, D [3V,B], vcol [V,3], tex [Ht,Wt,Ch], P, A [C,4,4]
-        (numpy, e.g. fpc_diffrend_b200.rig.Rig)."""
+        (numpy, e.g. fpc_diffrend_b200.rig.Rig).  frame_ids: take-wide indices of this session's frames (free / combined
+        modes; default 0..n_frames-1)."""
         self.cfg = config or FitConfig()
         cfg = self.cfg
         if not torch.cuda.is_available():
@@ -135,6 +146,43 @@ class FitSession:
         self.d_q_cam = self.cam_grads[C * 3:].view(C, 4)
         self.step_count = torch.zeros(1, **f32)
         self.loss = torch.zeros(1, **f32)
+        if cfg.mode not in ('prior', 'free', 'combined'):
+            raise ValueError("mode must be 'prior', 'free' or 'combined'")
+        self.use_basis = cfg.mode != 'prior'
+        if self.use_basis:
+            # learned basis shared by all frames of the take (setup_dataset_free, fit.py:166-179): m1 = m2 = I, m3 = 0
+            Fn = int(cfg.n_frames_total or F)
+            ids = np.arange(F) if frame_ids is None else np.asarray(frame_ids)
+            if ids.shape != (F,) or ids.min() < 0 or ids.max() >= Fn or len(set(ids.tolist())) != F:
+                raise ValueError('frame_ids must be %d distinct indices in [0, %d)' % (F, Fn))
+            self.Fn = Fn
+            self.frame_ids = torch.tensor(ids, dtype=torch.int32, device=dev)
+            nb = 2 * Fn * Fn + 3 * V * Fn
+            self.basis = torch.zeros(nb, **f32)
+            self.basis_grads = torch.zeros_like(self.basis)
+            self.basis_m = torch.zeros_like(self.basis)
+            self.basis_v = torch.zeros_like(self.basis)
+            self.m1 = self.basis[:Fn * Fn].view(Fn, Fn)
+            self.m2 = self.basis[Fn * Fn:2 * Fn * Fn].view(Fn, Fn)
+            self.m3 = self.basis[2 * Fn * Fn:].view(3 * V, Fn)
+            self.m1.copy_(torch.eye(Fn))
+            self.m2.copy_(torch.eye(Fn))
+            self.d_m1 = self.basis_grads[:Fn * Fn].view(Fn, Fn)
+            self.d_m2 = self.basis_grads[Fn * Fn:2 * Fn * Fn].view(Fn, Fn)
+            self.d_m3 = self.basis_grads[2 * Fn * Fn:].view(3 * V, Fn)
+            self.x1 = torch.zeros(F, Fn, **f32)
+            self.x2 = torch.zeros(F, Fn, **f32)
+            self.d_x2 = torch.zeros(F, Fn, **f32)
+            self.basis_coef = 1.0 if cfg.mode == 'free' else float(cfg.combined_coefficient)
+            self.basis_lr = cfg.lr_base if cfg.mode == 'free' else 0.1 * cfg.lr_base          # corrective_lr, fit.py:466-480
+            cs = cfg.corrective_start
+            self.basis_start = float(cs if cs is not None else (0 if cfg.mode == 'free' else cfg.max_iter // 2 + 2))
+            self.use_reg_corr = bool(cfg.regularize_correctives and cfg.mode == 'combined')
+            if self.use_reg_corr:
+                self.corr = torch.zeros(F, V * 3, **f32)
+                self.d_corr = torch.zeros(F, V * 3, **f32)
+        self.use_reg_prior = bool(cfg.regularize_prior and cfg.mode == 'prior')
+        self.reg_l2_term = torch.zeros(1, **f32)
         if cfg.optimize_texture:
             if cfg.shading != 'texture':
                 raise ValueError("optimize_texture needs shading='texture'")
@@ -187,7 +235,7 @@ class FitSession:
         fg = cfg.fused_geometry
         if fg is None:
             fg = F <= 4
-        self.use_geom_fused = bool(fg and L.fpc_geometry_fused_supported(V, B, F, C))
+        self.use_geom_fused = bool(fg and not self.use_basis and L.fpc_geometry_fused_supported(V, B, F, C))
         tc = cfg.tc_blend
         if tc is None:
             tc = F >= 8
@@ -198,6 +246,8 @@ class FitSession:
                      L.fpc_mesh_reg_scratch_bytes(F, V, self.n_quads) if self.use_reg else 0,
                      L.fpc_geometry_bwd_scratch_bytes(V, B, F, C), L.fpc_rasterize_scratch_bytes(self.N, T, H, W), L.fpc_render_loss_fused_scratch_bytes(self.N, T, H, W),
                      L.fpc_blend_bwd_scratch_bytes(V * 3, B, F),
+                     L.fpc_blend_bwd_scratch_bytes(V * 3, self.Fn, F) if self.use_basis else 0,
+                     L.fpc_l2_reg_scratch_bytes(F * max(V * 3, B)),
                      L.fpc_project_bwd_scratch_bytes(F, C, V), L.fpc_image_loss_scratch_bytes(self.N, H, W, Ch))
         self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         self.graph = None
@@ -333,10 +383,7 @@ class FitSession:
                  _p(self.w), V, B, F, C, _p(self.mvp), _p(self.verts), _p(self.pos_clip), s); n += 1
         else:
             call('pose_mvp_fwd', 'fpc_pose_mvp_fwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), *self._cam(), F, C, _p(self.mvp), s); n += 1
-            if self.use_tc_blend:
-                call('blend_fwd', 'fpc_blend_fwd_tc', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
-            else:
-                call('blend_fwd', 'fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
+            n += self._blend_forward()
             call('project_fwd', 'fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
         if self.use_fused:
             return n + self._fused(True) if with_loss else self._fused(False)
@@ -359,6 +406,48 @@ class FitSession:
         call('image_loss', 'fpc_image_loss_fwd_bwd', _p(final), _p(self.rast), _p(self.ref), N, H, W, Ch, cfg.bg, 1.0 / self.C_total,
              _p(self.loss), _p(self.d_colour), None, _p(self.scratch), self.scratch.numel(), s); n += 2
         return n
+
+    def _blend_forward(self):
+        """verts [F,3V] of the current parameters in the configured mode (separate-kernel path)."""
+        cfg, s, call = self.cfg, self._stream(), self._timed
+        F, V, B = self.F, self.V, self.B
+        n = 0
+        if cfg.mode != 'free':
+            name = 'fpc_blend_fwd_tc' if self.use_tc_blend else 'fpc_blend_fwd'
+            call('blend_fwd', name, _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
+        if self.use_basis:
+            Fn = self.Fn
+            call('basis_fwd', 'fpc_basis_code_fwd', _p(self.m1), _p(self.m2), _p(self.frame_ids), Fn, F, _p(self.x1), _p(self.x2), s); n += 1
+            free = cfg.mode == 'free'
+            call('basis_fwd', 'fpc_blend_fwd_ex', _p(self.m3), _p(self.v_base) if free else None, _p(self.x2), V * 3, Fn, F,
+                 self.basis_coef, 0 if free else 1, _p(self.verts), s); n += 1
+            if self.use_reg_corr:
+                call('basis_fwd', 'fpc_blend_fwd_ex', _p(self.m3), None, _p(self.x2), V * 3, Fn, F, 1.0, 0, _p(self.corr), s); n += 1
+        return n
+
+    def _basis_backward(self):
+        """d_verts -> d_m1, d_m2, d_m3 (and the regularize_correctives term)."""
+        s, call = self._stream(), self._timed
+        F, V, Fn = self.F, self.V, self.Fn
+        dv, coef, n = self.d_verts, self.basis_coef, 0
+        if self.use_reg_corr:
+            # d loss / d (m3 x2) = coef * d_verts + 2 corr / 3V; the term itself joins the loss
+            call('basis_bwd', 'fpc_l2_reg_fwd_bwd', _p(self.corr), F, V * 3, 1.0, _p(self.loss), _p(self.reg_l2_term), _p(self.d_verts), coef,
+                 _p(self.d_corr), _p(self.scratch), self.scratch.numel(), s); n += 2
+            dv, coef = self.d_corr, 1.0
+        call('basis_bwd', 'fpc_blend_bwd', _p(self.m3), _p(dv), V * 3, Fn, F, _p(self.d_x2), _p(self.scratch), self.scratch.numel(), s); n += 2
+        call('basis_bwd', 'fpc_basis_grad', _p(dv), _p(self.x2), V * 3, Fn, F, coef, _p(self.d_m3), s); n += 1
+        call('basis_bwd', 'fpc_basis_code_bwd', _p(self.m2), _p(self.x1), _p(self.d_x2), _p(self.frame_ids), Fn, F, coef,
+             _p(self.d_m1), _p(self.d_m2), s); n += 3
+        return n
+
+    def _prior_reg(self):
+        """regularize_prior (fit.py:591-595): loss += mean(w_f^2), d_w += 2 w_f / B."""
+        if not self.use_reg_prior:
+            return 0
+        self._timed('prior_reg', 'fpc_l2_reg_fwd_bwd', _p(self.w), self.F, self.B, 1.0, _p(self.loss), _p(self.reg_l2_term), _p(self.d_w), 1.0,
+                    _p(self.d_w), _p(self.scratch), self.scratch.numel(), self._stream())
+        return 2
 
     def _fused(self, with_loss):
         """render + loss + d loss / d pos_clip in one kernel (csrc/fused.cu); with_loss=False renders images instead."""
@@ -422,15 +511,20 @@ class FitSession:
                  _p(self.mvp), _p(self.g_pos), _p(self.d_verts_reg) if self.use_reg else None, self.V, B, F, C,
                  _p(self.d_w), _p(self.d_t), _p(self.d_q), None, _p(self.d_mvp) if self.cfg.optimize_cam_pose else None,
                  _p(self.scratch), self.scratch.numel(), s)
-            return n + 2 + self._cam_pose_bwd()
+            return n + 2 + self._prior_reg() + self._cam_pose_bwd()
         call('project_bwd', 'fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
              _p(self.scratch), self.scratch.numel(), s); n += 2
         if self.use_reg:
             n += self._mesh_reg(self.d_verts, 1)
-        if self.use_tc_blend:
+        if self.cfg.mode == 'free':
+            pass                                        # no rig prior: d_w stays 0
+        elif self.use_tc_blend:
             call('blend_bwd', 'fpc_blend_bwd_tc', _p(self.DT), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
         else:
             call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
+        n += self._prior_reg()
+        if self.use_basis:
+            n += self._basis_backward()
         call('pose_mvp_bwd', 'fpc_pose_mvp_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), *self._cam(), _p(self.d_mvp), F, C,
              _p(self.d_t), _p(self.d_q), s); n += 1
         return n + self._cam_pose_bwd()
@@ -479,6 +573,11 @@ class FitSession:
             allreduce_gradients(self.d_tex)
             call('adam_tex', 'fpc_adam_step', _p(self.tex), _p(self.d_tex), _p(self.tex_m), _p(self.tex_v), self.tex.numel(),
                  cfg.lr_base * cfg.lr_tex_coef, cfg.beta1, cfg.beta2, cfg.eps, cfg.lr_ramp, float(cfg.max_iter), _p(self.step_count), s); n += 1
+        if self.use_basis:
+            # m1, m2, m3 are shared by every frame and every camera: partial sums on every rank in both sharding modes
+            allreduce_gradients(self.basis_grads)
+            call('adam_basis', 'fpc_adam_step_from', _p(self.basis), _p(self.basis_grads), _p(self.basis_m), _p(self.basis_v), self.basis.numel(),
+                 self.basis_lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.lr_ramp, float(cfg.max_iter), _p(self.step_count), self.basis_start, s); n += 1
         nw = F * B
         if F * (B + 7) <= (1 << 22):
             call('adam', 'fpc_adam_fused', _p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), B, F, 1 if cfg.optimize_pose else 0,
@@ -531,7 +630,10 @@ class FitSession:
     # ---- results -------------------------------------------------------------------------------------
     def result_vertices(self):
         """[F, 3V] blended vertices of the current parameters (fit.py:642 `result`)."""
-        _lib.call('fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), self.V * 3, self.B, self.F, _p(self.verts), self._stream())
+        if self.use_basis or self.use_tc_blend:
+            self._blend_forward()
+        else:
+            _lib.call('fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), self.V * 3, self.B, self.F, _p(self.verts), self._stream())
         return self.verts.clone()
 
 
@@ -541,6 +643,8 @@ def synthesize_reference(rig, w_true, t_true, q_true, config, device=None, out_d
     Frames are rendered `chunk` at a time so that long sequences need no float copy of the whole stack."""
     F = w_true.shape[0]
     out, sessions = None, {}
+    # ground truth is always rendered from the rig prior with the given texture
+    config = replace(config, mode='prior', optimize_texture=False, regularize_prior=False, regularize_correctives=False)
     for a in range(0, F, chunk):
         b = min(a + chunk, F)
         s = sessions.get(b - a)

@@ -99,10 +99,35 @@ int fpc_antialias_bwd(const float* color, const float* rast, const float* pos, c
 /* D [R,B] (R = 3V rows, xyz interleaved), base [R], w [F,B]  ->  verts [F,R] */
 int fpc_blend_fwd(const float* D, const float* base, const float* w, int R, int B, int F, float* verts,
                   fpc_stream_t stream);
+/* General form: verts[f,r] = init + coef * sum_b D[r,b] w[f,b] with init = verts[f,r] (accumulate != 0), base[r], or 0
+ * (base == NULL).  Used for the learned basis of the free / combined modes (D := m3, w := x2, below). */
+int fpc_blend_fwd_ex(const float* D, const float* base, const float* w, int R, int B, int F, float coef, int accumulate,
+                     float* verts, fpc_stream_t stream);
 /* transpose gradient: d_verts [F,R] -> d_w [F,B] (overwritten) = D^T d_verts.  Deterministic two-stage reduction. */
 size_t fpc_blend_bwd_scratch_bytes(int R, int B, int F);
 int fpc_blend_bwd(const float* D, const float* d_verts, int R, int B, int F, float* d_w,
                   void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
+/* ---- learned vertex basis of the "free" and "combined" modes (replaces blend_free fit.py:47-62 and the learned half of
+ *      blend_combined fit.py:66-99 with setup_dataset_free fit.py:166-179) -----------------------
+ * m1, m2 [Fn,Fn], m3 [R,Fn] are shared by the Fn frames of the take; frame_ids [Fb] = take-wide ids of the batch's frames
+ * (distinct).  x1[b,:] = m1[:, id_b] (m1 e_f), x2[b,:] = m2 x1[b,:];  the vertices follow from
+ * fpc_blend_fwd_ex(m3, base-or-accumulate, x2, R, Fn, Fb, coef, ...).  Backward: d_x2 [Fb,Fn] = fpc_blend_bwd(m3, d_verts),
+ *   fpc_basis_grad:      d_m3 [R,Fn]  = coef * d_verts^T x2                         (overwritten)
+ *   fpc_basis_code_bwd:  d_m2 [Fn,Fn] = coef * d_x2^T x1,  d_m1[:, id_b] = coef * m2^T d_x2[b,:], 0 elsewhere (overwritten)
+ * Fixed summation order, no atomics. */
+int fpc_basis_code_fwd(const float* m1, const float* m2, const int32_t* frame_ids, int Fn, int Fb, float* x1, float* x2,
+                       fpc_stream_t stream);
+int fpc_basis_grad(const float* d_verts, const float* x2, int R, int Fn, int Fb, float coef, float* d_m3, fpc_stream_t stream);
+int fpc_basis_code_bwd(const float* m2, const float* x1, const float* d_x2, const int32_t* frame_ids, int Fn, int Fb, float coef,
+                       float* d_m1, float* d_m2, fpc_stream_t stream);
+/* The optional L2 terms of the loop: regularize_prior, loss += mean(activations^2) (fit.py:591-595), and
+ * regularize_correctives, loss += mean(deformations^2) (fit.py:584-589).  x [F,n]:
+ *   term [1] (nullable) = weight * sum_f mean_n x^2;  loss_accum [1] (nullable) += term;
+ *   g_out [F,n] (nullable; may alias g_in) = g_scale * g_in (0 if g_in == NULL) + (2 weight / n) x. */
+size_t fpc_l2_reg_scratch_bytes(long long total);
+int fpc_l2_reg_fwd_bwd(const float* x, int F, long long n, float weight, float* loss_accum, float* term,
+                       const float* g_in, float g_scale, float* g_out, void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
 /* Tensor-core path for frame batches (north-star item 1): the same mathematics as fpc_blend_fwd / fpc_blend_bwd as one
  * TMA + tcgen05 (kind::tf32, 3xTF32 hi/lo split: fp32-level accuracy) GEMM kernel with the accumulator in TMEM.
@@ -217,6 +242,12 @@ int fpc_mesh_reg_fwd_bwd(const float* verts, int F, int V, const int32_t* nbr_of
  * torch.optim.Adam update rule with bias correction, betas (b1,b2), eps, no weight decay / amsgrad. */
 int fpc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                   float lr_ramp, float max_iter, const float* step_count, fpc_stream_t stream);
+/* The same for a parameter group that is unlocked at optimiser step `start_step` (combined mode: the learned basis gets
+ * requires_grad after max_iter/2, fit.py:603-608): no-op while step_count < start_step (torch skips parameters without a
+ * gradient, their state stays untouched); afterwards Adam's t = step_count - start_step + 1, the LambdaLR factor still
+ * follows the global step_count. */
+int fpc_adam_step_from(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                       float lr_ramp, float max_iter, const float* step_count, float start_step, fpc_stream_t stream);
 /* step_count [1] += 1 (device side, so the iteration stays graph-capturable) */
 int fpc_adam_advance(float* step_count, fpc_stream_t stream);
 /* q [n,4] /= norm.  mode 0: per-row norm (default of this build);  mode 1: Frobenius norm of the whole tensor

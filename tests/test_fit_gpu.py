@@ -447,3 +447,163 @@ def test_fit_take_from_disk(tmp_path):
     pose = json.load(open(d / 'pose.json'))
     assert np.allclose(pose['rotation'], res['q']) and np.allclose(pose['translation'], res['t'])
     assert "iters_per_frame: '150'" in open(out_dir / 'config.txt').read()
+
+
+def test_basis_kernels_match_reference_kat():
+    """fpc_basis_code_fwd + fpc_blend_fwd_ex and their backward (fpc_blend_bwd, fpc_basis_grad, fpc_basis_code_bwd) on the
+    vectors the reference's own blend_free / blend_combined produced (tests/golden/blend_kat.json), all frames as one batch."""
+    import ctypes
+    import json
+    import os
+    from fpc_diffrend_b200 import _lib
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'blend_kat.json')) as f:
+        k = json.load(f)
+    R, B, Fn = k['R'], k['B'], k['F']
+    cu = lambda name: torch.tensor(k[name], dtype=torch.float32).cuda().contiguous()
+    v_base, D, M1, M2, m1, m2, m3, dy = (cu(n) for n in ('v_base', 'D', 'M1', 'M2', 'm1', 'm2', 'm3', 'dy'))
+    ids = torch.tensor([3, 0, 4, 1, 2], dtype=torch.int32).cuda()         # a shuffled batch of all frames
+    Fb = ids.numel()
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x1, x2 = torch.empty(Fb, Fn, device='cuda'), torch.empty(Fb, Fn, device='cuda')
+    _lib.call('fpc_basis_code_fwd', P(m1), P(m2), P(ids), Fn, Fb, P(x1), P(x2), st)
+    scratch = torch.empty(int(_lib.load().fpc_blend_bwd_scratch_bytes(R, max(B, Fn), Fb)), dtype=torch.uint8, device='cuda')
+    d_verts = dy[None].repeat(Fb, 1).contiguous()
+    for mode, coef in (('free', 1.0), ('combined', 0.5)):
+        verts = torch.full((Fb, R), float('nan'), device='cuda')
+        if mode == 'free':
+            _lib.call('fpc_blend_fwd_ex', P(m3), P(v_base), P(x2), R, Fn, Fb, 1.0, 0, P(verts), st)
+        else:
+            w = (M2 @ M1[:, ids.long()]).t().contiguous()                  # [Fb,B] activations of the prior half
+            _lib.call('fpc_blend_fwd', P(D), P(v_base), P(w), R, B, Fb, P(verts), st)
+            _lib.call('fpc_blend_fwd_ex', P(m3), None, P(x2), R, Fn, Fb, coef, 1, P(verts), st)
+        d_x2 = torch.empty(Fb, Fn, device='cuda')
+        d_m1, d_m2, d_m3 = torch.full((Fn, Fn), 7.0, device='cuda'), torch.full((Fn, Fn), 7.0, device='cuda'), torch.full((R, Fn), 7.0, device='cuda')
+        _lib.call('fpc_blend_bwd', P(m3), P(d_verts), R, Fn, Fb, P(d_x2), P(scratch), scratch.numel(), st)
+        _lib.call('fpc_basis_grad', P(d_verts), P(x2), R, Fn, Fb, coef, P(d_m3), st)
+        _lib.call('fpc_basis_code_bwd', P(m2), P(x1), P(d_x2), P(ids), Fn, Fb, coef, P(d_m1), P(d_m2), st)
+        torch.cuda.synchronize()
+        g1, g2, g3 = torch.zeros(Fn, Fn), torch.zeros(Fn, Fn), torch.zeros(R, Fn)
+        for b, f in enumerate(ids.tolist()):
+            rec = k['frames'][str(f)][mode]
+            ref = torch.tensor(rec['vtx_pos'])
+            assert (verts[b].cpu() - ref).abs().max() <= 1e-5 * ref.abs().max(), (mode, f)
+            g1 += torch.tensor(rec['grad']['m1']); g2 += torch.tensor(rec['grad']['m2']); g3 += torch.tensor(rec['grad']['m3'])
+        # the batch gradient is the sum of the reference's single-frame gradients
+        assert rel(d_m1.cpu(), g1) < 1e-5 and rel(d_m2.cpu(), g2) < 1e-5 and rel(d_m3.cpu(), g3) < 1e-5, mode
+
+
+def _oracle_mode_iteration(rig, s, mode, ids, ref, H, W, opp, reg_corr=False, reg_prior=False):
+    """Loss and parameter gradients of one batch iteration in the given mode through the oracle (torch CPU stages + golden
+    ops with autograd), the blend written exactly as the reference's blend / blend_free / blend_combined."""
+    F, C, Fn = s.F, rig.P.shape[0], (s.Fn if mode != 'prior' else s.F)
+    w = s.w.cpu().clone().requires_grad_(True)
+    t = s.t.cpu().clone().requires_grad_(True)
+    q = s.q.cpu().clone().requires_grad_(True)
+    ms = [x.cpu().clone().requires_grad_(True) for x in (s.m1, s.m2, s.m3)] if mode != 'prior' else None
+    vb, D = torch.tensor(rig.v_base), torch.tensor(rig.D)
+    total = 0.0
+    for f in range(F):
+        if mode == 'prior':
+            verts = G.blend(vb, D, w[f])
+        else:
+            e = torch.zeros(Fn)
+            e[int(ids[f])] = 1.0
+            corr = ms[2] @ (ms[1] @ (ms[0] @ e))
+            verts = G.blend_free(vb, ms[0], ms[1], ms[2], e) if mode == 'free' else G.blend(vb, D, w[f]) + s.basis_coef * corr
+            if reg_corr:
+                total = total + torch.mean(corr ** 2)
+        if reg_prior:
+            total = total + torch.mean(w[f] ** 2)
+        verts = verts.reshape(-1, 3)
+        for c in range(C):
+            mvp = G.mvp_chain(torch.tensor(rig.P[c]), torch.tensor(rig.A[c]), t[f], q[f])
+            img = G.render(mvp, verts, torch.tensor(rig.pos_idx), (H, W), vcol=torch.tensor(rig.vcol), tri_opp=opp, use_antialias=False)
+            total = total + G.image_loss(ref[f, c], img) / C
+    total.backward()
+    return float(total.detach()), w.grad, t.grad, q.grad, ([m.grad for m in ms] if ms else None)
+
+
+@pytest.mark.parametrize('mode,reg', [('free', False), ('combined', False), ('combined', True), ('prior', True)])
+def test_free_and_combined_modes(tiny_rig, mode, reg):
+    """the 'free' (blend_free) and 'combined' (blend_combined) optimisation modes and the optional L2 terms.
+    One iteration's loss and gradients against the oracle from a state where every matrix is non-trivial, then the Adam
+    schedule of the learned basis (locked until corrective_start, its own bias-correction clock afterwards)."""
+    from fpc_diffrend_b200 import rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F, Fn = tiny_rig, 128, 128, 2, 5
+    ids = [3, 1]
+    cfg = FitConfig(resolution=(H, W), shading='vcol', antialias=False, mode=mode, n_frames_total=Fn, lr_base=1e-2, lr_t=1e-3, lr_q=1e-4,
+                    max_iter=8, regularize_correctives=reg and mode == 'combined', regularize_prior=reg and mode == 'prior')
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=2)
+    ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, cfg)
+    s = FitSession(rig, F, cfg, frame_ids=ids if mode != 'prior' else None)
+    s.set_reference(ref)
+    g = torch.Generator().manual_seed(5)
+    s.set_parameters(w=0.2 * torch.rand(F, rig.B, generator=g))
+    if mode != 'prior':
+        assert s.basis_start == (0 if mode == 'free' else cfg.max_iter // 2 + 2) and not s.use_geom_fused
+        s.m1.add_((0.1 * torch.randn(Fn, Fn, generator=g)).cuda())
+        s.m2.add_((0.1 * torch.randn(Fn, Fn, generator=g)).cuda())
+        s.m3.copy_((0.05 * torch.randn(3 * rig.V, Fn, generator=g)).cuda())
+    s.forward()
+    s.backward()
+    torch.cuda.synchronize()
+    opp = torch.tensor(G.topology_build(rig.pos_idx))
+    loss_o, gw, gt, gq, gm = _oracle_mode_iteration(rig, s, mode, ids, ref.cpu(), H, W, opp, reg_corr=cfg.regularize_correctives,
+                                                    reg_prior=cfg.regularize_prior)
+    # the render chain is discontinuous in its inputs (test_iteration_gradients): whole-chain comparisons carry ~1 % noise from
+    # single silhouette-pixel flips, the staged test above pins every link tightly; here the new links are what is checked
+    assert abs(float(s.loss) - loss_o) / loss_o < 2e-3
+    if mode != 'free':
+        assert rel(s.d_w.cpu(), gw) < 3e-2
+    else:
+        assert float(s.d_w.abs().max()) == 0.0
+    if mode != 'prior':
+        # exact link check: the basis gradients are linear maps of the GPU's own d_verts
+        dv = s.d_verts.cpu()
+        x1 = s.m1.cpu()[:, ids].t()
+        x2 = x1 @ s.m2.cpu().t()
+        c = s.basis_coef
+        dvc = c * dv + (2.0 * (x2 @ s.m3.cpu().t()) / (3 * rig.V) if cfg.regularize_correctives else 0.0)
+        d_x2 = dvc @ s.m3.cpu()
+        assert rel(s.d_m3.cpu(), dvc.t() @ x2) < 1e-5
+        assert rel(s.d_m2.cpu(), d_x2.t() @ x1) < 1e-5
+        d_m1 = torch.zeros(Fn, Fn)
+        d_m1[:, ids] = (d_x2 @ s.m2.cpu()).t()
+        assert rel(s.d_m1.cpu(), d_m1) < 1e-5
+        for a, b in zip((s.d_m1, s.d_m2, s.d_m3), gm):
+            assert rel(a.cpu(), b) < 3e-2
+    if reg:
+        vb = torch.tensor(rig.v_base)
+        if mode == 'prior':
+            term = sum(float(torch.mean(s.w[f].cpu() ** 2)) for f in range(F))
+        else:
+            term = sum(float(torch.mean((x2[f] @ s.m3.cpu().t()) ** 2)) for f in range(F))
+        assert abs(float(s.reg_l2_term) - term) <= 1e-5 * term
+
+    if mode == 'prior':
+        return
+    # Adam schedule of the basis group: torch.optim.Adam on the same gradient stream; the group is skipped while locked
+    s2 = FitSession(rig, F, cfg, frame_ids=ids)
+    s2.set_reference(ref)
+    basis_o = s2.basis.cpu().clone().requires_grad_(True)
+    opt = torch.optim.Adam([{'params': basis_o, 'lr': s2.basis_lr}])
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda x: cfg.lr_ramp ** (float(x) / float(cfg.max_iter)))
+    for it in range(cfg.max_iter):
+        s2.forward()
+        s2.backward()
+        grads = s2.basis_grads.cpu().clone()
+        before = s2.basis.clone()
+        s2.optimizer_step()
+        if it >= s2.basis_start:
+            opt.zero_grad()
+            basis_o.grad = grads
+            opt.step()
+        else:
+            assert torch.equal(before, s2.basis), 'the learned basis must stay locked before corrective_start'
+        sched.step()
+    torch.cuda.synchronize()
+    assert float((s2.basis.cpu() - torch.cat([torch.eye(Fn).flatten(), torch.eye(Fn).flatten(), torch.zeros(3 * rig.V * Fn)])).abs().max()) > 0
+    d = (s2.basis.cpu() - basis_o.detach()).abs().max()
+    assert float(d) <= 1e-6 + 1e-3 * s2.basis_lr * cfg.max_iter, float(d)

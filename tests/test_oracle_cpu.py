@@ -326,3 +326,42 @@ def test_raster_near_plane_clipper(small_rig3):
     assert (r1[..., 3] > 0).sum() > 100
     assert np.array_equal(r1[..., 3] > 0, r2[..., 3] > 0)
     assert np.abs(r1[..., 2] - r2[..., 2]).max() < 1e-5
+
+
+def _blend_kat():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'blend_kat.json')) as f:
+        return json.load(f)
+
+
+def test_blend_modes_match_reference_kat():
+    """The oracle's blend_prior / blend_free / blend_combined against vectors produced by the reference's own
+    functions (tests/golden/make_blend_kat.py executes fit.py:47-129 unchanged): values and autograd gradients."""
+    k = _blend_kat()
+    T = lambda name: torch.tensor(k[name], dtype=torch.float32)
+    v_base, D, dy = T('v_base'), T('D'), T('dy')
+    for frame, rec in k['frames'].items():
+        e = torch.zeros(k['F'])
+        e[int(frame)] = 1.0
+        for mode in ('prior', 'free', 'combined'):
+            P = {n: T(n).requires_grad_(True) for n in ('M1', 'M2', 'm1', 'm2', 'm3')}
+            if mode == 'prior':
+                v = G.blend_prior(v_base, D, P['M1'], P['M2'], e)
+            elif mode == 'free':
+                v = G.blend_free(v_base, P['m1'], P['m2'], P['m3'], e)
+            else:
+                v = G.blend_combined(v_base, D, P['M1'], P['M2'], P['m1'], P['m2'], P['m3'], e, learned_coefficient=0.5)
+            ref = torch.tensor(rec[mode]['vtx_pos'])
+            assert (v.detach() - ref).abs().max() <= 1e-5 * ref.abs().max()
+            (v * dy).sum().backward()
+            for n, g in rec[mode]['grad'].items():
+                if g is None:
+                    assert P[n].grad is None
+                else:
+                    g = torch.tensor(g)
+                    assert (P[n].grad - g).abs().max() <= 1e-5 * max(float(g.abs().max()), 1e-6), (mode, n)
+            # the north-star form V = base + D w with w = M2 M1 e_f is the same map
+            if mode == 'prior':
+                w = torch.tensor(k['M2']) @ torch.tensor(k['M1'])[:, int(frame)]
+                assert (G.blend(v_base, D, w) - ref).abs().max() <= 1e-5 * ref.abs().max()

@@ -32,6 +32,14 @@ SIGNATURES = {
     'fpc_interpolate_bwd': (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     'fpc_texture_linear_fwd': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
     'fpc_texture_linear_bwd': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'fpc_rasterize_bwd_db': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    'fpc_interpolate_da_fwd': (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'fpc_interpolate_da_bwd': (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    'fpc_texture_mip_levels': (_I, [_I, _I, _I]),
+    'fpc_texture_mip_floats': (_Z, [_I, _I, _I, _I, _I]),
+    'fpc_texture_mip_build': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    'fpc_texture_mip_fwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    'fpc_texture_mip_bwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     'fpc_topology_scratch_bytes': (_Z, [_I]),
     'fpc_topology_build': (_I, [_P, _I, _I, _P, _P, _Z, _P]),
     'fpc_antialias_fwd': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -101,7 +101,7 @@ class RasterizeGLContext(RasterizeCudaContext):
 
 class _rasterize_func(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, glctx, pos, tri, resolution, want_db):
+    def forward(ctx, glctx, pos, tri, resolution, want_db, grad_db):
         N, V, _ = pos.shape
         T = tri.shape[0]
         H, W = resolution
@@ -113,9 +113,11 @@ class _rasterize_func(torch.autograd.Function):
             _lib.call('fpc_rasterize_fwd', _ptr(pos), _ptr(tri), N, V, T, H, W, _ptr(rast), _ptr(rast_db),
                       _ptr(scratch), scratch.numel(), _stream())
         ctx.save_for_backward(pos, tri, rast)
+        ctx.grad_db = bool(grad_db and rast_db is not None)
         if rast_db is None:
             rast_db = torch.empty((N, H, W, 0), dtype=torch.float32, device=pos.device)
-        ctx.mark_non_differentiable(rast_db)
+        if not ctx.grad_db:
+            ctx.mark_non_differentiable(rast_db)
         return rast, rast_db
 
     @staticmethod
@@ -124,11 +126,16 @@ class _rasterize_func(torch.autograd.Function):
         N, V, _ = pos.shape
         _, H, W, _ = rast.shape
         g_pos = torch.empty_like(pos)
-        dy = dy.contiguous()
+        dy = dy.contiguous() if dy is not None else torch.zeros_like(rast)
         with torch.cuda.device(pos.device):
-            _lib.call('fpc_rasterize_bwd', _ptr(pos), _ptr(tri), _ptr(rast), _ptr(dy), N, V, tri.shape[0], H, W,
-                      _ptr(g_pos), _stream())
-        return None, g_pos, None, None, None
+            if ctx.grad_db and ddb is not None:
+                # upstream's rasterize_grad_db: the gradient also flows through the barycentric pixel differentials
+                _lib.call('fpc_rasterize_bwd_db', _ptr(pos), _ptr(tri), _ptr(rast), _ptr(dy), _ptr(ddb.contiguous()), N, V,
+                          tri.shape[0], H, W, _ptr(g_pos), _stream())
+            else:
+                _lib.call('fpc_rasterize_bwd', _ptr(pos), _ptr(tri), _ptr(rast), _ptr(dy), N, V, tri.shape[0], H, W,
+                          _ptr(g_pos), _stream())
+        return None, g_pos, None, None, None, None
 
 
 def rasterize(glctx, pos, tri, resolution, ranges=None, grad_db=True):
@@ -142,10 +149,9 @@ def rasterize(glctx, pos, tri, resolution, ranges=None, grad_db=True):
     _require(len(resolution) == 2 and int(resolution[0]) > 0 and int(resolution[1]) > 0, 'resolution must be [>0, >0]')
     _require(pos.device == tri.device, 'pos and tri must reside on the same device')
     _check_device(pos)
-    # grad_db only controls whether gradients flow into rast_db upstream; rast_db is not differentiable here
-    # (mip path is out of scope for this round).
+    # grad_db: whether gradients flow back through rast_db (mip-mapped texturing path, fit.py:153-155)
     return _rasterize_func.apply(glctx, pos.contiguous(), tri.contiguous(), (int(resolution[0]), int(resolution[1])),
-                                 glctx.output_db)
+                                 glctx.output_db, bool(grad_db))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -178,10 +184,43 @@ class _interpolate_func(torch.autograd.Function):
         return g_attr, g_rast, None
 
 
+class _interpolate_da_func(torch.autograd.Function):
+    """interpolate with attribute pixel differentials (upstream's interpolate_fwd_da / interpolate_grad_da)."""
+
+    @staticmethod
+    def forward(ctx, attr, rast, tri, rast_db, diff_list):
+        Na, Vt, A = attr.shape
+        N, H, W, _ = rast.shape
+        K = A if diff_list is None else len(diff_list)
+        sel = None if diff_list is None else (ctypes.c_int32 * K)(*diff_list)
+        out = torch.empty((N, H, W, A), dtype=torch.float32, device=rast.device)
+        out_da = torch.empty((N, H, W, 2 * K), dtype=torch.float32, device=rast.device)
+        with torch.cuda.device(rast.device):
+            _lib.call('fpc_interpolate_da_fwd', _ptr(attr), Na, Vt, A, _ptr(rast), _ptr(rast_db), _ptr(tri), sel, K, N, tri.shape[0],
+                      H, W, _ptr(out), _ptr(out_da), _stream())
+        ctx.save_for_backward(attr, rast, tri, rast_db)
+        ctx.sel, ctx.K = sel, K
+        return out, out_da
+
+    @staticmethod
+    def backward(ctx, dy, dda):
+        attr, rast, tri, rast_db = ctx.saved_tensors
+        Na, Vt, A = attr.shape
+        N, H, W, _ = rast.shape
+        g_attr, g_rast, g_db = torch.empty_like(attr), torch.empty_like(rast), torch.empty_like(rast_db)
+        dy = dy.contiguous() if dy is not None else None
+        dda = dda.contiguous() if (dda is not None and ctx.K > 0) else None
+        if dy is None and dda is None:
+            return torch.zeros_like(attr), torch.zeros_like(rast), None, torch.zeros_like(rast_db), None
+        with torch.cuda.device(rast.device):
+            _lib.call('fpc_interpolate_da_bwd', _ptr(attr), Na, Vt, A, _ptr(rast), _ptr(rast_db), _ptr(tri), ctx.sel, ctx.K, _ptr(dy),
+                      _ptr(dda), N, tri.shape[0], H, W, _ptr(g_attr), _ptr(g_rast), _ptr(g_db), _stream())
+        return g_attr, g_rast, None, g_db, None
+
+
 def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
-    """attr [1|N,V,A], rast [N,H,W,4], tri [T,3] -> (out [N,H,W,A], out_da [N,H,W,0])."""
-    _require(diff_attrs is None or (isinstance(diff_attrs, (list, tuple)) and len(diff_attrs) == 0),
-             'interpolate: attribute pixel differentials (diff_attrs) are not supported (mip path, SURVEY §8(f) rank 4)')
+    """attr [1|N,V,A], rast [N,H,W,4], tri [T,3] -> (out [N,H,W,A], out_da [N,H,W,2k]); k = 0 unless rast_db and diff_attrs
+    ('all' or a list of attribute indices) are given (fit.py:154)."""
     _check_tensor('attr', attr, torch.float32, 3)
     _check_tensor('rast', rast, torch.float32, 4)
     _check_tensor('tri', tri, torch.int32, 2)
@@ -191,6 +230,19 @@ def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
              'attr must have shape [1 or minibatch, >0, >0]')
     _require(attr.device == rast.device == tri.device, 'attr, rast and tri must reside on the same device')
     _check_device(rast)
+    diff_list = None
+    want_da = diff_attrs is not None and not (isinstance(diff_attrs, (list, tuple)) and len(diff_attrs) == 0)
+    if want_da:
+        _require(rast_db is not None, 'interpolate: diff_attrs needs rast_db')
+        _check_tensor('rast_db', rast_db, torch.float32, 4)
+        _require(tuple(rast_db.shape) == tuple(rast.shape), 'rast_db must have the shape of rast [N, H, W, 4]')
+        _require(rast_db.device == rast.device, 'rast_db must reside on the same device as rast')
+        if diff_attrs != 'all':
+            _require(isinstance(diff_attrs, (list, tuple)), "diff_attrs must be 'all' or a list of attribute indices")
+            diff_list = [int(i) for i in diff_attrs]
+            _require(all(0 <= i < attr.shape[2] for i in diff_list), 'diff_attrs indices out of range')
+        _require((attr.shape[2] if diff_list is None else len(diff_list)) <= 32, 'interpolate: at most 32 differentiated attributes')
+        return _interpolate_da_func.apply(attr.contiguous(), rast.contiguous(), tri.contiguous(), rast_db.contiguous(), diff_list)
     out = _interpolate_func.apply(attr.contiguous(), rast.contiguous(), tri.contiguous())
     out_da = torch.empty(tuple(out.shape[:3]) + (0,), dtype=torch.float32, device=out.device)
     return out, out_da
@@ -225,22 +277,116 @@ class _texture_func(torch.autograd.Function):
         return g_tex, g_uv
 
 
+class TextureMipWrapper:
+    """Pre-built mip stack (levels 1..L back to back) — the role of upstream's TextureMipWrapper."""
+
+    def __init__(self, mip, levels, tex_shape):
+        self.mip, self.levels, self.tex_shape = mip, levels, tuple(tex_shape)
+
+
+def _mip_levels(tex, max_mip_level):
+    L = _lib.load().fpc_texture_mip_levels(int(tex.shape[1]), int(tex.shape[2]), -1 if max_mip_level is None else int(max_mip_level))
+    if max_mip_level is None:
+        # upstream builds the chain down to 1x1 and refuses extents that stop being even on the way
+        _require((tex.shape[1] >> L) == 1 or (tex.shape[2] >> L) == 1,
+                 'texture: extents %dx%d do not halve evenly down to 1; pass max_mip_level' % (tex.shape[2], tex.shape[1]))
+    else:
+        _require(L == int(max_mip_level), 'texture: max_mip_level=%d needs extents divisible by %d (got %dx%d)'
+                 % (max_mip_level, 1 << int(max_mip_level), tex.shape[2], tex.shape[1]))
+    return L
+
+
+def _build_mip(tex, L):
+    Nt, Ht, Wt, C = tex.shape
+    mip = torch.empty(int(_lib.load().fpc_texture_mip_floats(Nt, Ht, Wt, C, L)), dtype=torch.float32, device=tex.device)
+    with torch.cuda.device(tex.device):
+        _lib.call('fpc_texture_mip_build', _ptr(tex), Nt, Ht, Wt, C, L, _ptr(mip), _stream())
+    return mip
+
+
+def texture_construct_mip(tex, max_mip_level=None, cube_mode=False):
+    """Build the mip stack of tex [1|N,Ht,Wt,C] once, for reuse across texture() calls with a constant texture."""
+    _require(not cube_mode, 'texture_construct_mip: cube maps are not supported')
+    _check_tensor('tex', tex, torch.float32, 4)
+    _check_device(tex)
+    tex = tex.contiguous()
+    L = _mip_levels(tex, max_mip_level)
+    return TextureMipWrapper(_build_mip(tex.detach(), L), L, tex.shape)
+
+
+class _texture_mip_func(torch.autograd.Function):
+    """upstream's texture_fwd_mip / texture_grad_linear_mipmap_{nearest,linear}"""
+
+    @staticmethod
+    def forward(ctx, tex, uv, uv_da, bias, mip, L, nearest, mip_const):
+        Nt, Ht, Wt, C = tex.shape
+        N, H, W, _ = uv.shape
+        if mip is None:
+            mip = _build_mip(tex, L)
+        out = torch.empty((N, H, W, C), dtype=torch.float32, device=uv.device)
+        with torch.cuda.device(uv.device):
+            _lib.call('fpc_texture_mip_fwd', _ptr(tex), _ptr(mip), Nt, Ht, Wt, C, L, _ptr(uv), _ptr(uv_da), _ptr(bias), nearest, N, H, W,
+                      _ptr(out), _stream())
+        ctx.save_for_backward(tex, uv, uv_da, bias, mip)
+        ctx.L, ctx.nearest, ctx.mip_const = L, nearest, mip_const
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        tex, uv, uv_da, bias, mip = ctx.saved_tensors
+        Nt, Ht, Wt, C = tex.shape
+        N, H, W, _ = uv.shape
+        g_tex = torch.empty_like(tex) if ctx.needs_input_grad[0] else None
+        g_mip = torch.empty_like(mip) if g_tex is not None else None
+        g_uv = torch.empty_like(uv)
+        g_da = torch.empty_like(uv_da) if uv_da is not None else None
+        g_bias = torch.empty_like(bias) if bias is not None else None
+        with torch.cuda.device(uv.device):
+            _lib.call('fpc_texture_mip_bwd', _ptr(tex), _ptr(mip), Nt, Ht, Wt, C, ctx.L, _ptr(uv), _ptr(uv_da), _ptr(bias), ctx.nearest,
+                      _ptr(dy.contiguous()), N, H, W, _ptr(g_tex), _ptr(g_mip), 1 if ctx.mip_const else 0, _ptr(g_uv), _ptr(g_da),
+                      _ptr(g_bias), _stream())
+        return g_tex, g_uv, g_da, g_bias, None, None, None, None
+
+
 def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode='auto', boundary_mode='wrap',
             max_mip_level=None):
-    """tex [1|N,Ht,Wt,C], uv [N,H,W,2] -> [N,H,W,C]; filter_mode 'linear' (or 'auto' without uv_da), boundary 'wrap'."""
+    """tex [1|N,Ht,Wt,C], uv [N,H,W,2] -> [N,H,W,C].  filter_mode 'linear', 'linear-mipmap-nearest' or 'linear-mipmap-linear'
+    ('auto' = the latter when uv_da / mip_level_bias is given, else 'linear'); boundary_mode 'wrap' (fit.py:155,158)."""
     if filter_mode == 'auto':
         filter_mode = 'linear-mipmap-linear' if (uv_da is not None or mip_level_bias is not None) else 'linear'
-    _require(filter_mode == 'linear',
-             "texture: only filter_mode='linear' is supported (got %r; mip modes are SURVEY §8(f) rank 4)" % (filter_mode,))
+    _require(filter_mode in ('linear', 'linear-mipmap-nearest', 'linear-mipmap-linear'),
+             "texture: filter_mode must be 'linear', 'linear-mipmap-nearest' or 'linear-mipmap-linear' (got %r)" % (filter_mode,))
     _require(boundary_mode == 'wrap', "texture: only boundary_mode='wrap' is supported (got %r)" % (boundary_mode,))
-    _require(uv_da is None and mip_level_bias is None and mip is None, 'texture: mip inputs are not supported with filter_mode=linear')
     _check_tensor('tex', tex, torch.float32, 4)
     _check_tensor('uv', uv, torch.float32, 4)
     _require(uv.shape[3] == 2 and min(uv.shape) > 0, 'uv must have shape [>0, >0, >0, 2]')
     _require(min(tex.shape) > 0 and tex.shape[0] in (1, uv.shape[0]), 'tex must have shape [1 or minibatch, >0, >0, >0]')
     _require(tex.device == uv.device, 'tex and uv must reside on the same device')
     _check_device(uv)
-    return _texture_func.apply(tex.contiguous(), uv.contiguous())
+    if filter_mode == 'linear':
+        # upstream ignores the mip inputs in the non-mip modes
+        return _texture_func.apply(tex.contiguous(), uv.contiguous())
+    _require(uv_da is not None or mip_level_bias is not None, 'texture: mip filter modes need uv_da or mip_level_bias')
+    if uv_da is not None:
+        _check_tensor('uv_da', uv_da, torch.float32, 4)
+        _require(tuple(uv_da.shape) == tuple(uv.shape[:3]) + (4,), 'uv_da must have shape [N, H, W, 4]')
+        _require(uv_da.device == uv.device, 'uv_da must reside on the same device as uv')
+        uv_da = uv_da.contiguous()
+    if mip_level_bias is not None:
+        _check_tensor('mip_level_bias', mip_level_bias, torch.float32, 3)
+        _require(tuple(mip_level_bias.shape) == tuple(uv.shape[:3]), 'mip_level_bias must have shape [N, H, W]')
+        _require(mip_level_bias.device == uv.device, 'mip_level_bias must reside on the same device as uv')
+        mip_level_bias = mip_level_bias.contiguous()
+    tex = tex.contiguous()
+    if mip is not None:
+        _require(isinstance(mip, TextureMipWrapper) and mip.tex_shape == tuple(tex.shape), 'mip must come from texture_construct_mip(tex)')
+        L, mip_buf = mip.levels, mip.mip
+        if max_mip_level is not None:
+            L = min(L, int(max_mip_level))
+    else:
+        L, mip_buf = _mip_levels(tex, max_mip_level), None
+    return _texture_mip_func.apply(tex, uv.contiguous(), uv_da, mip_level_bias, mip_buf, L, 1 if filter_mode == 'linear-mipmap-nearest' else 0,
+                                   mip is not None)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -52,6 +52,13 @@ def fit_take(basemeshpath, localblpath, imdir, calibpath, out_dir=None, iters_pe
     cfg.ref_dtype = 'u8'
     f0, f1 = shard.frame_shard(len(frames))
     mine = frames[f0:f1]
+    # parameters shared by all frames (texture, per-camera pose corrections, the learned basis of the free / combined modes)
+    # live in ONE session: such takes are fitted as a single batch per rank (their gradients are all-reduced over ranks)
+    shared = cfg.optimize_texture or cfg.optimize_cam_pose or cfg.mode != 'prior'
+    if shared:
+        frame_batch = max(frame_batch, len(mine))
+        if cfg.mode != 'prior':
+            cfg.n_frames_total = len(frames)
     verts, ws, ts, qs, losses = [], [], [], [], []
     sessions = {}
     for a in range(0, len(mine), frame_batch):
@@ -59,7 +66,7 @@ def fit_take(basemeshpath, localblpath, imdir, calibpath, out_dir=None, iters_pe
         ref = dataio.load_reference_frames(imdir, cams, batch, digits)
         s = sessions.get(len(batch))
         if s is None:
-            s = sessions[len(batch)] = FitSession(rig, len(batch), cfg)
+            s = sessions[len(batch)] = FitSession(rig, len(batch), cfg, frame_ids=list(range(f0 + a, f0 + a + len(batch))))
         else:                                         # fresh parameters and optimiser state for the next batch of frames
             s.params.zero_(); s.q[:, 3] = 1.0
             s.adam_m.zero_(); s.adam_v.zero_(); s.step_count.zero_()
@@ -82,6 +89,8 @@ def fit_take(basemeshpath, localblpath, imdir, calibpath, out_dir=None, iters_pe
     out = {k: v.cpu().numpy() for k, v in out.items()}
     out['loss'] = losses
     out['frames'] = frames
+    if cfg.optimize_texture and sessions:
+        rig.tex = next(iter(sessions.values())).tex[0].cpu().numpy()          # tex_opt is what fit.py:655 saves
     if out_dir is not None:
         dataio.save_results(out['vertices'], rig.uv, rig.tex, out['t'], out['q'], out_dir,
                             faces_lines=dataio.faces_lines_for(rig.pos_idx, rig.uv_idx))

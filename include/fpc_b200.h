@@ -183,6 +183,41 @@ int fpc_geometry_bwd(const float* P, const float* A, const float* t, const float
                      int V, int B, int F, int C, float* d_w, float* d_t, float* d_q, float* d_verts, float* d_mvp,
                      void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
+/* ---- mip-mapped texturing path (reference fit.py:153-155 with enable_mip) -------------------------
+ * Replaces, in nvdiffrast plugin terms: rasterize_grad_db, interpolate_fwd_da / interpolate_grad_da,
+ * texture_construct_mip, texture_fwd_mip, texture_grad_linear_mipmap_{nearest,linear}. */
+/* rasterize backward with the gradient of rast_db: d_rast [N,H,W,4] (u, v used), d_rast_db [N,H,W,4] -> grad_pos (overwritten) */
+int fpc_rasterize_bwd_db(const float* pos, const int32_t* tri, const float* rast, const float* d_rast, const float* d_rast_db,
+                         int N, int V, int T, int H, int W, float* grad_pos, fpc_stream_t stream);
+/* interpolate with attribute pixel differentials: diff_attrs = HOST array of K attribute indices (NULL = all A attributes,
+ * K ignored; at most 32); out [N,H,W,A], out_da [N,H,W,2K] = (d a_j / dX, d a_j / dY) per selected attribute. */
+int fpc_interpolate_da_fwd(const float* attr, int Na, int Vt, int A, const float* rast, const float* rast_db, const int32_t* tri,
+                           const int32_t* diff_attrs, int K, int N, int T, int H, int W, float* out, float* out_da,
+                           fpc_stream_t stream);
+/* dy [N,H,W,A] and/or dda [N,H,W,2K] (either may be NULL) -> grad_attr, grad_rast (overwritten), grad_rast_db (nullable) */
+int fpc_interpolate_da_bwd(const float* attr, int Na, int Vt, int A, const float* rast, const float* rast_db, const int32_t* tri,
+                           const int32_t* diff_attrs, int K, const float* dy, const float* dda, int N, int T, int H, int W,
+                           float* grad_attr, float* grad_rast, float* grad_rast_db, fpc_stream_t stream);
+/* Mip chain: level l has extents (Ht >> l, Wt >> l), every texel the mean of its 2x2 parents.  fpc_texture_mip_levels: how
+ * many levels exist (extents must stay even; max_mip_level < 0 = no limit; at most 16).  The levels 1..L are stored back to
+ * back in `mip` (fpc_texture_mip_floats floats). */
+int fpc_texture_mip_levels(int Ht, int Wt, int max_mip_level);
+size_t fpc_texture_mip_floats(int Nt, int Ht, int Wt, int C, int L);
+int fpc_texture_mip_build(const float* tex, int Nt, int Ht, int Wt, int C, int L, float* mip, fpc_stream_t stream);
+/* filter_mode 'linear-mipmap-linear' (nearest_level == 0) / 'linear-mipmap-nearest' (1), boundary wrap.
+ * level = 0.5 log2(squared major axis of the pixel's texel-space footprint from uv_da [N,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY))
+ *         + mip_level_bias [N,H,W] (either may be NULL, not both), clamped to [0, L]. */
+int fpc_texture_mip_fwd(const float* tex, const float* mip, int Nt, int Ht, int Wt, int C, int L, const float* uv,
+                        const float* uv_da, const float* mip_level_bias, int nearest_level, int N, int H, int W, float* out,
+                        fpc_stream_t stream);
+/* dy -> grad_uv (overwritten), grad_uv_da / grad_bias (nullable, overwritten), grad_tex (nullable, overwritten; needs grad_mip,
+ * a scratch of fpc_texture_mip_floats floats that receives the coarse levels' gradients, folded down the chain into grad_tex
+ * unless mip_is_constant != 0: a caller-supplied mip stack is treated as constant data). */
+int fpc_texture_mip_bwd(const float* tex, const float* mip, int Nt, int Ht, int Wt, int C, int L, const float* uv,
+                        const float* uv_da, const float* mip_level_bias, int nearest_level, const float* dy, int N, int H, int W,
+                        float* grad_tex, float* grad_mip, int mip_is_constant, float* grad_uv, float* grad_uv_da, float* grad_bias,
+                        fpc_stream_t stream);
+
 /* ---- background composite + image loss (replaces fit.py:161 and the first term of fit.py:579) --------------
  * colour [N,H,W,C], rast [N,H,W,4], ref [N,H,W,C] (grey levels, 0..255 scale):
  *   comp = rast.w > 0 ? colour : bg;   loss = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2

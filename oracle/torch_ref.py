@@ -182,3 +182,116 @@ def antialias(color, rast, pos, tri, tri_opp):
         pad1[s1] = add1
         out = out + pad0 + pad1
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# mip-mapped texturing path (reference fit.py:153-155 with enable_mip: rasterize -> rast_db, interpolate(...,
+# rast_db, diff_attrs='all') -> uv_da, texture(..., uv_da, filter_mode='linear-mipmap-linear', max_mip_level)).
+# PARITY UNPINNED like the other rendering ops: restated from the nvdiffrast paper (Laine et al. 2020, sec. 3.3-3.4:
+# analytic screen-space attribute derivatives, trilinear mip-mapped lookup with the footprint's major axis selecting
+# the level) and the recalled upstream conventions listed in SURVEY App. A.
+# ---------------------------------------------------------------------------------------------------------
+
+def barycentric_diffs(pos, tri, tri_id, H, W):
+    """rast_db = (du/dX, du/dY, dv/dX, dv/dY), X/Y in pixels (App. A.1), for given per-pixel triangle ids (-1 = bg).
+    a_k = C_k + A_k fx + B_k fy  ->  du/dfx = (A_0 - u sum A) / sum a,  fx = (2 X + 1)/W - 1  ->  d fx / dX = 2 / W."""
+    N = pos.shape[0]
+    dt = pos.dtype
+    px, py = _pixel_grid(N, H, W, dt)
+    fx = (2.0 * px + 1.0) / W - 1.0
+    fy = (2.0 * py + 1.0) / H - 1.0
+    mask = tri_id >= 0
+    vi = tri.long()[tri_id.clamp(min=0)]
+    n_idx = torch.arange(N)[:, None, None, None].expand_as(vi)
+    p = pos[n_idx, vi]
+    x, y, w = p[..., 0], p[..., 1], p[..., 3]
+    nxt, prv = [1, 2, 0], [2, 0, 1]
+    A = y[..., nxt] * w[..., prv] - w[..., nxt] * y[..., prv]
+    B = w[..., nxt] * x[..., prv] - x[..., nxt] * w[..., prv]
+    C = x[..., nxt] * y[..., prv] - y[..., nxt] * x[..., prv]
+    a = C + A * fx[..., None] + B * fy[..., None]
+    at = torch.where(mask, a.sum(-1), torch.ones_like(fx))
+    u, v = a[..., 0] / at, a[..., 1] / at
+    At, Bt = A.sum(-1), B.sum(-1)
+    xs, ys = 2.0 / W, 2.0 / H
+    db = torch.stack([xs * (A[..., 0] - u * At) / at, ys * (B[..., 0] - u * Bt) / at,
+                      xs * (A[..., 1] - v * At) / at, ys * (B[..., 1] - v * Bt) / at], dim=-1)
+    return torch.where(mask[..., None], db, torch.zeros_like(db))
+
+
+def interpolate_da(attr, rast, tri, rast_db, diff_attrs='all'):
+    """App. A.2 with pixel differentials: out_da [N,H,W,2k] = (da/dX, da/dY) per selected attribute."""
+    N = rast.shape[0]
+    tid = rast[..., 3].long() - 1
+    mask = tid >= 0
+    vi = tri.long()[tid.clamp(min=0)]
+    if attr.shape[0] == 1:
+        a = attr[0][vi]
+    else:
+        n_idx = torch.arange(N)[:, None, None, None].expand_as(vi)
+        a = attr[n_idx, vi]
+    sel = list(range(attr.shape[2])) if diff_attrs == 'all' else list(diff_attrs)
+    a = a[..., sel]                                           # [N,H,W,3,k]
+    e0, e1 = a[..., 0, :] - a[..., 2, :], a[..., 1, :] - a[..., 2, :]
+    dadx = rast_db[..., 0:1] * e0 + rast_db[..., 2:3] * e1
+    dady = rast_db[..., 1:2] * e0 + rast_db[..., 3:4] * e1
+    da = torch.stack([dadx, dady], dim=-1).reshape(a.shape[:3] + (2 * len(sel),))
+    return torch.where(mask[..., None], da, torch.zeros_like(da))
+
+
+def texture_construct_mip(tex, max_mip_level=None):
+    """Mip stack [level 0 = tex, level 1, ...]: every texel of a level is the mean of its 2x2 parents.  Levels are added
+    while both extents are even (and > 1) and max_mip_level is not exceeded."""
+    levels = [tex]
+    while (max_mip_level is None or len(levels) - 1 < max_mip_level):
+        t = levels[-1]
+        h, w = t.shape[1], t.shape[2]
+        if h < 2 or w < 2 or h % 2 or w % 2:
+            break
+        levels.append(0.25 * (t[:, 0::2, 0::2] + t[:, 0::2, 1::2] + t[:, 1::2, 0::2] + t[:, 1::2, 1::2]))
+    return levels
+
+
+def mip_level(uv_da, Ht, Wt, bias=None):
+    """Mip level from the texture-space footprint of a pixel: half the log2 of the squared major axis of the ellipse
+    spanned by (ds/dX, dt/dX), (ds/dY, dt/dY) in texels."""
+    dsdx, dsdy = uv_da[..., 0] * Wt, uv_da[..., 1] * Wt
+    dtdx, dtdy = uv_da[..., 2] * Ht, uv_da[..., 3] * Ht
+    A = dsdx * dsdx + dtdx * dtdx
+    B = dsdy * dsdy + dtdy * dtdy
+    C = dsdx * dsdy + dtdx * dtdy
+    l2b = 0.5 * (A + B)
+    l2n = 0.25 * (A - B) * (A - B) + C * C
+    major = l2b + torch.sqrt(l2n)
+    lev = 0.5 * torch.log2(major)
+    return lev if bias is None else lev + bias
+
+
+def texture_mip(tex, uv, uv_da=None, mip_level_bias=None, max_mip_level=None, filter_mode='linear-mipmap-linear'):
+    """Trilinear (or nearest-level) mip-mapped lookup, boundary wrap.  The level is clamped to [0, L]; at or below 0 the
+    lookup is plain bilinear on level 0, at L bilinear on the coarsest level."""
+    levels = texture_construct_mip(tex, max_mip_level)
+    L = len(levels) - 1
+    Ht, Wt = tex.shape[1], tex.shape[2]
+    if uv_da is not None:
+        lev = mip_level(uv_da, Ht, Wt, mip_level_bias)
+    else:
+        lev = mip_level_bias
+    lev = torch.nan_to_num(lev, nan=0.0, neginf=0.0, posinf=float(L))
+    levc = lev.clamp(0.0, float(L))
+    if filter_mode == 'linear-mipmap-nearest':
+        l0 = torch.floor(levc + 0.5).long().clamp(max=L)
+        out = torch.zeros(uv.shape[:3] + (tex.shape[3],), dtype=tex.dtype)
+        for l in range(L + 1):
+            out = torch.where((l0 == l)[..., None], texture_linear(levels[l], uv), out)
+        return out
+    l0 = torch.floor(levc).long().clamp(max=L)
+    l1 = (l0 + 1).clamp(max=L)
+    f = (levc - l0.to(levc.dtype))[..., None]
+    c0 = torch.zeros(uv.shape[:3] + (tex.shape[3],), dtype=tex.dtype)
+    c1 = torch.zeros_like(c0)
+    for l in range(L + 1):
+        s = texture_linear(levels[l], uv)
+        c0 = torch.where((l0 == l)[..., None], s, c0)
+        c1 = torch.where((l1 == l)[..., None], s, c1)
+    return c0 + (c1 - c0) * f

@@ -403,3 +403,144 @@ def test_rasterize_near_plane_clipper(dr, small_rig3):
     torch.cuda.synchronize()
     assert abs(float(loss) - float(loss_o.detach())) / float(loss_o.detach()) < 1e-5
     assert rel_err(g_pos.cpu().numpy(), tp.grad.numpy()) < REL_GRAD
+
+
+# ---------------------------------------------------------------------------------------------------------
+# mip-mapped texturing path (reference fit.py:153-155 with enable_mip) against oracle/torch_ref.py
+# ---------------------------------------------------------------------------------------------------------
+
+def test_rasterize_grad_db(dr, small_rig3):
+    """Gradient through rast_db (upstream's rasterize_grad_db) against float64 autograd of the App. A.1 formulas."""
+    from oracle import torch_ref as TR
+    rig, H, W = small_rig3, 152, 200
+    pc, rast, db, _ = _scene(rig, H, W)
+    rng = np.random.default_rng(11)
+    dy = rng.normal(size=rast.shape).astype(np.float32)
+    ddb = rng.normal(size=rast.shape).astype(np.float32)
+    ctx = dr.RasterizeCudaContext()
+    pos = cu(pc).requires_grad_(True)
+    out, out_db = dr.rasterize(ctx, pos, cu(rig.pos_idx), resolution=(H, W))
+    assert out_db.requires_grad
+    ((out * cu(dy)).sum() + (out_db * cu(ddb)).sum()).backward()
+    p64 = torch.tensor(pc, dtype=torch.float64, requires_grad=True)
+    tid = torch.tensor(rast[..., 3]).long() - 1
+    u, v, _ = TR.barycentrics(p64, torch.tensor(rig.pos_idx), tid, H, W)
+    d64 = TR.barycentric_diffs(p64, torch.tensor(rig.pos_idx), tid, H, W)
+    assert rel_err(out_db.detach().cpu().numpy(), d64.detach().numpy()) < 1e-4
+    t = lambda a: torch.tensor(a, dtype=torch.float64)
+    ((u * t(dy[..., 0])).sum() + (v * t(dy[..., 1])).sum() + (d64 * t(ddb)).sum()).backward()
+    g = pos.grad.cpu().numpy()
+    assert rel_err(g, p64.grad.numpy()) < REL_GRAD
+    assert np.abs(g[..., 2]).max() == 0
+    # grad_db=False: rast_db carries no gradient (upstream semantics)
+    pos2 = cu(pc).requires_grad_(True)
+    _, db2 = dr.rasterize(ctx, pos2, cu(rig.pos_idx), resolution=(H, W), grad_db=False)
+    assert not db2.requires_grad
+
+
+@pytest.mark.parametrize('diff', ['all', [1], [2, 0]])
+def test_interpolate_da(dr, small_rig3, diff):
+    from oracle import torch_ref as TR
+    rig, H, W = small_rig3, 152, 200
+    pc, rast, db, _ = _scene(rig, H, W)
+    N, A = rast.shape[0], 3
+    rng = np.random.default_rng(12)
+    attr = rng.normal(size=(1, rig.V, A)).astype(np.float32)
+    K = A if diff == 'all' else len(diff)
+    at, ra, rd = cu(attr).requires_grad_(True), cu(rast).requires_grad_(True), cu(db).requires_grad_(True)
+    out, out_da = dr.interpolate(at, ra, cu(rig.pos_idx), rast_db=rd, diff_attrs=diff)
+    assert out_da.shape == (N, H, W, 2 * K)
+    a64, r64, d64 = (torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (attr, rast, db))
+    ref = TR.interpolate(a64, r64, torch.tensor(rig.pos_idx))
+    ref_da = TR.interpolate_da(a64, r64, torch.tensor(rig.pos_idx), d64, diff)
+    assert np.abs(out.detach().cpu().numpy() - ref.detach().numpy()).max() <= ABS_FWD
+    assert rel_err(out_da.detach().cpu().numpy(), ref_da.detach().numpy()) < 1e-5
+    dy = rng.normal(size=ref.shape).astype(np.float32)
+    dda = rng.normal(size=ref_da.shape).astype(np.float32)
+    ((out * cu(dy)).sum() + (out_da * cu(dda)).sum()).backward()
+    ((ref * torch.tensor(dy, dtype=torch.float64)).sum() + (ref_da * torch.tensor(dda, dtype=torch.float64)).sum()).backward()
+    assert rel_err(at.grad.cpu().numpy(), a64.grad.numpy()) < REL_GRAD
+    assert rel_err(ra.grad.cpu().numpy()[..., :2], r64.grad.numpy()[..., :2]) < REL_GRAD
+    assert rel_err(rd.grad.cpu().numpy(), d64.grad.numpy()) < REL_GRAD
+
+
+@pytest.mark.parametrize('mode', ['linear-mipmap-linear', 'linear-mipmap-nearest'])
+@pytest.mark.parametrize('C,Nt,use_bias', [(1, 1, False), (3, 2, True)])
+def test_texture_mip(dr, mode, C, Nt, use_bias):
+    from oracle import torch_ref as TR
+    rng = np.random.default_rng(13 + C)
+    N, H, W, Ht, Wt, maxl = 2, 33, 47, 32, 64, 4
+    tex = rng.random((Nt, Ht, Wt, C)).astype(np.float32)
+    uv = rng.uniform(-0.5, 1.5, size=(N, H, W, 2)).astype(np.float32)
+    # footprints from well below one texel (level 0) to beyond the coarsest level
+    uv_da = (rng.normal(size=(N, H, W, 4)) * np.exp(rng.uniform(-7.5, -1.0, size=(N, H, W, 1)))).astype(np.float32)
+    uv_da[0, 0, 0] = 0.0                                       # degenerate footprint (background pixel): level 0
+    bias = rng.uniform(-1.0, 1.0, size=(N, H, W)).astype(np.float32) if use_bias else None
+    tt, tu, td = cu(tex).requires_grad_(True), cu(uv).requires_grad_(True), cu(uv_da).requires_grad_(True)
+    tb = cu(bias).requires_grad_(True) if use_bias else None
+    out = dr.texture(tt, tu, td, mip_level_bias=tb, filter_mode=mode, max_mip_level=maxl)
+    t64, u64, d64 = (torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (tex, uv, uv_da))
+    b64 = torch.tensor(bias, dtype=torch.float64, requires_grad=True) if use_bias else None
+    lev = TR.mip_level(d64.detach()[1:], Ht, Wt, b64.detach()[1:] if use_bias else None)
+    assert float(lev.min()) < 0 and float(lev.max()) > maxl and ((lev > 0.5) & (lev < maxl - 0.5)).float().mean() > 0.3
+    ref = TR.texture_mip(t64, u64, d64, b64, max_mip_level=maxl, filter_mode=mode)
+    if mode == 'linear-mipmap-nearest':
+        # the level switch is a step: compare away from the half-integer switching points (fp32 vs fp64 level arithmetic)
+        levf = TR.mip_level(d64.detach(), Ht, Wt, b64.detach() if use_bias else None)
+        ok = ((levf + 0.5) - torch.floor(levf + 0.5)).sub(0.5).abs().lt(0.499).numpy() | ~np.isfinite(levf.numpy())
+    else:
+        ok = np.ones((N, H, W), bool)
+    assert np.abs(out.detach().cpu().numpy() - ref.detach().numpy())[ok].max() <= ABS_FWD
+    dy = rng.normal(size=ref.shape).astype(np.float32) * ok[..., None]
+    out.backward(cu(dy))
+    (ref * torch.tensor(dy, dtype=torch.float64)).sum().backward()
+    assert rel_err(tt.grad.cpu().numpy(), t64.grad.numpy()) < REL_GRAD
+    assert rel_err(tu.grad.cpu().numpy(), u64.grad.numpy()) < REL_GRAD
+    if mode == 'linear-mipmap-linear':
+        gd = np.nan_to_num(d64.grad.numpy())
+        assert np.abs(gd).max() > 0 and rel_err(td.grad.cpu().numpy(), gd) < REL_GRAD
+        if use_bias:
+            assert rel_err(tb.grad.cpu().numpy(), b64.grad.numpy()) < REL_GRAD
+    # a pre-built mip stack gives the same forward result
+    mipw = dr.texture_construct_mip(cu(tex), max_mip_level=maxl)
+    out2 = dr.texture(cu(tex), cu(uv), cu(uv_da), mip_level_bias=cu(bias) if use_bias else None, mip=mipw, filter_mode=mode)
+    assert torch.equal(out2, out.detach())
+    with pytest.raises(RuntimeError):
+        dr.texture(cu(tex[:, :30]), cu(uv), cu(uv_da), filter_mode=mode, max_mip_level=maxl)      # 30 rows do not halve 4 times
+
+
+def test_render_chain_mip_like_reference(dr, tiny_rig):
+    """The enable_mip branch of the reference's render() (fit.py:151-161) written against the drop-in, vs the oracle chain
+    (golden rasterizer for visibility, torch_ref for the differentiable stages), forward and d loss / d pos_clip."""
+    from oracle import torch_ref as TR
+    rig, H, W, maxl = tiny_rig, 128, 128, 3
+    pc = clip_positions(rig, w=np.linspace(0, 0.4, rig.B))
+    rng = np.random.default_rng(14)
+    dy = rng.normal(size=(1, H, W, rig.tex.shape[2])).astype(np.float32)
+    glctx = dr.RasterizeGLContext(device='cuda')
+    pos_clip = cu(pc).requires_grad_(True)
+    tex = cu(rig.tex)[None].requires_grad_(True)
+    rast_out, rast_out_db = dr.rasterize(glctx, pos_clip, cu(rig.pos_idx), resolution=(H, W))
+    texc, texd = dr.interpolate(cu(rig.uv)[None, ...], rast_out, cu(rig.uv_idx), rast_db=rast_out_db, diff_attrs='all')
+    colour = dr.texture(tex, texc, texd, filter_mode='linear-mipmap-linear', max_mip_level=maxl)
+    colour = dr.antialias(colour, rast_out, pos_clip, cu(rig.pos_idx))
+    colour = torch.where(rast_out[..., 3:] > 0, colour, torch.tensor(45.0 / 255.0).cuda())
+    (colour * cu(dy)).sum().backward()
+    # oracle
+    rast_g, _, _ = G.rasterize_fwd(pc, rig.pos_idx, (H, W))
+    assert np.array_equal(rast_out[..., 3].detach().cpu().numpy(), rast_g[..., 3])
+    tid = torch.tensor(rast_g[..., 3]).long() - 1
+    p64 = torch.tensor(pc, dtype=torch.float64, requires_grad=True)
+    t64 = torch.tensor(rig.tex, dtype=torch.float64)[None].requires_grad_(True)
+    tri, uvi = torch.tensor(rig.pos_idx), torch.tensor(rig.uv_idx)
+    u, v, zw = TR.barycentrics(p64, tri, tid, H, W)
+    r64 = torch.stack([u, v, zw, torch.tensor(rast_g[..., 3], dtype=torch.float64)], dim=-1)
+    d64 = TR.barycentric_diffs(p64, tri, tid, H, W)
+    uv64 = torch.tensor(rig.uv, dtype=torch.float64)[None]
+    c = TR.texture_mip(t64, TR.interpolate(uv64, r64, uvi), TR.interpolate_da(uv64, r64, uvi, d64), max_mip_level=maxl)
+    c = TR.antialias(c, r64, p64, tri, torch.tensor(G.topology_build(rig.pos_idx)))
+    c = torch.where(r64[..., 3:] > 0, c, torch.tensor(45.0 / 255.0, dtype=torch.float64))
+    assert np.abs(colour.detach().cpu().numpy() - c.detach().numpy()).max() <= 2e-5
+    (c * torch.tensor(dy, dtype=torch.float64)).sum().backward()
+    assert rel_err(tex.grad.cpu().numpy(), t64.grad.numpy()) < REL_GRAD
+    assert rel_err(pos_clip.grad.cpu().numpy(), p64.grad.numpy()) < 1e-3

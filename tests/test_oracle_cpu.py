@@ -365,3 +365,42 @@ def test_blend_modes_match_reference_kat():
             if mode == 'prior':
                 w = torch.tensor(k['M2']) @ torch.tensor(k['M1'])[:, int(frame)]
                 assert (G.blend(v_base, D, w) - ref).abs().max() <= 1e-5 * ref.abs().max()
+
+
+def test_mip_path_oracle_is_self_consistent(small_rig3):
+    """The torch restatement of the mip path: (a) barycentric_diffs equals the golden rasterizer's rast_db, (b) they are the
+    pixel-to-pixel differences of (u, v) inside a triangle, (c) texture_mip degenerates to bilinear lookups of the right
+    level at the clamps and interpolates in between, (d) the mip chain preserves the mean."""
+    rig, H, W = small_rig3, 152, 200
+    pc = clip_positions(rig)
+    rast, db, _ = G.rasterize_fwd(pc, rig.pos_idx, (H, W))
+    tid = torch.tensor(rast[..., 3]).long() - 1
+    p64 = torch.tensor(pc, dtype=torch.float64)
+    d64 = TR.barycentric_diffs(p64, torch.tensor(rig.pos_idx), tid, H, W).numpy()
+    assert np.abs(d64 - db).max() <= 1e-4 * np.abs(db).max()        # fp32 golden vs fp64: sliver triangles cancel digits
+    # (b) u is a ratio of affine functions: across one pixel step inside the same triangle the mean of the two end-point
+    # derivatives matches the finite difference to second order
+    same = (rast[:, :, 1:, 3] == rast[:, :, :-1, 3]) & (rast[:, :, 1:, 3] > 0)
+    fd = rast[:, :, 1:, 0] - rast[:, :, :-1, 0]
+    mid = 0.5 * (db[:, :, 1:, 0] + db[:, :, :-1, 0])
+    inner = same & (rast[:, :, 1:, 0] > 0) & (rast[:, :, 1:, 0] < 1) & (rast[:, :, :-1, 0] > 0) & (rast[:, :, :-1, 0] < 1)
+    assert inner.sum() > 1000 and np.abs(fd - mid)[inner].max() < 1e-3 * np.abs(fd[inner]).max()
+    # (c), (d)
+    g = torch.Generator().manual_seed(3)
+    tex = torch.rand(1, 16, 32, 2, generator=g, dtype=torch.float64)
+    uv = torch.rand(1, 9, 11, 2, generator=g, dtype=torch.float64) * 2 - 0.5
+    levels = TR.texture_construct_mip(tex, 3)
+    assert len(levels) == 4 and levels[3].shape == (1, 2, 4, 2)
+    for l in levels:
+        assert torch.allclose(l.mean(dim=(1, 2)), tex.mean(dim=(1, 2)))
+    zeros = torch.zeros(1, 9, 11)
+    for lev, expect in ((-2.0, TR.texture_linear(levels[0], uv)), (1.0, TR.texture_linear(levels[1], uv)),
+                        (7.0, TR.texture_linear(levels[3], uv)),
+                        (1.25, 0.75 * TR.texture_linear(levels[1], uv) + 0.25 * TR.texture_linear(levels[2], uv))):
+        out = TR.texture_mip(tex, uv, None, zeros + lev, max_mip_level=3)
+        assert torch.allclose(out, expect, atol=1e-12)
+    # an isotropic footprint of 2^k texels selects level k
+    da = torch.zeros(1, 9, 11, 4, dtype=torch.float64)
+    da[..., 0] = 4.0 / 32
+    da[..., 3] = 4.0 / 16
+    assert torch.allclose(TR.mip_level(da, 16, 32), torch.full((1, 9, 11), 2.0, dtype=torch.float64))

@@ -116,6 +116,18 @@ def algorithmic_bytes(wl, F, Vt, C=None):
     return b
 
 
+def measured_traffic(workload, stage, F):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels for ONE launch, from the committed ncu --set full
+    captures (profiles/traffic.json, written by hand from profiles/*_ncu_full_*.txt); None when no capture covers it."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            t = json.load(f)
+        e = t[workload][stage]
+        return int(e['bytes_per_frame'] * F), e['source']
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def measured_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -377,14 +389,15 @@ def run_ours(args, wl):
     alg = algorithmic_bytes(wl, F, rig.uv.shape[0], sess.C)
     peak, peak_src = measured_peak()
     achieved = alg[top] / (stage_ms[top] * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(args.workload, top, F)
     roofline = {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[top],
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[top],
                 'avg_ms_per_launch': stage_ms[top], 'share_of_step': stage_ms[top] / total_stage,
                 'timing': 'CUDA events around the C-ABI call on its stream, eager pass of the same K steps'}
     if top == 'render_loss_fused':
         ab = alg['render_loss_fused_as_built']
-        roofline['byte_model'] = ('SURVEY 8(d) fused-path algorithmic bytes: (56+20C) B/px + geometry; the call spans 6 launches '
-                                  '(k_setup, k_scan, k_fill, k_fused[_aa], k_tri_grad, k_fused_loss_reduce)')
+        roofline['byte_model'] = ('SURVEY 8(d) fused-path algorithmic bytes: (56+20C) B/px + geometry; the call spans 4 launches '
+                                  '(k_setup, k_fill, k_fused[_aa], k_tri_grad with the loss reduction riding along)')
         roofline['as_built_bytes_per_launch'] = ab
         roofline['as_built_GBps'] = ab / (stage_ms[top] * 1e-3) / 1e9
         roofline['note'] = ('the kernels keep every per-pixel intermediate on chip, so their compulsory HBM traffic (as_built_*) is ~10x '

@@ -427,9 +427,30 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     }
 }
 
-// one thread per (view, triangle): moments -> d loss / d pos (9 float REDs per visible triangle)
-__global__ void __launch_bounds__(256) k_tri_grad(RasterParams rp, const float* __restrict__ moments, float* __restrict__ grad_pos)
+// fixed-order sum of the per-CTA loss partials (deterministic), by one CTA of 256 threads
+__device__ __forceinline__ void loss_reduce_cta(const double* __restrict__ partial, int n, float k, float* __restrict__ loss)
 {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)(red[0] * (double)k);
+}
+
+// one thread per (view, triangle): moments -> d loss / d pos (9 float REDs per visible triangle).  The loss partials of the
+// fused kernel are complete by now as well: one extra CTA (the last) sums them, which saves a launch on the critical path.
+__global__ void __launch_bounds__(256) k_tri_grad(RasterParams rp, const float* __restrict__ moments, float* __restrict__ grad_pos,
+                                                  const double* __restrict__ loss_partial, int n_partial, float k, float* __restrict__ loss)
+{
+    if (blockIdx.x == gridDim.x - 1) {
+        loss_reduce_cta(loss_partial, n_partial, k, loss);
+        return;
+    }
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)rp.N * rp.T) return;
     const float* M = moments + gid * 9;
@@ -450,16 +471,7 @@ __global__ void __launch_bounds__(256) k_tri_grad(RasterParams rp, const float* 
 
 __global__ void __launch_bounds__(256) k_fused_loss_reduce(const double* __restrict__ partial, int n, float k, float* __restrict__ loss)
 {
-    __shared__ double red[256];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) loss[0] = (float)(red[0] * (double)k);
+    loss_reduce_cta(partial, n, k, loss);
 }
 
 // keys + per-warp triangle staging + the reference-frame tile (u8 or f32, C channels)
@@ -552,11 +564,13 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     }
     if (st != FPC_OK) return st;
     if (grad_pos) {
-        k_tri_grad<<<fpc_div_up((long long)N * T, 256), 256, 0, stream>>>(rp, fp.moments, grad_pos);
+        // + 1 CTA: the loss reduction rides along
+        k_tri_grad<<<fpc_div_up((long long)N * T, 256) + 1, 256, 0, stream>>>(rp, fp.moments, grad_pos, fp.loss_partial, N * rp.NB, fp.k, loss);
+        FPC_LAUNCH_CHECK();
+    } else {
+        k_fused_loss_reduce<<<1, 256, 0, stream>>>(fp.loss_partial, N * rp.NB, fp.k, loss);
         FPC_LAUNCH_CHECK();
     }
-    k_fused_loss_reduce<<<1, 256, 0, stream>>>(fp.loss_partial, N * rp.NB, fp.k, loss);
-    FPC_LAUNCH_CHECK();
     return FPC_OK;
 }
 

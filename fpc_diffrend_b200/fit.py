@@ -472,7 +472,7 @@ class FitSession:
                     N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, _p(self.loss), _p(self.g_pos),
                     _p(self.d_tex) if cfg.optimize_texture else None, None, None,
                     _p(self.scratch), self.scratch.numel(), s)
-        return 6 + (1 if cfg.optimize_texture else 0)
+        return 4 + (1 if cfg.optimize_texture else 0)      # k_setup, k_fill, k_fused[_aa], k_tri_grad (+ loss reduction) [+ memset]
 
     def backward(self):
         cfg, s, call = self.cfg, self._stream(), self._timed

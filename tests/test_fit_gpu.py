@@ -452,7 +452,7 @@ def test_fit_take_from_disk(tmp_path):
     # pose rendered from every camera reproduce what the fit session itself renders from the fitted parameters
     from fpc_diffrend_b200.fit import FitSession
     from fpc_diffrend_b200.render import render_result
-    imgs = render_result(str(d), calib, cams, (H, W), reproduce_pose=True, y_offset=170.0, out_dir=str(tmp_path / 'frames'))
+    imgs = render_result(str(d), calib, cams, (H, W), reproduce_pose=True, y_offset=170.0, out_dir=str(tmp_path / 'rendered'))
     assert imgs.shape == (F, len(cams), H, W, 1) and imgs.dtype == np.uint8
     s = FitSession(rig, F, FitConfig(resolution=(H, W), shading='texture', antialias=True))
     s.tex.copy_(torch.tensor((rig.tex * 255).astype(np.uint8) / 255.0).reshape(s.tex.shape))   # texture.png: 8-bit, truncated (fit.py:270)
@@ -460,7 +460,7 @@ def test_fit_take_from_disk(tmp_path):
     own = torch.flip(s.forward(with_loss=False).reshape(F, len(cams), H, W, 1), dims=[2]) * 255.0
     diff = np.abs(own.cpu().numpy() - imgs.astype(np.float32))
     assert diff.max() <= 2.0 and (diff > 0.51).mean() < 1e-3, (diff.max(), (diff > 0.51).mean())
-    assert len(os.listdir(tmp_path / 'frames')) == F * len(cams)
+    assert len(os.listdir(tmp_path / 'rendered')) == F * len(cams)
 
 
 def test_basis_kernels_match_reference_kat():

@@ -193,7 +193,7 @@ class ClockSampler:
 # CPU oracle arm (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------------------
 
-def cpu_oracle_rate(wl, budget_s=15.0, max_iters=10):
+def cpu_oracle_rate(wl, budget_s=15.0, max_iters=60):
     """Fit iterations/s of the CPU oracle (torch CPU blend/project/loss + golden rasterizer with autograd +
     torch Adam) on one frame of the workload; bounded sample: 1 warm-up + up to max_iters timed iterations."""
     import torch

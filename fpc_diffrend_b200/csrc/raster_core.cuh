@@ -270,6 +270,8 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
     const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
     WarpStage& st = stage[warp];
 #if FPC_DYN_BATCH
+    // (smaller claims for sparsely filled bins were measured: no gain — the barrier stalls after this phase are not a
+    // batch-granularity effect, gpurun_out/exp_variants.jsonl round 1)
     for (;;) {
         int base = 0;
         if (lane == 0) base = atomicAdd(&next_batch, 32);

@@ -19,6 +19,10 @@ using namespace fpc;
 
 namespace {
 
+#ifndef FPC_TRIGRAD_REAL
+#define FPC_TRIGRAD_REAL float
+#endif
+
 struct FusedParams {
     const float* attr;       // [Va, A]  vertex colours (A == C) or uv (A == 2, textured)
     const int32_t* attr_tri; // [T,3]
@@ -54,33 +58,34 @@ __device__ __forceinline__ void triangle_pos_grad(const float* m, float fx0, flo
                                                   const float4& q0, const float4& q1, const float4& q2, float* G,
                                                   int i0, int i1, int i2)
 {
-    const float S0 = m[0], S1 = m[1], S2 = m[2];
-    const float X0 = xs * m[3], X1 = xs * m[4], X2 = xs * m[5];     // sum g_k (fx - fx0)
-    const float Y0 = ys * m[6], Y1 = ys * m[7], Y2 = ys * m[8];     // sum g_k (fy - fy0)
+    typedef FPC_TRIGRAD_REAL real_t;
+    const real_t S0 = m[0], S1 = m[1], S2 = m[2];
+    const real_t X0 = (real_t)xs * m[3], X1 = (real_t)xs * m[4], X2 = (real_t)xs * m[5];     // sum g_k (fx - fx0)
+    const real_t Y0 = (real_t)ys * m[6], Y1 = (real_t)ys * m[7], Y2 = (real_t)ys * m[8];     // sum g_k (fy - fy0)
     // vertex positions relative to the anchor: p_m = (x_m - fx0 w_m, y_m - fy0 w_m)
-    float p0x = q0.x - fx0 * q0.w, p0y = q0.y - fy0 * q0.w;
-    float p1x = q1.x - fx0 * q1.w, p1y = q1.y - fy0 * q1.w;
-    float p2x = q2.x - fx0 * q2.w, p2y = q2.y - fy0 * q2.w;
+    real_t p0x = q0.x - (real_t)fx0 * q0.w, p0y = q0.y - (real_t)fy0 * q0.w;
+    real_t p1x = q1.x - (real_t)fx0 * q1.w, p1y = q1.y - (real_t)fy0 * q1.w;
+    real_t p2x = q2.x - (real_t)fx0 * q2.w, p2y = q2.y - (real_t)fy0 * q2.w;
     // sum_px g_k p_my(px) = S_k p_my - w_m Y_k ;  sum_px g_k p_mx(px) = S_k p_mx - w_m X_k
 #define SY_(k, pmy, wm) (S##k * (pmy) - (wm) * Y##k)
 #define SX_(k, pmx, wm) (S##k * (pmx) - (wm) * X##k)
-    float g0x = -SY_(1, p2y, q2.w) + SY_(2, p1y, q1.w);
-    float g0y = SX_(1, p2x, q2.w) - SX_(2, p1x, q1.w);
-    float g1x = SY_(0, p2y, q2.w) - SY_(2, p0y, q0.w);
-    float g1y = -SX_(0, p2x, q2.w) + SX_(2, p0x, q0.w);
-    float g2x = -SY_(0, p1y, q1.w) + SY_(1, p0y, q0.w);
-    float g2y = SX_(0, p1x, q1.w) - SX_(1, p0x, q0.w);
+    real_t g0x = -SY_(1, p2y, q2.w) + SY_(2, p1y, q1.w);
+    real_t g0y = SX_(1, p2x, q2.w) - SX_(2, p1x, q1.w);
+    real_t g1x = SY_(0, p2y, q2.w) - SY_(2, p0y, q0.w);
+    real_t g1y = -SX_(0, p2x, q2.w) + SX_(2, p0x, q0.w);
+    real_t g2x = -SY_(0, p1y, q1.w) + SY_(1, p0y, q0.w);
+    real_t g2y = SX_(0, p1x, q1.w) - SX_(1, p0x, q0.w);
 #undef SY_
 #undef SX_
     // d loss / d A_k = sum g_k fx, d loss / d B_k = sum g_k fy
-    float dA0 = fx0 * S0 + X0, dA1 = fx0 * S1 + X1, dA2 = fx0 * S2 + X2;
-    float dB0 = fy0 * S0 + Y0, dB1 = fy0 * S1 + Y1, dB2 = fy0 * S2 + Y2;
-    float g0w = q2.y * dA1 - q2.x * dB1 - q1.y * dA2 + q1.x * dB2;
-    float g1w = -q2.y * dA0 + q2.x * dB0 + q0.y * dA2 - q0.x * dB2;
-    float g2w = q1.y * dA0 - q1.x * dB0 - q0.y * dA1 + q0.x * dB1;
-    red_vertex(G, i0, g0x, g0y, g0w);
-    red_vertex(G, i1, g1x, g1y, g1w);
-    red_vertex(G, i2, g2x, g2y, g2w);
+    real_t dA0 = fx0 * S0 + X0, dA1 = fx0 * S1 + X1, dA2 = fx0 * S2 + X2;
+    real_t dB0 = fy0 * S0 + Y0, dB1 = fy0 * S1 + Y1, dB2 = fy0 * S2 + Y2;
+    real_t g0w = q2.y * dA1 - q2.x * dB1 - q1.y * dA2 + q1.x * dB2;
+    real_t g1w = -q2.y * dA0 + q2.x * dB0 + q0.y * dA2 - q0.x * dB2;
+    real_t g2w = q1.y * dA0 - q1.x * dB0 - q0.y * dA1 + q0.x * dB1;
+    red_vertex(G, i0, (float)g0x, (float)g0y, (float)g0w);
+    red_vertex(G, i1, (float)g1x, (float)g1y, (float)g1w);
+    red_vertex(G, i2, (float)g2x, (float)g2y, (float)g2w);
 }
 
 // Moments of (g0, g1, g2) = d loss / d (a0, a1, a2) per triangle: runs of equal triangle id inside the warp are combined
@@ -115,11 +120,14 @@ __device__ __forceinline__ void accumulate_moments(float* __restrict__ M, unsign
     const unsigned above = (lane == 31) ? 0u : (hm & (0xFFFFFFFEu << lane));
     const unsigned len = (head && tid != 0xFFFFFFFFu) ? (unsigned)((above ? __ffs(above) - 1 : 32) - lane) : 0u;
     const unsigned maxlen = __reduce_max_sync(0xffffffffu, len);
+    // segments are RUNS, not triangle ids: a triangle that is occluded in the middle of the row owns two runs, each with its
+    // own head lane and its own REDs — partial sums must not travel across the gap (that would count pixels twice)
+    const int myhead = 31 - __clz(hm & (0xFFFFFFFFu >> (31 - lane)));
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         if ((unsigned)d >= maxlen) break;
-        unsigned to = __shfl_down_sync(0xffffffffu, tid, d);
-        bool take = (lane + d < 32) && (to == tid);
+        const int to = __shfl_down_sync(0xffffffffu, myhead, d);
+        bool take = (lane + d < 32) && (to == myhead);
 #pragma unroll
         for (int c = 0; c < NM; c++) {
             float o = __shfl_down_sync(0xffffffffu, m[c], d);
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
                 ShadeLazy sh = shade_pixel_lazy(p0, p1, p2, fx, fy);
                 zn = sh.zn; wn = sh.wn;
                 float u = clamp01(sh.u), v = clamp01(sh.v);
-                su = sh.u; sv = sh.v; siw = sh.iw;
+                if (fp.moments) { const ShadeGrad sg = shade_pixel_grad(p0, p1, p2, fx, fy); su = sg.u; sv = sg.v; siw = sg.iw; }
                 rout = make_float4(u, v, 0.f, (float)(t + 1));
                 int j0 = i0, j1 = i1, j2 = i2;
                 if (fp.attr_tri4) { const int4 tj = __ldg(fp.attr_tri4 + t); j0 = tj.x; j1 = tj.y; j2 = tj.z; }

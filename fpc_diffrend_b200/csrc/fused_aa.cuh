@@ -252,12 +252,15 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 }
             }
             // d loss / d a_k = sum_c g_c K[k][c]   (u = a0/at, v = a1/at, unclamped barycentrics as in the op-level backward)
+            if (inner && fp.moments) {
+                const ShadeGrad sg = shade_pixel_grad(p0, p1, p2, fx, fy);      // backward-only barycentrics (common.cuh)
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                float k2 = -sh.iw * (ku[c] * sh.u + kv[c] * sh.v);
-                K[2 * C + c] = k2;
-                K[0 * C + c] = sh.iw * ku[c] + k2;
-                K[1 * C + c] = sh.iw * kv[c] + k2;
+                for (int c = 0; c < C; c++) {
+                    float k2 = -sg.iw * (ku[c] * sg.u + kv[c] * sg.v);
+                    K[2 * C + c] = k2;
+                    K[0 * C + c] = sg.iw * ku[c] + k2;
+                    K[1 * C + c] = sg.iw * kv[c] + k2;
+                }
             }
         }
         keys[idx] = slot;

@@ -24,6 +24,17 @@ namespace {
 constexpr int BIN_TPB = 1024;
 constexpr int HIST_MAX_BINS = 8192;
 
+// Origin of a triangle's gradient moments (fused.cu): the pixel that holds the centroid, clamped to the image.  The position
+// gradient is assembled from sums of g_k times (pixel - origin); with the origin ON the triangle the vertex offsets stay as
+// small as in a per-pixel evaluation.  (A corner of the bounding box is far from a diagonal sliver in its thin direction:
+// measured 20x the rounding error of the op-level kernel on such triangles.)
+__device__ __forceinline__ int moment_origin(const SnappedTri& s, const RasterParams& rp)
+{
+    const int cx = (s.x0 + s.x1 + s.x2) / 3, cy = (s.y0 + s.y1 + s.y2) / 3;       // 1/16 px
+    const int px = min(max(cx >> 4, 0), rp.W - 1), py = min(max(cy >> 4, 0), rp.H - 1);
+    return px | (py << 16);
+}
+
 template <bool HIST>
 __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
 {
@@ -42,7 +53,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
         if (load_triangle<false>(rp, n, t, p0, p1, p2)) {
             if (p0.w > 0.f && p1.w > 0.f && p2.w > 0.f) {
                 if (setup_triangle(p0, p1, p2, rp, s)) {
-                    rp.tri_anchor[gid] = s.pxa | (s.pya << 16);
+                    rp.tri_anchor[gid] = moment_origin(s, rp);
                     const BinRange br = bin_range(s, rp);
                     const int bx0 = br.bx0, bx1 = br.bx1, by0 = br.by0, by1 = br.by1;
                     if (!is_small(s, br)) {
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
                     rp.clip_verts[3 * (size_t)slot] = c[0]; rp.clip_verts[3 * (size_t)slot + 1] = c[k + 1]; rp.clip_verts[3 * (size_t)slot + 2] = c[k + 2];
                     rp.clip_parent[slot] = t;
                     rp.large_list[(size_t)n * 2 * rp.T + atomicAdd(rp.large_count + n, 1)] = rp.T + slot;
-                    if (!anchored) { rp.tri_anchor[gid] = s.pxa | (s.pya << 16); anchored = true; }
+                    if (!anchored) { rp.tri_anchor[gid] = moment_origin(s, rp); anchored = true; }
                 }
             }
         }

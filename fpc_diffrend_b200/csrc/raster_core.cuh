@@ -61,7 +61,7 @@ struct RasterParams {
     int* clip_parent;                // [clip_cap]   id of the triangle a piece belongs to
     int* clip_count;                 // [1]          pieces allocated so far (all instances share the pool)
     int clip_cap;
-    int* tri_anchor;                 // [N*T]  pxa | pya << 16: first pixel of the image-clamped bbox (moment origin)
+    int* tri_anchor;                 // [N*T]  px | py << 16: pixel of the triangle's centroid, clamped to the image (moment origin)
     int4* tri4;                      // [T] (i0, i1, i2, 0): 16-byte copy of tri written by k_setup, one load per triangle
     const int32_t* pad_i_src; int4* pad_i_dst; int pad_i_n;          // nullable job for k_setup: int [n,3] -> int4 [n]
     float* clear_tri9;               // nullable: [N*T*9] zeroed by k_setup (moment accumulators of fused.cu)

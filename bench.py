@@ -116,6 +116,31 @@ def algorithmic_bytes(wl, F, Vt, C=None):
     return b
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's host threads (and with them its pinned staging buffers, first-touch) to the NUMA node of its GPU, so
+    that the per-step uploads of the `e2e` leg do not cross the socket interconnect.  Best effort: returns a description."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/numa_node' % dev) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return 'gpu %s: no NUMA node reported' % dev
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                a, _, b = part.partition('-')
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 'gpu %s: NUMA node %d has no allowed cpu' % (dev, node)
+        os.sched_setaffinity(0, cpus)
+        return 'gpu %s -> NUMA node %d (%d cpus)' % (dev, node, len(cpus))
+    except (OSError, ValueError, AttributeError) as e:
+        return 'not bound (%s)' % e
+
+
 def measured_traffic(workload, stage, F):
     """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels for ONE launch, from the committed ncu --set full
     captures (profiles/traffic.json, written by hand from profiles/*_ncu_full_*.txt); None when no capture covers it."""
@@ -282,6 +307,8 @@ def run_ours(args, wl):
     if not torch.cuda.is_available():
         raise RuntimeError('bench.py needs a CUDA device: the fit hot path has no CPU fallback (use --impl reference for the CPU oracle)')
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 and not os.environ.get('FPC_NO_NUMA_BIND') else 'single process: not bound'
+    sys.stderr.write('rank %d: %s\n' % (rank, numa))
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from fpc_diffrend_b200 import shard
@@ -434,7 +461,7 @@ def run_ours(args, wl):
                                 'frames over ranks, no data-path collective'),
                    'cache': 'per-step working set (~GBs of per-pixel buffers) exceeds the 126 MB L2; D (48 MB) and geometry stay L2-resident across steps',
                    'reference_frames': ref_dtype + ' grey levels, resident in HBM for `value`, pinned host memory for `e2e`',
-                   'launch': 'CUDA graph replay' if use_graph else 'eager', 'loss_final': float(sess.loss)},
+                   'launch': 'CUDA graph replay' if use_graph else 'eager', 'loss_final': float(sess.loss), 'host_affinity': numa},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches * args.steps), 'roofline': roofline, 'stages': stages,
     }
     if not args.no_cpu_baseline and world == 1:

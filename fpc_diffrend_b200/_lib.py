@@ -72,6 +72,9 @@ SIGNATURES = {
     'fpc_render_loss_fused_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'fpc_render_loss_fused': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'fpc_render_loss_fused_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_raster_bin_px': (_I, []),
+    'fpc_render_loss_fused_band': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _I, _I,
+                                        _P, _P, _P, _P, _P, _P, _Z, _P]),
     'fpc_mesh_reg_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_mesh_reg_fwd_bwd': (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _F, _F, _F, _F, _P, _P, _P, _I, _P, _Z, _P]),
     'fpc_adam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P]),

@@ -38,9 +38,17 @@ struct FusedParams {
     float* grad_tex;         // [Ht,Wt,C] or null: d loss / d tex accumulated with REDs (cleared by the host function)
     float* rast_out;         // [N,H,W,4] or null
     float* colour_out;       // [N,H,W,C] or null (composited image)
+    int vpf, row_lo, row_hi; // band split: views per frame; the first view of a frame renders bin rows >= row_lo, the last < row_hi
     double* loss_partial;    // [N*NB]
     float* moments;          // [N*T*9] zeroed by the host function
 };
+
+// band split of the camera-split mode: bin row `by` of view n belongs to this rank?
+__device__ __forceinline__ bool outside_band(const FusedParams& fp, int n, int by)
+{
+    const int c = n % fp.vpf;
+    return (c == 0 && by < fp.row_lo) || (c == fp.vpf - 1 && by >= fp.row_hi);
+}
 
 __device__ __forceinline__ void red_vertex(float* G, int vi, float gx, float gy, float gw)
 {
@@ -255,6 +263,10 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    if (outside_band(fp, n, bin / rp.BW)) {            // another rank renders this bin row (shard.view_band_shard)
+        if (threadIdx.x == 0) fp.loss_partial[(size_t)n * rp.NB + bin] = 0.0;
+        return;
+    }
     if (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0) {      // ~2/3 of the bins of a head shot
         background_bin<C>(rp, fp, n, bin, ox, oy, red);
         return;
@@ -533,6 +545,7 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
                                   const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
                                   int N, int V, int T, int H, int W, int C, float bg, float scale,
                                   float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                                  int views_per_frame, int row_lo, int row_hi,
                                   void* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
     FPC_CHECK_ARG(attr && attr_tri && ref && loss, "%s: attr, attr_tri, ref and loss must be non-null", who);
@@ -561,6 +574,13 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     fp.attr = attr; fp.attr_tri = attr_tri; fp.attr_tri4 = attr_tri4; fp.Va = Va; fp.A = A; fp.tex = tex; fp.Ht = Ht; fp.Wt = Wt;
     fp.ref = ref; fp.ref_u8 = ref_is_u8; fp.C = C; fp.bg = bg; fp.k = scale / ((float)H * (float)W * (float)C);
     fp.grad_pos = grad_pos; fp.grad_tex = grad_tex; fp.rast_out = rast_out; fp.colour_out = colour_out;
+    const int rows = fpc_div_up(H, BIN);
+    if (views_per_frame <= 0) { views_per_frame = 1; row_lo = 0; row_hi = rows; }         // no band split
+    FPC_CHECK_ARG(N % views_per_frame == 0 && row_lo >= 0 && row_lo < rows && row_hi > 0 && row_hi <= rows,
+                  "%s: band split needs N %% views_per_frame == 0 and 0 <= row_lo < %d, 0 < row_hi <= %d (got %d, %d, %d)", who, rows, rows,
+                  views_per_frame, row_lo, row_hi);
+    FPC_CHECK_ARG(views_per_frame > 1 || row_lo < row_hi, "%s: empty band [%d, %d)", who, row_lo, row_hi);
+    fp.vpf = views_per_frame; fp.row_lo = row_lo; fp.row_hi = row_hi;
     fp.loss_partial = loss_partial;
     fp.moments = moments;
     if (tri_opp) {
@@ -589,7 +609,7 @@ extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const
                                      void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     return render_loss_fused_impl("render_loss_fused", pos, tri, nullptr, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, scratch, scratch_bytes, (cudaStream_t)stream_);
+                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, 0, 0, 0, scratch, scratch_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
@@ -600,5 +620,18 @@ extern "C" int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, co
 {
     FPC_CHECK_ARG(tri_opp, "render_loss_fused_aa: tri_opp must be non-null (fpc_topology_build)");
     return render_loss_fused_impl("render_loss_fused_aa", pos, tri, tri_opp, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, scratch, scratch_bytes, (cudaStream_t)stream_);
+                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, 0, 0, 0, scratch, scratch_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
+                                          const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
+                                          const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
+                                          int views_per_frame, int row_lo, int row_hi,
+                                          float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                                          void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
+{
+    FPC_CHECK_ARG(views_per_frame > 0, "render_loss_fused_band: views_per_frame must be positive");
+    return render_loss_fused_impl("render_loss_fused_band", pos, tri, tri_opp, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
+                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, views_per_frame, row_lo, row_hi,
+                                  scratch, scratch_bytes, (cudaStream_t)stream_);
 }

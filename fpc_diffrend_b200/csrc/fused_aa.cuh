@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ref_pitch = AA_REF_W * C * esz;                   // bytes per reference tile row (multiple of 4)
 
+    if (outside_band(fp, n, bin / rp.BW)) {            // another rank renders this bin row (shard.view_band_shard)
+        if (threadIdx.x == 0) fp.loss_partial[(size_t)n * rp.NB + bin] = 0.0;
+        return;
+    }
     // bins are widened by the halo when triangles are binned: an empty list means an all-background tile
     if (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0) {
         background_bin<C, AA_THREADS>(rp, fp, n, bin, ox, oy, red);

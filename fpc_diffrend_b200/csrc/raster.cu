@@ -400,6 +400,8 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
 
 }  // namespace fpc
 
+extern "C" int fpc_raster_bin_px(void) { return BIN; }
+
 extern "C" size_t fpc_rasterize_scratch_bytes(int N, int T, int H, int W)
 {
     if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return 256;

@@ -59,6 +59,8 @@ class FitConfig:
     regularize_correctives: bool = False  # combined: loss += mean((m3 m2 m1 e_f)^2)  (fit.py:584-589)
     regularize_prior: bool = False        # prior: loss += mean(w_f^2)                 (fit.py:591-595)
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
+    cam_band: tuple = None                # (row_lo, row_hi): of view `start` only the 32-px bin rows >= row_lo, of view `stop - 1`
+                                          # only those < row_hi are rendered here (shard.view_band_shard); needs cam_slice, fused
     fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
     # mesh regularisers of the shipped loss (fit.py:578-582; main.py:37-40 ships 5000 / 0 / 0.05 / 0, and fit.py:580 passes
@@ -195,6 +197,13 @@ class FitSession:
         self.verts = torch.empty(F, V * 3, **f32)
         self.pos_clip = torch.empty(self.N, V, 4, **f32)
         self.use_fused = bool(cfg.fused)
+        if cfg.cam_band is not None:
+            if cfg.cam_slice is None or not self.use_fused:
+                raise ValueError('cam_band needs cam_slice and the fused path (fused=True)')
+            rows = -(-H // int(_lib.load().fpc_raster_bin_px()))
+            lo, hi = (int(x) for x in cfg.cam_band)
+            if not (0 <= lo < rows and 0 < hi <= rows and (C > 1 or lo < hi)):
+                raise ValueError('cam_band %r is not a valid bin-row range for height %d (%d rows)' % (cfg.cam_band, H, rows))
         if cfg.ref_dtype not in ('f32', 'u8'):
             raise ValueError("ref_dtype must be 'f32' or 'u8'")
         if cfg.ref_dtype == 'u8' and not self.use_fused:
@@ -467,6 +476,15 @@ class FitSession:
                       _p(img), _p(self.scratch), self.scratch.numel(), s)
             return img
         assert self.ref is not None, 'call set_reference() first'
+        if cfg.cam_band is not None:
+            # camera split cut at bin-row granularity: the same kernels, bins of other ranks exit at once
+            self._timed('render_loss_fused', 'fpc_render_loss_fused_band', _p(self.pos_clip), _p(self.pos_idx),
+                        _p(self.tri_opp) if cfg.antialias else None, _p(self.attr), _p(self.attr_idx),
+                        self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
+                        N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, self.C, int(cfg.cam_band[0]), int(cfg.cam_band[1]),
+                        _p(self.loss), _p(self.g_pos), _p(self.d_tex) if cfg.optimize_texture else None, None, None,
+                        _p(self.scratch), self.scratch.numel(), s)
+            return 4 + (1 if cfg.optimize_texture else 0)
         self._timed('render_loss_fused', name, *head, _p(self.attr), _p(self.attr_idx),
                     self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
                     N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, _p(self.loss), _p(self.g_pos),

@@ -4,7 +4,8 @@ Two axes, both used by `bench.py` and `FitSession`:
 
 * frames  — every frame owns its activations w_f and pose (t_f, q_f); D, topology, UVs and cameras are replicated
             constants.  Frame ranges are independent units: NO data-path collective (BASELINE config 4).
-* cameras — each rank renders a contiguous subset of the views of the SAME frames (`FitConfig.cam_slice`), the packed
+* cameras — each rank renders a contiguous subset of the views of the SAME frames (`FitConfig.cam_slice`, optionally cut at
+            bin-row granularity with `FitConfig.cam_band` so that 9 views balance over 2/4/8 ranks), the packed
             gradient vector [d_w | d_t | d_q] ((B+7) floats per frame) is all-reduced (sum) once per iteration and the
             Adam step is replicated (BASELINE config 5).  The loss of a view is scaled by 1 / C_total on every rank, so
             the partial gradients simply add up.
@@ -42,6 +43,21 @@ def camera_shard(n_cams, rank=None, world=None):
     if s[0] == s[1]:
         raise ValueError('camera split needs at least one view per rank (%d views, %d ranks)' % (n_cams, world))
     return s
+
+
+def view_band_shard(n_cams, height, rank=None, world=None, bin_px=32):
+    """Camera split at the granularity of bin rows (9 views do not divide evenly over 2/4/8 GPUs, a rank that
+    renders 2 views while the others render 1 sets the pace).  The n_cams * R rows of 32-px bins (R = ceil(height / 32)) of
+    all views, in (view, row) order, are split evenly: returns ((c0, c1), (row_lo, row_hi)) — this rank renders views
+    [c0, c1), of view c0 only the bin rows >= row_lo and of view c1 - 1 only the bin rows < row_hi.  Pass them as
+    FitConfig.cam_slice and FitConfig.cam_band.  Every pixel (and every antialias pixel pair, owned by its lower / left
+    pixel) belongs to exactly one bin, so the partial losses and gradients of the ranks add up to the full ones."""
+    rank, world = _rank_world(rank, world)
+    R = -(-int(height) // bin_px)
+    a, b = split_range(n_cams * R, rank, world)
+    if a == b:
+        raise ValueError('band split needs at least one bin row per rank (%d rows, %d ranks)' % (n_cams * R, world))
+    return (a // R, (b - 1) // R + 1), (a % R, (b - 1) % R + 1)
 
 
 def _rank_world(rank, world):

@@ -255,6 +255,21 @@ int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t
                              float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                              void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
+/* Camera split at bin-row granularity (multi-GPU; fpc_diffrend_b200/shard.py: view_band_shard): the same
+ * kernels (tri_opp == NULL: without antialias), but of the first view of every frame (view index n with
+ * n % views_per_frame == 0) only the rows of fpc_raster_bin_px()-pixel bins >= row_lo are rendered, and of the last view
+ * (n % views_per_frame == views_per_frame - 1) only the rows < row_hi; the other bins contribute neither loss nor gradient
+ * (another rank renders them) and their rast_out / colour_out pixels are left untouched.  Every pixel, and every antialias
+ * pixel pair (owned by its lower / left pixel), belongs to exactly one bin: the ranks' losses and gradients add up to those of
+ * the unsplit call. */
+int fpc_raster_bin_px(void);
+int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
+                               const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
+                               const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
+                               int views_per_frame, int row_lo, int row_hi,
+                               float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                               void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
 /* ---- mesh regularisers (replaces the pytorch3d terms of fit.py:578-582: weight_laplacian * laplacian(mesh)^2 +
  *      weight_meshedge * mesh_edge_loss(mesh, target) + weight_normalconsistency * mesh_normal_consistency(mesh)) -------
  * verts [F,V,3]; static topology (fpc_diffrend_b200/topology.py): neighbour CSR nbr_off [V+1] / nbr_idx [2E] over the E

@@ -355,6 +355,42 @@ def test_fit_stream_matches_resident(tiny_rig):
     assert torch.allclose(a.w, b.w, atol=1e-5)
 
 
+@pytest.mark.parametrize('use_aa', [False, True])
+def test_view_band_split_adds_up(small_rig3, use_aa):
+    """Camera split at bin-row granularity (shard.view_band_shard, fpc_render_loss_fused_band): the partial losses and packed
+    gradients of the shares of 2, 3 and 5 ranks — rendered here one after the other on one GPU — add up to the unsplit
+    iteration (every pixel and every antialias pair is owned by exactly one bin; only the summation order differs)."""
+    from fpc_diffrend_b200 import rig as rigmod, shard
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F = small_rig3, 152, 200, 2
+    C = rig.P.shape[0]
+    base = dict(resolution=(H, W), shading='texture', antialias=use_aa, optimize_texture=True)
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
+    ref = synthesize_reference(rig, w_true, 0.2 * t_true, q_true, FitConfig(**base))
+    rng = np.random.default_rng(0)
+    w0 = (0.05 * rng.random((F, rig.B))).astype(np.float32)
+    full = FitSession(rig, F, FitConfig(**base))
+    full.set_reference(ref)
+    full.set_parameters(w=w0)
+    full.forward(); full.backward()
+    torch.cuda.synchronize()
+    for world in (2, 3, 5):
+        loss, grads, d_tex = 0.0, torch.zeros_like(full.grads), torch.zeros_like(full.d_tex)
+        for r in range(world):
+            sl, band = shard.view_band_shard(C, H, r, world)
+            s = FitSession(rig, F, FitConfig(cam_slice=sl, cam_band=band, **base))
+            s.set_reference(ref[:, sl[0]:sl[1]])
+            s.set_parameters(w=w0)
+            s.forward(); s.backward()
+            torch.cuda.synchronize()
+            loss += float(s.loss)
+            grads += s.grads
+            d_tex += s.d_tex
+        assert abs(loss - float(full.loss)) / float(full.loss) < 1e-5, world
+        assert rel(grads.cpu(), full.grads.cpu()) < 1e-5, world
+        assert rel(d_tex.cpu(), full.d_tex.cpu()) < 1e-5, world
+
+
 def _cam_split_worker(rank, world, port, out):
     import os
     import torch.distributed as dist
@@ -368,7 +404,9 @@ def _cam_split_worker(rank, world, port, out):
         rig = rigmod.make_rig(n_vertices=600, n_shapes=8, n_cams=3, width=200, height=152, tex_size=32, seed=3)
         F, H, W = 2, 152, 200
         w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
-        cfg = FitConfig(resolution=(H, W), shading='texture', antialias=True, cam_slice=shard.camera_shard(3), lr_base=1e-2)
+        # rank 0 renders view 0 and the lower half of view 1, rank 1 the rest (bin-row granularity)
+        sl, band = shard.view_band_shard(3, H)
+        cfg = FitConfig(resolution=(H, W), shading='texture', antialias=True, cam_slice=sl, cam_band=band, lr_base=1e-2)
         ref = synthesize_reference(rig, w_true, 0.2 * t_true, q_true, cfg)
         s = FitSession(rig, F, cfg)
         s.set_reference(ref)
@@ -382,8 +420,8 @@ def _cam_split_worker(rank, world, port, out):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
 def test_camera_split_two_gpus(tmp_path):
-    """Camera-split mode over NCCL: the all-reduced packed gradient of 2 ranks (2 + 1 views) equals the single-GPU
-    gradient over all 3 views (summation order differs -> tolerance), and the replicated Adam step follows."""
+    """Camera-split mode over NCCL: the all-reduced packed gradient of 2 ranks (1.5 + 1.5 views, cut at a bin row) equals the
+    single-GPU gradient over all 3 views (summation order differs -> tolerance), and the replicated Adam step follows."""
     import socket
     import torch.multiprocessing as mp
     from fpc_diffrend_b200 import rig as rigmod

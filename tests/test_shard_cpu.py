@@ -32,6 +32,31 @@ def test_split_range_properties():
         shard.split_range(4, 2, 2)
 
 
+def test_view_band_shard_covers_every_bin_row_once():
+    """Camera split at bin-row granularity: over all ranks every (view, bin row) is rendered exactly once and the ranks'
+    shares differ by at most one row."""
+    for C, H, world in ((9, 2048, 8), (9, 2048, 2), (9, 1024, 4), (3, 152, 2), (3, 152, 5), (2, 64, 4), (9, 1600, 16)):
+        R = -(-H // 32)
+        seen = np.zeros((C, R), int)
+        sizes = []
+        for r in range(world):
+            (c0, c1), (lo, hi) = shard.view_band_shard(C, H, r, world)
+            assert 0 <= c0 < c1 <= C and 0 <= lo < R and 0 < hi <= R
+            n = 0
+            for c in range(c0, c1):
+                a = lo if c == c0 else 0
+                b = hi if c == c1 - 1 else R
+                assert a < b
+                seen[c, a:b] += 1
+                n += b - a
+            sizes.append(n)
+        assert (seen == 1).all(), (C, H, world)
+        assert max(sizes) - min(sizes) <= 1
+    assert shard.view_band_shard(9, 2048, 0, 8) == ((0, 2), (0, 8))          # 72 of 576 rows: view 0 and an eighth of view 1
+    with pytest.raises(ValueError):
+        shard.view_band_shard(1, 32, 1, 2)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))

@@ -659,3 +659,12 @@ def test_free_and_combined_modes(tiny_rig, mode, reg):
     assert float((s2.basis.cpu() - torch.cat([torch.eye(Fn).flatten(), torch.eye(Fn).flatten(), torch.zeros(3 * rig.V * Fn)])).abs().max()) > 0
     d = (s2.basis.cpu() - basis_o.detach()).abs().max()
     assert float(d) <= 1e-6 + 1e-3 * s2.basis_lr * cfg.max_iter, float(d)
+
+
+def test_every_kernel_family_runs_on_a_ragged_resolution():
+    """scripts/sanitize_target.py: three iterations in every configuration family (fused with / without antialias, texture and
+    camera-correction gradients, op-level path, free / combined modes, L2 terms, mesh regularisers, tensor-core blend, band
+    split, mip chain) at 72 x 104 — no CUDA error, finite parameters and losses."""
+    import os
+    import runpy
+    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'scripts', 'sanitize_target.py'), run_name='__main__')

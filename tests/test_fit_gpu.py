@@ -668,3 +668,55 @@ def test_every_kernel_family_runs_on_a_ragged_resolution():
     import os
     import runpy
     runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'scripts', 'sanitize_target.py'), run_name='__main__')
+
+
+def test_camera_and_prior_blend_kernels_match_reference_kat():
+    """The geometry kernels on the vectors the REFERENCE's own code produced: (a) fpc_pose_mvp_fwd + fpc_project_fwd on the real
+    calibration against camera.py's P, MV, MVP and clip-space points (tests/golden/camera_kat.json); (b) fpc_blend_fwd / fpc_blend_bwd
+    against fit.py's blend() and its autograd gradient of the intermediate mapping (tests/golden/blend_kat.json)."""
+    import ctypes
+    import json
+    import os
+    from fpc_diffrend_b200 import _lib, camera
+    here = os.path.dirname(os.path.abspath(__file__))
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    with open(os.path.join(here, 'golden', 'camera_kat.json')) as f:
+        kat = json.load(f)
+    names = sorted(kat['cameras'])
+    entries = [kat['cameras'][n] for n in names]
+    Pc, Ac = camera.camera_constants(entries)
+    C = len(names)
+    dP, dA = torch.tensor(Pc).reshape(C, 16).cuda(), torch.tensor(Ac).reshape(C, 16).cuda()
+    t0, q0 = torch.zeros(1, 3, device='cuda'), torch.tensor([[0., 0, 0, 1]], device='cuda')
+    mvp = torch.empty(C, 16, device='cuda')
+    _lib.call('fpc_pose_mvp_fwd', P(dP), P(dA), P(t0), P(q0), None, None, 1, C, P(mvp), st)
+    mvp_ref = np.stack([np.asarray(e['MVP'], np.float32) for e in entries]).reshape(C, 16)
+    assert rel(mvp.cpu().numpy(), mvp_ref) < 1e-6
+    pts = torch.tensor(kat['points'], dtype=torch.float32).cuda().contiguous()          # [3,3]
+    clip = torch.empty(C, pts.shape[0], 4, device='cuda')
+    _lib.call('fpc_project_fwd', P(pts), P(mvp), 1, C, pts.shape[0], P(clip), st)
+    clip_ref = np.stack([np.asarray(e['clip'], np.float32) for e in entries])
+    assert np.abs(clip.cpu().numpy() - clip_ref).max() <= 1e-5 * np.abs(clip_ref).max()
+
+    with open(os.path.join(here, 'golden', 'blend_kat.json')) as f:
+        k = json.load(f)
+    R, B, Fn = k['R'], k['B'], k['F']
+    T = lambda name: torch.tensor(k[name], dtype=torch.float32)
+    M1, M2 = T('M1'), T('M2')
+    w = (M2 @ M1).t().contiguous()                                    # [Fn,B]: w_f = M2 M1 e_f for every frame
+    dD, dbase, dw = T('D').cuda().contiguous(), T('v_base').cuda(), w.cuda()
+    verts = torch.empty(Fn, R, device='cuda')
+    _lib.call('fpc_blend_fwd', P(dD), P(dbase), P(dw), R, B, Fn, P(verts), st)
+    d_verts = T('dy')[None].repeat(Fn, 1).cuda().contiguous()
+    scratch = torch.empty(int(_lib.load().fpc_blend_bwd_scratch_bytes(R, B, Fn)), dtype=torch.uint8, device='cuda')
+    d_w = torch.empty(Fn, B, device='cuda')
+    _lib.call('fpc_blend_bwd', P(dD), P(d_verts), R, B, Fn, P(d_w), P(scratch), scratch.numel(), st)
+    torch.cuda.synchronize()
+    for f in range(Fn):
+        rec = k['frames'][str(f)]['prior']
+        ref = torch.tensor(rec['vtx_pos'])
+        assert (verts[f].cpu() - ref).abs().max() <= 1e-5 * ref.abs().max()
+        # d loss / d M2 = d_w (x) (M1 e_f): the reference's autograd gradient of the intermediate mapping
+        g_m2 = torch.outer(d_w[f].cpu(), M1[:, f])
+        assert rel(g_m2, torch.tensor(rec['grad']['M2'])) < 1e-5

@@ -1,5 +1,5 @@
 """Precision of d loss / d pos_clip at the shipped resolution: fused kernel and op-level chain against float64 autograd
-(oracle/torch_ref.py) for one view.  usage: python scripts/check_grad_precision.py [H W V]"""
+(oracle/torch_ref.py) for one view.  usage: python tests/tools/check_grad_precision.py [H W V]"""
 import ctypes
 import os
 import sys
@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from conftest import clip_positions  # noqa: E402

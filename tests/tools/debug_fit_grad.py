@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from fpc_diffrend_b200 import rig as rigmod
 from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference

@@ -489,3 +489,11 @@ def get_log_level():
 def set_log_level(level):
     global _log_level
     _log_level = int(level)
+
+
+class DepthPeeler:
+    """Upstream's depth-peeling context manager.  The reference never uses it; constructing one fails loudly
+    instead of rendering something else."""
+
+    def __init__(self, glctx, pos, tri, resolution, ranges=None, grad_db=True):
+        raise RuntimeError('DepthPeeler is not supported by fpc_diffrend_b200.ops (the fit path renders the first surface only)')

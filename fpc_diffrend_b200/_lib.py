@@ -68,12 +68,12 @@ SIGNATURES = {
     'fpc_geometry_bwd_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'fpc_geometry_bwd': (_I, [_P] * 11 + [_I] * 4 + [_P] * 6 + [_Z, _P]),
     'fpc_image_loss_scratch_bytes': (_Z, [_I, _I, _I, _I]),
-    'fpc_image_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _Z, _P]),
+    'fpc_image_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _Z, _P]),
     'fpc_render_loss_fused_scratch_bytes': (_Z, [_I, _I, _I, _I]),
-    'fpc_render_loss_fused': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _Z, _P]),
-    'fpc_render_loss_fused_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_render_loss_fused': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_render_loss_fused_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'fpc_raster_bin_px': (_I, []),
-    'fpc_render_loss_fused_band': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _I, _I,
+    'fpc_render_loss_fused_band': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _I, _I, _I,
                                         _P, _P, _P, _P, _P, _P, _Z, _P]),
     'fpc_mesh_reg_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_mesh_reg_fwd_bwd': (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _F, _F, _F, _F, _P, _P, _P, _I, _P, _Z, _P]),

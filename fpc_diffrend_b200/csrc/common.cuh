@@ -115,5 +115,13 @@ __device__ __forceinline__ ShadeGrad shade_pixel_grad(const float4& p0, const fl
     return s;
 }
 
+// image loss per channel value e = ref - 255 colour (fit.py:579 is the L2 form; the north-star also asks for L1):
+//   L2: term e^2, d term / d colour = -510 e;   L1: term |e|, d term / d colour = -255 sign(e)  (sign(0) = 0, as torch.abs)
+__device__ __forceinline__ float loss_term(float e, int l1) { return l1 ? fabsf(e) : e * e; }
+__device__ __forceinline__ float loss_dcolour(float e, float k, int l1)
+{
+    return l1 ? (-255.f * k) * (float)((e > 0.f) - (e < 0.f)) : (-510.f * k) * e;
+}
+
 // pixel centre in NDC: fx = (2/W) * px + (1/W - 1), evaluated as separate mul/add
 __device__ __forceinline__ float pixel_ndc(int p, float scale, float offset) { return xadd(xmul(scale, (float)p), offset); }

@@ -34,6 +34,7 @@ struct FusedParams {
     int ref_u8;
     int C;
     float bg, k;             // k = scale / (H*W*C)
+    int l1;                  // 0: squared error (fit.py:579), 1: absolute error
     float* grad_pos;         // [N,V,4]
     float* grad_tex;         // [Ht,Wt,C] or null: d loss / d tex accumulated with REDs (cleared by the host function)
     float* rast_out;         // [N,H,W,4] or null
@@ -206,13 +207,13 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
                         float e = (float)((w4[k] >> (8 * b)) & 0xffu) - b255;
-                        sacc += e * e;
+                        sacc += loss_term(e, fp.l1);
                     }
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     float e = __uint_as_float(w4[k]) - b255;
-                    sacc += e * e;
+                    sacc += loss_term(e, fp.l1);
                 }
             }
             acc += (double)sacc;
@@ -223,7 +224,7 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
             size_t gi = (((size_t)n * rp.H + oy + r) * rp.W + ox) * C + e0;
             float rv = fp.ref_u8 ? (float)__ldg(rbase + gi) : __ldg(reinterpret_cast<const float*>(rbase) + gi);
             float e = rv - b255;
-            acc += (double)(e * e);
+            acc += (double)loss_term(e, fp.l1);
         }
     }
     if (fp.rast_out || fp.colour_out) {
@@ -401,8 +402,8 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 float e = refv[c] - 255.f * col[c];
-                loss_acc += (double)(e * e);
-                gc[c] = (-510.f * fp.k) * e;
+                loss_acc += (double)loss_term(e, fp.l1);
+                gc[c] = loss_dcolour(e, fp.k, fp.l1);
             }
             if (fg) {
                 float gu = 0.f, gv = 0.f;
@@ -543,13 +544,14 @@ extern "C" size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W
 
 static int render_loss_fused_impl(const char* who, const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                   const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
-                                  int N, int V, int T, int H, int W, int C, float bg, float scale,
+                                  int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                   float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                                   int views_per_frame, int row_lo, int row_hi,
                                   void* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
     FPC_CHECK_ARG(attr && attr_tri && ref && loss, "%s: attr, attr_tri, ref and loss must be non-null", who);
     FPC_CHECK_ARG(C == 1 || C == 3, "%s: C must be 1 or 3 (got %d)", who, C);
+    FPC_CHECK_ARG(loss_kind == 0 || loss_kind == 1, "%s: loss_kind must be 0 (L2) or 1 (L1), got %d", who, loss_kind);
     FPC_CHECK_ARG(Va > 0, "%s: Va must be positive", who);
     if (tex) FPC_CHECK_ARG(A == 2 && Ht > 0 && Wt > 0, "%s: textured shading needs A == 2 (uv) and a non-empty texture", who);
     else FPC_CHECK_ARG(A == C, "%s: vertex-colour shading needs A == C (got A=%d, C=%d)", who, A, C);
@@ -572,7 +574,7 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     if (st != FPC_OK) return st;
     FusedParams fp;
     fp.attr = attr; fp.attr_tri = attr_tri; fp.attr_tri4 = attr_tri4; fp.Va = Va; fp.A = A; fp.tex = tex; fp.Ht = Ht; fp.Wt = Wt;
-    fp.ref = ref; fp.ref_u8 = ref_is_u8; fp.C = C; fp.bg = bg; fp.k = scale / ((float)H * (float)W * (float)C);
+    fp.ref = ref; fp.ref_u8 = ref_is_u8; fp.C = C; fp.bg = bg; fp.k = scale / ((float)H * (float)W * (float)C); fp.l1 = loss_kind;
     fp.grad_pos = grad_pos; fp.grad_tex = grad_tex; fp.rast_out = rast_out; fp.colour_out = colour_out;
     const int rows = fpc_div_up(H, BIN);
     if (views_per_frame <= 0) { views_per_frame = 1; row_lo = 0; row_hi = rows; }         // no band split
@@ -604,34 +606,34 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
 
 extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* attr, const int32_t* attr_tri, int Va, int A,
                                      const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
-                                     int N, int V, int T, int H, int W, int C, float bg, float scale,
+                                     int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                      float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                                      void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     return render_loss_fused_impl("render_loss_fused", pos, tri, nullptr, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, 0, 0, 0, scratch, scratch_bytes, (cudaStream_t)stream_);
+                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, 0, 0, 0, scratch, scratch_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                         const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
-                                        const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
+                                        const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                         float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                                         void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     FPC_CHECK_ARG(tri_opp, "render_loss_fused_aa: tri_opp must be non-null (fpc_topology_build)");
     return render_loss_fused_impl("render_loss_fused_aa", pos, tri, tri_opp, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, 0, 0, 0, scratch, scratch_bytes, (cudaStream_t)stream_);
+                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, 0, 0, 0, scratch, scratch_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                           const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
-                                          const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
+                                          const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                           int views_per_frame, int row_lo, int row_hi,
                                           float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                                           void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     FPC_CHECK_ARG(views_per_frame > 0, "render_loss_fused_band: views_per_frame must be positive");
     return render_loss_fused_impl("render_loss_fused_band", pos, tri, tri_opp, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss, grad_pos, grad_tex, rast_out, colour_out, views_per_frame, row_lo, row_hi,
+                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, views_per_frame, row_lo, row_hi,
                                   scratch, scratch_bytes, (cudaStream_t)stream_);
 }

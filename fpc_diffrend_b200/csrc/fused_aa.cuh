@@ -361,10 +361,10 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 const float refv = fp.ref_u8 ? (float)s_ref[rb] : *reinterpret_cast<const float*>(s_ref + rb);
                 const float e = refv - 255.f * comp;
                 if (inner) {
-                    loss_acc += (double)(e * e);
+                    loss_acc += (double)loss_term(e, fp.l1);
                     if (fp.colour_out) fp.colour_out[(((size_t)n * rp.H + py) * rp.W + px) * C + c] = comp;
                 }
-                if (fg) gcv[c] = (-510.f * fp.k) * e;
+                if (fg) gcv[c] = loss_dcolour(e, fp.k, fp.l1);
             }
         }
         // region0 still holds the work list for other threads of phase 3b? no: a barrier separates the phases

@@ -41,7 +41,7 @@ constexpr int LOSS_PER_THREAD = 8;
 // comp = id > 0 ? colour : bg ; e = ref - 255 comp ; loss += e^2 ; d_colour = id > 0 ? -2*255*k*e : 0
 // k = scale / (H*W*C).  Block partial sums are written out and reduced in a fixed order by k_loss_reduce.
 __global__ void __launch_bounds__(LOSS_THREADS) k_image_loss(const float* __restrict__ colour, const float* __restrict__ rast,
-                                                             const float* __restrict__ ref, long long npx, int C, float bg, float k,
+                                                             const float* __restrict__ ref, long long npx, int C, float bg, float k, int l1,
                                                              float* __restrict__ d_colour, float* __restrict__ comp,
                                                              double* __restrict__ partial)
 {
@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_image_loss(const float* __rest
         for (int c = 0; c < C; c++) {
             float col = fg ? __ldg(colour + pi * C + c) : bg;
             float e = __ldg(ref + pi * C + c) - 255.f * col;
-            acc += (double)(e * e);
-            d_colour[pi * C + c] = fg ? (-510.f * k) * e : 0.f;
+            acc += (double)loss_term(e, l1);
+            d_colour[pi * C + c] = fg ? loss_dcolour(e, k, l1) : 0.f;
             if (comp) comp[pi * C + c] = col;
         }
     }
@@ -142,7 +142,7 @@ extern "C" size_t fpc_image_loss_scratch_bytes(int N, int H, int W, int C)
 }
 
 extern "C" int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, const float* ref, int N, int H, int W, int C,
-                                      float bg, float scale, float* loss, float* d_colour, float* comp,
+                                      float bg, float scale, int loss_kind, float* loss, float* d_colour, float* comp,
                                       void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -152,7 +152,8 @@ extern "C" int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, co
     long long npx = (long long)N * H * W;
     int nblk = fpc_div_up(npx, LOSS_THREADS * LOSS_PER_THREAD);
     float k = scale / ((float)H * (float)W * (float)C);
-    k_image_loss<<<nblk, LOSS_THREADS, 0, stream>>>(colour, rast, ref, npx, C, bg, k, d_colour, comp, (double*)scratch);
+    FPC_CHECK_ARG(loss_kind == 0 || loss_kind == 1, "image_loss_fwd_bwd: loss_kind must be 0 (L2) or 1 (L1)");
+    k_image_loss<<<nblk, LOSS_THREADS, 0, stream>>>(colour, rast, ref, npx, C, bg, k, loss_kind, d_colour, comp, (double*)scratch);
     FPC_LAUNCH_CHECK();
     k_loss_reduce<<<1, 256, 0, stream>>>((const double*)scratch, nblk, k, loss);
     FPC_LAUNCH_CHECK();

@@ -43,6 +43,7 @@ class FitConfig:
     beta2: float = 0.999
     eps: float = 1e-8
     bg: float = BG
+    loss: str = 'l2'                      # image loss: 'l2' = mean((ref - 255 c)^2) (fit.py:579) or 'l1' = mean(|ref - 255 c|) (north-star)
     quat_norm: str = 'row'                # 'row' (default) or 'frobenius' (reference quirk)
     optimize_pose: bool = True
     optimize_cam_pose: bool = False       # per-camera pose corrections t_opt / q_opt (fit.py:443-448,498-499), shared by all frames
@@ -197,6 +198,9 @@ class FitSession:
         self.verts = torch.empty(F, V * 3, **f32)
         self.pos_clip = torch.empty(self.N, V, 4, **f32)
         self.use_fused = bool(cfg.fused)
+        if cfg.loss not in ('l2', 'l1'):
+            raise ValueError("loss must be 'l2' or 'l1'")
+        self.loss_kind = 1 if cfg.loss == 'l1' else 0
         if cfg.cam_band is not None:
             if cfg.cam_slice is None or not self.use_fused:
                 raise ValueError('cam_band needs cam_slice and the fused path (fused=True)')
@@ -412,7 +416,7 @@ class FitSession:
             comp = torch.where(self.rast[..., 3:] > 0, final, torch.tensor(cfg.bg, device=self.device))
             return comp
         assert self.ref is not None, 'call set_reference() first'
-        call('image_loss', 'fpc_image_loss_fwd_bwd', _p(final), _p(self.rast), _p(self.ref), N, H, W, Ch, cfg.bg, 1.0 / self.C_total,
+        call('image_loss', 'fpc_image_loss_fwd_bwd', _p(final), _p(self.rast), _p(self.ref), N, H, W, Ch, cfg.bg, 1.0 / self.C_total, self.loss_kind,
              _p(self.loss), _p(self.d_colour), None, _p(self.scratch), self.scratch.numel(), s); n += 2
         return n
 
@@ -472,7 +476,7 @@ class FitSession:
             img = torch.empty(N, H, W, Ch, dtype=torch.float32, device=self.device)
             dummy = torch.zeros(N, H, W, Ch, dtype=torch.uint8, device=self.device)
             _lib.call(name, *head, _p(self.attr), _p(self.attr_idx), self.attr.shape[1],
-                      self.attr.shape[2], _p(tex), Ht, Wt, _p(dummy), 1, N, V, T, H, W, Ch, cfg.bg, 1.0, _p(self.loss), None, None, None,
+                      self.attr.shape[2], _p(tex), Ht, Wt, _p(dummy), 1, N, V, T, H, W, Ch, cfg.bg, 1.0, 0, _p(self.loss), None, None, None,
                       _p(img), _p(self.scratch), self.scratch.numel(), s)
             return img
         assert self.ref is not None, 'call set_reference() first'
@@ -481,13 +485,13 @@ class FitSession:
             self._timed('render_loss_fused', 'fpc_render_loss_fused_band', _p(self.pos_clip), _p(self.pos_idx),
                         _p(self.tri_opp) if cfg.antialias else None, _p(self.attr), _p(self.attr_idx),
                         self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
-                        N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, self.C, int(cfg.cam_band[0]), int(cfg.cam_band[1]),
+                        N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, self.loss_kind, self.C, int(cfg.cam_band[0]), int(cfg.cam_band[1]),
                         _p(self.loss), _p(self.g_pos), _p(self.d_tex) if cfg.optimize_texture else None, None, None,
                         _p(self.scratch), self.scratch.numel(), s)
             return 4 + (1 if cfg.optimize_texture else 0)
         self._timed('render_loss_fused', name, *head, _p(self.attr), _p(self.attr_idx),
                     self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
-                    N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, _p(self.loss), _p(self.g_pos),
+                    N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, self.loss_kind, _p(self.loss), _p(self.g_pos),
                     _p(self.d_tex) if cfg.optimize_texture else None, None, None,
                     _p(self.scratch), self.scratch.numel(), s)
         return 4 + (1 if cfg.optimize_texture else 0)      # k_setup, k_fill, k_fused[_aa], k_tri_grad (+ loss reduction) [+ memset]

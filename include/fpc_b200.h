@@ -220,11 +220,13 @@ int fpc_texture_mip_bwd(const float* tex, const float* mip, int Nt, int Ht, int 
 
 /* ---- background composite + image loss (replaces fit.py:161 and the first term of fit.py:579) --------------
  * colour [N,H,W,C], rast [N,H,W,4], ref [N,H,W,C] (grey levels, 0..255 scale):
- *   comp = rast.w > 0 ? colour : bg;   loss = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2
+ *   comp = rast.w > 0 ? colour : bg;   loss = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2      (loss_kind 0, fit.py:579)
+ *                                      loss = scale * sum_n mean_{h,w,c} |ref - 255 comp|        (loss_kind 1: the L1 form the
+ *                                      north-star also asks for; d|e|/de = sign(e), 0 at e = 0)
  * -> loss [1] (overwritten), d_colour [N,H,W,C] (overwritten; 0 on background), comp [N,H,W,C] or NULL. */
 size_t fpc_image_loss_scratch_bytes(int N, int H, int W, int C);
 int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, const float* ref, int N, int H, int W, int C,
-                           float bg, float scale, float* loss, float* d_colour, float* comp,
+                           float bg, float scale, int loss_kind, float* loss, float* d_colour, float* comp,
                            void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
 /* ---- fused render + loss + gradient (no antialias): rasterize -> interpolate -> [texture] -> background ->
@@ -232,7 +234,7 @@ int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, const float* 
  *      fit.py:151-158,161,579 and its part of loss.backward() (fit.py:611) when antialias is off.
  * attr [Va,A] + attr_tri [T,3]: vertex colours (tex == NULL, A == C) or uv (tex [Ht,Wt,C] given, A == 2);
  * ref [N,H,W,C] float32 (ref_is_u8 == 0) or uint8 (ref_is_u8 == 1) grey levels on the 0..255 scale; C in {1,3}.
- *   loss [1]            = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2                     (overwritten)
+ *   loss [1]            = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2  (loss_kind 0) or |ref - 255 comp| (loss_kind 1), overwritten
  *   grad_pos [N,V,4]    = d loss / d pos (x, y, w; z = 0), overwritten; NULL = forward only
  *   grad_tex [Ht,Wt,C]  = d loss / d tex (texture optimisation, tex_opt of fit.py:439,502), overwritten; NULL to skip
  *                         (needs tex and grad_pos; 4C float REDs per covered pixel)
@@ -240,7 +242,7 @@ int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, const float* 
 size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W);
 int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* attr, const int32_t* attr_tri, int Va, int A,
                           const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
-                          int N, int V, int T, int H, int W, int C, float bg, float scale,
+                          int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                           float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                           void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
@@ -251,7 +253,7 @@ int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* att
  * Same scratch size as fpc_render_loss_fused; colour_out is the antialiased, composited image. */
 int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                              const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
-                             const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
+                             const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                              float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                              void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
@@ -265,7 +267,7 @@ int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t
 int fpc_raster_bin_px(void);
 int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
-                               const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale,
+                               const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                int views_per_frame, int row_lo, int row_hi,
                                float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
                                void* scratch, size_t scratch_bytes, fpc_stream_t stream);

@@ -720,3 +720,43 @@ def test_camera_and_prior_blend_kernels_match_reference_kat():
         # d loss / d M2 = d_w (x) (M1 e_f): the reference's autograd gradient of the intermediate mapping
         g_m2 = torch.outer(d_w[f].cpu(), M1[:, f])
         assert rel(g_m2, torch.tensor(rec['grad']['M2'])) < 1e-5
+
+
+@pytest.mark.parametrize('fused,use_aa', [(True, False), (True, True), (False, True)])
+def test_l1_image_loss(small_rig3, fused, use_aa):
+    """loss='l1' (north-star: L1/L2 loss): mean(|ref - 255 colour|) and its gradient (sign of the residual) through the fused
+    kernels and the op-level image-loss kernel, against the oracle fed the GPU's pos_clip bits."""
+    from fpc_diffrend_b200 import rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F = small_rig3, 152, 200, 2
+    C = rig.P.shape[0]
+    cfg = FitConfig(resolution=(H, W), shading='texture', antialias=use_aa, fused=fused, loss='l1')
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
+    ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, cfg)
+    s = FitSession(rig, F, cfg)
+    s.set_reference(ref)
+    s.set_parameters(w=(0.05 * np.random.default_rng(0).random((F, rig.B))).astype(np.float32))
+    s.forward()
+    s.backward()
+    torch.cuda.synchronize()
+    opp = torch.tensor(G.topology_build(rig.pos_idx))
+    total, g_ref = 0.0, []
+    for n in range(F * C):
+        pc = s.pos_clip[n:n + 1].cpu().clone().requires_grad_(True)
+        rast, _ = G.rasterize(pc, torch.tensor(rig.pos_idx), (H, W))
+        col = G.texture(torch.tensor(rig.tex)[None], G.interpolate(torch.tensor(rig.uv)[None], rast, torch.tensor(rig.uv_idx)))
+        if use_aa:
+            col = G.antialias(col, rast, pc, torch.tensor(rig.pos_idx), opp)
+        img = torch.where(rast[..., 3:] > 0, col, torch.tensor(G.BG))[0]
+        loss = G.image_loss(ref.cpu()[n // C, n % C], img, 'l1') / C
+        loss.backward()
+        total += float(loss.detach())
+        g_ref.append(pc.grad[0])
+    assert abs(float(s.loss) - total) / total < 1e-5
+    assert rel(s.g_pos.cpu(), torch.stack(g_ref)) < 1e-4
+    # and a few Adam steps reduce it
+    l0 = float(s.loss)
+    s.cfg.lr_base = 5e-3
+    for _ in range(15):
+        s.iteration()
+    assert float(s.loss) < l0

@@ -192,8 +192,9 @@ def test_render_chain_like_reference(dr, tiny_rig):
 
 
 @pytest.mark.parametrize('aa', [False, True])
-@pytest.mark.parametrize('textured,C,u8', [(False, 3, False), (False, 1, True), (True, 1, False), (True, 3, True)])
-def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
+@pytest.mark.parametrize('textured,C,u8,l1', [(False, 3, False, False), (False, 1, True, False), (True, 1, False, False), (True, 3, True, False),
+                                              (False, 3, True, True), (True, 1, False, True)])
+def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa, l1):
     """fpc_render_loss_fused[_aa] (rasterize+interpolate+[texture]+[antialias]+bg+loss+backward in one kernel) vs the
     oracle chain."""
     import ctypes
@@ -222,7 +223,7 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
         opp = G.topology_build(rig.pos_idx)
         col_o = G.antialias(col_o, r_o, tp, torch.tensor(rig.pos_idx), torch.tensor(opp))
     comp_o = torch.where(r_o[..., 3:] > 0, col_o, torch.tensor(G.BG))
-    loss_o = scale * sum(G.image_loss(torch.tensor(ref[n]), comp_o[n]) for n in range(N))
+    loss_o = scale * sum(G.image_loss(torch.tensor(ref[n]), comp_o[n], 'l1' if l1 else 'l2') for n in range(N))
     loss_o.backward()
     # kernel
     P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
@@ -240,7 +241,7 @@ def test_fused_render_loss(dr, small_rig3, textured, C, u8, aa):
     head = (P(d_pos), P(d_tri)) + ((P(d_opp),) if aa else ())
     _lib.call('fpc_render_loss_fused_aa' if aa else 'fpc_render_loss_fused', *head, P(d_attr), P(d_idx), attr.shape[0], attr.shape[1], P(d_tex),
               tex.shape[0] if textured else 0, tex.shape[1] if textured else 0, P(d_ref), 1 if u8 else 0, N, V, T, H, W, C,
-              G.BG, scale, P(loss), P(g_pos), P(g_tex), P(rast_out), P(col_out), P(scratch), scratch.numel(),
+              G.BG, scale, 1 if l1 else 0, P(loss), P(g_pos), P(g_tex), P(rast_out), P(col_out), P(scratch), scratch.numel(),
               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert np.array_equal(rast_out[..., 3].cpu().numpy(), rast[..., 3])
@@ -399,7 +400,7 @@ def test_rasterize_near_plane_clipper(dr, small_rig3):
     nbytes = int(_lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W))
     scratch = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
     _lib.call('fpc_render_loss_fused', P(d_pos), P(d_tri), P(d_attr), P(d_tri), V, C, None, 0, 0, P(d_ref), 1, N, V, T, H, W, C,
-              G.BG, 1.0, P(loss), P(g_pos), None, None, None, P(scratch), nbytes, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+              G.BG, 1.0, 0, P(loss), P(g_pos), None, None, None, P(scratch), nbytes, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert abs(float(loss) - float(loss_o.detach())) / float(loss_o.detach()) < 1e-5
     assert rel_err(g_pos.cpu().numpy(), tp.grad.numpy()) < REL_GRAD
@@ -619,7 +620,7 @@ def test_shipped_resolution_fused_equals_op_chain(dr):
     scratch = torch.empty(int(_lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W)), dtype=torch.uint8, device='cuda')
     d_uv, d_uvi, d_tri, d_ref = cu(rig.uv), cu(rig.uv_idx), cu(rig.pos_idx), cu(ref)
     _lib.call('fpc_render_loss_fused_aa', P(pos.detach()), P(d_tri), P(opp), P(d_uv), P(d_uvi), rig.uv.shape[0], 2, P(tex.detach()),
-              rig.tex.shape[0], rig.tex.shape[1], P(d_ref), 1, N, V, T, H, W, C, G.BG, 1.0, P(loss), P(g_pos), P(g_tex), P(rast_out), P(col_out),
+              rig.tex.shape[0], rig.tex.shape[1], P(d_ref), 1, N, V, T, H, W, C, G.BG, 1.0, 0, P(loss), P(g_pos), P(g_tex), P(rast_out), P(col_out),
               P(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert torch.equal(rast_out[..., 3], rast[..., 3])
@@ -702,7 +703,7 @@ def test_full_scale_gradient_precision(dr):
     scratch = torch.empty(int(_lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W)), dtype=torch.uint8, device='cuda')
     d_uv, d_uvi, d_tri, d_ref = cu(rig.uv), cu(rig.uv_idx), cu(rig.pos_idx), cu(ref)
     _lib.call('fpc_render_loss_fused_aa', P(pos.detach()), P(d_tri), P(opp), P(d_uv), P(d_uvi), rig.uv.shape[0], 2, P(tex), rig.tex.shape[0],
-              rig.tex.shape[1], P(d_ref), 1, N, V, T, H, W, C, G.BG, 1.0, P(loss), P(g_pos), None, None, None, P(scratch), scratch.numel(),
+              rig.tex.shape[1], P(d_ref), 1, N, V, T, H, W, C, G.BG, 1.0, 0, P(loss), P(g_pos), None, None, None, P(scratch), scratch.numel(),
               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     g_fused = g_pos.cpu().numpy()

@@ -43,7 +43,7 @@ scratch = torch.empty(int(_lib.load().fpc_render_loss_fused_scratch_bytes(N, T, 
 d_uv, d_uvi, d_tri, d_ref = cu(rig.uv), cu(rig.uv_idx), cu(rig.pos_idx), cu(ref)
 head = (P(pos.detach()), P(d_tri)) + ((P(opp),) if aa else ())
 _lib.call('fpc_render_loss_fused_aa' if aa else 'fpc_render_loss_fused', *head, P(d_uv), P(d_uvi), rig.uv.shape[0], 2, P(tex),
-          rig.tex.shape[0], rig.tex.shape[1], P(d_ref), 1, N, rig.V, T, H, W, C, G.BG, 1.0, P(loss), P(g_pos), None, None, None,
+          rig.tex.shape[0], rig.tex.shape[1], P(d_ref), 1, N, rig.V, T, H, W, C, G.BG, 1.0, 0, P(loss), P(g_pos), None, None, None,
           P(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
 torch.cuda.synchronize()
 g_fused = g_pos.cpu().numpy()

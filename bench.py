@@ -107,6 +107,9 @@ def algorithmic_bytes(wl, F, Vt, C=None):
         'pose_mvp_fwd': 64 * 3 * N,
         'pose_mvp_bwd': 64 * 3 * N,
     }
+    # single-frame path: pose -> MVP, blend (an HBM / L2-bound GEMV over D) and the clip transform in one kernel per direction
+    b['geometry_fwd'] = b['blend_fwd'] + b['project_fwd'] + b['pose_mvp_fwd']
+    b['geometry_bwd'] = b['blend_bwd'] + b['project_bwd'] + b['pose_mvp_bwd']
     if wl['shading'] == 'texture':
         b['texture_fwd'] = (8 + 4 * Ch) * px + 4 * Ch * wl['tex'] ** 2
         b['texture_bwd'] = (4 * Ch + 8 + 8) * px + 4 * Ch * wl['tex'] ** 2

@@ -364,12 +364,27 @@ def run_ours(args, wl):
     step = sess.replay if use_graph else sess.iteration
 
     # ---- value: inputs resident in HBM ----
+    # Timing hygiene: the fused kernels materialise nothing per pixel, so one iteration's inputs (u8 frames, D, geometry:
+    # ~100 MB at config 2) would FIT the 126 MB L2.  A buffer larger than L2 is therefore written between timed steps and
+    # every step is bracketed by its own CUDA-event pair on the launching stream (the flush lies outside the pairs).  The
+    # back-to-back figure without the flush is reported next to it as `steady_state` (the same frame re-read every iteration
+    # is what a real single-frame fit does; it is not the headline).
     for _ in range(max(args.warmup, 3)):
         step()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
+    for a, b in pairs:
+        flush.zero_()
+        a.record()
+        step()
+        b.record()
+    barrier()
+    ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in pairs))
+    ms_per_step = ms_total / args.steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -377,8 +392,8 @@ def run_ours(args, wl):
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms_total / args.steps
+    ms_steady = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    del flush
     if wl.get('total_frames') or cam_split:
         # one job-wide iteration updates all n_total frames (frame batches or views are spread over the ranks)
         value = 1000.0 / ms_per_step
@@ -463,9 +478,11 @@ def run_ours(args, wl):
                    'sharding': ('single GPU' if world == 1 else
                                 'views over ranks (cut at 32-px bin rows), NCCL all-reduce of the packed (B+7)*F gradient vector per iteration' if cam_split else
                                 'frames over ranks, no data-path collective'),
-                   'cache': 'per-step working set (~GBs of per-pixel buffers) exceeds the 126 MB L2; D (48 MB) and geometry stay L2-resident across steps',
+                   'cache': 'L2 flushed between timed steps (a 256 MB buffer is written outside the per-step CUDA-event pairs); `steady_state` = the same K steps back to back without the flush',
                    'reference_frames': ref_dtype + ' grey levels, resident in HBM for `value`, pinned host memory for `e2e`',
                    'launch': 'CUDA graph replay' if use_graph else 'eager', 'loss_final': float(sess.loss), 'host_affinity': numa},
+        'steady_state': {'ms_per_step': ms_steady, 'value': value * ms_per_step / ms_steady,
+                         'note': 'no L2 flush: the iteration re-reads the same frames, D and geometry, part of which the 126 MB L2 retains'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches * args.steps), 'roofline': roofline, 'stages': stages,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -138,48 +138,73 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restric
 #pragma unroll
     for (int i = 0; i < 16; i++) am[i] = 0.f;
 
+    // Vertices that no view sees (the back of a head seen from the front: close to half of them) carry a zero gradient, and
+    // D^T d V does not need their rows of D: the clip-space gradient of a vertex is fetched TWO vertices ahead, so that by the
+    // time the rows of the next vertex would be requested the warp knows whether it needs them.  (With mesh regularisers every
+    // vertex has a gradient and nothing is skipped.)
+    const bool dense = d_verts_add != nullptr;
+    auto load_g = [&](int v) -> float4 {
+        return (lane < C && v < V) ? ldg4(g_pos + (((size_t)f * C + lane) * V + v) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto nonzero = [&](const float4& g) -> bool {
+        return dense || __any_sync(0xffffffffu, g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f);
+    };
+    float4 g0 = load_g(gw), g1 = load_g(gw + nw);
+    bool nz0 = gw < V && nonzero(g0);
     float4 cur[K];
-    if (gw < V) load_rows<K>(D, gw, B, n4, lane, cur);
+#pragma unroll
+    for (int k = 0; k < K; k++) cur[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nz0) load_rows<K>(D, gw, B, n4, lane, cur);
     for (int v = gw; v < V; v += nw) {
+        const float4 g2 = load_g(v + 2 * nw);                         // decided on in the next iteration
+        const bool nz1 = (v + nw < V) && nonzero(g1);
         float4 nxt[K];
-        if (v + nw < V) load_rows<K>(D, v + nw, B, n4, lane, nxt);     // in flight while this vertex is processed
+#pragma unroll
+        for (int k = 0; k < K; k++) nxt[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nz1) load_rows<K>(D, v + nw, B, n4, lane, nxt);            // in flight while this vertex is processed
         float gx = 0.f, gy = 0.f, gz = 0.f;
-        if (lane < C) {
-            float4 g = ldg4(g_pos + (((size_t)f * C + lane) * V + v) * 4);
-            const float* m = s_mvp + 16 * lane;
-            gx = m[0] * g.x + m[4] * g.y + m[8] * g.z + m[12] * g.w;
-            gy = m[1] * g.x + m[5] * g.y + m[9] * g.z + m[13] * g.w;
-            gz = m[2] * g.x + m[6] * g.y + m[10] * g.z + m[14] * g.w;
-            const float* p = verts + ((size_t)f * V + v) * 3;
-            float vh[4] = {__ldg(p), __ldg(p + 1), __ldg(p + 2), 1.f};
-            float gg[4] = {g.x, g.y, g.z, g.w};
+        if (nz0) {
+            if (lane < C) {
+                const float4 g = g0;
+                const float* m = s_mvp + 16 * lane;
+                gx = m[0] * g.x + m[4] * g.y + m[8] * g.z + m[12] * g.w;
+                gy = m[1] * g.x + m[5] * g.y + m[9] * g.z + m[13] * g.w;
+                gz = m[2] * g.x + m[6] * g.y + m[10] * g.z + m[14] * g.w;
+                const float* p = verts + ((size_t)f * V + v) * 3;
+                float vh[4] = {__ldg(p), __ldg(p + 1), __ldg(p + 2), 1.f};
+                float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) am[4 * i + j] += gg[i] * vh[j];
-        }
+                    for (int j = 0; j < 4; j++) am[4 * i + j] += gg[i] * vh[j];
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            gx += __shfl_xor_sync(0xffffffffu, gx, o);
-            gy += __shfl_xor_sync(0xffffffffu, gy, o);
-            gz += __shfl_xor_sync(0xffffffffu, gz, o);
-        }
-        if (d_verts_add) {
-            const float* e = d_verts_add + ((size_t)f * V + v) * 3;
-            gx += __ldg(e); gy += __ldg(e + 1); gz += __ldg(e + 2);
+            for (int o = 16; o > 0; o >>= 1) {
+                gx += __shfl_xor_sync(0xffffffffu, gx, o);
+                gy += __shfl_xor_sync(0xffffffffu, gy, o);
+                gz += __shfl_xor_sync(0xffffffffu, gz, o);
+            }
+            if (d_verts_add) {
+                const float* e = d_verts_add + ((size_t)f * V + v) * 3;
+                gx += __ldg(e); gy += __ldg(e + 1); gz += __ldg(e + 2);
+            }
         }
         if (d_verts && lane == 0) {
             float* o = d_verts + ((size_t)f * V + v) * 3;
             o[0] = gx; o[1] = gy; o[2] = gz;
         }
+        if (nz0) {
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            int e = 4 * (lane + 32 * k);
-            int r = (e >= B) + (e >= 2 * B);
-            float gv = (r == 0) ? gx : ((r == 1) ? gy : gz);       // rows beyond 3B were loaded as zeros
-            acc[k].x += cur[k].x * gv; acc[k].y += cur[k].y * gv; acc[k].z += cur[k].z * gv; acc[k].w += cur[k].w * gv;
-            cur[k] = nxt[k];
+            for (int k = 0; k < K; k++) {
+                int e = 4 * (lane + 32 * k);
+                int r = (e >= B) + (e >= 2 * B);
+                float gv = (r == 0) ? gx : ((r == 1) ? gy : gz);       // rows beyond 3B were loaded as zeros
+                acc[k].x += cur[k].x * gv; acc[k].y += cur[k].y * gv; acc[k].z += cur[k].z * gv; acc[k].w += cur[k].w * gv;
+            }
         }
+#pragma unroll
+        for (int k = 0; k < K; k++) cur[k] = nxt[k];
+        g0 = g1; g1 = g2; nz0 = nz1;
     }
     // per-warp partials -> shared memory, then a fixed-order sum over warps (and over the 3 rows of a vertex)
     float4* mine = reinterpret_cast<float4*>(s_w + (size_t)warp * 3 * B);

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-    raster_bin(rp, n, bin, keys, stage);
+    const bool packed = raster_bin(rp, n, bin, keys, stage);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
         int px = ox + lx, py = oy + ly;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
         int an = 0;
-        unsigned long long key = keys[idx];
+        unsigned long long key = tile_key(keys, idx, packed, rp.idbits);
         if (px < rp.W && py < rp.H) {
             size_t pi = ((size_t)n * rp.H + py) * rp.W + px;
             float refv[C];

@@ -62,6 +62,9 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
                         info = 2 << 22;
                     } else {
                         info = bx0 | (by0 << 10) | ((bx1 - bx0) << 20) | ((by1 - by0) << 21) | (1 << 22);
+                        // depth window of the triangle (32-bit key mode of the fine rasterizer): the per-vertex z/w of depth_plane()
+                        const unsigned k0 = depth_key(xdiv(p0.z, p0.w)), k1 = depth_key(xdiv(p1.z, p1.w)), k2 = depth_key(xdiv(p2.z, p2.w));
+                        rp.tri_zrange[gid] = make_uint2(min(k0, min(k1, k2)), max(k0, max(k1, k2)));
                         for (int by = by0; by <= by1; by++)
                             for (int bx = bx0; bx <= bx1; bx++) {
                                 if (HIST) atomicAdd(hist + by * rp.BW + bx, 1);
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(FINE_THREADS) k_fine(RasterParams rp, float* _
     WarpStage* stage = reinterpret_cast<WarpStage*>(smem + sizeof(unsigned long long) * BIN * BIN);
     const int bin = blockIdx.x, n = blockIdx.y;
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
-    raster_bin(rp, n, bin, keys, stage);
+    const bool packed = raster_bin(rp, n, bin, keys, stage);
 
     // ---- shade: (u, v, z/w, id+1) and the barycentric pixel differentials ----
     const float* P = rp.pos + (size_t)n * rp.V * 4;
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(FINE_THREADS) k_fine(RasterParams rp, float* _
         int px = ox + lx, py = oy + ly;
         if (px >= rp.W || py >= rp.H) continue;
         size_t pi = ((size_t)n * rp.H + py) * rp.W + px;
-        unsigned long long key = keys[idx];
+        unsigned long long key = tile_key(keys, idx, packed, rp.idbits);
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f), odb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (key != KEY_EMPTY) {
             int t = (int)(key & 0xFFFFFFFFu);
@@ -340,6 +343,7 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_clip_parent = o; o += align_up((size_t)L.clip_cap * 4);
     L.off_anchor = o;      o += align_up((size_t)N * T * 4);
     L.off_tri4 = o;        o += align_up((size_t)T * 16);
+    L.off_zrange = o;      o += align_up((size_t)N * T * 8);
     L.total = o;
     return L;
 }
@@ -369,6 +373,9 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.large_list = (int*)(s + L.off_large);
     rp.tri_anchor = (int*)(s + L.off_anchor);
     rp.tri4 = (int4*)(s + L.off_tri4);
+    rp.tri_zrange = (uint2*)(s + L.off_zrange);
+    rp.idbits = 1;
+    while ((1 << rp.idbits) < T) rp.idbits++;
     rp.clip_count = (int*)(s + L.off_clip_count);
     rp.clip_verts = (float4*)(s + L.off_clip_verts);
     rp.clip_parent = (int*)(s + L.off_clip_parent);

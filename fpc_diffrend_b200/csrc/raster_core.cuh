@@ -31,6 +31,9 @@ namespace fpc {
 #ifndef FPC_WALK_MASK
 #define FPC_WALK_MASK 1      // row coverage as a bit mask, then only the covered span is depth-tested
 #endif
+#ifndef FPC_KEY32
+#define FPC_KEY32 1          // 32-bit packed (depth - bin base, id) keys + native ATOMS.MIN where a bin's depth range allows it
+#endif
 #ifndef FPC_CAS_MANUAL
 #define FPC_CAS_MANUAL 0     // 1: CAS loop seeded by the early-out read — measured 40 % SLOWER than atomicMin on B200
 #endif
@@ -41,6 +44,7 @@ constexpr int FINE_WARPS = FINE_THREADS / 32;
 constexpr float SNAP_LIMIT = 16777216.0f;
 constexpr int SMALL_EXTENT = 2048;   // 128 px in 1/16-px units
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned KEY32_MARGIN = 256u;
 
 struct RasterParams {
     const float* pos;
@@ -66,6 +70,8 @@ struct RasterParams {
     const int32_t* pad_i_src; int4* pad_i_dst; int pad_i_n;          // nullable job for k_setup: int [n,3] -> int4 [n]
     float* clear_tri9;               // nullable: [N*T*9] zeroed by k_setup (moment accumulators of fused.cu)
     float* clear_vtx4;               // nullable: [N*V*4] zeroed by k_setup (position-gradient accumulator)
+    uint2* tri_zrange;               // [N*T] (min, max) of depth_key(z/w) over the vertices of a SMALL triangle (k_setup)
+    int idbits;                      // bits of a triangle id: ceil(log2(T))
 };
 
 struct SnappedTri {
@@ -220,6 +226,19 @@ __device__ __forceinline__ void emit_fragment_at(unsigned long long* kp, float z
 #endif
 }
 
+// 32-bit mode (FPC_KEY32): key = (depth_key - base) << idbits | id, one native shared-memory atomicMin per fragment.  A depth
+// outside the window the bin promised (never observed; the window carries a margin) raises `overflow` and the CTA redoes the
+// bin with 64-bit keys, so the result is the 64-bit result in every case.
+struct Key32Mode { unsigned base, limit; int idbits; int* overflow; };
+
+__device__ __forceinline__ void emit_fragment32(unsigned* kp, float zd, int t, const Key32Mode& km)
+{
+    if (!(zd >= -1.f && zd <= 1.f)) return;
+    const unsigned d = depth_key(zd) - km.base;
+    if (d >= km.limit) { *km.overflow = 1; return; }
+    atomicMin(kp, (d << km.idbits) | (unsigned)t);
+}
+
 template <int TW>
 __device__ __forceinline__ void emit_fragment(unsigned long long* keys, float zd, int t, int lx, int ly)
 {
@@ -246,35 +265,25 @@ struct WarpStage {
     int prefix[32];      // inclusive prefix sum of rows
 };
 
-// Resolve the visibility of the TW x TW pixel tile with origin (ox, oy) — bin `bin` of instance n, widened by
-// rp.halo px on every side when TW == BIN + 2 halo (the origin may then be negative) — into keys[TW*TW] (shared
-// memory, initialised here).  `stage` is NT/32 WarpStage records in shared memory.  All NT threads of the CTA
-// must call this.
-template <int TW, int NT = FINE_THREADS>
-__device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int bin, int ox, int oy, unsigned long long* keys, WarpStage* stage)
+__device__ __forceinline__ void emit_any(unsigned long long* kp, float zd, int t, const Key32Mode&) { emit_fragment_at(kp, zd, t); }
+__device__ __forceinline__ void emit_any(unsigned* kp, float zd, int t, const Key32Mode& km) { emit_fragment32(kp, zd, t, km); }
+
+// The small triangles of a bin: warps claim batches of 32, every lane sets one triangle up and stages it, the warp then walks
+// the batch's (triangle, row) items.  KeyT = unsigned long long (depth_key << 32 | id, CAS-loop atomicMin) or unsigned
+// (Key32Mode, native atomicMin).
+template <int TW, int NT, typename KeyT>
+__device__ __forceinline__ void walk_small(const RasterParams& rp, int n, const int* __restrict__ list, int count, int ox, int oy,
+                                           int min_x, int min_y, int lim_x, int lim_y, KeyT* keys, WarpStage& st, int* next_batch,
+                                           const Key32Mode& km)
 {
-    const int min_x = max(ox, 0), min_y = max(oy, 0);
-    const int lim_x = min(ox + TW, rp.W) - 1, lim_y = min(oy + TW, rp.H) - 1;
-    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
-    const int nlarge = rp.large_count[n];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-#if FPC_DYN_BATCH
-    __shared__ int next_batch;       // warps claim batches of 32 triangles dynamically (balances uneven batches)
-    if (threadIdx.x == 0) next_batch = 0;
-#endif
-    for (int i = threadIdx.x; i < TW * TW; i += NT) keys[i] = KEY_EMPTY;
-    __syncthreads();
-
-    // ---- small triangles ----
-    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
-    WarpStage& st = stage[warp];
+    (void)warp;
 #if FPC_DYN_BATCH
     // (smaller claims for sparsely filled bins were measured: no gain — the barrier stalls after this phase are not a
     // batch-granularity effect, gpurun_out/exp_variants.jsonl round 1)
     for (;;) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(&next_batch, 32);
+        if (lane == 0) base = atomicAdd(next_batch, 32);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
 #else
@@ -348,25 +357,106 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
             }
             if (m) {
                 const int first = __ffs(m) - 1, cnt = __popc(m);
-                unsigned long long* kp = keys + ly * TW + lx + first;
+                KeyT* kp = keys + ly * TW + lx + first;
                 float xf = (float)(dx + first);
-                for (int c = 0; c < cnt; c++, kp++, xf += 1.f) emit_fragment_at(kp, __fmaf_rn(dzdx, xf, zrow), t);
+                for (int c = 0; c < cnt; c++, kp++, xf += 1.f) emit_any(kp, __fmaf_rn(dzdx, xf, zrow), t, km);
             }
             if (TW > 32) {
                 for (int x = 32; x < wd; x++) {
-                    if ((e0 | e1 | e2) >= 0) emit_fragment_at(keys + ly * TW + lx + x, __fmaf_rn(dzdx, (float)(dx + x), zrow), t);
+                    if ((e0 | e1 | e2) >= 0) emit_any(keys + ly * TW + lx + x, __fmaf_rn(dzdx, (float)(dx + x), zrow), t, km);
                     e0 += a0; e1 += a1; e2 += a2;
                 }
             }
 #else
             for (int x = 0; x < wd; x++) {
-                if ((e0 | e1 | e2) >= 0) emit_fragment_at(keys + ly * TW + lx + x, __fmaf_rn(dzdx, (float)(dx + x), zrow), t);
+                if ((e0 | e1 | e2) >= 0) emit_any(keys + ly * TW + lx + x, __fmaf_rn(dzdx, (float)(dx + x), zrow), t, km);
                 e0 += a0; e1 += a1; e2 += a2;
             }
 #endif
         }
         __syncwarp();
     }
+
+}
+
+// Resolve the visibility of the TW x TW pixel tile with origin (ox, oy) — bin `bin` of instance n, widened by
+// rp.halo px on every side when TW == BIN + 2 halo (the origin may then be negative) — into keys[TW*TW] (shared
+// memory, initialised here).  `stage` is NT/32 WarpStage records in shared memory.  All NT threads of the CTA
+// must call this.
+// Returns true when the keys were left in the packed 32-bit layout (only if `widen` is false): read them with tile_key().
+template <int TW, int NT = FINE_THREADS>
+__device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int bin, int ox, int oy, unsigned long long* keys, WarpStage* stage,
+                                            bool widen = true)
+{
+    const int min_x = max(ox, 0), min_y = max(oy, 0);
+    const int lim_x = min(ox + TW, rp.W) - 1, lim_y = min(oy + TW, rp.H) - 1;
+    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
+    const int nlarge = rp.large_count[n];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    __shared__ int next_batch;       // warps claim batches of 32 triangles dynamically (balances uneven batches)
+    __shared__ int s_overflow;
+    __shared__ unsigned s_zlo, s_zhi;
+    if (threadIdx.x == 0) { next_batch = 0; s_overflow = 0; s_zlo = 0xFFFFFFFFu; s_zhi = 0u; }
+    __syncthreads();
+
+    // ---- small triangles ----
+    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
+    WarpStage& st = stage[warp];
+    Key32Mode km;
+    km.base = 0u; km.limit = 0u; km.idbits = rp.idbits; km.overflow = &s_overflow;
+    bool mode32 = false;
+#if FPC_KEY32
+    // depth window of the bin from the per-triangle vertex depth ranges (k_setup); a fragment of a covered pixel lies inside its
+    // triangle, so its plane depth stays within that range up to rounding: KEY32_MARGIN keys of slack on either side
+    if (nlarge == 0 && count > 0 && rp.idbits <= 24) {
+        unsigned zlo = 0xFFFFFFFFu, zhi = 0u;
+        for (int i = threadIdx.x; i < count; i += NT) {
+            const uint2 zr = __ldg(rp.tri_zrange + (size_t)n * rp.T + list[i]);
+            zlo = min(zlo, zr.x); zhi = max(zhi, zr.y);
+        }
+        zlo = __reduce_min_sync(0xffffffffu, zlo); zhi = __reduce_max_sync(0xffffffffu, zhi);
+        if (lane == 0) { atomicMin(&s_zlo, zlo); atomicMax(&s_zhi, zhi); }
+        __syncthreads();
+        zlo = s_zlo; zhi = s_zhi;
+        const unsigned span = (1u << (32 - rp.idbits)) - 1u;          // the all-ones key stays free for "empty"
+        if (zlo >= KEY32_MARGIN && zhi >= zlo && (zhi - zlo) < span - 2u * KEY32_MARGIN) {
+            mode32 = true;
+            km.base = zlo - KEY32_MARGIN; km.limit = span;
+        }
+    }
+    if (mode32) {
+        unsigned* keys32 = reinterpret_cast<unsigned*>(keys);
+        for (int i = threadIdx.x; i < TW * TW; i += NT) keys32[i] = 0xFFFFFFFFu;
+        __syncthreads();
+        walk_small<TW, NT, unsigned>(rp, n, list, count, ox, oy, min_x, min_y, lim_x, lim_y, keys32, st, &next_batch, km);
+        __syncthreads();
+        if (!s_overflow && !widen) return true;               // the caller decodes the packed keys itself (tile_key)
+        if (!s_overflow) {
+            // widen in place to the 64-bit layout the shading phases read (only the id part is used downstream): every
+            // thread reads its keys, then all write
+            constexpr int PER = (TW * TW + NT - 1) / NT;
+            unsigned k32[PER];
+#pragma unroll
+            for (int j = 0; j < PER; j++) { const int i = threadIdx.x + j * NT; k32[j] = (i < TW * TW) ? keys32[i] : 0xFFFFFFFFu; }
+            __syncthreads();
+            const unsigned idmask = (1u << rp.idbits) - 1u;
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                const int i = threadIdx.x + j * NT;
+                if (i < TW * TW) keys[i] = (k32[j] == 0xFFFFFFFFu) ? KEY_EMPTY : (unsigned long long)(k32[j] & idmask);
+            }
+            __syncthreads();
+            return false;
+        }
+        // (never observed) a depth left the window: redo the bin with 64-bit keys
+        if (threadIdx.x == 0) next_batch = 0;
+        __syncthreads();
+    }
+#endif
+    for (int i = threadIdx.x; i < TW * TW; i += NT) keys[i] = KEY_EMPTY;
+    __syncthreads();
+    walk_small<TW, NT, unsigned long long>(rp, n, list, count, ox, oy, min_x, min_y, lim_x, lim_y, keys, st, &next_batch, km);
 
     // ---- large triangles: the whole CTA cooperates on each one (16 pixels per thread), int64 edge math ----
     const int* llist = rp.large_list + (size_t)n * 2 * rp.T;
@@ -397,18 +487,27 @@ __device__ __forceinline__ void raster_tile(const RasterParams& rp, int n, int b
         }
     }
     __syncthreads();
+    return false;
 }
 
-// the plain bin (no halo)
-__device__ __forceinline__ void raster_bin(const RasterParams& rp, int n, int bin, unsigned long long* keys, WarpStage* stage)
+// the plain bin (no halo); keys may come back packed: read them with tile_key(keys, idx, packed, rp.idbits)
+__device__ __forceinline__ bool raster_bin(const RasterParams& rp, int n, int bin, unsigned long long* keys, WarpStage* stage)
 {
-    raster_tile<BIN>(rp, n, bin, (bin % rp.BW) * BIN, (bin / rp.BW) * BIN, keys, stage);
+    return raster_tile<BIN>(rp, n, bin, (bin % rp.BW) * BIN, (bin / rp.BW) * BIN, keys, stage, false);
+}
+
+// key of tile pixel idx in the 64-bit convention the shading phases use (KEY_EMPTY, or the triangle id in the low 32 bits)
+__device__ __forceinline__ unsigned long long tile_key(const unsigned long long* keys, int idx, bool packed, int idbits)
+{
+    if (!packed) return keys[idx];
+    const unsigned k = reinterpret_cast<const unsigned*>(keys)[idx];
+    return (k == 0xFFFFFFFFu) ? KEY_EMPTY : (unsigned long long)(k & ((1u << idbits) - 1u));
 }
 
 // Host side: scratch layout + the three binning launches.
 struct ScratchLayout {
     size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_clip_count, off_clip_verts, off_clip_parent, total;
+    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_zrange, off_clip_count, off_clip_verts, off_clip_parent, total;
     int clip_cap;
 };
 

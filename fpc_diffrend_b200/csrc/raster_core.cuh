@@ -420,7 +420,7 @@ __device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int b
         __syncthreads();
         zlo = s_zlo; zhi = s_zhi;
         const unsigned span = (1u << (32 - rp.idbits)) - 1u;          // the all-ones key stays free for "empty"
-        if (zlo >= KEY32_MARGIN && zhi >= zlo && (zhi - zlo) < span - 2u * KEY32_MARGIN) {
+        if (span > 2u * KEY32_MARGIN && zlo >= KEY32_MARGIN && zhi >= zlo && (zhi - zlo) < span - 2u * KEY32_MARGIN) {
             mode32 = true;
             km.base = zlo - KEY32_MARGIN; km.limit = span;
         }

@@ -723,3 +723,34 @@ def test_full_scale_gradient_precision(dr):
         assert ev.max() < 3e-4, (name, ev.max())
         assert (ev > REL_GRAD).mean() < 1e-3, (name, (ev > REL_GRAD).sum())
     assert rel_err(g_fused, g_ops) < 1e-5
+
+
+@pytest.mark.parametrize('depth', ['compressed', 'wide'])
+def test_rasterize_triangle_soup_key_modes(dr, depth):
+    """A soup of small triangles with many overlaps and EXACT duplicates (depth ties -> the lower id must win), against the
+    oracle.  'compressed' depths (z/w within a few hundred ulps, as under the reference's zn = 0.01 / zf = 200 projection) take
+    the rasterizer's 32-bit packed-key path, 'wide' depths (z/w spread over [-0.9, 0.9]) exceed the per-bin window and take the
+    64-bit path: both must reproduce the oracle's tri_id bit for bit."""
+    rng = np.random.default_rng(31)
+    H, W, T = 96, 130, 400
+    c = rng.uniform(-0.9, 0.9, size=(T, 1, 2))
+    xy = c + rng.uniform(-0.12, 0.12, size=(T, 3, 2))
+    if depth == 'compressed':
+        z = 0.9999 + rng.integers(0, 300, size=(T, 1)) * 6e-8 + rng.integers(0, 40, size=(T, 3)) * 6e-8
+    else:
+        z = rng.uniform(-0.9, 0.9, size=(T, 1)) + rng.uniform(-0.05, 0.05, size=(T, 3))
+    w = rng.uniform(0.8, 1.6, size=(T, 3))
+    pos = np.concatenate([xy * w[..., None], (z * w)[..., None], w[..., None]], axis=-1).astype(np.float32)      # [T,3,4]
+    pos[T // 2:T // 2 + 60] = pos[:60]                                   # exact duplicates of the first 60 triangles: depth ties
+    verts = pos.reshape(1, 3 * T, 4)
+    tri = np.arange(3 * T, dtype=np.int32).reshape(T, 3)
+    rast, db, sec = G.rasterize_fwd(verts, tri, (H, W), with_second=True)
+    ctx = dr.RasterizeCudaContext()
+    out, out_db = dr.rasterize(ctx, cu(verts), cu(tri), resolution=(H, W))
+    ids, ids_ref = out[..., 3].cpu().numpy(), rast[..., 3]
+    assert (ids_ref > 0).mean() > 0.25
+    assert np.array_equal(ids, ids_ref)                                   # ties included: same op order on both sides
+    dup = (ids_ref > 0) & (ids_ref <= 60)
+    assert dup.sum() > 20 and not ((ids_ref > T // 2) & (ids_ref <= T // 2 + 60)).any()      # the duplicate with the higher id never wins
+    ok = ids == ids_ref
+    assert np.abs(out.cpu().numpy()[..., :3] - rast[..., :3])[ok].max() <= ABS_FWD

@@ -760,3 +760,41 @@ def test_l1_image_loss(small_rig3, fused, use_aa):
     for _ in range(15):
         s.iteration()
     assert float(s.loss) < l0
+
+
+def test_fit_recovers_ground_truth_activations():
+    """End-to-end sanity of the analysis-by-synthesis loop: starting from the neutral face, 400 graph-replayed iterations against
+    frames rendered from known activations (3 cameras, vertex colours + antialias, the reference's decaying learning-rate
+    schedule) bring the image loss down several-fold and move activations and blended vertices most of the way to the ground
+    truth.  Two properties of rasterization-based gradients bound what to expect (tests/tools/convergence_probe.py): the loss is
+    only piecewise smooth — single pixels popping across silhouettes are 0.06 each here, and Adam turns that noise into steps of
+    the size of the learning rate, so the schedule has to decay for the loss to settle —, and the silhouette term of the gradient
+    comes from the antialias op alone, which sees an outline pixel only when the triangle covering it owns the silhouette edge
+    (rim triangles of a smooth mesh are sub-pixel slivers): along the line to the ground truth the analytic slope has the right
+    sign and a quarter of the long-baseline finite-difference slope.  The fused and the op-level paths agree on it."""
+    from fpc_diffrend_b200 import rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    H, W, F, iters = 192, 192, 2, 400
+    rig = rigmod.make_rig(n_vertices=1500, n_shapes=12, n_cams=3, width=W, height=H, tex_size=128, seed=5)
+    cfg = FitConfig(resolution=(H, W), shading='vcol', antialias=True, lr_base=2e-2, lr_ramp=0.005, max_iter=iters, optimize_pose=False)
+    _, t_true, q_true = rigmod.make_targets(F, rig.B, seed=7)
+    w_true = np.random.default_rng(7).uniform(0.3, 0.9, size=(F, rig.B)).astype(np.float32)       # every shape clearly active
+    ref = synthesize_reference(rig, w_true, 0.0 * t_true, q_true * 0 + np.array([0, 0, 0, 1], np.float32), cfg)
+    s = FitSession(rig, F, cfg)
+    s.set_reference(ref)
+    v_true = torch.tensor(rig.v_base)[None] + torch.tensor(w_true) @ torch.tensor(rig.D).t()
+    err0 = float((s.result_vertices().cpu() - v_true).abs().mean())
+    s.iteration()
+    torch.cuda.synchronize()
+    loss0 = float(s.loss)
+    s.capture()
+    for _ in range(iters - 1):
+        s.replay()
+    torch.cuda.synchronize()
+    loss1 = float(s.loss)
+    err1 = float((s.result_vertices().cpu() - v_true).abs().mean())
+    werr0, werr1 = float(np.abs(w_true).mean()), float((s.w.cpu() - torch.tensor(w_true)).abs().mean())
+    print('loss %.4f -> %.4f, vertex error %.4f -> %.4f, activation error %.3f -> %.3f' % (loss0, loss1, err0, err1, werr0, werr1))
+    assert loss1 < 0.5 * loss0, (loss0, loss1)
+    assert err1 < 0.4 * err0, (err0, err1)
+    assert werr1 < 0.6 * werr0, (werr0, werr1)

@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('FPC_B200_LIB') or os.path.join(_HERE, 'libfpc_b200.so')
 HEADER_PATH = os.path.join(_HERE, '..', 'include', 'fpc_b200.h')
 
+ABI_VERSION = 2        # FPC_B200_ABI_VERSION of include/fpc_b200.h these signatures were written against
+
 _lib = None
 
 _c = ctypes
@@ -106,6 +108,9 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if lib.fpc_abi_version() != ABI_VERSION:
+            raise RuntimeError('libfpc_b200.so at %s has ABI version %d, this package expects %d — rebuild it with '
+                               '`python -m fpc_diffrend_b200.build --force`' % (LIB_PATH, lib.fpc_abi_version(), ABI_VERSION))
         _lib = lib
     return _lib
 

@@ -6,6 +6,9 @@ The reference calls exactly these:
     dr.interpolate(attr[None], rast_out, idx)                             fit.py:157
     dr.texture(tex[None], texc, filter_mode='linear')                     fit.py:158
     dr.antialias(colour, rast_out, pos_clip, pos_idx)                     fit.py:160
+and, in the enable_mip branch of its render() (fit.py:153-155; off in the shipped configuration):
+    dr.interpolate(uv[None], rast_out, uv_idx, rast_db=rast_out_db, diff_attrs='all')
+    dr.texture(tex[None], texc, texd, filter_mode='linear-mipmap-linear', max_mip_level=k)
 Signatures, defaults, tensor layouts (rast = (u, v, z/w, tri_id+1), row 0 = bottom) and the error
 behaviour (RuntimeError naming the offending argument) follow upstream nvdiffrast v0.3.x.  Every op is a
 torch.autograd.Function whose forward/backward call the C-ABI of include/fpc_b200.h on the current CUDA

@@ -5,9 +5,16 @@
  * (reference: /root/reference/src/torch/fit.py:524-642).  Each entry point states the reference
  * interface it replaces.  For the four rendering ops that interface is the nvdiffrast plugin the
  * reference binds through `import nvdiffrast.torch as dr` (fit.py:13): upstream plugin functions
- * `rasterize_fwd_cuda / rasterize_grad / interpolate_fwd / interpolate_grad / texture_fwd /
- * texture_grad_linear / antialias_construct_topology_hash / antialias_fwd / antialias_grad`
- * (SURVEY.md §8(b)).  The binding a maintainer adds on the reference side is shown in INTEGRATION.md.
+ * `rasterize_fwd_cuda / rasterize_grad / rasterize_grad_db / interpolate_fwd / interpolate_fwd_da /
+ * interpolate_grad / interpolate_grad_da / texture_construct_mip / texture_fwd / texture_fwd_mip /
+ * texture_grad_linear / texture_grad_linear_mipmap_{nearest,linear} / antialias_construct_topology_hash /
+ * antialias_fwd / antialias_grad`.  The binding a maintainer adds on the reference side is
+ * shown in INTEGRATION.md.
+ *
+ * Groups, in file order: status / device check; the four rendering ops of the drop-in (+ their mip-mapped variants);
+ * blendshape combination (SIMT, tcgen05, learned basis of the free / combined modes); pose -> MVP and clip transform;
+ * fused geometry stages; image loss (L2 or L1); fused render + loss + gradient (plain, antialiased, band-split for the
+ * camera-split mode); mesh regularisers; Adam.
  *
  * Conventions
  *   - plain pointers and sizes only; all pointers are DEVICE pointers on the current CUDA device unless
@@ -42,7 +49,7 @@ typedef enum fpc_status {
 
 typedef void* fpc_stream_t; /* cudaStream_t */
 
-#define FPC_B200_ABI_VERSION 1
+#define FPC_B200_ABI_VERSION 2   /* 2: loss_kind / grad_tex arguments of the loss and fused entries, band-split entry */
 
 /* ---- library ------------------------------------------------------------------------------------- */
 int fpc_abi_version(void);

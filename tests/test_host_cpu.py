@@ -202,3 +202,23 @@ def test_take_formats_roundtrip(tmp_path):
     assert np.array_equal(png, (np.flip(rig.tex, 0) * 255).astype(np.uint8)[..., 0])
     dataio.write_config(str(out), {'max_iter': 5, 'mode': 'prior'})
     assert open(out / 'config.txt').read() == "max_iter: '5'\nmode: 'prior'\n"
+
+
+def test_algorithmic_byte_model_matches_survey():
+    """bench.py's per-op algorithmic bytes are the formulas of SURVEY.md §8(d): per-pixel terms of the op-boundary chain and the
+    fused-path model (56 + 20 C) B/px + geometry the bench line's roofline is quoted on."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(HERE, '..', 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = bench.WORKLOADS['config2']
+    b = bench.algorithmic_bytes(wl, 1, wl['V'])
+    px = 9 * 1024 * 1024
+    geo = 9 * 16 * wl['V'] + 12 * (2 * wl['V'] - 4)
+    # rasterize fwd 16 px + geo, bwd 32 px + geo + 16 N V; interpolate (A = 3) fwd 28 px, bwd 44 px (+ index / attribute terms)
+    assert b['rasterize_fwd'] == 16 * px + geo and b['rasterize_bwd'] == 32 * px + geo + 16 * 9 * wl['V']
+    assert b['interpolate_fwd'] // px == 28 and b['interpolate_bwd'] // px == 44
+    assert b['render_loss_fused'] == (56 + 20 * 3) * px + geo + 12 * (2 * wl['V'] - 4) + 4 * 3 * wl['V']
+    assert abs(b['render_loss_fused'] / 1e9 - 1.0988) < 1e-3           # the figure the bench line's roofline is quoted on
+    # the single-frame GEMV streams D once per direction
+    assert b['geometry_fwd'] > 4 * 3 * wl['V'] * wl['B'] and b['geometry_fwd'] < 1.1 * 4 * 3 * wl['V'] * wl['B']

@@ -43,6 +43,8 @@ class FitConfig:
     beta2: float = 0.999
     eps: float = 1e-8
     bg: float = BG
+    enable_mip: bool = False              # the mip branch of the reference's render() (fit.py:153-155; main.py:26 ships False):
+    max_mip_level: int = None             # trilinear mip-mapped texture lookups with footprints from rast_db; op-level path only
     loss: str = 'l2'                      # image loss: 'l2' = mean((ref - 255 c)^2) (fit.py:579) or 'l1' = mean(|ref - 255 c|) (north-star)
     quat_norm: str = 'row'                # 'row' (default) or 'frobenius' (reference quirk)
     optimize_pose: bool = True
@@ -221,9 +223,25 @@ class FitSession:
             self.g_attr = torch.empty_like(self.attr)
         self.d_verts = torch.empty(F, V * 3, **f32)
         self.d_mvp = torch.empty(self.N, 16, **f32)
+        self.use_mip = bool(cfg.enable_mip)
+        if self.use_mip and (self.use_fused or cfg.shading != 'texture'):
+            raise ValueError("enable_mip needs shading='texture' and the op-level path (fused=False)")
         if cfg.shading == 'texture' and not self.use_fused:
             self.texc = torch.empty(self.N, H, W, 2, **f32)
             self.g_texc = torch.empty(self.N, H, W, 2, **f32)
+        if self.use_mip:
+            L = _lib.load()
+            Ht, Wt = self.tex.shape[1], self.tex.shape[2]
+            self.mip_levels = int(L.fpc_texture_mip_levels(Ht, Wt, -1 if cfg.max_mip_level is None else int(cfg.max_mip_level)))
+            if cfg.max_mip_level is not None and self.mip_levels != int(cfg.max_mip_level):
+                raise ValueError('max_mip_level=%d needs texture extents divisible by %d (got %dx%d)' % (cfg.max_mip_level, 1 << cfg.max_mip_level, Wt, Ht))
+            nmip = int(L.fpc_texture_mip_floats(1, Ht, Wt, Ch, self.mip_levels))
+            self.mip = torch.empty(nmip, **f32)
+            self.g_mip = torch.empty(nmip, **f32)
+            self.rast_db = torch.empty(self.N, H, W, 4, **f32)
+            self.g_rast_db = torch.empty(self.N, H, W, 4, **f32)
+            self.texd = torch.empty(self.N, H, W, 4, **f32)
+            self.g_texd = torch.empty(self.N, H, W, 4, **f32)
         if cfg.antialias:
             if not self.use_fused:
                 self.colour_aa = torch.empty(self.N, H, W, Ch, **f32)
@@ -400,10 +418,19 @@ class FitSession:
             call('project_fwd', 'fpc_project_fwd', _p(self.verts), _p(self.mvp), F, C, V, _p(self.pos_clip), s); n += 1
         if self.use_fused:
             return n + self._fused(True) if with_loss else self._fused(False)
-        call('rasterize_fwd', 'fpc_rasterize_fwd', _p(self.pos_clip), _p(self.pos_idx), N, V, T, H, W, _p(self.rast), None,
+        call('rasterize_fwd', 'fpc_rasterize_fwd', _p(self.pos_clip), _p(self.pos_idx), N, V, T, H, W, _p(self.rast),
+             _p(self.rast_db) if self.use_mip else None,
              _p(self.scratch), self.scratch.numel(), s); n += 4
         if cfg.shading == 'vcol':
             call('interpolate_fwd', 'fpc_interpolate_fwd', _p(self.attr), 1, V, Ch, _p(self.rast), _p(self.attr_idx), N, T, H, W, _p(self.colour), s); n += 1
+        elif self.use_mip:
+            # fit.py:154-155: uv and its pixel differentials, then the trilinear lookup (the chain is rebuilt from the current texture)
+            Ht, Wt, L = self.tex.shape[1], self.tex.shape[2], self.mip_levels
+            call('interpolate_fwd', 'fpc_interpolate_da_fwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.rast_db), _p(self.attr_idx),
+                 None, 2, N, T, H, W, _p(self.texc), _p(self.texd), s); n += 1
+            call('texture_fwd', 'fpc_texture_mip_build', _p(self.tex), 1, Ht, Wt, Ch, L, _p(self.mip), s); n += L
+            call('texture_fwd', 'fpc_texture_mip_fwd', _p(self.tex), _p(self.mip), 1, Ht, Wt, Ch, L, _p(self.texc), _p(self.texd), None, 0, N, H, W,
+                 _p(self.colour), s); n += 1
         else:
             call('interpolate_fwd', 'fpc_interpolate_fwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), N, T, H, W, _p(self.texc), s); n += 1
             call('texture_fwd', 'fpc_texture_linear_fwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), N, H, W, _p(self.colour), s); n += 1
@@ -510,13 +537,24 @@ class FitSession:
         if cfg.shading == 'vcol':
             call('interpolate_bwd', 'fpc_interpolate_bwd', _p(self.attr), 1, V, Ch, _p(self.rast), _p(self.attr_idx), _p(g_colour), N, T, H, W,
                  _p(self.g_attr), _p(self.g_rast), s); n += 2
+        elif self.use_mip:
+            Ht, Wt, L = self.tex.shape[1], self.tex.shape[2], self.mip_levels
+            call('texture_bwd', 'fpc_texture_mip_bwd', _p(self.tex), _p(self.mip), 1, Ht, Wt, Ch, L, _p(self.texc), _p(self.texd), None, 0, _p(g_colour),
+                 N, H, W, _p(self.d_tex) if cfg.optimize_texture else None, _p(self.g_mip) if cfg.optimize_texture else None, 0,
+                 _p(self.g_texc), _p(self.g_texd), None, s); n += 1 + ((2 + L) if cfg.optimize_texture else 0)
+            call('interpolate_bwd', 'fpc_interpolate_da_bwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.rast_db), _p(self.attr_idx),
+                 None, 2, _p(self.g_texc), _p(self.g_texd), N, T, H, W, _p(self.g_attr), _p(self.g_rast), _p(self.g_rast_db), s); n += 2
         else:
             call('texture_bwd', 'fpc_texture_linear_bwd', _p(self.tex), 1, self.tex.shape[1], self.tex.shape[2], Ch, _p(self.texc), _p(g_colour),
                  N, H, W, _p(self.d_tex) if cfg.optimize_texture else None, _p(self.g_texc), s); n += 1 + (1 if cfg.optimize_texture else 0)
             call('interpolate_bwd', 'fpc_interpolate_bwd', _p(self.attr), 1, self.attr.shape[1], 2, _p(self.rast), _p(self.attr_idx), _p(self.g_texc),
                  N, T, H, W, _p(self.g_attr), _p(self.g_rast), s); n += 2
-        call('rasterize_bwd', 'fpc_rasterize_bwd', _p(self.pos_clip), _p(self.pos_idx), _p(self.rast), _p(self.g_rast), N, V, T, H, W,
-             _p(self.g_pos), s); n += 2
+        if self.use_mip:
+            call('rasterize_bwd', 'fpc_rasterize_bwd_db', _p(self.pos_clip), _p(self.pos_idx), _p(self.rast), _p(self.g_rast), _p(self.g_rast_db),
+                 N, V, T, H, W, _p(self.g_pos), s); n += 2
+        else:
+            call('rasterize_bwd', 'fpc_rasterize_bwd', _p(self.pos_clip), _p(self.pos_idx), _p(self.rast), _p(self.g_rast), N, V, T, H, W,
+                 _p(self.g_pos), s); n += 2
         if cfg.antialias:
             self.g_pos.add_(self.g_pos_aa); n += 1
         return n + self._backward_geometry()

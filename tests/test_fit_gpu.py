@@ -798,3 +798,48 @@ def test_fit_recovers_ground_truth_activations():
     assert loss1 < 0.5 * loss0, (loss0, loss1)
     assert err1 < 0.4 * err0, (err0, err1)
     assert werr1 < 0.6 * werr0, (werr0, werr1)
+
+
+@pytest.mark.parametrize('opt_tex', [False, True])
+def test_fit_session_mip_path(small_rig3, opt_tex):
+    """FitConfig.enable_mip (the mip branch of the reference's render(), fit.py:153-155, inside the accelerated loop): loss and
+    gradients of the C-ABI chain against the SAME chain written with the drop-in ops under torch autograd (render.render with
+    enable_mip=True), which the op-level tests pin against the float64 oracle."""
+    from fpc_diffrend_b200 import rig as rigmod, render as R
+    import fpc_diffrend_b200.ops as dr
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F, maxl = small_rig3, 152, 200, 2, 3
+    C = rig.P.shape[0]
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
+    ref = synthesize_reference(rig, w_true, t_true * 0.2, q_true, FitConfig(resolution=(H, W), shading='texture', antialias=True))
+    cfg = FitConfig(resolution=(H, W), shading='texture', antialias=True, fused=False, enable_mip=True, max_mip_level=maxl, optimize_texture=opt_tex)
+    s = FitSession(rig, F, cfg)
+    s.set_reference(ref)
+    s.set_parameters(w=(0.05 * np.random.default_rng(0).random((F, rig.B))).astype(np.float32))
+    s.forward()
+    s.backward()
+    torch.cuda.synchronize()
+    glctx = dr.RasterizeGLContext(device='cuda')
+    tex = s.tex[0].clone().requires_grad_(True)
+    uv, uvi, tri = s.attr[0], s.attr_idx, s.pos_idx
+    total, g_pos = 0.0, []
+    for n in range(F * C):
+        pc = s.pos_clip[n].clone().requires_grad_(True)                      # [V,4]: feed the session's own clip positions
+        rast, rast_db = dr.rasterize(glctx, pc[None], tri, resolution=(H, W))
+        texc, texd = dr.interpolate(uv[None], rast, uvi, rast_db=rast_db, diff_attrs='all')
+        col = dr.texture(tex[None], texc, texd, filter_mode='linear-mipmap-linear', max_mip_level=maxl)
+        col = dr.antialias(col, rast, pc[None], tri)
+        img = torch.where(rast[..., 3:] > 0, col, torch.tensor(R.BG, device='cuda'))[0]
+        loss = torch.mean((ref[n // C, n % C] - 255.0 * img) ** 2) / C
+        loss.backward()
+        total += float(loss.detach())
+        g_pos.append(pc.grad)
+    assert abs(float(s.loss) - total) / total < 1e-5
+    assert rel(s.g_pos.cpu(), torch.stack(g_pos).cpu()) < 1e-4
+    if opt_tex:
+        assert rel(s.d_tex.cpu(), tex.grad[None].cpu()) < 1e-4
+    l0 = float(s.loss)
+    s.cfg.lr_base = 5e-3
+    for _ in range(10):
+        s.iteration()
+    assert float(s.loss) < l0

@@ -34,6 +34,9 @@ namespace fpc {
 #ifndef FPC_KEY32
 #define FPC_KEY32 1          // 32-bit packed (depth - bin base, id) keys + native ATOMS.MIN where a bin's depth range allows it
 #endif
+#ifndef FPC_KEY32_TEST_OVERFLOW
+#define FPC_KEY32_TEST_OVERFLOW 0
+#endif
 #ifndef FPC_CAS_MANUAL
 #define FPC_CAS_MANUAL 0     // 1: CAS loop seeded by the early-out read — measured 40 % SLOWER than atomicMin on B200
 #endif
@@ -235,6 +238,9 @@ __device__ __forceinline__ void emit_fragment32(unsigned* kp, float zd, int t, c
 {
     if (!(zd >= -1.f && zd <= 1.f)) return;
     const unsigned d = depth_key(zd) - km.base;
+#if FPC_KEY32_TEST_OVERFLOW
+    if ((t % 5) == 0) { *km.overflow = 1; return; }           // test build only: exercises the 64-bit redo of the bin
+#endif
     if (d >= km.limit) { *km.overflow = 1; return; }
     atomicMin(kp, (d << km.idbits) | (unsigned)t);
 }

@@ -754,3 +754,37 @@ def test_rasterize_triangle_soup_key_modes(dr, depth):
     assert dup.sum() > 20 and not ((ids_ref > T // 2) & (ids_ref <= T // 2 + 60)).any()      # the duplicate with the higher id never wins
     ok = ids == ids_ref
     assert np.abs(out.cpu().numpy()[..., :3] - rast[..., :3])[ok].max() <= ABS_FWD
+
+
+def test_packed_key_overflow_redo_path(tmp_path):
+    """The safety net of the 32-bit packed-key mode: a fragment whose depth leaves the bin's window flags the CTA, which then
+    redoes the bin with 64-bit keys.  The window never overflows on real input, so a TEST BUILD of the library
+    (-DFPC_KEY32_TEST_OVERFLOW=1: every fifth triangle raises the flag) is run in a subprocess on the triangle soup and a rig
+    view; the tri_id planes must still equal the oracle's."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, 'fpc_diffrend_b200', 'libfpc_b200_ovf.so')
+    if not os.path.exists(lib):
+        from fpc_diffrend_b200 import build as B
+        B.build(defines=('FPC_KEY32_TEST_OVERFLOW=1',), tag='_ovf')
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import clip_positions
+from oracle import golden as G
+from fpc_diffrend_b200 import rig as rigmod
+import fpc_diffrend_b200.ops as dr
+rig = rigmod.make_rig(n_vertices=1000, n_shapes=4, n_cams=2, width=160, height=128, tex_size=32, seed=0)
+pc = clip_positions(rig)
+ref, _, _ = G.rasterize_fwd(pc, rig.pos_idx, (128, 160))
+out, _ = dr.rasterize(dr.RasterizeCudaContext(), torch.tensor(pc).cuda(), torch.tensor(rig.pos_idx).cuda(), resolution=(128, 160))
+assert (ref[..., 3] > 0).mean() > 0.1
+assert np.array_equal(out[..., 3].cpu().numpy(), ref[..., 3]), 'tri_id differs after the 64-bit redo'
+assert np.abs(out.cpu().numpy() - ref).max() <= 1e-5
+print('redo path ok')
+''' % (root, os.path.join(root, 'tests'))
+    env = dict(os.environ, FPC_B200_LIB=lib)
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'redo path ok' in r.stdout, r.stdout + r.stderr

@@ -15,6 +15,7 @@ torch.autograd.Function whose forward/backward call the C-ABI of include/fpc_b20
 stream.  There is no CPU or PyTorch fallback: tensors must live on a CUDA device of compute capability 10.x.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -421,14 +422,21 @@ def antialias_construct_topology_hash(tri):
 
 
 def _topology_for(tri):
-    key = (tri.data_ptr(), tri._version, tuple(tri.shape), tri.device)
+    """Adjacency table of `tri`, cached per tensor OBJECT (upstream rebuilds its edge hash on every call unless topology_hash is
+    passed; the reference never passes it, fit.py:160, but hands over the same pos_idx tensor every iteration).  The entry holds a
+    weak reference to the tensor it was built from: a different tensor that merely reuses a freed tensor's address, or an in-place
+    modification (version counter), rebuilds."""
+    key = tri.data_ptr()
     hit = _topology_cache.get(key)
-    if hit is None:
-        if len(_topology_cache) > 16:
-            _topology_cache.clear()
-        hit = antialias_construct_topology_hash(tri)
-        _topology_cache[key] = hit
-    return hit
+    if hit is not None:
+        ref, version, wrapper = hit
+        if ref() is tri and version == tri._version:
+            return wrapper
+    if len(_topology_cache) > 16:
+        _topology_cache.clear()
+    wrapper = antialias_construct_topology_hash(tri)
+    _topology_cache[key] = (weakref.ref(tri), tri._version, wrapper)
+    return wrapper
 
 
 class _antialias_func(torch.autograd.Function):

@@ -788,3 +788,26 @@ print('redo path ok')
     env = dict(os.environ, FPC_B200_LIB=lib)
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'redo path ok' in r.stdout, r.stdout + r.stderr
+
+
+def test_antialias_topology_cache_is_per_tensor(dr):
+    """The adjacency table antialias() builds when no topology_hash is passed is cached per tensor object: a NEW triangle tensor
+    that lands on the address of a freed one (same shape, different connectivity) must not inherit the old table.  (Found by
+    tests/tools/parity_sweep.py: consecutive rigs of equal size.)"""
+    from fpc_diffrend_b200 import rig as rigmod
+    outs = []
+    for seed in (11, 12, 13):
+        rig = rigmod.make_rig(n_vertices=200, n_shapes=4, n_cams=1, width=96, height=96, tex_size=16, seed=seed)
+        pc = clip_positions(rig)
+        ctx = dr.RasterizeCudaContext()
+        tri = cu(rig.pos_idx)                                  # freed at the end of the iteration: the next one may reuse its address
+        rast, _ = dr.rasterize(ctx, cu(pc), tri, resolution=(96, 96))
+        col = torch.rand(1, 96, 96, 1, device='cuda', generator=torch.Generator(device='cuda').manual_seed(seed))
+        got = dr.antialias(col, rast, cu(pc), tri)
+        want = dr.antialias(col, rast, cu(pc), tri, topology_hash=dr.antialias_construct_topology_hash(tri))
+        assert torch.equal(got, want), seed
+        ref = G.antialias_fwd(col.cpu().numpy(), rast.cpu().numpy(), pc, rig.pos_idx, G.topology_build(rig.pos_idx))
+        assert np.abs(got.cpu().numpy() - ref).max() <= ABS_FWD
+        outs.append(int((got != col).sum()))
+        del tri, rast, got, want
+    assert min(outs) > 10

@@ -1,0 +1,111 @@
+"""Randomised parity sweep (developer tool): rasterizer tri_id / barycentrics against the oracle and the fused kernels against the
+op-level chain over random rigs, poses, resolutions and shading modes.   python tests/tools/parity_sweep.py [n_cases] [seed]"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from conftest import clip_positions  # noqa: E402
+from fpc_diffrend_b200 import _lib, rig as rigmod  # noqa: E402
+import fpc_diffrend_b200.ops as dr  # noqa: E402
+from oracle import golden as G  # noqa: E402
+
+
+def draw_case(rng):
+    """All random inputs of one case (numpy only, so that cases can be re-drawn without evaluating them)."""
+    c = {}
+    c['V'] = int(rng.choice([200, 500, 1200, 3000]))
+    c['H'], c['W'] = int(rng.integers(40, 300)), int(rng.integers(40, 300))
+    c['C'] = int(rng.choice([1, 3]))
+    c['textured'], c['aa'], c['u8'] = bool(rng.integers(2)), bool(rng.integers(2)), bool(rng.integers(2))
+    c['rig'] = rigmod.make_rig(n_vertices=c['V'], n_shapes=6, n_cams=2, width=c['W'], height=c['H'], tex_size=32, seed=int(rng.integers(1 << 30)))
+    rig = c['rig']
+    w = rng.uniform(0, 0.8, size=rig.B)
+    t = rng.normal(size=3) * rng.choice([0.2, 3.0])                     # sometimes partly off screen
+    q = rng.normal(size=4) * 0.05 + np.array([0, 0, 0, 1.0])
+    q /= np.linalg.norm(q)
+    c['pc'] = clip_positions(rig, w=w, t=t, q=q)
+    if c['textured']:
+        c['tex'] = (rng.random((16, 24, c['C'])) * 0.6).astype(np.float32)
+    else:
+        c['attr'] = (rng.random((rig.V, c['C'])) * 0.6).astype(np.float32)
+    c['ref'] = np.round(rng.uniform(0, 140, size=(c['pc'].shape[0], c['H'], c['W'], c['C']))).astype(np.float32)
+    return c
+
+
+def eval_case(c, case, verbose=False):
+    V, H, W, C, textured, aa, u8, rig, pc, ref = (c[k] for k in ('V', 'H', 'W', 'C', 'textured', 'aa', 'u8', 'rig', 'pc', 'ref'))
+    N, T = pc.shape[0], rig.T
+    cu = lambda a: torch.as_tensor(a).cuda().contiguous()
+    rast, db, sec = G.rasterize_fwd(pc, rig.pos_idx, (H, W), with_second=True)
+    ctx = dr.RasterizeCudaContext()
+    pos = cu(pc).requires_grad_(True)
+    out, out_db = dr.rasterize(ctx, pos, cu(rig.pos_idx), resolution=(H, W))
+    bad_id = int((out[..., 3].detach().cpu().numpy() != rast[..., 3]).sum())
+    err_uv = float(np.abs(out.detach().cpu().numpy() - rast).max())
+    # fused vs op-level chain
+    if textured:
+        attr, aidx = cu(rig.uv), cu(rig.uv_idx)
+        tex = cu(c['tex'])
+        a, _ = dr.interpolate(attr[None], out, aidx)
+        col = dr.texture(tex[None], a, filter_mode='linear')
+    else:
+        attr, aidx, tex = cu(c['attr']), cu(rig.pos_idx), None
+        col, _ = dr.interpolate(attr[None], out, aidx)
+    if aa:
+        col = dr.antialias(col, out, pos, cu(rig.pos_idx))
+    comp = torch.where(out[..., 3:] > 0, col, torch.tensor(G.BG, device='cuda'))
+    loss_ops = ((cu(ref) - 255.0 * comp) ** 2).mean(dim=(1, 2, 3)).sum()
+    loss_ops.backward()
+    P = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None else None
+    opp = dr.antialias_construct_topology_hash(cu(rig.pos_idx)).tri_opp if aa else None
+    loss = torch.zeros(1, device='cuda')
+    g_pos = torch.empty(N, rig.V, 4, device='cuda')
+    col_out = torch.empty(N, H, W, C, device='cuda')
+    scratch = torch.empty(int(_lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W)), dtype=torch.uint8, device='cuda')
+    d_ref = cu(ref.astype(np.uint8)) if u8 else cu(ref)
+    d_tri = cu(rig.pos_idx)
+    head = (P(pos.detach()), P(d_tri)) + ((P(opp),) if aa else ())
+    _lib.call('fpc_render_loss_fused_aa' if aa else 'fpc_render_loss_fused', *head, P(attr), P(aidx), attr.shape[0], attr.shape[1], P(tex),
+              tex.shape[0] if textured else 0, tex.shape[1] if textured else 0, P(d_ref), 1 if u8 else 0, N, rig.V, T, H, W, C, G.BG, 1.0, 0,
+              P(loss), P(g_pos), None, None, P(col_out), P(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    g_ops = pos.grad
+    gmax = float(g_ops.abs().max())
+    err_g = float((g_pos - g_ops).abs().max()) / max(gmax, 1e-30)
+    err_c = float((col_out - comp.detach()).abs().max())
+    err_l = abs(float(loss) - float(loss_ops)) / max(float(loss_ops), 1e-30)
+    cov = float((rast[..., 3] > 0).mean())
+    status = 'ok' if (bad_id == 0 and err_uv <= 1e-5 and err_g < 1e-4 and err_c <= 1e-5 and err_l < 1e-5) else 'MISMATCH'
+    print('%3d %-8s V=%4d %3dx%3d C=%d tex=%d aa=%d u8=%d cover=%.2f  id-mismatch=%d  |rast err|=%.1e  |image err|=%.1e  loss rel=%.1e  grad rel err=%.1e' %
+          (case, status, V, H, W, C, textured, aa, u8, cov, bad_id, err_uv, err_c, err_l, err_g))
+    if verbose:
+        e = (g_pos - g_ops).abs().amax(dim=2).cpu().numpy() / gmax                      # [N,V]
+        for n in range(N):
+            worst = np.argsort(-e[n])[:6]
+            w = pc[n, :, 3]
+            ndc = pc[n, :, :2] / w[:, None]
+            print('   view %d: vertices above 1e-4: %d; worst %s' % (n, int((e[n] > 1e-4).sum()),
+                  ', '.join('%d:%.2e (ndc %.2f %.2f, w %.1f)' % (v, e[n, v], ndc[v, 0], ndc[v, 1], w[v]) for v in worst)))
+            print('      fused', g_pos[n, worst[0]].cpu().numpy(), 'ops', g_ops[n, worst[0]].cpu().numpy())
+    return status == 'ok'
+
+
+if __name__ == '__main__':
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    only = int(sys.argv[3]) if len(sys.argv) > 3 else None
+    good = total = 0
+    for i in range(n):
+        c = draw_case(rng)
+        if only is not None and i != only:
+            continue
+        total += 1
+        good += eval_case(c, i, verbose=only is not None)
+    print('%d / %d cases clean' % (good, total))
+    sys.exit(0 if good == total else 1)

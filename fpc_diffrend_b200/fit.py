@@ -578,7 +578,10 @@ class FitSession:
             n += self._mesh_reg(self.d_verts, 1)
         if self.cfg.mode == 'free':
             pass                                        # no rig prior: d_w stays 0
-        elif self.use_tc_blend:
+        elif self.use_tc_blend and not self.use_reg:
+            # (with mesh regularisers d_verts carries a large, strongly cancelling Laplacian component: the contraction is
+            # ill-conditioned and the 3xTF32 products, accurate to ~1e-6 of sum |a||b|, were measured 5e-4 off in d_w; the
+            # fp32 SIMT kernel below is used for the transpose in that case — the blend is < 1 % of a batched iteration)
             call('blend_bwd', 'fpc_blend_bwd_tc', _p(self.DT), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2
         else:
             call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts), V * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 2

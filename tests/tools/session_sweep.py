@@ -1,0 +1,71 @@
+"""Randomised consistency sweep of FitSession (developer tool): for random rigs / batch sizes / shading modes, the loss and the
+packed gradient [d_w | d_t | d_q] (and d_tex) of the fully fused configuration against the op-level configuration with separate
+geometry kernels — two independent code paths through the C-ABI.   python tests/tools/session_sweep.py [n_cases] [seed]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from fpc_diffrend_b200 import rig as rigmod  # noqa: E402
+from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference  # noqa: E402
+
+
+def rel(a, b):
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+
+
+def one(rng, case):
+    V = int(rng.choice([300, 800, 2000]))
+    B = int(rng.choice([4, 8, 12, 20]))
+    Cc = int(rng.choice([1, 2, 3]))
+    H, W = int(rng.integers(48, 200)), int(rng.integers(48, 200))
+    F = int(rng.choice([1, 2, 3, 5, 9]))
+    shading = str(rng.choice(['vcol', 'texture']))
+    aa = bool(rng.integers(2))
+    loss = str(rng.choice(['l2', 'l1']))
+    reg = bool(rng.integers(2))
+    opt_tex = bool(rng.integers(2)) and shading == 'texture'
+    cam_pose = bool(rng.integers(2))
+    rig = rigmod.make_rig(n_vertices=V, n_shapes=B, n_cams=Cc, width=W, height=H, tex_size=32, seed=int(rng.integers(1 << 30)))
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=int(rng.integers(1 << 30)))
+    base = dict(resolution=(H, W), shading=shading, antialias=aa, loss=loss, optimize_texture=opt_tex, optimize_cam_pose=cam_pose,
+                weight_laplacian=50.0 if reg else 0.0, weight_meshedge=1.0 if reg else 0.0)
+    ref = synthesize_reference(rig, w_true, 0.3 * t_true, q_true, FitConfig(**base))
+    w0 = (0.3 * rng.random((F, rig.B))).astype(np.float32)
+    t0 = (0.3 * rng.normal(size=(F, 3))).astype(np.float32)
+    q0 = (rng.normal(size=(F, 4)) * 0.02 + np.array([0, 0, 0, 1.0])).astype(np.float32)
+    q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    tc = np.float32(0.1) * rng.normal(size=(Cc, 3)).astype(np.float32)
+    out = []
+    variants = ((True, None, None), (False, False, False)) + (((True, None, False),) if os.environ.get('SWEEP_NO_TC') else ())
+    for fused, geom, tcb in variants:
+        s = FitSession(rig, F, FitConfig(fused=fused, fused_geometry=geom, tc_blend=tcb, **base))
+        s.set_reference(ref)
+        s.set_parameters(w=w0, t=t0, q=q0)
+        if cam_pose:
+            s.t_cam.copy_(torch.tensor(tc))
+        s.forward(); s.backward()
+        torch.cuda.synchronize()
+        out.append((float(s.loss), s.grads.clone(), s.d_tex.clone() if opt_tex else None, s.cam_grads.clone() if cam_pose else None,
+                    s.use_geom_fused, s.use_tc_blend))
+    if len(out) == 3:
+        print('      fused without the tensor-core blend vs op-level: grads %.1e' % rel(out[2][1], out[1][1]))
+    (la, ga, ta, ca, gfa, tca), (lb, gb, tb, cb, gfb, tcb_) = out[0], out[1]
+    el, eg = abs(la - lb) / max(abs(lb), 1e-30), rel(ga, gb)
+    et = rel(ta, tb) if opt_tex else 0.0
+    ec = rel(ca, cb) if cam_pose else 0.0
+    ok = el < 1e-5 and eg < 2e-4 and et < 2e-4 and ec < 2e-4
+    print('%3d %-8s V=%4d B=%2d cams=%d %3dx%3d F=%d %-7s aa=%d %s reg=%d tex=%d campose=%d geomfused=%d tcblend=%d | loss %.1e grads %.1e d_tex %.1e cam %.1e' %
+          (case, 'ok' if ok else 'MISMATCH', V, B, Cc, H, W, F, shading, aa, loss, reg, opt_tex, cam_pose, gfa, tca, el, eg, et, ec))
+    return ok
+
+
+if __name__ == '__main__':
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    good = sum(one(rng, i) for i in range(n))
+    print('%d / %d cases clean' % (good, n))
+    sys.exit(0 if good == n else 1)

@@ -869,3 +869,16 @@ def test_batched_fit_with_regularisers_matches_op_level(small_rig3):
     assert got[0][2] and not got[1][2]                          # the forward blend of the first session does run on tcgen05
     assert abs(got[0][0] - got[1][0]) / got[1][0] < 1e-5
     assert rel(got[0][1].cpu(), got[1][1].cpu()) < 1e-4
+
+
+@pytest.mark.parametrize('tool,n,seed', [('parity_sweep.py', 16, 4), ('session_sweep.py', 16, 4)])
+def test_randomised_sweeps(tool, n, seed):
+    """tests/tools/parity_sweep.py (rasterizer vs oracle, fused kernels vs op-level chain, op-level chain vs oracle chain over random
+    rigs, poses — partly off screen —, ragged resolutions, shading modes) and tests/tools/session_sweep.py (fully fused FitSession
+    vs op-level FitSession over random batch sizes, losses, regularisers, shared parameters): a seeded slice of each."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tests', 'tools', tool), str(n), str(seed)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and ('%d / %d cases clean' % (n, n)) in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

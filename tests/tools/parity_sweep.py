@@ -76,14 +76,27 @@ def eval_case(c, case, verbose=False):
               P(loss), P(g_pos), None, None, P(col_out), P(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     g_ops = pos.grad
+    # op-level chain against the ORACLE chain (golden ops with autograd), forward image and d loss / d pos
+    tp = torch.tensor(pc, requires_grad=True)
+    r_o, _ = G.rasterize(tp, torch.tensor(rig.pos_idx), (H, W))
+    if textured:
+        col_o = G.texture(torch.tensor(c['tex'])[None], G.interpolate(torch.tensor(rig.uv)[None], r_o, torch.tensor(rig.uv_idx)))
+    else:
+        col_o = G.interpolate(torch.tensor(c['attr'])[None], r_o, torch.tensor(rig.pos_idx))
+    if aa:
+        col_o = G.antialias(col_o, r_o, tp, torch.tensor(rig.pos_idx), torch.tensor(G.topology_build(rig.pos_idx)))
+    comp_o = torch.where(r_o[..., 3:] > 0, col_o, torch.tensor(G.BG))
+    ((torch.tensor(ref) - 255.0 * comp_o) ** 2).mean(dim=(1, 2, 3)).sum().backward()
+    err_oc = float((comp.detach().cpu() - comp_o.detach()).abs().max())
+    err_og = float((g_ops.cpu() - tp.grad).abs().max()) / max(float(tp.grad.abs().max()), 1e-30)
     gmax = float(g_ops.abs().max())
     err_g = float((g_pos - g_ops).abs().max()) / max(gmax, 1e-30)
     err_c = float((col_out - comp.detach()).abs().max())
     err_l = abs(float(loss) - float(loss_ops)) / max(float(loss_ops), 1e-30)
     cov = float((rast[..., 3] > 0).mean())
-    status = 'ok' if (bad_id == 0 and err_uv <= 1e-5 and err_g < 1e-4 and err_c <= 1e-5 and err_l < 1e-5) else 'MISMATCH'
-    print('%3d %-8s V=%4d %3dx%3d C=%d tex=%d aa=%d u8=%d cover=%.2f  id-mismatch=%d  |rast err|=%.1e  |image err|=%.1e  loss rel=%.1e  grad rel err=%.1e' %
-          (case, status, V, H, W, C, textured, aa, u8, cov, bad_id, err_uv, err_c, err_l, err_g))
+    status = 'ok' if (bad_id == 0 and err_uv <= 1e-5 and err_g < 1e-4 and err_c <= 1e-5 and err_l < 1e-5 and err_oc <= 1e-5 and err_og < 1e-4) else 'MISMATCH'
+    print('%3d %-8s V=%4d %3dx%3d C=%d tex=%d aa=%d u8=%d cover=%.2f  id-mismatch=%d  |rast err|=%.1e | fused vs ops: image %.1e loss %.1e grad %.1e | ops vs oracle: image %.1e grad %.1e' %
+          (case, status, V, H, W, C, textured, aa, u8, cov, bad_id, err_uv, err_c, err_l, err_g, err_oc, err_og))
     if verbose:
         e = (g_pos - g_ops).abs().amax(dim=2).cpu().numpy() / gmax                      # [N,V]
         for n in range(N):

@@ -19,8 +19,9 @@ from oracle import golden as G  # noqa: E402
 def draw_case(rng):
     """All random inputs of one case (numpy only, so that cases can be re-drawn without evaluating them)."""
     c = {}
-    c['V'] = int(rng.choice([200, 500, 1200, 3000]))
-    c['H'], c['W'] = int(rng.integers(40, 300)), int(rng.integers(40, 300))
+    big = bool(os.environ.get('SWEEP_BIG'))                               # full-scale meshes / resolutions (slow oracle)
+    c['V'] = int(rng.choice([5000, 20000] if big else [200, 500, 1200, 3000]))
+    c['H'], c['W'] = (int(rng.integers(400, 1100)), int(rng.integers(400, 1100))) if big else (int(rng.integers(40, 300)), int(rng.integers(40, 300)))
     c['C'] = int(rng.choice([1, 3]))
     c['textured'], c['aa'], c['u8'] = bool(rng.integers(2)), bool(rng.integers(2)), bool(rng.integers(2))
     c['rig'] = rigmod.make_rig(n_vertices=c['V'], n_shapes=6, n_cams=2, width=c['W'], height=c['H'], tex_size=32, seed=int(rng.integers(1 << 30)))
@@ -94,7 +95,8 @@ def eval_case(c, case, verbose=False):
     err_c = float((col_out - comp.detach()).abs().max())
     err_l = abs(float(loss) - float(loss_ops)) / max(float(loss_ops), 1e-30)
     cov = float((rast[..., 3] > 0).mean())
-    status = 'ok' if (bad_id == 0 and err_uv <= 1e-5 and err_g < 1e-4 and err_c <= 1e-5 and err_l < 1e-5 and err_oc <= 1e-5 and err_og < 1e-4) else 'MISMATCH'
+    status = 'ok' if (bad_id == 0 and err_uv <= 1e-5 and err_g < 1e-4 and err_c <= 1e-5 and err_l < 1e-5 and err_oc <= 1e-5 and
+                      err_og < (3e-4 if os.environ.get('SWEEP_BIG') else 1e-4)) else 'MISMATCH'   # full scale: fp32 slivers, see test_full_scale_gradient_precision
     print('%3d %-8s V=%4d %3dx%3d C=%d tex=%d aa=%d u8=%d cover=%.2f  id-mismatch=%d  |rast err|=%.1e | fused vs ops: image %.1e loss %.1e grad %.1e | ops vs oracle: image %.1e grad %.1e' %
           (case, status, V, H, W, C, textured, aa, u8, cov, bad_id, err_uv, err_c, err_l, err_g, err_oc, err_og))
     if verbose:

@@ -290,10 +290,9 @@ int launch_gemm(const float* A, const float* Bm, long long M, long long N, long 
     if (st != FPC_OK) return st;
     st = make_map(&map_b, Bm, N, K, TC_BN);
     if (st != FPC_OK) return st;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static FpcPerDeviceOnce attr_set;
+    if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        attr_set = true;
     }
     const int num_kb = fpc_div_up(K, TC_BK);
     const int per = fpc_div_up(num_kb, splits);

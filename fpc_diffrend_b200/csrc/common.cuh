@@ -34,6 +34,20 @@ void fpc_set_error(const char* fmt, ...);
 
 static inline int fpc_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute() is per DEVICE: a launcher remembers which devices it has configured (one process may drive several).
+struct FpcPerDeviceOnce {
+    unsigned long long mask[2] = {0ull, 0ull};
+    bool need()
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) return true;
+        d &= 127;
+        const bool first = !((mask[d >> 6] >> (d & 63)) & 1ull);
+        mask[d >> 6] |= 1ull << (d & 63);
+        return first;
+    }
+};
+
 // ---- exact fp32 ops: never contracted to FMA, so coverage / depth decisions are bit-identical to the
 //      CPU golden model compiled with -ffp-contract=off (DESIGN.md "Rasterizer semantics") ----------------
 __device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }

@@ -501,10 +501,9 @@ __host__ size_t fused_smem(int C, int ref_u8) { return sizeof(unsigned long long
 template <int C, bool TEX>
 int launch_fused(const RasterParams& rp, const FusedParams& fp, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static FpcPerDeviceOnce attr_set;
+    if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_fused<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(C, 0)));
-        attr_set = true;
     }
     k_fused<C, TEX><<<dim3(rp.NB, rp.N), FINE_THREADS, fused_smem(C, fp.ref_u8), stream>>>(rp, fp);
     FPC_LAUNCH_CHECK();
@@ -522,10 +521,9 @@ namespace {
 template <int C, bool TEX>
 int launch_fused_aa(const RasterParams& rp, const FusedParams& fp, const int32_t* tri_opp, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static FpcPerDeviceOnce attr_set;
+    if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_fused_aa<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aa_smem_layout(C, 4, TEX).total));
-        attr_set = true;
     }
     k_fused_aa<C, TEX><<<dim3(rp.NB, rp.N), AA_THREADS, aa_smem_layout(C, fp.ref_u8 ? 1 : 4, TEX && fp.grad_tex).total, stream>>>(rp, fp, tri_opp);
     FPC_LAUNCH_CHECK();

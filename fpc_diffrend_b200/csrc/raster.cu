@@ -388,10 +388,9 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
         size_t hb = (size_t)rp.NB * sizeof(int);
         k_setup<true><<<grid, BIN_TPB, hb, stream>>>(rp);
         FPC_LAUNCH_CHECK();
-        static bool fill_attr_set = false;
-        if (!fill_attr_set) {
+        static FpcPerDeviceOnce fill_attr_set;
+        if (fill_attr_set.need()) {
             FPC_CUDA(cudaFuncSetAttribute(k_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * HIST_MAX_BINS * (int)sizeof(int)));
-            fill_attr_set = true;
         }
         k_fill<true><<<grid, BIN_TPB, 2 * hb, stream>>>(rp);              // scans the bin counters itself
     } else {
@@ -425,10 +424,9 @@ extern "C" int fpc_rasterize_fwd(const float* pos, const int32_t* tri, int N, in
     int st = raster_bin_triangles("rasterize_fwd", pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp);
     if (st != FPC_OK) return st;
     const size_t smem = sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static FpcPerDeviceOnce attr_set;
+    if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     k_fine<<<dim3(rp.NB, N), FINE_THREADS, smem, stream>>>(rp, rast, rast_db);
     FPC_LAUNCH_CHECK();

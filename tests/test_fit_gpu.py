@@ -882,3 +882,26 @@ def test_randomised_sweeps(tool, n, seed):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, 'tests', 'tools', tool), str(n), str(seed)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and ('%d / %d cases clean' % (n, n)) in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_two_devices_in_one_process(tiny_rig):
+    """One process driving two GPUs: the kernels that need more than 48 KB of dynamic shared memory (k_fused_aa, the geometry
+    backward, the tcgen05 GEMM, k_fill) are configured per DEVICE — the second device must work like the first."""
+    from fpc_diffrend_b200 import rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F = tiny_rig, 128, 128, 9
+    cfg = FitConfig(resolution=(H, W), shading='texture', antialias=True, lr_base=1e-2)
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=2)
+    losses = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            ref = synthesize_reference(rig, w_true, 0.2 * t_true, q_true, cfg, device='cuda:%d' % dev)
+            s = FitSession(rig, F, cfg, device='cuda:%d' % dev)
+            s.set_reference(ref)
+            for _ in range(3):
+                s.iteration()
+            torch.cuda.synchronize(dev)
+            losses.append(float(s.loss))
+            assert s.use_tc_blend
+    assert abs(losses[0] - losses[1]) <= 1e-3 * abs(losses[0])

@@ -51,15 +51,36 @@ def one(rng, case):
         torch.cuda.synchronize()
         out.append((float(s.loss), s.grads.clone(), s.d_tex.clone() if opt_tex else None, s.cam_grads.clone() if cam_pose else None,
                     s.use_geom_fused, s.use_tc_blend))
+        if os.environ.get('SWEEP_VERBOSE_CASE') == str(case):
+            globals().setdefault('_dbg', []).append((s.g_pos.clone(), s.d_w.clone(), s.d_t.clone(), s.d_q.clone(), s.pos_clip.clone()))
     if len(out) == 3:
         print('      fused without the tensor-core blend vs op-level: grads %.1e' % rel(out[2][1], out[1][1]))
     (la, ga, ta, ca, gfa, tca), (lb, gb, tb, cb, gfb, tcb_) = out[0], out[1]
-    el, eg = abs(la - lb) / max(abs(lb), 1e-30), rel(ga, gb)
+    nw, nt = F * rig.B, F * 3
+    el = abs(la - lb) / max(abs(lb), 1e-30)
+    # per parameter group.  The rotation gradients (d_q, camera d_q) are the ill-conditioned ones: the rigid transforms act in
+    # camera space, ~230 units from the head, so d R is a difference of lever-arm-sized terms and two fp32 summation orders
+    # differ by up to ~1e-3 of it (either is what the reference's fp32 autograd would give; tests/tools/geometry_precision_probe.py)
+    eg = max(rel(ga[:nw], gb[:nw]), rel(ga[nw:nw + nt], gb[nw:nw + nt]))
+    eq = rel(ga[nw + nt:], gb[nw + nt:])
     et = rel(ta, tb) if opt_tex else 0.0
-    ec = rel(ca, cb) if cam_pose else 0.0
-    ok = el < 1e-5 and eg < 2e-4 and et < 2e-4 and ec < 2e-4
-    print('%3d %-8s V=%4d B=%2d cams=%d %3dx%3d F=%d %-7s aa=%d %s reg=%d tex=%d campose=%d geomfused=%d tcblend=%d | loss %.1e grads %.1e d_tex %.1e cam %.1e' %
-          (case, 'ok' if ok else 'MISMATCH', V, B, Cc, H, W, F, shading, aa, loss, reg, opt_tex, cam_pose, gfa, tca, el, eg, et, ec))
+    ec = rel(ca[:Cc * 3], cb[:Cc * 3]) if cam_pose else 0.0
+    eq = max(eq, rel(ca[Cc * 3:], cb[Cc * 3:])) if cam_pose else eq
+    # Discrete effects set the floor of a comparison between two sessions: the L1 gradient is the SIGN of the residual (a 1-ulp
+    # difference in a colour flips it where the residual is ~0), and a batch large enough for the tensor-core blend renders from
+    # vertices that differ in the last bits (3xTF32), which can pop a silhouette pixel (test_iteration_gradients).  The strict
+    # like-for-like comparison on identical inputs is parity_sweep.py.
+    tol = 2e-4 if (loss == 'l2' and not tca) else 5e-3
+    ok = el < 1e-5 and eg < tol and et < tol and ec < tol and eq < max(tol, 3e-3)
+    if os.environ.get('SWEEP_VERBOSE_CASE') == str(case):
+        (ga_, wa, ta_, qa, pa), (gb_, wb, tb_, qb, pb) = globals()['_dbg']
+        print('   pos_clip identical: %s; g_pos rel diff %.2e; d_w %.2e d_t %.2e d_q %.2e' % (bool(torch.equal(pa, pb)), rel(ga_, gb_), rel(wa, wb), rel(ta_, tb_), rel(qa, qb)))
+        d = (ga_ - gb_).abs().amax(dim=2)
+        n_, v_ = np.unravel_index(int(d.argmax()), d.shape)
+        print('   worst vertex: view %d vertex %d fused %s ops %s; vertices off by > 1e-4 of max: %d' % (n_, v_, ga_[n_, v_].cpu().numpy(), gb_[n_, v_].cpu().numpy(),
+              int((d > 1e-4 * float(gb_.abs().max())).sum())))
+    print('%3d %-8s V=%4d B=%2d cams=%d %3dx%3d F=%d %-7s aa=%d %s reg=%d tex=%d campose=%d geomfused=%d tcblend=%d | loss %.1e d_w,d_t %.1e d_q %.1e d_tex %.1e cam t %.1e' %
+          (case, 'ok' if ok else 'MISMATCH', V, B, Cc, H, W, F, shading, aa, loss, reg, opt_tex, cam_pose, gfa, tca, el, eg, eq, et, ec))
     return ok
 
 

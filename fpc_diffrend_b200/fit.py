@@ -338,19 +338,26 @@ class FitSession:
         if getattr(self, '_stream_bufs', None) is None:
             self._stream_bufs = [torch.empty(shape, dtype=dt, device=self.device) for _ in range(2)]
             self._stream_graphs = [None, None]
-            self._copy_stream = torch.cuda.Stream(device=self.device)
+            # two copy streams: each half of a frame batch travels on its own stream, so that two DMA engines can work on one
+            # upload (on hosts where a single engine does not saturate the link)
+            self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
             self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-        bufs, graphs, cs = self._stream_bufs, self._stream_graphs, self._copy_stream
+        bufs, graphs, css = self._stream_bufs, self._stream_graphs, self._copy_streams
         compute = torch.cuda.current_stream()
-        uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+        uploaded = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
         consumed = [None, None]
+        half = (self.N + 1) // 2 if self.N > 1 else 1
 
         def upload(slot, frames):
-            if consumed[slot] is not None:
-                cs.wait_event(consumed[slot])          # the step that last read this buffer has finished
-            with torch.cuda.stream(cs):
-                bufs[slot].copy_(frames.reshape(shape), non_blocking=True)
-                uploaded[slot].record(cs)
+            src = frames.reshape(shape)
+            for i, cs in enumerate(css):
+                a, b = (0, half) if i == 0 else (half, self.N)
+                if consumed[slot] is not None:
+                    cs.wait_event(consumed[slot])      # the step that last read this buffer has finished
+                with torch.cuda.stream(cs):
+                    if b > a:
+                        bufs[slot][a:b].copy_(src[a:b], non_blocking=True)
+                    uploaded[slot][i].record(cs)
 
         it = iter(frames_iter)
         try:
@@ -367,7 +374,8 @@ class FitSession:
                 nxt = None
             if nxt is not None:
                 upload(slot ^ 1, nxt)                  # overlaps with the compute of step k
-            compute.wait_event(uploaded[slot])
+            for ev in uploaded[slot]:
+                compute.wait_event(ev)
             self.ref = bufs[slot]
             if use_graph:
                 if graphs[slot] is None:

@@ -293,6 +293,7 @@ int launch_gemm(const float* A, const float* Bm, long long M, long long N, long 
     static FpcPerDeviceOnce attr_set;
     if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        attr_set.done();
     }
     const int num_kb = fpc_div_up(K, TC_BK);
     const int per = fpc_div_up(num_kb, splits);

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/fpc_b200.h"
 
 // ---- error plumbing (C-ABI never throws; see include/fpc_b200.h) -------------------------------------
@@ -34,17 +36,28 @@ void fpc_set_error(const char* fmt, ...);
 
 static inline int fpc_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// cudaFuncSetAttribute() is per DEVICE: a launcher remembers which devices it has configured (one process may drive several).
+// cudaFuncSetAttribute() is per DEVICE: a launcher remembers which devices it has configured (one process may drive several,
+// from several host threads).  Usage:  if (once.need()) { FPC_CUDA(cudaFuncSetAttribute(...)); once.done(); }
+// The bit is set only after the attribute call succeeded; two threads racing here both make the (idempotent) call.
 struct FpcPerDeviceOnce {
-    unsigned long long mask[2] = {0ull, 0ull};
-    bool need()
+    std::atomic<unsigned long long> mask[2];
+    FpcPerDeviceOnce() { mask[0].store(0ull); mask[1].store(0ull); }
+    static int device()
     {
         int d = 0;
-        if (cudaGetDevice(&d) != cudaSuccess) return true;
-        d &= 127;
-        const bool first = !((mask[d >> 6] >> (d & 63)) & 1ull);
-        mask[d >> 6] |= 1ull << (d & 63);
-        return first;
+        if (cudaGetDevice(&d) != cudaSuccess) return -1;
+        return d & 127;
+    }
+    bool need() const
+    {
+        const int d = device();
+        if (d < 0) return true;
+        return !((mask[d >> 6].load(std::memory_order_acquire) >> (d & 63)) & 1ull);
+    }
+    void done()
+    {
+        const int d = device();
+        if (d >= 0) mask[d >> 6].fetch_or(1ull << (d & 63), std::memory_order_release);
     }
 };
 

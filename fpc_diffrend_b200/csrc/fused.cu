@@ -504,6 +504,7 @@ int launch_fused(const RasterParams& rp, const FusedParams& fp, cudaStream_t str
     static FpcPerDeviceOnce attr_set;
     if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_fused<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(C, 0)));
+        attr_set.done();
     }
     k_fused<C, TEX><<<dim3(rp.NB, rp.N), FINE_THREADS, fused_smem(C, fp.ref_u8), stream>>>(rp, fp);
     FPC_LAUNCH_CHECK();
@@ -524,6 +525,7 @@ int launch_fused_aa(const RasterParams& rp, const FusedParams& fp, const int32_t
     static FpcPerDeviceOnce attr_set;
     if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_fused_aa<C, TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aa_smem_layout(C, 4, TEX).total));
+        attr_set.done();
     }
     k_fused_aa<C, TEX><<<dim3(rp.NB, rp.N), AA_THREADS, aa_smem_layout(C, fp.ref_u8 ? 1 : 4, TEX && fp.grad_tex).total, stream>>>(rp, fp, tri_opp);
     FPC_LAUNCH_CHECK();

@@ -373,6 +373,7 @@ int launch_bwd(dim3 grid, size_t smem, cudaStream_t stream, const float* D, cons
     static FpcPerDeviceOnce attr_set;
     if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_geom_bwd<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set.done();
     }
     k_geom_bwd<K><<<grid, GEO_THREADS, smem, stream>>>(D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp);
     FPC_LAUNCH_CHECK();
@@ -444,6 +445,7 @@ extern "C" int fpc_geometry_bwd(const float* P, const float* A, const float* t, 
     static FpcPerDeviceOnce red_attr_set;
     if (red_attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_geom_bwd_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (33 * 32 * 16 + 12 * 32) * (int)sizeof(float)));
+        red_attr_set.done();
     }
     k_geom_bwd_reduce<<<dim3(F, fpc_div_up(B, 32) + 1), RED_THREADS, (size_t)(33 * C * 16 + 12 * C) * sizeof(float), stream>>>(
         part_w, part_mvp, nblk, P, A, t, q, t_cam, q_cam, B, F, C, d_w, d_mvp, d_t, d_q);

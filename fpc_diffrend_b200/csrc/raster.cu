@@ -391,6 +391,7 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
         static FpcPerDeviceOnce fill_attr_set;
         if (fill_attr_set.need()) {
             FPC_CUDA(cudaFuncSetAttribute(k_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * HIST_MAX_BINS * (int)sizeof(int)));
+            fill_attr_set.done();
         }
         k_fill<true><<<grid, BIN_TPB, 2 * hb, stream>>>(rp);              // scans the bin counters itself
     } else {
@@ -427,6 +428,7 @@ extern "C" int fpc_rasterize_fwd(const float* pos, const int32_t* tri, int N, in
     static FpcPerDeviceOnce attr_set;
     if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.done();
     }
     k_fine<<<dim3(rp.NB, N), FINE_THREADS, smem, stream>>>(rp, rast, rast_db);
     FPC_LAUNCH_CHECK();

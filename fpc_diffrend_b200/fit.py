@@ -186,11 +186,18 @@ class FitSession:
             if self.use_reg_corr:
                 self.corr = torch.zeros(F, V * 3, **f32)
                 self.d_corr = torch.zeros(F, V * 3, **f32)
-        self.use_reg_prior = bool(cfg.regularize_prior and cfg.mode == 'prior')
+        # Camera-split mode: the ranks' gradient vectors are SUMMED (optimizer_step), so every term that does not depend on the
+        # views — mesh regularisers, regularize_prior, regularize_correctives — is evaluated by ONE rank only (the one that
+        # renders the first bin row of view 0); otherwise it would be counted world_size times.
+        self.reg_owner = cfg.cam_slice is None or (c0 == 0 and (cfg.cam_band is None or int(cfg.cam_band[0]) == 0))
+        if self.use_basis and not self.reg_owner:
+            self.use_reg_corr = False
+        self.use_reg_prior = bool(cfg.regularize_prior and cfg.mode == 'prior' and self.reg_owner)
         self.reg_l2_term = torch.zeros(1, **f32)
         if cfg.optimize_texture:
             if cfg.shading != 'texture':
                 raise ValueError("optimize_texture needs shading='texture'")
+            self.tex0 = self.tex.clone()
             self.d_tex = torch.zeros_like(self.tex)
             self.tex_m = torch.zeros_like(self.tex)
             self.tex_v = torch.zeros_like(self.tex)
@@ -210,6 +217,9 @@ class FitSession:
             lo, hi = (int(x) for x in cfg.cam_band)
             if not (0 <= lo < rows and 0 < hi <= rows and (C > 1 or lo < hi)):
                 raise ValueError('cam_band %r is not a valid bin-row range for height %d (%d rows)' % (cfg.cam_band, H, rows))
+            if cfg.optimize_cam_pose:
+                # a view cut by a band is rendered by two ranks: each would step that camera's correction with a partial gradient
+                raise ValueError('optimize_cam_pose needs whole views per rank: use cam_slice without cam_band')
         if cfg.ref_dtype not in ('f32', 'u8'):
             raise ValueError("ref_dtype must be 'f32' or 'u8'")
         if cfg.ref_dtype == 'u8' and not self.use_fused:
@@ -251,7 +261,7 @@ class FitSession:
             sc = torch.empty(int(_lib.load().fpc_topology_scratch_bytes(T)), dtype=torch.uint8, device=dev)
             _lib.call('fpc_topology_build', _p(self.pos_idx), T, V, _p(self.tri_opp), _p(sc), sc.numel(), self._stream())
         self.ref = None
-        self.use_reg = any(x != 0.0 for x in (cfg.weight_laplacian, cfg.weight_meshedge, cfg.weight_normalconsistency))
+        self.use_reg = self.reg_owner and any(x != 0.0 for x in (cfg.weight_laplacian, cfg.weight_meshedge, cfg.weight_normalconsistency))
         if self.use_reg:
             from .topology import build_topology
             tp = build_topology(rig.pos_idx, V)
@@ -282,6 +292,9 @@ class FitSession:
                      L.fpc_project_bwd_scratch_bytes(F, C, V), L.fpc_image_loss_scratch_bytes(self.N, H, W, Ch))
         self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         self.graph = None
+        self._warmed = False
+        self._stream_bufs = None
+        self._stream_graphs = [None, None]
         self.launches_per_iteration = 0
         self.stage_events = None          # when a dict: stage name -> list of (start, end) CUDA events (bench.py)
 
@@ -304,7 +317,12 @@ class FitSession:
             self.ref.copy_(ref)                       # same buffer: a captured graph keeps reading the right frames
         else:
             self.ref = ref.contiguous()
-            self.graph = None
+            self.invalidate_graphs()
+
+    def invalidate_graphs(self):
+        """Drop every captured graph (they bake in buffer addresses and the configuration)."""
+        self.graph = None
+        self._stream_graphs = [None, None]
 
     def iteration_from_host(self, frames_host, loss_host=None):
         """One step with HOST buffers, unpipelined: upload this step's reference frames (pinned host memory -> the
@@ -335,14 +353,14 @@ class FitSession:
         loss is read back (4 bytes, device -> pinned host) before it is yielded."""
         dt = torch.uint8 if self.cfg.ref_dtype == 'u8' else torch.float32
         shape = (self.N, self.H, self.W, self.Ch)
-        if getattr(self, '_stream_bufs', None) is None:
+        if self._stream_bufs is None:
             self._stream_bufs = [torch.empty(shape, dtype=dt, device=self.device) for _ in range(2)]
             self._stream_graphs = [None, None]
             # two copy streams: each half of a frame batch travels on its own stream, so that two DMA engines can work on one
             # upload (on hosts where a single engine does not saturate the link)
             self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
             self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-        bufs, graphs, css = self._stream_bufs, self._stream_graphs, self._copy_streams
+        bufs, css = self._stream_bufs, self._copy_streams
         compute = torch.cuda.current_stream()
         uploaded = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
         consumed = [None, None]
@@ -378,9 +396,10 @@ class FitSession:
                 compute.wait_event(ev)
             self.ref = bufs[slot]
             if use_graph:
-                if graphs[slot] is None:
-                    graphs[slot] = self._capture_current()
-                graphs[slot].replay()
+                if self._stream_graphs[slot] is None:
+                    self.warm_up()                     # never let a kernel's first launch fall inside the capture
+                    self._stream_graphs[slot] = self._capture_current()
+                self._stream_graphs[slot].replay()
             else:
                 self.iteration()
             ev = torch.cuda.Event()
@@ -685,13 +704,18 @@ class FitSession:
             self.iteration()
         return g
 
-    def capture(self):
-        """Run one eager warm-up iteration on a side stream, then capture one iteration into self.graph."""
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            self.iteration()
-        torch.cuda.current_stream().wait_stream(side)
+    def capture(self, keep_state=False):
+        """Run one eager warm-up iteration on a side stream, then capture one iteration into self.graph.  The warm-up is a
+        real optimiser step unless keep_state is set (then parameters and optimiser state are restored after it)."""
+        if keep_state:
+            self.warm_up()
+        else:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.iteration()
+            torch.cuda.current_stream().wait_stream(side)
+            self._warmed = True
         self.graph = self._capture_current()
         return self.graph
 
@@ -699,6 +723,52 @@ class FitSession:
         self.graph.replay()
 
     # ---- results -------------------------------------------------------------------------------------
+    def total_loss(self):
+        """Loss of the last iteration as a float.  In the camera-split mode self.loss is this rank's partial sum (its views,
+        plus the regularisers on the owner rank): the partials are summed over ranks here."""
+        l = self.loss.clone()
+        if self.cfg.cam_slice is not None:
+            allreduce_gradients(l)
+        return float(l)
+
+    def reset_state(self):
+        """Back to the initial parameters (w = 0, t = 0, q = identity; shared parameters likewise) and a fresh optimiser:
+        used between frame batches of a take and after the eager warm-up iteration that precedes a graph capture."""
+        self.params.zero_(); self.q[:, 3] = 1.0
+        self.adam_m.zero_(); self.adam_v.zero_(); self.step_count.zero_()
+        self.cam_params.zero_(); self.q_cam[:, 3] = 1.0
+        self.cam_m.zero_(); self.cam_v.zero_()
+        if self.use_basis:
+            self.basis.zero_(); self.basis_m.zero_(); self.basis_v.zero_()
+            eye = torch.eye(self.Fn, device=self.device)
+            self.m1.copy_(eye); self.m2.copy_(eye)
+        if self.cfg.optimize_texture:
+            self.tex.copy_(self.tex0); self.tex_m.zero_(); self.tex_v.zero_()
+
+    def _state_tensors(self):
+        ts = [self.params, self.adam_m, self.adam_v, self.step_count, self.cam_params, self.cam_m, self.cam_v, self.loss]
+        if self.use_basis:
+            ts += [self.basis, self.basis_m, self.basis_v]
+        if self.cfg.optimize_texture:
+            ts += [self.tex, self.tex_m, self.tex_v]
+        return ts
+
+    def warm_up(self):
+        """One eager iteration on a side stream with parameters and optimiser state restored afterwards: the first launch
+        of every kernel (cudaFuncSetAttribute, lazy module loading, NCCL communicator set-up in the camera-split mode) must
+        not happen inside a stream capture.  Idempotent."""
+        if self._warmed:
+            return
+        saved = [t.clone() for t in self._state_tensors()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        for t, c in zip(self._state_tensors(), saved):
+            t.copy_(c)
+        self._warmed = True
+
     def result_vertices(self):
         """[F, 3V] blended vertices of the current parameters (fit.py:642 `result`)."""
         if self.use_basis or self.use_tc_blend:

@@ -8,6 +8,7 @@ and stay on the device as uint8 instead of one PIL decode + H2D copy per iterati
 renders ALL cameras of every frame of the batch instead of one random (camera, frame) pair (fit.py:525-526); frame
 batches are sharded over the ranks of torch.distributed when it is initialised (no exchange step).
 """
+from dataclasses import replace
 from types import SimpleNamespace
 
 import numpy as np
@@ -38,18 +39,22 @@ def load_take_rig(basemeshpath, localblpath, calibpath, cams, texpath=None, texs
 
 
 def fit_take(basemeshpath, localblpath, imdir, calibpath, out_dir=None, iters_per_frame=200, frame_batch=16, frames=None,
-             cams=None, texpath=None, config=None, blend_order='listdir', use_graph=True, log=None):
+             cams=None, texpath=None, config=None, blend_order='listdir', use_graph=True, log=None, max_iter=None):
     """Fit every frame of a take; returns dict(vertices [F,3V], w [F,B], t [F,3], q [F,4], loss [F_batches]) on rank 0
-    (None elsewhere) and, when out_dir is given, writes result/<i>.obj, pose.json, texture.png and config.txt there."""
+    (None elsewhere) and, when out_dir is given, writes result/<i>.obj, pose.json, texture.png and config.txt there.
+
+    Every batch of frames runs exactly `iters_per_frame` optimiser steps from fresh parameters.  The schedule the reference
+    spans over its whole run — LambdaLR lr_ramp ** (i / max_iter), correctives unlocked after max_iter / 2 (fit.py:503-505,
+    603-608) — spans one batch here: its length is `max_iter` (default: iters_per_frame; `config.max_iter` is not used, and
+    the caller's config object is not modified)."""
     cams = list(cams) if cams is not None else dataio.list_cameras(imdir)
     n_frames, digits = dataio.assert_num_frames(cams, imdir)
     frames = list(range(n_frames)) if frames is None else list(frames)
     rig = load_take_rig(basemeshpath, localblpath, calibpath, cams, texpath=texpath, blend_order=blend_order)
     first = dataio.read_frame(dataio.frame_path(imdir, cams[0], frames[0], digits))
     H, W = first.shape[:2]
-    cfg = config or FitConfig(shading='texture', antialias=True)
-    cfg.resolution = (H, W)
-    cfg.ref_dtype = 'u8'
+    cfg = replace(config or FitConfig(shading='texture', antialias=True), resolution=(H, W), ref_dtype='u8',
+                  max_iter=int(max_iter or iters_per_frame))
     f0, f1 = shard.frame_shard(len(frames))
     mine = frames[f0:f1]
     # parameters shared by all frames (texture, per-camera pose corrections, the learned basis of the free / combined modes)
@@ -58,7 +63,7 @@ def fit_take(basemeshpath, localblpath, imdir, calibpath, out_dir=None, iters_pe
     if shared:
         frame_batch = max(frame_batch, len(mine))
         if cfg.mode != 'prior':
-            cfg.n_frames_total = len(frames)
+            cfg = replace(cfg, n_frames_total=len(frames))
     verts, ws, ts, qs, losses = [], [], [], [], []
     sessions = {}
     for a in range(0, len(mine), frame_batch):
@@ -67,12 +72,10 @@ def fit_take(basemeshpath, localblpath, imdir, calibpath, out_dir=None, iters_pe
         s = sessions.get(len(batch))
         if s is None:
             s = sessions[len(batch)] = FitSession(rig, len(batch), cfg, frame_ids=list(range(f0 + a, f0 + a + len(batch))))
-        else:                                         # fresh parameters and optimiser state for the next batch of frames
-            s.params.zero_(); s.q[:, 3] = 1.0
-            s.adam_m.zero_(); s.adam_v.zero_(); s.step_count.zero_()
         s.set_reference(torch.from_numpy(ref))
         if use_graph and s.graph is None:
-            s.capture()
+            s.capture(keep_state=True)                # the eager warm-up iteration is not one of the iters_per_frame steps
+        s.reset_state()                               # fresh parameters and optimiser state for this batch of frames
         for _ in range(iters_per_frame):
             s.replay() if use_graph else s.iteration()
         torch.cuda.synchronize()

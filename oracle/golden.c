@@ -13,6 +13,7 @@
  *   interpolate fit.py:157   -> gold_interpolate_fwd / gold_interpolate_bwd  (App. A.2)
  *   texture     fit.py:158   -> gold_texture_linear_fwd / _bwd               (App. A.3, 'linear', wrap)
  *   antialias   fit.py:160   -> gold_topology_build / gold_antialias_fwd / _bwd (App. A.4)
+ * Forward and backward passes run the views of a batch in parallel (OpenMP); shared-tensor gradients are summed in view order.
  * Its analytic backward passes are themselves pinned against a float64 torch-autograd restatement
  * (oracle/torch_ref.py) in tests/test_oracle.py.
  *
@@ -264,6 +265,7 @@ void gold_rasterize_bwd(const float* pos, const int32_t* tri, const float* rast,
     double* acc = (double*)calloc((size_t)N * V * 4, sizeof(double));
     float xs = 2.0f / (float)W, xo = 1.0f / (float)W - 1.0f;
     float ys = 2.0f / (float)H, yo = 1.0f / (float)H - 1.0f;
+#pragma omp parallel for schedule(dynamic, 1)
     for (int n = 0; n < N; n++) {
         const f4* P = (const f4*)pos + (size_t)n * V;
         double* A = acc + (size_t)n * V * 4;
@@ -331,11 +333,14 @@ void gold_interpolate_bwd(const float* attr, int Na, int Vt, int A, const float*
 {
     size_t npx = (size_t)H * W;
     size_t na = (size_t)(Na > 1 ? N : 1) * Vt * A;
-    double* acc = (double*)calloc(na, sizeof(double));
+    size_t per = (size_t)Vt * A;
+    /* one accumulator per view (views run in parallel); a shared attribute tensor sums them in view order below */
+    double* acc = (double*)calloc((size_t)N * per, sizeof(double));
+#pragma omp parallel for schedule(dynamic, 1)
     for (int n = 0; n < N; n++) {
         size_t ao = (Na > 1 ? (size_t)n * Vt * A : 0);
         const float* at = attr + ao;
-        double* ga = acc + ao;
+        double* ga = acc + (size_t)n * per;
         for (size_t p = 0; p < npx; p++) {
             const float* r = rast + ((size_t)n * npx + p) * 4;
             const float* d = dy + ((size_t)n * npx + p) * A;
@@ -355,7 +360,16 @@ void gold_interpolate_bwd(const float* attr, int Na, int Vt, int A, const float*
             gr[0] = (float)gu; gr[1] = (float)gv;
         }
     }
-    for (size_t i = 0; i < na; i++) g_attr[i] = (float)acc[i];
+    if (Na > 1) {
+        for (size_t i = 0; i < na; i++) g_attr[i] = (float)acc[i];
+    } else {
+#pragma omp parallel for
+        for (size_t i = 0; i < per; i++) {
+            double t = 0.0;
+            for (int n = 0; n < N; n++) t += acc[(size_t)n * per + i];
+            g_attr[i] = (float)t;
+        }
+    }
     free(acc);
 }
 
@@ -410,11 +424,13 @@ void gold_texture_linear_bwd(const float* tex, int Nt, int Ht, int Wt, int C, co
 {
     size_t npx = (size_t)H * W;
     size_t nt = (size_t)(Nt > 1 ? N : 1) * Ht * Wt * C;
-    double* acc = (double*)calloc(nt, sizeof(double));
+    size_t per = (size_t)Ht * Wt * C;
+    double* acc = (double*)calloc((size_t)N * per, sizeof(double));     /* per view, summed in view order below */
+#pragma omp parallel for schedule(dynamic, 1)
     for (int n = 0; n < N; n++) {
         size_t to = (Nt > 1 ? (size_t)n * Ht * Wt * C : 0);
         const float* tx = tex + to;
-        double* gt = acc + to;
+        double* gt = acc + (size_t)n * per;
         for (size_t p = 0; p < npx; p++) {
             const float* q = uv + ((size_t)n * npx + p) * 2;
             const float* d = dy + ((size_t)n * npx + p) * C;
@@ -435,7 +451,16 @@ void gold_texture_linear_bwd(const float* tex, int Nt, int Ht, int Wt, int C, co
             g_uv[((size_t)n * npx + p) * 2 + 1] = (float)(gv * Ht);
         }
     }
-    for (size_t i = 0; i < nt; i++) g_tex[i] = (float)acc[i];
+    if (Nt > 1) {
+        for (size_t i = 0; i < nt; i++) g_tex[i] = (float)acc[i];
+    } else {
+#pragma omp parallel for
+        for (size_t i = 0; i < per; i++) {
+            double t = 0.0;
+            for (int n = 0; n < N; n++) t += acc[(size_t)n * per + i];
+            g_tex[i] = (float)t;
+        }
+    }
     free(acc);
 }
 
@@ -564,6 +589,7 @@ void gold_antialias_bwd(const float* color, const float* rast, const float* pos,
     double* gp = (double*)calloc((size_t)N * V * 4, sizeof(double));
     for (size_t i = 0; i < (size_t)N * npx * C; i++) gc[i] = dy[i];
     float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
+#pragma omp parallel for schedule(dynamic, 1)
     for (int n = 0; n < N; n++) {
         const float* r = rast + (size_t)n * npx * 4;
         const float* col = color + (size_t)n * npx * C;
@@ -615,3 +641,11 @@ void gold_antialias_bwd(const float* color, const float* rast, const float* pos,
     for (size_t i = 0; i < (size_t)N * V * 4; i++) g_pos[i] = (float)gp[i];
     free(gc); free(gp);
 }
+
+/* threads the OpenMP loops above run on (1 when built without OpenMP): reported as cpu_baseline.cores by bench.py */
+#ifdef _OPENMP
+#include <omp.h>
+int gold_omp_threads(void) { return omp_get_max_threads(); }
+#else
+int gold_omp_threads(void) { return 1; }
+#endif

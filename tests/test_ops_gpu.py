@@ -811,3 +811,74 @@ def test_antialias_topology_cache_is_per_tensor(dr):
         outs.append(int((got != col).sum()))
         del tri, rast, got, want
     assert min(outs) > 10
+
+
+def test_config5_size_view_against_oracle(dr):
+    """BASELINE config 5 size against the ORACLE (not only properties): one view of the 50k-vertex / 100k-triangle rig at
+    2048 x 2048 — tri_id bit-exact, (u, v, z/w) and rast_db within 1e-5, then the textured + antialiased image and its loss
+    gradient w.r.t. the clip-space positions through the fused kernel against the golden chain with autograd."""
+    import ctypes
+    from fpc_diffrend_b200 import _lib
+    from fpc_diffrend_b200 import rig as rigmod
+    H = W = 2048
+    rig = rigmod.make_rig(n_vertices=50000, n_shapes=4, n_cams=1, width=W, height=H, tex_size=256, seed=0)
+    pc = clip_positions(rig)
+    rast_ref, db_ref, _ = G.rasterize_fwd(pc, rig.pos_idx, (H, W))
+    ctx = dr.RasterizeCudaContext()
+    out, db = dr.rasterize(ctx, cu(pc), cu(rig.pos_idx), resolution=(H, W))
+    assert np.array_equal(out[..., 3].cpu().numpy(), rast_ref[..., 3])
+    assert np.abs(out.cpu().numpy() - rast_ref).max() <= 1e-5
+    fg = rast_ref[..., 3] > 0
+    assert fg.mean() > 0.15
+    scale = np.abs(db_ref[fg]).max()
+    assert np.abs(db.cpu().numpy() - db_ref)[fg].max() <= 1e-5 * max(scale, 1.0)
+    # fused textured + antialias loss / gradient vs the golden chain
+    opp = torch.tensor(G.topology_build(rig.pos_idx))
+    g = torch.Generator().manual_seed(1)
+    ref = (torch.rand(H, W, 1, generator=g) * 140.0)
+    pos = torch.tensor(pc, requires_grad=True)
+    tri_t = torch.tensor(rig.pos_idx)
+    r, _ = G.rasterize(pos, tri_t, (H, W))
+    texc = G.interpolate(torch.tensor(rig.uv)[None], r, torch.tensor(rig.uv_idx))
+    col = G.antialias(G.texture(torch.tensor(rig.tex)[None], texc), r, pos, tri_t, opp)
+    img = torch.where(r[..., 3:] > 0, col, torch.tensor(G.BG))[0]
+    loss_ref = G.image_loss(ref, img)
+    loss_ref.backward()
+    L = _lib.load()
+    T, V = rig.pos_idx.shape[0], pc.shape[1]
+    d = lambda x, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(x)).to(dt).cuda().contiguous()
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    tri_d, uvi_d, uv_d, tex_d, pos_d = d(rig.pos_idx, torch.int32), d(rig.uv_idx, torch.int32), d(rig.uv), d(rig.tex), d(pc)
+    opp_d = torch.empty(T, 3, dtype=torch.int32, device='cuda')
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sc = torch.empty(int(L.fpc_topology_scratch_bytes(T)), dtype=torch.uint8, device='cuda')
+    _lib.call('fpc_topology_build', p(tri_d), T, V, p(opp_d), p(sc), sc.numel(), st)
+    scratch = torch.empty(int(L.fpc_render_loss_fused_scratch_bytes(1, T, H, W)), dtype=torch.uint8, device='cuda')
+    loss = torch.zeros(1, device='cuda')
+    gpos = torch.empty(1, V, 4, device='cuda')
+    ref_d = ref.reshape(1, H, W, 1).cuda().contiguous()
+    _lib.call('fpc_render_loss_fused_aa', p(pos_d), p(tri_d), p(opp_d), p(uv_d), p(uvi_d), rig.uv.shape[0], 2, p(tex_d), rig.tex.shape[0], rig.tex.shape[1],
+              p(ref_d), 0, 1, V, T, H, W, 1, G.BG, 1.0, 0, p(loss), p(gpos), None, None, None, p(scratch), scratch.numel(), st)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    gr = pos.grad.numpy()
+    assert np.abs(gpos.cpu().numpy() - gr).max() <= 1e-4 * np.abs(gr).max()
+
+
+def test_against_nvdiffrast_when_installed(dr, small_rig3):
+    """The north-star's own yardstick: the reference's nvdiffrast CUDA path on identical tensors.  nvdiffrast is an un-vendored,
+    un-pinned dependency that cannot be installed offline: the test probes for it (site-packages, baseline/_ref)
+    and SKIPS with the reason when it is absent — it is what turns "parity unpinned" into a pinned comparison the day a box
+    has it.  tri_id bit-exact outside depth ties, forward 1e-5 abs, gradients 1e-4 rel."""
+    from oracle import nvdiffrast_arm as NA
+    ref_dr = NA.probe()
+    if ref_dr is None:
+        pytest.skip('nvdiffrast not importable here: %s' % NA.probe.reason)
+    rig, H, W = small_rig3, 152, 200
+    pc = cu(clip_positions(rig))
+    for tex, attr, idx in ((None, cu(rig.vcol)[None], cu(rig.pos_idx)), (cu(rig.tex)[None], cu(rig.uv)[None], cu(rig.uv_idx))):
+        for aa in (False, True):
+            rep = NA.compare_render(ref_dr, dr, pc, cu(rig.pos_idx), (H, W), attr, idx, tex=tex, antialias=aa)
+            assert rep['tri_id_mismatch_outside_depth_ties'] == 0, rep
+            assert rep['rast_uvz_max_abs'] <= 1e-5 and rep['colour_max_abs'] <= 1e-5, rep
+            assert rep['grad_pos_rel'] <= 1e-4, rep

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('FPC_B200_LIB') or os.path.join(_HERE, 'libfpc_b200.so')
 HEADER_PATH = os.path.join(_HERE, '..', 'include', 'fpc_b200.h')
 
-ABI_VERSION = 2        # FPC_B200_ABI_VERSION of include/fpc_b200.h these signatures were written against
+ABI_VERSION = 3        # FPC_B200_ABI_VERSION of include/fpc_b200.h these signatures were written against
 
 _lib = None
 
@@ -72,11 +72,13 @@ SIGNATURES = {
     'fpc_image_loss_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'fpc_image_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _Z, _P]),
     'fpc_render_loss_fused_scratch_bytes': (_Z, [_I, _I, _I, _I]),
-    'fpc_render_loss_fused': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
-    'fpc_render_loss_fused_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_render_loss_fused': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_render_loss_fused_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_vertex_adjacency_scratch_bytes': (_Z, [_I]),
+    'fpc_vertex_adjacency_build': (_I, [_P, _I, _I, _P, _P, _P, _Z, _P]),
     'fpc_raster_bin_px': (_I, []),
     'fpc_render_loss_fused_band': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _I, _I, _I,
-                                        _P, _P, _P, _P, _P, _P, _Z, _P]),
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'fpc_mesh_reg_scratch_bytes': (_Z, [_I, _I, _I]),
     'fpc_mesh_reg_fwd_bwd': (_I, [_P, _I, _I, _P, _P, _I, _P, _I, _F, _F, _F, _F, _P, _P, _P, _I, _P, _Z, _P]),
     'fpc_adam_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P]),
@@ -122,3 +124,18 @@ def check(status):
 
 def call(name, *args):
     check(getattr(load(), name)(*args))
+
+
+def vertex_adjacency(tri, n_vertices):
+    """vadj_off [V+1], vadj_item [3T] (int32, on tri's device): the vertex -> (triangle, corner) adjacency the fused kernels'
+    gradient gather needs (fpc_vertex_adjacency_build; once per mesh).  tri: contiguous int32 CUDA tensor [T,3]."""
+    import torch
+    T, V = int(tri.shape[0]), int(n_vertices)
+    off = torch.empty(V + 1, dtype=torch.int32, device=tri.device)
+    item = torch.empty(3 * T, dtype=torch.int32, device=tri.device)
+    sc = torch.empty(int(load().fpc_vertex_adjacency_scratch_bytes(V)), dtype=torch.uint8, device=tri.device)
+    with torch.cuda.device(tri.device):
+        call('fpc_vertex_adjacency_build', ctypes.c_void_p(tri.data_ptr()), T, V, ctypes.c_void_p(off.data_ptr()), ctypes.c_void_p(item.data_ptr()),
+             ctypes.c_void_p(sc.data_ptr()), sc.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.current_stream().synchronize()      # sc is freed on return
+    return off, item

@@ -96,16 +96,14 @@ __device__ __forceinline__ AAPair aa_analyze(const AAParams& ap, int n, int px, 
     return r;
 }
 
-// silhouette position gradient of one accepted pair (handled by the thread that owns pix0)
-__device__ __forceinline__ void aa_pos_grad(const AAParams& ap, int n, const AAPair& a, int d, float dd, float* __restrict__ g_pos)
+// Silhouette position gradient of one accepted pair: gradient (x, y, w) of the two end points of the crossing edge —
+// corners (di + 1) % 3 and (di + 2) % 3 of the pair's triangle, clip-space positions p1, p2 — for the pair analysed at pixel
+// (apx, apy) in direction d, given dd = sum_c d loss / d out_c (colour_1 - colour_0) of the pair.
+__device__ __forceinline__ void aa_pair_corner_grads(float xh, float yh, const float4& p1, const float4& p2, int apx, int apy, int d, float dd,
+                                                     float (&gp1)[3], float (&gp2)[3])
 {
-    int t = a.tri;
-    int i1 = __ldg(ap.tri + 3 * t + (a.di + 1) % 3), i2 = __ldg(ap.tri + 3 * t + (a.di + 2) % 3);
-    const float* P = ap.pos + (size_t)n * ap.V * 4;
-    float4 p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
-    float xh = ap.xh, yh = ap.yh;
     float w1 = xrcp(p1.w), w2 = xrcp(p2.w);
-    float fx = xsub(xadd((float)a.px, 0.5f), xh), fy = xsub(xadd((float)a.py, 0.5f), yh);
+    float fx = xsub(xadd((float)apx, 0.5f), xh), fy = xsub(xadd((float)apy, 0.5f), yh);
     float x1 = xsub(xmul(xmul(p1.x, w1), xh), fx), y1 = xsub(xmul(xmul(p1.y, w1), yh), fy);
     float x2 = xsub(xmul(xmul(p2.x, w2), xh), fx), y2 = xsub(xmul(xmul(p2.y, w2), yh), fy);
     if (d) { float s; s = x1; x1 = y1; y1 = s; s = x2; x2 = y2; y2 = s; }
@@ -118,11 +116,23 @@ __device__ __forceinline__ void aa_pos_grad(const AAParams& ap, int n, const AAP
     float gp1x = iw1 * s1 * y2, gp2x = iw2 * s1 * y1;
     float gp1y = iw1 * s2 * (dby - x2), gp2y = iw2 * s2 * (dby - x1);
     if (d) { float s; s = gp1x; gp1x = gp1y; gp1y = s; s = gp2x; gp2x = gp2y; gp2y = s; }
-    float gp1w = -(p1.x * gp1x + p1.y * gp1y) * w1;
-    float gp2w = -(p2.x * gp2x + p2.y * gp2y) * w2;
+    gp1[0] = gp1x; gp1[1] = gp1y; gp1[2] = -(p1.x * gp1x + p1.y * gp1y) * w1;
+    gp2[0] = gp2x; gp2[1] = gp2y; gp2[2] = -(p2.x * gp2x + p2.y * gp2y) * w2;
+}
+
+// op-level antialias backward: the pair's gradient is scattered with float REDs (as upstream); handled by the thread that
+// owns pix0
+__device__ __forceinline__ void aa_pos_grad(const AAParams& ap, int n, const AAPair& a, int d, float dd, float* __restrict__ g_pos)
+{
+    int t = a.tri;
+    int i1 = __ldg(ap.tri + 3 * t + (a.di + 1) % 3), i2 = __ldg(ap.tri + 3 * t + (a.di + 2) % 3);
+    const float* P = ap.pos + (size_t)n * ap.V * 4;
+    float4 p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
+    float gp1[3], gp2[3];
+    aa_pair_corner_grads(ap.xh, ap.yh, p1, p2, a.px, a.py, d, dd, gp1, gp2);
     float* G = g_pos + (size_t)n * ap.V * 4;
-    atomicAdd(G + 4 * (size_t)i1 + 0, gp1x); atomicAdd(G + 4 * (size_t)i1 + 1, gp1y); atomicAdd(G + 4 * (size_t)i1 + 3, gp1w);
-    atomicAdd(G + 4 * (size_t)i2 + 0, gp2x); atomicAdd(G + 4 * (size_t)i2 + 1, gp2y); atomicAdd(G + 4 * (size_t)i2 + 3, gp2w);
+    atomicAdd(G + 4 * (size_t)i1 + 0, gp1[0]); atomicAdd(G + 4 * (size_t)i1 + 1, gp1[1]); atomicAdd(G + 4 * (size_t)i1 + 3, gp1[2]);
+    atomicAdd(G + 4 * (size_t)i2 + 0, gp2[0]); atomicAdd(G + 4 * (size_t)i2 + 1, gp2[1]); atomicAdd(G + 4 * (size_t)i2 + 3, gp2[2]);
 }
 
 }  // namespace fpc

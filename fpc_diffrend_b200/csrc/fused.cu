@@ -6,12 +6,16 @@
 // compulsory HBM traffic is reading the reference frame (4C or C bytes / px) and the geometry.
 //
 // Per CTA:  (1) raster_bin(): visibility keys in shared memory (raster_core.cuh);
-//           (2) pixel-parallel shading, loss and (d u, d v) per pixel -> shared memory;
-//               The barycentric numerators are affine in the pixel position, so the position gradient of a triangle
-//               needs only nine moments of d loss / d a_k over its visible pixels; runs of pixels of the same
-//               triangle inside a warp are combined with a segmented warp-shuffle reduction and each run issues
-//               9 float REDs into a per-(view,triangle) moment buffer;
-//           (3) k_tri_grad (one thread per (view, triangle)) turns the moments into d loss / d pos.
+//           (2) pixel-parallel shading, loss and d loss / d (a0, a1, a2) per pixel -> shared memory;
+//           (3) triangle-parallel gather: the barycentric numerators are affine in the pixel position, so the position
+//               gradient of a triangle needs only nine moments of d loss / d a_k over its visible pixels.  One thread per
+//               entry of the bin's triangle list walks the entry's bounding box IN A FIXED ORDER, sums the moments of the
+//               pixels the triangle won, converts them to the gradient of its three corners and stores the nine floats
+//               in the slot of (view, triangle, bin): written exactly once, no atomics, no zero-fill, bit-reproducible;
+//           (4) k_vtx_gather (one thread per (view, vertex)) sums, in the fixed order of a vertex -> triangle adjacency
+//               list, the slots of the triangles around the vertex -> d loss / d pos_clip.
+// (Triangles too large for the bin lists — more than 2 x 2 bins or 128 px, or clipped by the near plane — are resolved
+// by whole CTAs; their moments are the one thing still accumulated with float REDs.)
 #include "antialias.cuh"
 #include "raster_core.cuh"
 
@@ -35,13 +39,13 @@ struct FusedParams {
     int C;
     float bg, k;             // k = scale / (H*W*C)
     int l1;                  // 0: squared error (fit.py:579), 1: absolute error
-    float* grad_pos;         // [N,V,4]
+    float* grad_pos;         // [N,V,4] (written by k_vtx_gather)
     float* grad_tex;         // [Ht,Wt,C] or null: d loss / d tex accumulated with REDs (cleared by the host function)
     float* rast_out;         // [N,H,W,4] or null
     float* colour_out;       // [N,H,W,C] or null (composited image)
     int vpf, row_lo, row_hi; // band split: views per frame; the first view of a frame renders bin rows >= row_lo, the last < row_hi
     double* loss_partial;    // [N*NB]
-    float* moments;          // [N*T*9] zeroed by the host function
+    float* slots;            // [N*T*4*9] gradient slots (RasterParams::slot_grad), or null: forward only
 };
 
 // band split of the camera-split mode: bin row `by` of view n belongs to this rank?
@@ -51,21 +55,14 @@ __device__ __forceinline__ bool outside_band(const FusedParams& fp, int n, int b
     return (c == 0 && by < fp.row_lo) || (c == fp.vpf - 1 && by >= fp.row_hi);
 }
 
-__device__ __forceinline__ void red_vertex(float* G, int vi, float gx, float gy, float gw)
-{
-    if (gx != 0.f) atomicAdd(G + 4 * (size_t)vi + 0, gx);
-    if (gy != 0.f) atomicAdd(G + 4 * (size_t)vi + 1, gy);
-    if (gw != 0.f) atomicAdd(G + 4 * (size_t)vi + 3, gw);
-}
-
 // The barycentric numerators are affine in the pixel position:  a_k(px) = C_k + A_k fx + B_k fy  with
 //   C0 = x1 y2 - y1 x2, A0 = y1 w2 - w1 y2, B0 = w1 x2 - x1 w2   (and cyclic),
 // so d loss / d pos of a triangle needs only nine sums over its visible pixels, m = (S_k, SX_k, SY_k) with
 // g_k = d loss / d a_k at the pixel and (lx, ly) the pixel offset from the triangle's anchor pixel (fx0, fy0).
-// Same result as summing k_raster_bwd's per-pixel formula (oracle: gold_rasterize_bwd).
-__device__ __forceinline__ void triangle_pos_grad(const float* m, float fx0, float fy0, float xs, float ys,
-                                                  const float4& q0, const float4& q1, const float4& q2, float* G,
-                                                  int i0, int i1, int i2)
+// out = (d x, d y, d w) of corner 0, 1, 2.  Same result as summing k_raster_bwd's per-pixel formula (oracle:
+// gold_rasterize_bwd).
+__device__ __forceinline__ void triangle_corner_grads(const float* m, float fx0, float fy0, float xs, float ys,
+                                                      const float4& q0, const float4& q1, const float4& q2, float* out)
 {
     typedef FPC_TRIGRAD_REAL real_t;
     const real_t S0 = m[0], S1 = m[1], S2 = m[2];
@@ -78,88 +75,105 @@ __device__ __forceinline__ void triangle_pos_grad(const float* m, float fx0, flo
     // sum_px g_k p_my(px) = S_k p_my - w_m Y_k ;  sum_px g_k p_mx(px) = S_k p_mx - w_m X_k
 #define SY_(k, pmy, wm) (S##k * (pmy) - (wm) * Y##k)
 #define SX_(k, pmx, wm) (S##k * (pmx) - (wm) * X##k)
-    real_t g0x = -SY_(1, p2y, q2.w) + SY_(2, p1y, q1.w);
-    real_t g0y = SX_(1, p2x, q2.w) - SX_(2, p1x, q1.w);
-    real_t g1x = SY_(0, p2y, q2.w) - SY_(2, p0y, q0.w);
-    real_t g1y = -SX_(0, p2x, q2.w) + SX_(2, p0x, q0.w);
-    real_t g2x = -SY_(0, p1y, q1.w) + SY_(1, p0y, q0.w);
-    real_t g2y = SX_(0, p1x, q1.w) - SX_(1, p0x, q0.w);
+    out[0] = (float)(-SY_(1, p2y, q2.w) + SY_(2, p1y, q1.w));
+    out[1] = (float)(SX_(1, p2x, q2.w) - SX_(2, p1x, q1.w));
+    out[3] = (float)(SY_(0, p2y, q2.w) - SY_(2, p0y, q0.w));
+    out[4] = (float)(-SX_(0, p2x, q2.w) + SX_(2, p0x, q0.w));
+    out[6] = (float)(-SY_(0, p1y, q1.w) + SY_(1, p0y, q0.w));
+    out[7] = (float)(SX_(0, p1x, q1.w) - SX_(1, p0x, q0.w));
 #undef SY_
 #undef SX_
     // d loss / d A_k = sum g_k fx, d loss / d B_k = sum g_k fy
     real_t dA0 = fx0 * S0 + X0, dA1 = fx0 * S1 + X1, dA2 = fx0 * S2 + X2;
     real_t dB0 = fy0 * S0 + Y0, dB1 = fy0 * S1 + Y1, dB2 = fy0 * S2 + Y2;
-    real_t g0w = q2.y * dA1 - q2.x * dB1 - q1.y * dA2 + q1.x * dB2;
-    real_t g1w = -q2.y * dA0 + q2.x * dB0 + q0.y * dA2 - q0.x * dB2;
-    real_t g2w = q1.y * dA0 - q1.x * dB0 - q0.y * dA1 + q0.x * dB1;
-    red_vertex(G, i0, (float)g0x, (float)g0y, (float)g0w);
-    red_vertex(G, i1, (float)g1x, (float)g1y, (float)g1w);
-    red_vertex(G, i2, (float)g2x, (float)g2y, (float)g2w);
+    out[2] = (float)(q2.y * dA1 - q2.x * dB1 - q1.y * dA2 + q1.x * dB2);
+    out[5] = (float)(-q2.y * dA0 + q2.x * dB0 + q0.y * dA2 - q0.x * dB2);
+    out[8] = (float)(q1.y * dA0 - q1.x * dB0 - q0.y * dA1 + q0.x * dB1);
 }
 
-// Moments of (g0, g1, g2) = d loss / d (a0, a1, a2) per triangle: runs of equal triangle id inside the warp are combined
-// with a segmented shuffle reduction, then the head lane of each run issues <= 9 float REDs into M [T,9] (this view's
-// moment buffer).  tid = 0xFFFFFFFF on background; `an` = packed anchor pixel of the triangle (valid on every foreground lane).
-// The 32 lanes of a warp hold consecutive pixels of ONE image row (BIN is a multiple of 32), so the y-moments of a run are
-// ly * sum(g_k): only six values travel through the shuffles.  Must be called by all 32 lanes.
-#ifndef FPC_MOM6
-#define FPC_MOM6 1
-#endif
-static_assert(BIN % 32 == 0, "a warp must cover pixels of a single row");
-__device__ __forceinline__ void accumulate_moments(float* __restrict__ M, unsigned tid, bool live, float g0, float g1, float g2,
-                                                   int px, int py, int an, int lane)
+// ---- layout of the per-pixel gradient terms the gather phase reads (shared memory) ----
+// After the visibility phase the key tile holds one 32-bit word per pixel in its first BIN*BIN*4 bytes (packed keys, or ids
+// narrowed from the 64-bit keys); the three planes g0 | g1 | g2 (d loss / d a_k per pixel) follow it, over the second half of
+// the key tile and the WarpStage records, both free by then.
+constexpr int PIX = BIN * BIN;
+static_assert(sizeof(unsigned long long) * PIX + sizeof(WarpStage) * FINE_WARPS >= 4 * sizeof(float) * PIX, "g planes must fit behind the ids");
+
+// 64-bit keys -> 32-bit ids in place (0xFFFFFFFF = empty); all NT threads of the CTA; ends with a barrier
+template <int NPIX, int NT>
+__device__ __forceinline__ void narrow_keys(unsigned long long* keys)
 {
-    if (!__any_sync(0xffffffffu, live)) return;
-#if FPC_MOM6
-    constexpr int NM = 6;
-#else
-    constexpr int NM = 9;
-#endif
-    float m[NM];
-    const float flx = live ? (float)(px - (an & 0xffff)) : 0.f;
-    m[0] = g0; m[1] = g1; m[2] = g2;
-    m[3] = g0 * flx; m[4] = g1 * flx; m[5] = g2 * flx;
-#if !FPC_MOM6
-    { const float fly = live ? (float)(py - (int)((unsigned)an >> 16)) : 0.f; m[6] = g0 * fly; m[7] = g1 * fly; m[8] = g2 * fly; }
-#endif
-    // longest run of one triangle in this warp: shuffle steps with d >= that length combine nothing
-    unsigned tprev = __shfl_up_sync(0xffffffffu, tid, 1);
-    const bool head = (lane == 0) || (tprev != tid);
-    const unsigned hm = __ballot_sync(0xffffffffu, head);
-    const unsigned above = (lane == 31) ? 0u : (hm & (0xFFFFFFFEu << lane));
-    const unsigned len = (head && tid != 0xFFFFFFFFu) ? (unsigned)((above ? __ffs(above) - 1 : 32) - lane) : 0u;
-    const unsigned maxlen = __reduce_max_sync(0xffffffffu, len);
-    // segments are RUNS, not triangle ids: a triangle that is occluded in the middle of the row owns two runs, each with its
-    // own head lane and its own REDs — partial sums must not travel across the gap (that would count pixels twice)
-    const int myhead = 31 - __clz(hm & (0xFFFFFFFFu >> (31 - lane)));
+    constexpr int PER = (NPIX + NT - 1) / NT;
+    unsigned id[PER];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        if ((unsigned)d >= maxlen) break;
-        const int to = __shfl_down_sync(0xffffffffu, myhead, d);
-        bool take = (lane + d < 32) && (to == myhead);
+    for (int j = 0; j < PER; j++) {
+        const int i = threadIdx.x + j * NT;
+        const unsigned long long k = (i < NPIX) ? keys[i] : KEY_EMPTY;
+        id[j] = (k == KEY_EMPTY) ? 0xFFFFFFFFu : (unsigned)k;
+    }
+    __syncthreads();
+    unsigned* k32 = reinterpret_cast<unsigned*>(keys);
 #pragma unroll
-        for (int c = 0; c < NM; c++) {
-            float o = __shfl_down_sync(0xffffffffu, m[c], d);
-            if (take) m[c] += o;
+    for (int j = 0; j < PER; j++) {
+        const int i = threadIdx.x + j * NT;
+        if (i < NPIX) k32[i] = id[j];
+    }
+    __syncthreads();
+}
+
+// Moments of one list entry (triangle t) over the pixels it won inside the window [xa,xb] x [ya,yb] of a tile whose ids
+// are ids[(y - ty0) * TW + (x - tx0)] and whose gradient planes are g[0..2][(y - gy0) * GW + (x - gx0)], in row-major
+// pixel order (fixed -> bit-reproducible).  (anx, any) = the triangle's anchor pixel.
+template <int TW, int GW>
+__device__ __forceinline__ bool gather_moments(const int* __restrict__ ids, const float* __restrict__ g0p, const float* __restrict__ g1p,
+                                               const float* __restrict__ g2p, int t, int xa, int xb, int ya, int yb, int tx0, int ty0,
+                                               int gx0, int gy0, int anx, int any, float (&m)[9])
+{
+#pragma unroll
+    for (int c = 0; c < 9; c++) m[c] = 0.f;
+    bool seen = false;
+    for (int y = ya; y <= yb; y++) {
+        const int* idr = ids + (y - ty0) * TW - tx0;
+        const int gr = (y - gy0) * GW - gx0;
+        const float fly = (float)(y - any);
+        for (int x = xa; x <= xb; x++) {
+            if (idr[x] != t) continue;
+            seen = true;
+            const float a = g0p[gr + x], b = g1p[gr + x], c = g2p[gr + x];
+            const float flx = (float)(x - anx);
+            m[0] += a; m[1] += b; m[2] += c;
+            m[3] += a * flx; m[4] += b * flx; m[5] += c * flx;
+            m[6] += a * fly; m[7] += b * fly; m[8] += c * fly;
         }
     }
-    if (tid != 0xFFFFFFFFu && head) {
-        // the head lane's anchor is the run's (callers load `an` for every foreground pixel, live or not)
-        const float ly = (float)(py - (int)((unsigned)an >> 16));
-        float* Mt = M + (size_t)tid * 9;
+    return seen;
+}
+
+__device__ __forceinline__ float* slot_ptr(float* slots, size_t gid, int k) { return slots + (gid * SLOTS_PER_TRI + k) * SLOT_FLOATS; }
+
+// a bin another rank renders (band split): its list entries still own slots the vertex gather reads -> zero them
+__device__ __forceinline__ void zero_bin_slots(const RasterParams& rp, float* slots, int n, int bin, int nthreads)
+{
+    if (!slots) return;
+    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
+    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
+    const int bx = bin % rp.BW, by = bin / rp.BW;
+    for (int i = threadIdx.x; i < count; i += nthreads) {
+        const size_t gid = (size_t)n * rp.T + list[i];
+        float* o = slot_ptr(slots, gid, slot_index_k(rp.tri_info[gid], bx, by));
 #pragma unroll
-        for (int c = 0; c < NM; c++)
-            if (m[c] != 0.f) atomicAdd(Mt + c, m[c]);
-#if FPC_MOM6
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const float v = m[c] * ly;
-            if (v != 0.f) atomicAdd(Mt + 6 + c, v);
-        }
-#else
-        (void)ly;
-#endif
+        for (int c = 0; c < SLOT_FLOATS; c++) o[c] = 0.f;
     }
+}
+
+// moments of a LARGE triangle's pixel: float REDs into the triangle's accumulator slot 1 (zeroed by k_setup)
+__device__ __forceinline__ void large_pixel_moments(float* slots, size_t gid, float g0, float g1, float g2, int px, int py, int an)
+{
+    float* M = slot_ptr(slots, gid, 1);
+    const float flx = (float)(px - (an & 0xffff)), fly = (float)(py - (int)((unsigned)an >> 16));
+    const float v[9] = {g0, g1, g2, g0 * flx, g1 * flx, g2 * flx, g0 * fly, g1 * fly, g2 * fly};
+#pragma unroll
+    for (int c = 0; c < 9; c++)
+        if (v[c] != 0.f) atomicAdd(M + c, v[c]);
 }
 
 // d loss / d tex of one pixel: g_c times the four bilinear weights, RED into grad_tex [Ht,Wt,C] (texture.cu: k_tex_bwd).
@@ -266,6 +280,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
 
     if (outside_band(fp, n, bin / rp.BW)) {            // another rank renders this bin row (shard.view_band_shard)
         if (threadIdx.x == 0) fp.loss_partial[(size_t)n * rp.NB + bin] = 0.0;
+        zero_bin_slots(rp, fp.slots, n, bin, FINE_THREADS);
         return;
     }
     if (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0) {      // ~2/3 of the bins of a head shot
@@ -304,18 +319,26 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     }
 
     const bool packed = raster_bin(rp, n, bin, keys, stage);
+    if (!packed) narrow_keys<PIX, FINE_THREADS>(keys);           // rare: the bin's depth range did not fit the packed keys
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    int* ids = reinterpret_cast<int*>(keys);                      // packed key or id per pixel; rewritten below as id / -1
+    float* sg0 = reinterpret_cast<float*>(smem) + PIX;             // d loss / d a_k per pixel (gather phase)
+    float* sg1 = sg0 + PIX;
+    float* sg2 = sg1 + PIX;
+    const unsigned idmask = packed ? ((1u << rp.idbits) - 1u) : 0xFFFFFFFFu;
+    const bool any_large = rp.large_count[n] != 0;
 
     // ---- (2) shade + loss + (d u, d v) per pixel ----
     const float* P = rp.pos + (size_t)n * rp.V * 4;
     double loss_acc = 0.0;
-    for (int idx = threadIdx.x; idx < BIN * BIN; idx += FINE_THREADS) {
+    for (int idx = threadIdx.x; idx < PIX; idx += FINE_THREADS) {
         int lx = idx & (BIN - 1), ly = idx >> BIN_LOG2;
         int px = ox + lx, py = oy + ly;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        int an = 0;
-        unsigned long long key = tile_key(keys, idx, packed, rp.idbits);
+        const unsigned kw = (unsigned)ids[idx];
+        const bool fg = kw != 0xFFFFFFFFu;
+        const int t = fg ? (int)(kw & idmask) : -1;
         if (px < rp.W && py < rp.H) {
             size_t pi = ((size_t)n * rp.H + py) * rp.W + px;
             float refv[C];
@@ -326,23 +349,20 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             float col[C];
             float4 rout = make_float4(0.f, 0.f, 0.f, 0.f);
             float zn = 0.f, wn = 1.f;
-            bool fg = key != KEY_EMPTY;
             float a0c[TEX ? 2 : C], a1c[TEX ? 2 : C], a2c[TEX ? 2 : C];
             float dudc[C], dvdc[C];      // TEX: d colour_c / d texU, d texV
             float su = 0.f, sv = 0.f, siw = 0.f;
             unsigned tix = 0u, tiy = 0u;     // TEX: packed texel columns / rows (lo 16 bits = index 0, hi = index 1)
             float twx = 0.f, twy = 0.f;
             if (fg) {
-                int t = (int)(key & 0xFFFFFFFFu);
                 const int4 ti = tri_indices(rp, t);
                 const int i0 = ti.x, i1 = ti.y, i2 = ti.z;
-                if (fp.moments) an = __ldg(rp.tri_anchor + (size_t)n * rp.T + t);     // early: consumed by the moments below
                 float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
                 float fx = pixel_ndc(px, rp.xs, rp.xo), fy = pixel_ndc(py, rp.ys, rp.yo);
                 ShadeLazy sh = shade_pixel_lazy(p0, p1, p2, fx, fy);
                 zn = sh.zn; wn = sh.wn;
                 float u = clamp01(sh.u), v = clamp01(sh.v);
-                if (fp.moments) { const ShadeGrad sg = shade_pixel_grad(p0, p1, p2, fx, fy); su = sg.u; sv = sg.v; siw = sg.iw; }
+                if (fp.slots) { const ShadeGrad sg = shade_pixel_grad(p0, p1, p2, fx, fy); su = sg.u; sv = sg.v; siw = sg.iw; }
                 rout = make_float4(u, v, 0.f, (float)(t + 1));
                 int j0 = i0, j1 = i1, j2 = i2;
                 if (fp.attr_tri4) { const int4 tj = __ldg(fp.attr_tri4 + t); j0 = tj.x; j1 = tj.y; j2 = tj.z; }
@@ -433,10 +453,15 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
                 for (int c = 0; c < C; c++) fp.colour_out[pi * C + c] = col[c];
             }
         }
-        // ---- moments of (g0, g1, g2) per triangle: combine runs of equal triangle id inside the warp, then RED ----
-        if (fp.moments)
-            accumulate_moments(fp.moments + (size_t)n * rp.T * 9, (unsigned)(key & 0xFFFFFFFFu), (g0 != 0.f || g1 != 0.f || g2 != 0.f),
-                               g0, g1, g2, px, py, an, lane);
+        // ---- per-pixel terms of the gather phase (own slot only: no hazard with the pixels other threads still read) ----
+        if (fp.slots) {
+            ids[idx] = t;
+            sg0[idx] = g0; sg1[idx] = g1; sg2[idx] = g2;
+            if (any_large && fg && (g0 != 0.f || g1 != 0.f || g2 != 0.f)) {
+                const size_t gid = (size_t)n * rp.T + t;
+                if ((rp.tri_info[gid] >> 22) == 2) large_pixel_moments(fp.slots, gid, g0, g1, g2, px, py, rp.tri_anchor[gid]);
+            }
+        }
     }
     for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
     if (lane == 0) red[warp] = loss_acc;
@@ -445,6 +470,35 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
         double s = 0.0;
         for (int w = 0; w < FINE_WARPS; w++) s += red[w];
         fp.loss_partial[(size_t)n * rp.NB + bin] = s;
+    }
+    if (!fp.slots) return;
+
+    // ---- (3) gather: one thread per entry of the bin's list sums the moments of the pixels its triangle won, in row-major
+    //          order, and stores the gradient of the triangle's three corners in the slot of (view, triangle, this bin) ----
+    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
+    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
+    const int bx = bin % rp.BW, by = bin / rp.BW;
+    for (int i = threadIdx.x; i < count; i += FINE_THREADS) {
+        const int t = list[i];
+        const size_t gid = (size_t)n * rp.T + t;
+        const ushort4 bb = rp.tri_bbox[gid];
+        const int an = rp.tri_anchor[gid];
+        const int info = rp.tri_info[gid];
+        float m[9];
+        const bool seen = gather_moments<BIN, BIN>(ids, sg0, sg1, sg2, t, max((int)bb.x, ox), min((int)bb.z, ox + BIN - 1), max((int)bb.y, oy),
+                                                   min((int)bb.w, oy + BIN - 1), ox, oy, ox, oy, an & 0xffff, (int)((unsigned)an >> 16), m);
+        float out[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) out[c] = 0.f;
+        if (seen) {
+            const int4 ti = tri_indices(rp, t);
+            const float4 p0 = ldg4(P + 4 * (size_t)ti.x), p1 = ldg4(P + 4 * (size_t)ti.y), p2 = ldg4(P + 4 * (size_t)ti.z);
+            const float fx0 = pixel_ndc(an & 0xffff, rp.xs, rp.xo), fy0 = pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo);
+            triangle_corner_grads(m, fx0, fy0, rp.xs, rp.ys, p0, p1, p2, out);
+        }
+        float* o = slot_ptr(fp.slots, gid, slot_index_k(info, bx, by));
+#pragma unroll
+        for (int c = 0; c < 9; c++) o[c] = out[c];
     }
 }
 
@@ -463,31 +517,126 @@ __device__ __forceinline__ void loss_reduce_cta(const double* __restrict__ parti
     if (threadIdx.x == 0) loss[0] = (float)(red[0] * (double)k);
 }
 
-// one thread per (view, triangle): moments -> d loss / d pos (9 float REDs per visible triangle).  The loss partials of the
-// fused kernel are complete by now as well: one extra CTA (the last) sums them, which saves a launch on the critical path.
-__global__ void __launch_bounds__(256) k_tri_grad(RasterParams rp, const float* __restrict__ moments, float* __restrict__ grad_pos,
-                                                  const double* __restrict__ loss_partial, int n_partial, float k, float* __restrict__ loss)
+// One thread per (view, vertex): d loss / d pos_clip of the vertex = sum, in the fixed order of its adjacency list, of the
+// gradient slots of the triangles around it (each triangle: its at most 2 x 2 bin slots in k order) — a gather: no atomics,
+// every element of grad_pos is written exactly once (nothing to zero), bit-reproducible.  vadj_off [V+1], vadj_item [3T]
+// (item = triangle * 4 + corner), built once per mesh by fpc_vertex_adjacency_build.  The loss partials of the fused kernel
+// are complete by now as well: one extra CTA (the last) sums them, which saves a launch on the critical path.
+__global__ void __launch_bounds__(256) k_vtx_gather(RasterParams rp, const float* __restrict__ slots, const int32_t* __restrict__ vadj_off,
+                                                    const int32_t* __restrict__ vadj_item, float* __restrict__ grad_pos,
+                                                    const double* __restrict__ loss_partial, int n_partial, float k, float* __restrict__ loss)
 {
     if (blockIdx.x == gridDim.x - 1) {
         loss_reduce_cta(loss_partial, n_partial, k, loss);
         return;
     }
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)rp.N * rp.T) return;
-    const float* M = moments + gid * 9;
-    float m[9];
-    bool any = false;
+    const long long gv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gv >= (long long)rp.N * rp.V) return;
+    const int n = (int)(gv / rp.V), v = (int)(gv - (long long)n * rp.V);
+    float gx = 0.f, gy = 0.f, gw = 0.f;
+    const int j0 = __ldg(vadj_off + v), j1 = __ldg(vadj_off + v + 1);
+    for (int j = j0; j < j1; j++) {
+        const int item = __ldg(vadj_item + j);
+        const int t = item >> 2, corner = item & 3;
+        const size_t gid = (size_t)n * rp.T + t;
+        const int info = rp.tri_info[gid];
+        const int cls = info >> 22;
+        if (cls == 1) {
+            const float* S = slots + gid * (SLOTS_PER_TRI * SLOT_FLOATS) + 3 * corner;
+            const int nbx = (info >> 20) & 1, nby = (info >> 21) & 1;
 #pragma unroll
-    for (int c = 0; c < 9; c++) { m[c] = M[c]; any = any || (m[c] != 0.f); }
-    if (!any) return;
-    int n = (int)(gid / rp.T), t = (int)(gid - (long long)n * rp.T);
-    const int4 ti = tri_indices(rp, t);
-    const int i0 = ti.x, i1 = ti.y, i2 = ti.z;
-    const float* P = rp.pos + (size_t)n * rp.V * 4;
-    float4 p0 = ldg4(P + 4 * (size_t)i0), p1 = ldg4(P + 4 * (size_t)i1), p2 = ldg4(P + 4 * (size_t)i2);
-    int an = rp.tri_anchor[gid];
-    float fx0 = pixel_ndc(an & 0xffff, rp.xs, rp.xo), fy0 = pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo);
-    triangle_pos_grad(m, fx0, fy0, rp.xs, rp.ys, p0, p1, p2, grad_pos + (size_t)n * rp.V * 4, i0, i1, i2);
+            for (int kk = 0; kk < 4; kk++)
+                if ((kk & 1) <= nbx && (kk >> 1) <= nby) { gx += S[kk * SLOT_FLOATS]; gy += S[kk * SLOT_FLOATS + 1]; gw += S[kk * SLOT_FLOATS + 2]; }
+        } else if (cls == 2) {
+            // large / near-clipped triangle: slot 1 holds its moments (float REDs), slot 2 the antialias corner terms
+            const float* M = slots + (gid * SLOTS_PER_TRI + 1) * SLOT_FLOATS;
+            float m[9];
+            bool any = false;
+#pragma unroll
+            for (int c = 0; c < 9; c++) { m[c] = M[c]; any = any || (m[c] != 0.f); }
+            if (any) {
+                const int4 ti = tri_indices(rp, t);
+                const float* P = rp.pos + (size_t)n * rp.V * 4;
+                const float4 p0 = ldg4(P + 4 * (size_t)ti.x), p1 = ldg4(P + 4 * (size_t)ti.y), p2 = ldg4(P + 4 * (size_t)ti.z);
+                const int an = rp.tri_anchor[gid];
+                float out[9];
+                triangle_corner_grads(m, pixel_ndc(an & 0xffff, rp.xs, rp.xo), pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo), rp.xs, rp.ys, p0, p1, p2, out);
+                gx += out[3 * corner]; gy += out[3 * corner + 1]; gw += out[3 * corner + 2];
+            }
+            const float* Aa = M + SLOT_FLOATS + 3 * corner;
+            gx += Aa[0]; gy += Aa[1]; gw += Aa[2];
+        }
+    }
+    reinterpret_cast<float4*>(grad_pos)[gv] = make_float4(gx, gy, 0.f, gw);
+}
+
+// ---- vertex -> (triangle, corner) adjacency (CSR), built once per mesh ------------------------------------------------
+__global__ void __launch_bounds__(256) k_vadj_count(const int32_t* __restrict__ tri, int T, int V, int* __restrict__ cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * T) return;
+    const int v = tri[i];
+    if ((unsigned)v < (unsigned)V) atomicAdd(cnt + v, 1);
+}
+
+// single CTA exclusive scan (V is at most a few 10^5; runs once per mesh)
+__global__ void __launch_bounds__(1024) k_vadj_scan(const int* __restrict__ cnt, int V, int32_t* __restrict__ off, int* __restrict__ cursor)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < V; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int c = (i < V) ? cnt[i] : 0;
+        int x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane], xs = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, xs, d);
+                if (lane >= d) xs += y;
+            }
+            wsum[lane] = xs - w;
+        }
+        __syncthreads();
+        const int excl = carry + wsum[warp] + x - c;
+        if (i < V) { off[i] = excl; cursor[i] = excl; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[V] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_vadj_fill(const int32_t* __restrict__ tri, int T, int V, int* __restrict__ cursor, int32_t* __restrict__ item)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * T) return;
+    const int v = tri[i];
+    if ((unsigned)v < (unsigned)V) item[atomicAdd(cursor + v, 1)] = (i / 3) * 4 + (i % 3);
+}
+
+// the fill order above depends on the atomics: sort every vertex's (short) list so that the gather order is canonical
+__global__ void __launch_bounds__(256) k_vadj_sort(const int32_t* __restrict__ off, int V, int32_t* __restrict__ item)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int a = off[v], b = off[v + 1];
+    for (int i = a + 1; i < b; i++) {
+        const int x = item[i];
+        int j = i - 1;
+        while (j >= a && item[j] > x) { item[j + 1] = item[j]; j--; }
+        item[j + 1] = x;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_fused_loss_reduce(const double* __restrict__ partial, int n, float k, float* __restrict__ loss)
@@ -538,17 +687,18 @@ extern "C" size_t fpc_render_loss_fused_scratch_bytes(int N, int T, int H, int W
 {
     if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return 256;
     int NB = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
-    return align256(raster_layout(N, T, NB).total) + align256((size_t)N * NB * sizeof(double)) + align256((size_t)N * T * 9 * sizeof(float)) +
-           align256((size_t)T * sizeof(int4));
+    return align256(raster_layout(N, T, NB).total) + align256((size_t)N * NB * sizeof(double)) +
+           align256((size_t)N * T * SLOTS_PER_TRI * SLOT_FLOATS * sizeof(float)) + align256((size_t)T * sizeof(int4));
 }
 
 static int render_loss_fused_impl(const char* who, const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                   const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
                                   int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                   float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
-                                  int views_per_frame, int row_lo, int row_hi,
+                                  const int32_t* vadj_off, const int32_t* vadj_item, int views_per_frame, int row_lo, int row_hi,
                                   void* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
+    FPC_CHECK_ARG(!grad_pos || (vadj_off && vadj_item), "%s: grad_pos needs the vertex adjacency of the mesh (fpc_vertex_adjacency_build)", who);
     FPC_CHECK_ARG(attr && attr_tri && ref && loss, "%s: attr, attr_tri, ref and loss must be non-null", who);
     FPC_CHECK_ARG(C == 1 || C == 3, "%s: C must be 1 or 3 (got %d)", who, C);
     FPC_CHECK_ARG(loss_kind == 0 || loss_kind == 1, "%s: loss_kind must be 0 (L2) or 1 (L1), got %d", who, loss_kind);
@@ -564,12 +714,13 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     RasterParams rp;
     const int NB0 = fpc_div_up(W, BIN) * fpc_div_up(H, BIN);
     double* loss_partial = (double*)((char*)scratch + align256(raster_layout(N, T, NB0).total));
-    float* moments_mem = (float*)((char*)loss_partial + align256((size_t)N * NB0 * sizeof(double)));
-    float* moments = grad_pos ? moments_mem : nullptr;
-    int4* attr_tri4 = (attr_tri != tri) ? (int4*)((char*)moments_mem + align256((size_t)N * T * 9 * sizeof(float))) : nullptr;
-    // k_setup clears the moment and gradient accumulators on its way (no separate memsets); with antialias the bins are
-    // widened by the 2-px halo the fused kernel resolves around its bin
-    int st = raster_bin_triangles(who, pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, moments, grad_pos, tri_opp ? AA_HALO : 0,
+    float* slots_mem = (float*)((char*)loss_partial + align256((size_t)N * NB0 * sizeof(double)));
+    float* slots = grad_pos ? slots_mem : nullptr;
+    int4* attr_tri4 = (attr_tri != tri) ? (int4*)((char*)slots_mem + align256((size_t)N * T * SLOTS_PER_TRI * SLOT_FLOATS * sizeof(float))) : nullptr;
+    // no accumulator is zero-filled: every gradient slot and every element of grad_pos is written exactly once (k_setup only
+    // zeroes the accumulator slots of large triangles); with antialias the bins are widened by the 2-px halo the fused kernel
+    // resolves around its bin
+    int st = raster_bin_triangles(who, pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, slots, tri_opp ? AA_HALO : 0,
                                   attr_tri4 ? attr_tri : nullptr, attr_tri4, T);
     if (st != FPC_OK) return st;
     FusedParams fp;
@@ -584,7 +735,7 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     FPC_CHECK_ARG(views_per_frame > 1 || row_lo < row_hi, "%s: empty band [%d, %d)", who, row_lo, row_hi);
     fp.vpf = views_per_frame; fp.row_lo = row_lo; fp.row_hi = row_hi;
     fp.loss_partial = loss_partial;
-    fp.moments = moments;
+    fp.slots = slots;
     if (tri_opp) {
         if (tex) st = (C == 1) ? launch_fused_aa<1, true>(rp, fp, tri_opp, stream) : launch_fused_aa<3, true>(rp, fp, tri_opp, stream);
         else st = (C == 1) ? launch_fused_aa<1, false>(rp, fp, tri_opp, stream) : launch_fused_aa<3, false>(rp, fp, tri_opp, stream);
@@ -595,7 +746,7 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     if (st != FPC_OK) return st;
     if (grad_pos) {
         // + 1 CTA: the loss reduction rides along
-        k_tri_grad<<<fpc_div_up((long long)N * T, 256) + 1, 256, 0, stream>>>(rp, fp.moments, grad_pos, fp.loss_partial, N * rp.NB, fp.k, loss);
+        k_vtx_gather<<<fpc_div_up((long long)N * V, 256) + 1, 256, 0, stream>>>(rp, fp.slots, vadj_off, vadj_item, grad_pos, fp.loss_partial, N * rp.NB, fp.k, loss);
         FPC_LAUNCH_CHECK();
     } else {
         k_fused_loss_reduce<<<1, 256, 0, stream>>>(fp.loss_partial, N * rp.NB, fp.k, loss);
@@ -608,21 +759,25 @@ extern "C" int fpc_render_loss_fused(const float* pos, const int32_t* tri, const
                                      const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
                                      int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                      float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                                     const int32_t* vadj_off, const int32_t* vadj_item,
                                      void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     return render_loss_fused_impl("render_loss_fused", pos, tri, nullptr, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, 0, 0, 0, scratch, scratch_bytes, (cudaStream_t)stream_);
+                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, vadj_off, vadj_item, 0, 0, 0, scratch, scratch_bytes,
+                                  (cudaStream_t)stream_);
 }
 
 extern "C" int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                         const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
                                         const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                         float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                                        const int32_t* vadj_off, const int32_t* vadj_item,
                                         void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     FPC_CHECK_ARG(tri_opp, "render_loss_fused_aa: tri_opp must be non-null (fpc_topology_build)");
     return render_loss_fused_impl("render_loss_fused_aa", pos, tri, tri_opp, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, 0, 0, 0, scratch, scratch_bytes, (cudaStream_t)stream_);
+                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, vadj_off, vadj_item, 0, 0, 0, scratch, scratch_bytes,
+                                  (cudaStream_t)stream_);
 }
 
 extern "C" int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
@@ -630,10 +785,37 @@ extern "C" int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, 
                                           const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                           int views_per_frame, int row_lo, int row_hi,
                                           float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                                          const int32_t* vadj_off, const int32_t* vadj_item,
                                           void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     FPC_CHECK_ARG(views_per_frame > 0, "render_loss_fused_band: views_per_frame must be positive");
     return render_loss_fused_impl("render_loss_fused_band", pos, tri, tri_opp, attr, attr_tri, Va, A, tex, Ht, Wt, ref, ref_is_u8, N, V, T, H, W, C,
-                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, views_per_frame, row_lo, row_hi,
+                                  bg, scale, loss_kind, loss, grad_pos, grad_tex, rast_out, colour_out, vadj_off, vadj_item, views_per_frame, row_lo, row_hi,
                                   scratch, scratch_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" size_t fpc_vertex_adjacency_scratch_bytes(int V)
+{
+    return V > 0 ? align256((size_t)V * sizeof(int)) * 2 : 256;
+}
+
+extern "C" int fpc_vertex_adjacency_build(const int32_t* tri, int T, int V, int32_t* vadj_off, int32_t* vadj_item,
+                                          void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FPC_CHECK_ARG(tri && vadj_off && vadj_item, "vertex_adjacency_build: null pointer argument");
+    FPC_CHECK_ARG(T > 0 && V > 0 && T < (1 << 24), "vertex_adjacency_build: T, V must be positive, T < 2^24 (got %d, %d)", T, V);
+    FPC_CHECK_ARG(scratch && scratch_bytes >= fpc_vertex_adjacency_scratch_bytes(V), "vertex_adjacency_build: scratch too small");
+    int* cnt = (int*)scratch;
+    int* cursor = (int*)((char*)scratch + align256((size_t)V * sizeof(int)));
+    FPC_CUDA(cudaMemsetAsync(cnt, 0, (size_t)V * sizeof(int), stream));
+    k_vadj_count<<<fpc_div_up(3LL * T, 256), 256, 0, stream>>>(tri, T, V, cnt);
+    FPC_LAUNCH_CHECK();
+    k_vadj_scan<<<1, 1024, 0, stream>>>(cnt, V, vadj_off, cursor);
+    FPC_LAUNCH_CHECK();
+    k_vadj_fill<<<fpc_div_up(3LL * T, 256), 256, 0, stream>>>(tri, T, V, cursor, vadj_item);
+    FPC_LAUNCH_CHECK();
+    k_vadj_sort<<<fpc_div_up(V, 256), 256, 0, stream>>>(vadj_off, V, vadj_item);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
 }

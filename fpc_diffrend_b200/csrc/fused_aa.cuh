@@ -12,8 +12,12 @@
 //   (3) pixel pairs (p,right) / (p,up) with different triangle ids are compacted into a work list and analysed
 //       densely (aa_analyze, the op-level code, bit-identical decisions) -> per-pixel alpha of its two own pairs;
 //   (4) ring-1 region (34x34): antialiased colour, loss (own pixels only) and d loss / d out;
-//   (5) own pixels: d loss / d colour gathered from the 4 pairs (no atomics), mapped to the triangle moments
-//       (as k_fused) and the silhouette position gradient of the two own pairs (sparse REDs into grad_pos).
+//   (5) own pixels: d loss / d colour gathered from the 4 pairs (no atomics) -> d loss / d (a0,a1,a2) of the pixel, and
+//       dd = sum_c d loss/d out_c (colour_1 - colour_0) of the pixel's two own pairs, all kept in shared memory;
+//   (6) triangle-parallel gather (as k_fused): one thread per entry of the bin's list walks the entry's bounding box inside
+//       the tile in a fixed order, sums the moments of its own pixels AND the silhouette terms of the pairs this bin owns
+//       whose crossing edge belongs to the triangle, and stores the gradient of the three corners in the slot of
+//       (view, triangle, bin): no atomics anywhere, bit-reproducible.
 // Each pair is owned by its lower/left pixel, each pixel by exactly one bin: nothing is counted twice.
 #pragma once
 
@@ -137,6 +141,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
 
     if (outside_band(fp, n, bin / rp.BW)) {            // another rank renders this bin row (shard.view_band_shard)
         if (threadIdx.x == 0) fp.loss_partial[(size_t)n * rp.NB + bin] = 0.0;
+        zero_bin_slots(rp, fp.slots, n, bin, AA_THREADS);
         return;
     }
     // bins are widened by the halo when triangles are binned: an empty list means an all-background tile
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 }
             }
             // d loss / d a_k = sum_c g_c K[k][c]   (u = a0/at, v = a1/at, unclamped barycentrics as in the op-level backward)
-            if (inner && fp.moments) {
+            if (inner && fp.slots) {
                 const ShadeGrad sg = shade_pixel_grad(p0, p1, p2, fx, fy);      // backward-only barycentrics (common.cuh)
 #pragma unroll
                 for (int c = 0; c < C; c++) {
@@ -373,23 +378,28 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     }
     __syncthreads();
 
-    // ---- (5) own pixels: d loss / d colour (gather over the 4 pairs), triangle moments, silhouette position gradient ----
-    for (int ii = threadIdx.x; ii < BIN * BIN; ii += AA_THREADS) {
+    // ---- (5) own pixels: d loss / d colour (gather over the 4 pairs) -> d loss / d (a0, a1, a2); dd of the two own pairs ----
+    static_assert(PIX % AA_THREADS == 0, "every thread owns PIX / AA_THREADS pixels");
+    constexpr int PER = PIX / AA_THREADS;
+    const bool any_large = rp.large_count[n] != 0;
+    float ddr_[PER], ddu_[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const int ii = threadIdx.x + j * AA_THREADS;
         const int ix = ii & (BIN - 1), iy = ii >> BIN_LOG2;
         const int tx = ix + AA_HALO, ty = iy + AA_HALO, idx = ty * AA_TW + tx;
         const int r = (iy + 1) * AA_R1 + (ix + 1);
         const int px = ox + ix, py = oy + iy;
         const bool in_img = px < rp.W && py < rp.H;
-        const unsigned long long key = keys[idx];
-        const unsigned idp1 = (unsigned)key;
+        const unsigned idp1 = (unsigned)keys[idx];
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        float ddr = 0.f, ddu = 0.f;
         if (in_img) {
             const float a0 = s_ar[idx], a1 = s_ar[idx - 1], a2 = s_au[idx], a3 = s_au[idx - AA_TW];
             // destination pixel (ring-1 index) of every pair: pix0 when alpha > 0, else pix1
             const int d0 = (a0 > 0.f) ? r : r + 1, d1 = (a1 > 0.f) ? r - 1 : r;
             const int d2 = (a2 > 0.f) ? r : r + AA_R1, d3 = (a3 > 0.f) ? r - AA_R1 : r;
             const unsigned info = s_info[idx];
-            float ddr = 0.f, ddu = 0.f;
             float gpre[C];             // d loss / d colour before antialias
 #pragma unroll
             for (int c = 0; c < C; c++) {
@@ -416,30 +426,36 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 tex_coords(fp, tc.x, tc.y, tix, tiy, twx, twy);
                 tex_grad_scatter<C>(fp, tix, tiy, twx, twy, gpre);
             }
-            if (fp.moments) {
-                if ((info & 8u) && ddr != 0.f) {
-                    AAPair a;
-                    const int f1 = (info >> 2) & 1;
-                    a.valid = true; a.di = info & 3; a.alpha = a0; a.px = px + f1; a.py = py;
-                    a.tri = (int)(unsigned)keys[idx + f1] - 1;
-                    aa_pos_grad(ap, n, a, 0, ddr, fp.grad_pos);
+            if (fp.slots && any_large) {
+                // large / near-clipped triangles are in no bin list: their terms are accumulated with float REDs (slots 1, 2)
+                if (idp1 && (g0 != 0.f || g1 != 0.f || g2 != 0.f)) {
+                    const size_t gid = (size_t)n * rp.T + (idp1 - 1u);
+                    if ((rp.tri_info[gid] >> 22) == 2) large_pixel_moments(fp.slots, gid, g0, g1, g2, px, py, rp.tri_anchor[gid]);
                 }
-                if ((info & 0x80u) && ddu != 0.f) {
-                    AAPair a;
-                    const int f1 = (info >> 6) & 1;
-                    a.valid = true; a.di = (info >> 4) & 3; a.alpha = a2; a.px = px; a.py = py + f1;
-                    a.tri = (int)(unsigned)keys[idx + f1 * AA_TW] - 1;
-                    aa_pos_grad(ap, n, a, 1, ddu, fp.grad_pos);
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    const unsigned inf = d ? (info >> 4) : info;
+                    const float dd = d ? ddu : ddr;
+                    if (!(inf & 8u) || dd == 0.f) continue;
+                    const int f1 = (inf >> 2) & 1;
+                    const int tt = (int)(unsigned)keys[idx + f1 * (d ? AA_TW : 1)] - 1;
+                    const size_t gid = (size_t)n * rp.T + tt;
+                    if (tt < 0 || (rp.tri_info[gid] >> 22) != 2) continue;
+                    const int di = inf & 3;
+                    const int4 ti = tri_indices(rp, tt);
+                    const int vi[3] = {ti.x, ti.y, ti.z};
+                    const int c1 = (di + 1) % 3, c2 = (di + 2) % 3;
+                    float gp1[3], gp2[3];
+                    aa_pair_corner_grads(ap.xh, ap.yh, ldg4(P + 4 * (size_t)vi[c1]), ldg4(P + 4 * (size_t)vi[c2]), px + (d ? 0 : f1), py + (d ? f1 : 0), d, dd, gp1, gp2);
+                    float* Aa = slot_ptr(fp.slots, gid, 2);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { atomicAdd(Aa + 3 * c1 + c, gp1[c]); atomicAdd(Aa + 3 * c2 + c, gp2[c]); }
                 }
             }
         }
-        if (fp.moments) {
-            int an = 0;
-            const unsigned tid = idp1 - 1u;                               // 0xFFFFFFFF on background
-            const bool live = (g0 != 0.f || g1 != 0.f || g2 != 0.f);
-            if (idp1) an = __ldg(rp.tri_anchor + (size_t)n * rp.T + tid);
-            accumulate_moments(fp.moments + (size_t)n * rp.T * 9, tid, live, g0, g1, g2, px, py, an, lane);
-        }
+        // the pixel's own coefficient slots become its gradient terms (read only by this thread above)
+        if (fp.slots) { s_coef[ii * 3 * C + 0] = g0; s_coef[ii * 3 * C + 1] = g1; s_coef[ii * 3 * C + 2] = g2; }
+        ddr_[j] = ddr; ddu_[j] = ddu;
     }
     for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
     if (lane == 0) red[warp] = loss_acc;
@@ -448,6 +464,103 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
         double s = 0.0;
         for (int w = 0; w < AA_WARPS; w++) s += red[w];
         fp.loss_partial[(size_t)n * rp.NB + bin] = s;
+    }
+    if (!fp.slots) return;
+    // the alphas have been consumed (barrier above): the alpha planes of the own pixels now carry the pairs' dd
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const int ii = threadIdx.x + j * AA_THREADS;
+        const int idx = ((ii >> BIN_LOG2) + AA_HALO) * AA_TW + (ii & (BIN - 1)) + AA_HALO;
+        s_ar[idx] = ddr_[j]; s_au[idx] = ddu_[j];
+    }
+    __syncthreads();
+
+    // ---- (6) gather per list entry: moments of the triangle's own pixels + silhouette terms of the pairs this bin owns ----
+    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
+    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
+    const int bx = bin % rp.BW, by = bin / rp.BW;
+    const int* idw = reinterpret_cast<const int*>(keys);            // low word of the 64-bit slot = id + 1
+    for (int i = threadIdx.x; i < count; i += AA_THREADS) {
+        const int t = list[i];
+        const size_t gid = (size_t)n * rp.T + t;
+        const ushort4 bb = rp.tri_bbox[gid];
+        const int an = rp.tri_anchor[gid];
+        const int info_t = rp.tri_info[gid];
+        const int anx = an & 0xffff, any = (int)((unsigned)an >> 16);
+        const int xa = max((int)bb.x, max(tx0, 0)), xb = min((int)bb.z, tx0 + AA_TW - 1);
+        const int ya = max((int)bb.y, max(ty0, 0)), yb = min((int)bb.w, ty0 + AA_TW - 1);
+        float m[9], cg[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) { m[c] = 0.f; cg[c] = 0.f; }
+        bool seen = false, have_p = false;
+        float4 pc[3];
+        auto pair_term = [&](int apx, int apy, int d, unsigned inf, float dd) {
+            if (dd == 0.f) return;
+            if (!have_p) {
+                const int4 ti = tri_indices(rp, t);
+                pc[0] = ldg4(P + 4 * (size_t)ti.x); pc[1] = ldg4(P + 4 * (size_t)ti.y); pc[2] = ldg4(P + 4 * (size_t)ti.z);
+                have_p = true;
+            }
+            const int di = inf & 3, c1 = (di + 1) % 3, c2 = (di + 2) % 3;
+            float gp1[3], gp2[3];
+            // (dynamic corner indices would put pc / cg in local memory: select with compares instead)
+            const float4 q1 = c1 == 0 ? pc[0] : (c1 == 1 ? pc[1] : pc[2]);
+            const float4 q2 = c2 == 0 ? pc[0] : (c2 == 1 ? pc[1] : pc[2]);
+            aa_pair_corner_grads(ap.xh, ap.yh, q1, q2, apx, apy, d, dd, gp1, gp2);
+#pragma unroll
+            for (int cnr = 0; cnr < 3; cnr++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (cnr == c1) cg[3 * cnr + c] += gp1[c];
+                    if (cnr == c2) cg[3 * cnr + c] += gp2[c];
+                }
+        };
+        for (int y = ya; y <= yb; y++) {
+            const bool own_y = y >= oy && y < oy + BIN;
+            const float fly = (float)(y - any);
+            for (int x = xa; x <= xb; x++) {
+                const int idx = (y - ty0) * AA_TW + (x - tx0);
+                if (idw[2 * idx] != t + 1) continue;
+                seen = true;
+                const bool own_x = x >= ox && x < ox + BIN;
+                if (own_x && own_y) {
+                    const int ii = (y - oy) * BIN + (x - ox);
+                    const float a = s_coef[ii * 3 * C + 0], b = s_coef[ii * 3 * C + 1], c = s_coef[ii * 3 * C + 2];
+                    const float flx = (float)(x - anx);
+                    m[0] += a; m[1] += b; m[2] += c;
+                    m[3] += a * flx; m[4] += b * flx; m[5] += c * flx;
+                    m[6] += a * fly; m[7] += b * fly; m[8] += c * fly;
+                    // this pixel's own pairs whose crossing edge belongs to its triangle (front1 == 0)
+                    const unsigned inf = s_info[idx];
+                    if ((inf & 8u) && !((inf >> 2) & 1u)) pair_term(x, y, 0, inf, s_ar[idx]);
+                    if ((inf & 0x80u) && !((inf >> 6) & 1u)) pair_term(x, y, 1, inf >> 4, s_au[idx]);
+                }
+                // pairs owned by the left / lower neighbour (a pixel of this bin) whose crossing edge belongs to THIS pixel's triangle
+                if (own_y && x - 1 >= ox && x - 1 < ox + BIN) {
+                    const unsigned inf = s_info[idx - 1];
+                    if ((inf & 8u) && ((inf >> 2) & 1u)) pair_term(x, y, 0, inf, s_ar[idx - 1]);
+                }
+                if (own_x && y - 1 >= oy && y - 1 < oy + BIN) {
+                    const unsigned inf = s_info[idx - AA_TW];
+                    if ((inf & 0x80u) && ((inf >> 6) & 1u)) pair_term(x, y, 1, inf >> 4, s_au[idx - AA_TW]);
+                }
+            }
+        }
+        float out[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) out[c] = 0.f;
+        if (seen) {
+            if (!have_p) {
+                const int4 ti = tri_indices(rp, t);
+                pc[0] = ldg4(P + 4 * (size_t)ti.x); pc[1] = ldg4(P + 4 * (size_t)ti.y); pc[2] = ldg4(P + 4 * (size_t)ti.z);
+            }
+            triangle_corner_grads(m, pixel_ndc(anx, rp.xs, rp.xo), pixel_ndc(any, rp.ys, rp.yo), rp.xs, rp.ys, pc[0], pc[1], pc[2], out);
+#pragma unroll
+            for (int c = 0; c < 9; c++) out[c] += cg[c];
+        }
+        float* o = slot_ptr(fp.slots, gid, slot_index_k(info_t, bx, by));
+#pragma unroll
+        for (int c = 0; c < 9; c++) o[c] = out[c];
     }
 }
 

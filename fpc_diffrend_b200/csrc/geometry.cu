@@ -10,7 +10,10 @@
 // A warp owns one vertex at a time: its three rows of D are 3B contiguous floats (HBM/L2-bound float4 stream,
 // the only large operand), reduced with warp shuffles; lanes 0..C-1 then act as the cameras of that vertex.
 // Everything is deterministic: per-warp partials are combined in a fixed order (no float atomics).
+#include <stdlib.h>
+
 #include "pose.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -29,84 +32,6 @@ __device__ __forceinline__ void load_rows(const float* __restrict__ D, int v, in
     for (int k = 0; k < K; k++) {
         int i = lane + 32 * k;
         d[k] = (i < n4) ? __ldg(row4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
-template <int K>   // K = ceil(3B/4 / 32): float4 of D per lane and vertex
-__global__ void __launch_bounds__(GEO_THREADS) k_geom_fwd(const float* __restrict__ P, const float* __restrict__ A,
-                                                          const float* __restrict__ t, const float* __restrict__ q,
-                                                          const float* __restrict__ t_cam, const float* __restrict__ q_cam,
-                                                          const float* __restrict__ D, const float* __restrict__ base,
-                                                          const float* __restrict__ w, int V, int B, int F, int C,
-                                                          float* __restrict__ mvp_out, float* __restrict__ verts,
-                                                          float* __restrict__ pos_clip)
-{
-    extern __shared__ float sm[];
-    float* s_mvp = sm;                 // [C][16]
-    float* s_w = sm + C * 16;          // [B]
-    const int f = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * GEO_WARPS + (threadIdx.x >> 5), nw = gridDim.x * GEO_WARPS;
-    const int n4 = (3 * B) >> 2;       // B % 4 == 0 (checked by the host function)
-    // the first vertex's rows are requested before the (serial, latency-bound) pose chain below
-    float4 cur[K];
-    if (gw < V) load_rows<K>(D, gw, B, n4, lane, cur);
-    for (int c = threadIdx.x; c < C; c += GEO_THREADS) {
-        M4 m = frame_camera_mvp(P, A, t, q, t_cam, q_cam, f, c);
-#pragma unroll
-        for (int i = 0; i < 16; i++) s_mvp[16 * c + i] = m.m[i >> 2][i & 3];
-        if (blockIdx.x == 0) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) mvp_out[((size_t)f * C + c) * 16 + i] = m.m[i >> 2][i & 3];
-        }
-    }
-    for (int i = threadIdx.x; i < B; i += GEO_THREADS) s_w[i] = w[(size_t)f * B + i];
-    __syncthreads();
-
-    // a lane always meets the same columns of D: its activations live in registers for the whole vertex loop
-    float4 wr[K];
-    int rsel[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        int e = 4 * (lane + 32 * k);
-        rsel[k] = (e >= B) + (e >= 2 * B);
-        wr[k] = (e < 3 * B) ? *reinterpret_cast<const float4*>(s_w + (e - rsel[k] * B)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-    for (int v = gw; v < V; v += nw) {
-        float4 nxt[K];
-        if (v + nw < V) load_rows<K>(D, v + nw, B, n4, lane, nxt);     // in flight while this vertex is reduced
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            // rows beyond 3B were loaded as zeros (and carry zero activations)
-            float s = cur[k].x * wr[k].x + cur[k].y * wr[k].y + cur[k].z * wr[k].z + cur[k].w * wr[k].w;
-            a0 += (rsel[k] == 0) ? s : 0.f;
-            a1 += (rsel[k] == 1) ? s : 0.f;
-            a2 += (rsel[k] == 2) ? s : 0.f;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        }
-        const float x = __ldg(base + 3 * (size_t)v) + a0, y = __ldg(base + 3 * (size_t)v + 1) + a1, z = __ldg(base + 3 * (size_t)v + 2) + a2;
-        if (lane == 0) {
-            float* o = verts + ((size_t)f * V + v) * 3;
-            o[0] = x; o[1] = y; o[2] = z;
-        }
-        for (int c = lane; c < C; c += 32) {
-            const float* m = s_mvp + 16 * c;
-            float4 o;      // same op order as k_project_fwd (project.cu)
-            o.x = m[0] * x + m[1] * y + m[2] * z + m[3];
-            o.y = m[4] * x + m[5] * y + m[6] * z + m[7];
-            o.z = m[8] * x + m[9] * y + m[10] * z + m[11];
-            o.w = m[12] * x + m[13] * y + m[14] * z + m[15];
-            reinterpret_cast<float4*>(pos_clip)[((size_t)f * C + c) * V + v] = o;
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++) cur[k] = nxt[k];
     }
 }
 
@@ -230,6 +155,136 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restric
         float s = 0.f;
         for (int wv = 0; wv < GEO_WARPS; wv++) s += s_m[(size_t)wv * C * 16 + i];
         part_mvp[((size_t)blockIdx.x * F + f) * C * 16 + i] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA variants (the ones the host functions launch): the rows of D are streamed by the copy engine
+// (cp.async.bulk, tma.cuh) into a ring of shared-memory stages — one stage = the 3B-float rows of GT_VB = 8 consecutive
+// vertices, one vertex per consumer warp — so the bytes in flight per SM are set by the ring depth (>= 2 CTAs x
+// stages x 8 x 12 B bytes) and not by how many registers a warp can spare for prefetching.  Warp 8 is the producer.
+// The arithmetic of a vertex (order of every sum) is unchanged from the register-prefetch kernels above.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GT_VB = 8;                            // vertices per stage = consumer warps
+constexpr int GT_THREADS = (GT_VB + 1) * 32;
+
+__device__ __forceinline__ size_t gt_ring_floats(int B, int stages) { return (size_t)stages * GT_VB * 3 * B; }
+
+template <int K>
+__device__ __forceinline__ void lds_rows(const float* __restrict__ rows, int n4, int lane, float4 (&d)[K])
+{
+    const float4* r4 = reinterpret_cast<const float4*>(rows);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        int i = lane + 32 * k;
+        d[k] = (i < n4) ? r4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(GT_THREADS) k_geom_fwd_tma(const float* __restrict__ P, const float* __restrict__ A,
+                                                             const float* __restrict__ t, const float* __restrict__ q,
+                                                             const float* __restrict__ t_cam, const float* __restrict__ q_cam,
+                                                             const float* __restrict__ D, const float* __restrict__ base,
+                                                             const float* __restrict__ w, int V, int B, int F, int C, int stages,
+                                                             float* __restrict__ mvp_out, float* __restrict__ verts,
+                                                             float* __restrict__ pos_clip)
+{
+    extern __shared__ __align__(128) float sm[];
+    const int rowf = 3 * B;
+    float* ring = sm;                                   // [stages][GT_VB][3B]
+    float* s_mvp = ring + gt_ring_floats(B, stages);    // [C][16]
+    float* s_w = s_mvp + C * 16;                        // [B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + B);      // full [stages] | empty [stages]   (8-byte aligned: B % 4 == 0)
+    const uint32_t full0 = fpc::smem_u32(bars), empty0 = full0 + 8 * stages;
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunk = (V + GT_VB - 1) / GT_VB;
+    const int n4 = rowf >> 2;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) { fpc::mbar_init(full0 + 8 * s, 1); fpc::mbar_init(empty0 + 8 * s, GT_VB); }
+        fpc::mbar_init_fence();
+    }
+    __syncthreads();
+    if (warp == GT_VB) {
+        // ---- producer: D is a constant of the fit, nothing to wait for: the stream starts before the pose chain below ----
+        if (lane == 0) {
+            int it = 0;
+            for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+                const int s = it % stages;
+                if (it >= stages) fpc::mbar_wait(empty0 + 8 * s, ((it / stages) & 1) ^ 1);
+                const int nv = min(GT_VB, V - c * GT_VB);
+                const uint32_t bytes = (uint32_t)nv * rowf * 4u;
+                fpc::mbar_expect_tx(full0 + 8 * s, bytes);
+                fpc::bulk_load(fpc::smem_u32(ring + (size_t)s * GT_VB * rowf), D + (size_t)c * GT_VB * rowf, bytes, full0 + 8 * s);
+            }
+        }
+        return;
+    }
+    // ---- consumers (256 threads; they synchronise among themselves on named barrier 1) ----
+    for (int c = threadIdx.x; c < C; c += GT_VB * 32) {
+        M4 m = frame_camera_mvp(P, A, t, q, t_cam, q_cam, f, c);
+#pragma unroll
+        for (int i = 0; i < 16; i++) s_mvp[16 * c + i] = m.m[i >> 2][i & 3];
+        if (blockIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) mvp_out[((size_t)f * C + c) * 16 + i] = m.m[i >> 2][i & 3];
+        }
+    }
+    for (int i = threadIdx.x; i < B; i += GT_VB * 32) s_w[i] = w[(size_t)f * B + i];
+    asm volatile("bar.sync 1, %0;" ::"n"(GT_VB * 32) : "memory");
+
+    // a lane always meets the same columns of D: its activations live in registers for the whole vertex loop
+    float4 wr[K];
+    int rsel[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        int e = 4 * (lane + 32 * k);
+        rsel[k] = (e >= B) + (e >= 2 * B);
+        wr[k] = (e < 3 * B) ? *reinterpret_cast<const float4*>(s_w + (e - rsel[k] * B)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int it = 0;
+    for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+        const int s = it % stages;
+        const int v = c * GT_VB + warp;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        if (v < V) { bx = __ldg(base + 3 * (size_t)v); by = __ldg(base + 3 * (size_t)v + 1); bz = __ldg(base + 3 * (size_t)v + 2); }
+        fpc::mbar_wait(full0 + 8 * s, (it / stages) & 1);
+        if (v < V) {
+            float4 cur[K];
+            lds_rows<K>(ring + ((size_t)s * GT_VB + warp) * rowf, n4, lane, cur);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                // rows beyond 3B were loaded as zeros (and carry zero activations)
+                float sdot = cur[k].x * wr[k].x + cur[k].y * wr[k].y + cur[k].z * wr[k].z + cur[k].w * wr[k].w;
+                a0 += (rsel[k] == 0) ? sdot : 0.f;
+                a1 += (rsel[k] == 1) ? sdot : 0.f;
+                a2 += (rsel[k] == 2) ? sdot : 0.f;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            const float x = bx + a0, y = by + a1, z = bz + a2;
+            if (lane == 0) {
+                float* o = verts + ((size_t)f * V + v) * 3;
+                o[0] = x; o[1] = y; o[2] = z;
+            }
+            for (int cc = lane; cc < C; cc += 32) {
+                const float* m = s_mvp + 16 * cc;
+                float4 o;      // same op order as k_project_fwd (project.cu)
+                o.x = m[0] * x + m[1] * y + m[2] * z + m[3];
+                o.y = m[4] * x + m[5] * y + m[6] * z + m[7];
+                o.z = m[8] * x + m[9] * y + m[10] * z + m[11];
+                o.w = m[12] * x + m[13] * y + m[14] * z + m[15];
+                reinterpret_cast<float4*>(pos_clip)[((size_t)f * C + cc) * V + v] = o;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) fpc::mbar_arrive(empty0 + 8 * s);     // this warp's rows of the stage are consumed
     }
 }
 
@@ -366,6 +421,48 @@ int geom_blocks(int V)
     return want < 296 ? want : 296;           // 2 CTAs per SM on 148 SMs; each warp strides over the vertices
 }
 
+// ring depth / shared memory / grid of the TMA kernels.  Two CTAs per SM while a stage is small enough for that to leave at
+// least 3 stages each; one CTA per SM with the whole shared memory otherwise (B > ~380).
+struct GtPlan { int stages, blocks; size_t smem; };
+
+GtPlan gt_plan(int V, int B, int F, int C, bool bwd)
+{
+    const size_t stage = (size_t)GT_VB * 3 * B * sizeof(float);
+    const size_t fixed = (bwd ? (size_t)(C * 16 + GT_VB * C * 16) : (size_t)(C * 16 + B)) * sizeof(float) + 8 * 2 * 16 + 4 * 16 + 128;
+    GtPlan p;
+    int per_sm = 2;
+    long long room = 110 * 1024 - (long long)fixed;
+    p.stages = (int)(room / (long long)stage);
+    if (p.stages < 3) {
+        per_sm = 1;
+        room = 224 * 1024 - (long long)fixed;
+        p.stages = (int)(room / (long long)stage);
+    }
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) p.stages = 2;          // B <= 1024 (fused_supported) keeps 2 stages within 227 KB
+    p.smem = (size_t)p.stages * stage + fixed;
+    const int nchunk = fpc_div_up(V, GT_VB);
+    int want = (148 * per_sm) / (F < 1 ? 1 : F);
+    if (want < 37) want = 37;
+    p.blocks = nchunk < want ? nchunk : want;
+    return p;
+}
+
+template <int K>
+int launch_fwd_tma(const GtPlan& pl, cudaStream_t stream, const float* P, const float* A, const float* t, const float* q, const float* t_cam,
+                   const float* q_cam, const float* D, const float* base, const float* w, int V, int B, int F, int C, float* mvp, float* verts,
+                   float* pos_clip)
+{
+    static FpcPerDeviceOnce attr_set;
+    if (attr_set.need()) {
+        FPC_CUDA(cudaFuncSetAttribute(k_geom_fwd_tma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set.done();
+    }
+    k_geom_fwd_tma<K><<<dim3(pl.blocks, F), GT_THREADS, pl.smem, stream>>>(P, A, t, q, t_cam, q_cam, D, base, w, V, B, F, C, pl.stages, mvp, verts, pos_clip);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
 template <int K>
 int launch_bwd(dim3 grid, size_t smem, cudaStream_t stream, const float* D, const float* verts, const float* mvp, const float* g_pos,
                const float* d_verts_add, int V, int B, int F, int C, float* d_verts, float* part_w, float* part_mvp)
@@ -396,17 +493,16 @@ extern "C" int fpc_geometry_fwd(const float* P, const float* A, const float* t, 
     FPC_CHECK_ARG((t_cam == nullptr) == (q_cam == nullptr), "geometry_fwd: t_cam and q_cam must both be given or both be NULL");
     FPC_CHECK_ARG(fpc_geometry_fused_supported(V, B, F, C),
                   "geometry_fwd: needs B %% 4 == 0, B <= 1024, F <= 65535, C <= 32 (got V=%d B=%d F=%d C=%d); use blend_fwd + project_fwd", V, B, F, C);
-    size_t smem = (size_t)(C * 16 + B) * sizeof(float);
-    dim3 grid(geom_blocks(V), F);
+    const GtPlan pl = gt_plan(V, B, F, C, false);
     const int K = fpc_div_up((3 * B) >> 2, 32);
-#define FPC_FWD_CASE(k) case k: k_geom_fwd<k><<<grid, GEO_THREADS, smem, stream>>>(P, A, t, q, t_cam, q_cam, D, base, w, V, B, F, C, mvp, verts, pos_clip); break
-    switch (K <= 8 ? K : (K <= 12 ? 12 : (K <= 16 ? 16 : 24))) {
+    int st = FPC_OK;
+#define FPC_FWD_CASE(k) case k: st = launch_fwd_tma<k>(pl, stream, P, A, t, q, t_cam, q_cam, D, base, w, V, B, F, C, mvp, verts, pos_clip); break
+    switch (K <= 8 ? K : (K <= 10 ? 10 : (K <= 12 ? 12 : (K <= 16 ? 16 : 24)))) {
         FPC_FWD_CASE(1); FPC_FWD_CASE(2); FPC_FWD_CASE(3); FPC_FWD_CASE(4); FPC_FWD_CASE(5); FPC_FWD_CASE(6);
-        FPC_FWD_CASE(7); FPC_FWD_CASE(8); FPC_FWD_CASE(12); FPC_FWD_CASE(16); FPC_FWD_CASE(24);
+        FPC_FWD_CASE(7); FPC_FWD_CASE(8); FPC_FWD_CASE(10); FPC_FWD_CASE(12); FPC_FWD_CASE(16); FPC_FWD_CASE(24);
     }
 #undef FPC_FWD_CASE
-    FPC_LAUNCH_CHECK();
-    return FPC_OK;
+    return st;
 }
 
 extern "C" size_t fpc_geometry_bwd_scratch_bytes(int V, int B, int F, int C)
@@ -430,14 +526,13 @@ extern "C" int fpc_geometry_bwd(const float* P, const float* A, const float* t, 
     const int nblk = geom_blocks(V);
     float* part_w = (float*)scratch;
     float* part_mvp = (float*)((char*)scratch + align256((size_t)nblk * F * B * sizeof(float)));
-    size_t smem = (size_t)(C * 16 + GEO_WARPS * 3 * B + GEO_WARPS * C * 16) * sizeof(float);
-    dim3 grid(nblk, F);
     const int K = fpc_div_up((3 * B) >> 2, 32);
     int st;
-#define FPC_BWD_CASE(k) case k: st = launch_bwd<k>(grid, smem, stream, D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp); break
-    switch (K <= 8 ? K : (K <= 12 ? 12 : (K <= 16 ? 16 : 24))) {
+    const size_t lsmem = (size_t)(C * 16 + GEO_WARPS * 3 * B + GEO_WARPS * C * 16) * sizeof(float);
+#define FPC_BWD_CASE(k) case k: st = launch_bwd<k>(dim3(nblk, F), lsmem, stream, D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp); break
+    switch (K <= 8 ? K : (K <= 10 ? 10 : (K <= 12 ? 12 : (K <= 16 ? 16 : 24)))) {
         FPC_BWD_CASE(1); FPC_BWD_CASE(2); FPC_BWD_CASE(3); FPC_BWD_CASE(4); FPC_BWD_CASE(5); FPC_BWD_CASE(6);
-        FPC_BWD_CASE(7); FPC_BWD_CASE(8); FPC_BWD_CASE(12); FPC_BWD_CASE(16); FPC_BWD_CASE(24);
+        FPC_BWD_CASE(7); FPC_BWD_CASE(8); FPC_BWD_CASE(10); FPC_BWD_CASE(12); FPC_BWD_CASE(16); FPC_BWD_CASE(24);
         default: st = FPC_ERR_UNSUPPORTED; fpc_set_error("geometry_bwd: unsupported B=%d", B);
     }
 #undef FPC_BWD_CASE

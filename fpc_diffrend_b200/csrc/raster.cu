@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
         float4 p0, p1, p2;
         SnappedTri s;
         int info = 0;
+        bool large = false;
         if (load_triangle<false>(rp, n, t, p0, p1, p2)) {
             if (p0.w > 0.f && p1.w > 0.f && p2.w > 0.f) {
                 if (setup_triangle(p0, p1, p2, rp, s)) {
@@ -60,7 +61,9 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
                         int slot = atomicAdd(rp.large_count + n, 1);
                         rp.large_list[(size_t)n * 2 * rp.T + slot] = t;
                         info = 2 << 22;
+                        large = true;
                     } else {
+                        rp.tri_bbox[gid] = make_ushort4((unsigned short)s.pxa, (unsigned short)s.pya, (unsigned short)s.pxb, (unsigned short)s.pyb);
                         info = bx0 | (by0 << 10) | ((bx1 - bx0) << 20) | ((by1 - by0) << 21) | (1 << 22);
                         // depth window of the triangle (32-bit key mode of the fine rasterizer): the per-vertex z/w of depth_plane()
                         const unsigned k0 = depth_key(xdiv(p0.z, p0.w)), k1 = depth_key(xdiv(p1.z, p1.w)), k2 = depth_key(xdiv(p2.z, p2.w));
@@ -87,25 +90,19 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
                     rp.clip_parent[slot] = t;
                     rp.large_list[(size_t)n * 2 * rp.T + atomicAdd(rp.large_count + n, 1)] = rp.T + slot;
                     if (!anchored) { rp.tri_anchor[gid] = moment_origin(s, rp); anchored = true; }
+                    info = 2 << 22;
+                    large = true;
                 }
             }
         }
         rp.tri_info[gid] = info;
-    }
-    // buffers the consumer of the bins accumulates into (fused.cu): cleared here instead of by separate memsets.
-    // The CTA's chunk of the moment buffer is 9 * BIN_TPB contiguous floats (36-byte records: 16-byte aligned as a whole).
-    if (rp.clear_tri9) {
-        const int t0 = blockIdx.x * BIN_TPB;
-        const int nt = min(BIN_TPB, rp.T - t0);
-        float* m = rp.clear_tri9 + ((size_t)n * rp.T + t0) * 9;
-        const int nfl = nt * 9;
-        const int head = (int)(((16 - (reinterpret_cast<size_t>(m) & 15)) & 15) >> 2);      // floats up to 16-byte alignment
-        const int h = head < nfl ? head : nfl;
-        const int n4 = (nfl - h) >> 2;
-        if (threadIdx.x < h) m[threadIdx.x] = 0.f;
-        float4* m4 = reinterpret_cast<float4*>(m + h);
-        for (int i = threadIdx.x; i < n4; i += BIN_TPB) m4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = h + 4 * n4 + threadIdx.x; i < nfl; i += BIN_TPB) m[i] = 0.f;
+        // large (and near-clipped) triangles are resolved by whole CTAs in every bin they touch: their gradient is accumulated
+        // (float REDs) in slots 1 (moments) and 2 (antialias corner terms), which start from zero
+        if (large && rp.slot_grad) {
+            float* z = rp.slot_grad + (gid * SLOTS_PER_TRI + 1) * SLOT_FLOATS;
+#pragma unroll
+            for (int i = 0; i < 2 * SLOT_FLOATS; i++) z[i] = 0.f;
+        }
     }
     if (n == 0) {
         // 16-byte copies of the index / attribute arrays the per-pixel phases gather from (one load instead of three)
@@ -113,9 +110,6 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
         for (int i = t; i < rp.pad_i_n; i += gridDim.x * BIN_TPB)
             rp.pad_i_dst[i] = make_int4(__ldg(rp.pad_i_src + 3 * i), __ldg(rp.pad_i_src + 3 * i + 1), __ldg(rp.pad_i_src + 3 * i + 2), 0);
     }
-    if (rp.clear_vtx4)
-        for (int v = t; v < rp.V; v += gridDim.x * BIN_TPB)
-            reinterpret_cast<float4*>(rp.clear_vtx4)[(size_t)n * rp.V + v] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (HIST) {
         __syncthreads();
         for (int b = threadIdx.x; b < rp.NB; b += BIN_TPB) {
@@ -344,13 +338,14 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_anchor = o;      o += align_up((size_t)N * T * 4);
     L.off_tri4 = o;        o += align_up((size_t)T * 16);
     L.off_zrange = o;      o += align_up((size_t)N * T * 8);
+    L.off_bbox = o;        o += align_up((size_t)N * T * 8);
     L.total = o;
     return L;
 }
 
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                          void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
-                         float* clear_tri9, float* clear_vtx4, int halo, const int32_t* pad_i_src, int4* pad_i_dst, int pad_i_n)
+                         float* slot_grad, int halo, const int32_t* pad_i_src, int4* pad_i_dst, int pad_i_n)
 {
     FPC_CHECK_ARG(pos && tri, "%s: pos and tri must be non-null", who);
     FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "%s: N, V, T, H, W must be positive (got %d %d %d %d %d)", who, N, V, T, H, W);
@@ -374,6 +369,7 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.tri_anchor = (int*)(s + L.off_anchor);
     rp.tri4 = (int4*)(s + L.off_tri4);
     rp.tri_zrange = (uint2*)(s + L.off_zrange);
+    rp.tri_bbox = (ushort4*)(s + L.off_bbox);
     rp.idbits = 1;
     while ((1 << rp.idbits) < T) rp.idbits++;
     rp.clip_count = (int*)(s + L.off_clip_count);
@@ -382,7 +378,7 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.clip_cap = L.clip_cap;
     rp.pad_i_src = pad_i_src; rp.pad_i_dst = pad_i_dst; rp.pad_i_n = pad_i_src ? pad_i_n : 0;
     FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
-    rp.clear_tri9 = clear_tri9; rp.clear_vtx4 = clear_vtx4;
+    rp.slot_grad = slot_grad;
     dim3 grid(fpc_div_up(T, BIN_TPB), N);
     if (rp.NB <= HIST_MAX_BINS) {
         size_t hb = (size_t)rp.NB * sizeof(int);

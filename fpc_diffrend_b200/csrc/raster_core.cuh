@@ -71,8 +71,9 @@ struct RasterParams {
     int* tri_anchor;                 // [N*T]  px | py << 16: pixel of the triangle's centroid, clamped to the image (moment origin)
     int4* tri4;                      // [T] (i0, i1, i2, 0): 16-byte copy of tri written by k_setup, one load per triangle
     const int32_t* pad_i_src; int4* pad_i_dst; int pad_i_n;          // nullable job for k_setup: int [n,3] -> int4 [n]
-    float* clear_tri9;               // nullable: [N*T*9] zeroed by k_setup (moment accumulators of fused.cu)
-    float* clear_vtx4;               // nullable: [N*V*4] zeroed by k_setup (position-gradient accumulator)
+    ushort4* tri_bbox;               // [N*T] (pxa, pya, pxb, pyb): candidate pixel range of a SMALL triangle, clamped to the image
+    float* slot_grad;                // nullable: [N*T*4*9] per-(view, triangle, bin k) gradient slots of fused.cu; k_setup zeroes
+                                     // the accumulator slots (1 and 2) of LARGE triangles, every other slot is written exactly once
     uint2* tri_zrange;               // [N*T] (min, max) of depth_key(z/w) over the vertices of a SMALL triangle (k_setup)
     int idbits;                      // bits of a triangle id: ceil(log2(T))
 };
@@ -208,9 +209,12 @@ __device__ __forceinline__ float plane_eval(float zref, float dzdx, float dzdy, 
 
 __device__ __forceinline__ unsigned depth_key(float zw)
 {
-    unsigned b = __float_as_uint(zw);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    // order-preserving map float -> unsigned: negative values are complemented, non-negative ones get the top bit
+    const unsigned b = __float_as_uint(zw);
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
 }
+constexpr unsigned DEPTH_KEY_MINUS1 = 0x407FFFFFu;     // depth_key(-1.0f)
+constexpr unsigned DEPTH_KEY_PLUS1 = 0xBF800000u;      // depth_key(+1.0f)
 
 // depth test + visibility update of one fragment at key slot kp; the CAS loop starts from the value the early-out read
 __device__ __forceinline__ void emit_fragment_at(unsigned long long* kp, float zd, int t)
@@ -231,12 +235,13 @@ __device__ __forceinline__ void emit_fragment_at(unsigned long long* kp, float z
 
 // 32-bit mode (FPC_KEY32): key = (depth_key - base) << idbits | id, one native shared-memory atomicMin per fragment.  A depth
 // outside the window the bin promised (never observed; the window carries a margin) raises `overflow` and the CTA redoes the
-// bin with 64-bit keys, so the result is the 64-bit result in every case.
+// bin with 64-bit keys, so the result is the 64-bit result in every case.  The window [base, base + limit) always lies inside
+// [depth_key(-1), depth_key(+1)] (raster_tile clamps it), so the one unsigned compare below is also the depth-range test: a
+// fragment outside [-1, 1] (or a NaN) lands outside the window and sends the bin to the 64-bit path, which discards it.
 struct Key32Mode { unsigned base, limit; int idbits; int* overflow; };
 
 __device__ __forceinline__ void emit_fragment32(unsigned* kp, float zd, int t, const Key32Mode& km)
 {
-    if (!(zd >= -1.f && zd <= 1.f)) return;
     const unsigned d = depth_key(zd) - km.base;
 #if FPC_KEY32_TEST_OVERFLOW
     if ((t % 5) == 0) { *km.overflow = 1; return; }           // test build only: exercises the 64-bit redo of the bin
@@ -427,8 +432,13 @@ __device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int b
         zlo = s_zlo; zhi = s_zhi;
         const unsigned span = (1u << (32 - rp.idbits)) - 1u;          // the all-ones key stays free for "empty"
         if (span > 2u * KEY32_MARGIN && zlo >= KEY32_MARGIN && zhi >= zlo && (zhi - zlo) < span - 2u * KEY32_MARGIN) {
-            mode32 = true;
-            km.base = zlo - KEY32_MARGIN; km.limit = span;
+            // clamp the window to the valid depth range [-1, 1] (see emit_fragment32)
+            const unsigned lo = max(zlo - KEY32_MARGIN, DEPTH_KEY_MINUS1);
+            const unsigned long long hi = min((unsigned long long)(zlo - KEY32_MARGIN) + span, (unsigned long long)DEPTH_KEY_PLUS1 + 1ull);
+            if (hi > lo) {
+                mode32 = true;
+                km.base = lo; km.limit = (unsigned)(hi - lo);
+            }
         }
     }
     if (mode32) {
@@ -513,16 +523,21 @@ __device__ __forceinline__ unsigned long long tile_key(const unsigned long long*
 // Host side: scratch layout + the three binning launches.
 struct ScratchLayout {
     size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_zrange, off_clip_count, off_clip_verts, off_clip_parent, total;
+    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_zrange, off_bbox, off_clip_count, off_clip_verts, off_clip_parent, total;
     int clip_cap;
 };
 
 ScratchLayout raster_layout(int N, int T, int NB);
 // Validates, fills rp and enqueues memset + k_setup + k_scan + k_fill.  Returns an fpc_status.
-// clear_tri9 [N*T*9] / clear_vtx4 [N*V*4] (nullable) are zero-filled by k_setup on the way.
+// slot_grad [N*T*4*9] (nullable): gradient slots of the fused kernels (see RasterParams).
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                          void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
-                         float* clear_tri9 = nullptr, float* clear_vtx4 = nullptr, int halo = 0,
+                         float* slot_grad = nullptr, int halo = 0,
                          const int32_t* pad_i_src = nullptr, int4* pad_i_dst = nullptr, int pad_i_n = 0);
+
+// slot of (view n, triangle t) in bin (bx, by): k = which of the (at most 2 x 2) bins the small triangle was listed in
+__device__ __forceinline__ int slot_index_k(int info, int bx, int by) { return ((by - ((info >> 10) & 1023)) << 1) | (bx - (info & 1023)); }
+constexpr int SLOT_FLOATS = 9;       // (x, y, w) gradient of the three corners
+constexpr int SLOTS_PER_TRI = 4;
 
 }  // namespace fpc

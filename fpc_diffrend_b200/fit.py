@@ -261,6 +261,8 @@ class FitSession:
             sc = torch.empty(int(_lib.load().fpc_topology_scratch_bytes(T)), dtype=torch.uint8, device=dev)
             _lib.call('fpc_topology_build', _p(self.pos_idx), T, V, _p(self.tri_opp), _p(sc), sc.numel(), self._stream())
         self.ref = None
+        # vertex -> (triangle, corner) adjacency: the fused kernels gather the position gradient per vertex (no atomics)
+        self.vadj_off, self.vadj_item = _lib.vertex_adjacency(self.pos_idx, V) if self.use_fused else (None, None)
         self.use_reg = self.reg_owner and any(x != 0.0 for x in (cfg.weight_laplacian, cfg.weight_meshedge, cfg.weight_normalconsistency))
         if self.use_reg:
             from .topology import build_topology
@@ -531,7 +533,7 @@ class FitSession:
             dummy = torch.zeros(N, H, W, Ch, dtype=torch.uint8, device=self.device)
             _lib.call(name, *head, _p(self.attr), _p(self.attr_idx), self.attr.shape[1],
                       self.attr.shape[2], _p(tex), Ht, Wt, _p(dummy), 1, N, V, T, H, W, Ch, cfg.bg, 1.0, 0, _p(self.loss), None, None, None,
-                      _p(img), _p(self.scratch), self.scratch.numel(), s)
+                      _p(img), None, None, _p(self.scratch), self.scratch.numel(), s)
             return img
         assert self.ref is not None, 'call set_reference() first'
         if cfg.cam_band is not None:
@@ -541,14 +543,14 @@ class FitSession:
                         self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
                         N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, self.loss_kind, self.C, int(cfg.cam_band[0]), int(cfg.cam_band[1]),
                         _p(self.loss), _p(self.g_pos), _p(self.d_tex) if cfg.optimize_texture else None, None, None,
-                        _p(self.scratch), self.scratch.numel(), s)
+                        _p(self.vadj_off), _p(self.vadj_item), _p(self.scratch), self.scratch.numel(), s)
             return 4 + (1 if cfg.optimize_texture else 0)
         self._timed('render_loss_fused', name, *head, _p(self.attr), _p(self.attr_idx),
                     self.attr.shape[1], self.attr.shape[2], _p(tex), Ht, Wt, _p(self.ref), 1 if self.ref.dtype == torch.uint8 else 0,
                     N, V, T, H, W, Ch, cfg.bg, 1.0 / self.C_total, self.loss_kind, _p(self.loss), _p(self.g_pos),
                     _p(self.d_tex) if cfg.optimize_texture else None, None, None,
-                    _p(self.scratch), self.scratch.numel(), s)
-        return 4 + (1 if cfg.optimize_texture else 0)      # k_setup, k_fill, k_fused[_aa], k_tri_grad (+ loss reduction) [+ memset]
+                    _p(self.vadj_off), _p(self.vadj_item), _p(self.scratch), self.scratch.numel(), s)
+        return 4 + (1 if cfg.optimize_texture else 0)      # k_setup, k_fill, k_fused[_aa], k_vtx_gather (+ loss reduction) [+ memset]
 
     def backward(self):
         cfg, s, call = self.cfg, self._stream(), self._timed

@@ -49,7 +49,8 @@ typedef enum fpc_status {
 
 typedef void* fpc_stream_t; /* cudaStream_t */
 
-#define FPC_B200_ABI_VERSION 2   /* 2: loss_kind / grad_tex arguments of the loss and fused entries, band-split entry */
+#define FPC_B200_ABI_VERSION 3   /* 2: loss_kind / grad_tex arguments of the loss and fused entries, band-split entry;
+                                    3: vadj_off / vadj_item arguments of the fused entries (atomics-free gradient gather) */
 
 /* ---- library ------------------------------------------------------------------------------------- */
 int fpc_abi_version(void);
@@ -242,7 +243,12 @@ int fpc_image_loss_fwd_bwd(const float* colour, const float* rast, const float* 
  * attr [Va,A] + attr_tri [T,3]: vertex colours (tex == NULL, A == C) or uv (tex [Ht,Wt,C] given, A == 2);
  * ref [N,H,W,C] float32 (ref_is_u8 == 0) or uint8 (ref_is_u8 == 1) grey levels on the 0..255 scale; C in {1,3}.
  *   loss [1]            = scale * sum_n mean_{h,w,c} (ref - 255 comp)^2  (loss_kind 0) or |ref - 255 comp| (loss_kind 1), overwritten
- *   grad_pos [N,V,4]    = d loss / d pos (x, y, w; z = 0), overwritten; NULL = forward only
+ *   grad_pos [N,V,4]    = d loss / d pos (x, y, w; z = 0), overwritten; NULL = forward only.  Needs vadj_off [V+1] /
+ *                         vadj_item [3T], the vertex -> (triangle, corner) adjacency of the mesh (fpc_vertex_adjacency_build,
+ *                         once per mesh): the position gradient is assembled WITHOUT atomics — every triangle's contribution is
+ *                         written once into a per-(view, triangle, bin) slot and a per-vertex pass gathers the slots around the
+ *                         vertex in a fixed order — so it is bit-reproducible from run to run (exception: triangles larger than
+ *                         128 px or 2 x 2 bins, or clipped by the near plane, accumulate with float REDs)
  *   grad_tex [Ht,Wt,C]  = d loss / d tex (texture optimisation, tex_opt of fit.py:439,502), overwritten; NULL to skip
  *                         (needs tex and grad_pos; 4C float REDs per covered pixel)
  *   rast_out [N,H,W,4], colour_out [N,H,W,C] (composited image): optional outputs, NULL to skip the HBM writes. */
@@ -251,17 +257,29 @@ int fpc_render_loss_fused(const float* pos, const int32_t* tri, const float* att
                           const float* tex, int Ht, int Wt, const void* ref, int ref_is_u8,
                           int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                           float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                          const int32_t* vadj_off, const int32_t* vadj_item,
                           void* scratch, size_t scratch_bytes, fpc_stream_t stream);
+
+/* Vertex -> (triangle, corner) adjacency of a mesh in CSR form, for the gradient gather of the fused kernels: vadj_off [V+1],
+ * vadj_item [3T] with item = triangle * 4 + corner, every vertex's items in ascending order (canonical: the gather order, and
+ * with it the rounding of grad_pos, does not depend on how the list was built).  Once per mesh (role of the per-call hash
+ * upstream's antialias builds; there is no reference counterpart for the rasterizer gradient, which upstream scatters with
+ * atomics). */
+size_t fpc_vertex_adjacency_scratch_bytes(int V);
+int fpc_vertex_adjacency_build(const int32_t* tri, int T, int V, int32_t* vadj_off, int32_t* vadj_item,
+                               void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
 /* The same with dr.antialias (fit.py:160) between shading and the background composite: replaces the chain
  * fit.py:151-161,579 and its part of loss.backward() (fit.py:611).  tri_opp [T,3] from fpc_topology_build.
- * One kernel per (32x32-px bin, view) resolves the bin plus a 2-px halo in shared memory; the antialias forward and the
- * colour gradient are atomics-free gathers, results equal fpc_antialias_fwd/bwd applied to the op-level chain.
+ * One kernel per (32x32-px bin, view) resolves the bin plus a 2-px halo in shared memory; the antialias forward, the colour
+ * gradient AND the silhouette position gradient are atomics-free gathers (the latter joins the per-(view, triangle, bin)
+ * gradient slots, see grad_pos above); results equal fpc_antialias_fwd/bwd applied to the op-level chain.
  * Same scratch size as fpc_render_loss_fused; colour_out is the antialiased, composited image. */
 int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                              const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
                              const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                              float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                             const int32_t* vadj_off, const int32_t* vadj_item,
                              void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
 /* Camera split at bin-row granularity (multi-GPU; fpc_diffrend_b200/shard.py: view_band_shard): the same
@@ -277,6 +295,7 @@ int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, const int32
                                const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,
                                int views_per_frame, int row_lo, int row_hi,
                                float* loss, float* grad_pos, float* grad_tex, float* rast_out, float* colour_out,
+                               const int32_t* vadj_off, const int32_t* vadj_item,
                                void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
 /* ---- mesh regularisers (replaces the pytorch3d terms of fit.py:578-582: weight_laplacian * laplacian(mesh)^2 +

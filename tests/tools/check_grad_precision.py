@@ -42,9 +42,10 @@ g_pos = torch.empty(N, rig.V, 4, device='cuda')
 scratch = torch.empty(int(_lib.load().fpc_render_loss_fused_scratch_bytes(N, T, H, W)), dtype=torch.uint8, device='cuda')
 d_uv, d_uvi, d_tri, d_ref = cu(rig.uv), cu(rig.uv_idx), cu(rig.pos_idx), cu(ref)
 head = (P(pos.detach()), P(d_tri)) + ((P(opp),) if aa else ())
+adj = _lib.vertex_adjacency(d_tri, rig.V)      # kept alive until the synchronize below
 _lib.call('fpc_render_loss_fused_aa' if aa else 'fpc_render_loss_fused', *head, P(d_uv), P(d_uvi), rig.uv.shape[0], 2, P(tex),
           rig.tex.shape[0], rig.tex.shape[1], P(d_ref), 1, N, rig.V, T, H, W, C, G.BG, 1.0, 0, P(loss), P(g_pos), None, None, None,
-          P(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+          P(adj[0]), P(adj[1]), P(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
 torch.cuda.synchronize()
 g_fused = g_pos.cpu().numpy()
 

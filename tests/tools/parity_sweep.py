@@ -72,9 +72,10 @@ def eval_case(c, case, verbose=False):
     d_ref = cu(ref.astype(np.uint8)) if u8 else cu(ref)
     d_tri = cu(rig.pos_idx)
     head = (P(pos.detach()), P(d_tri)) + ((P(opp),) if aa else ())
+    adj = _lib.vertex_adjacency(d_tri, rig.V)      # kept alive until the synchronize below
     _lib.call('fpc_render_loss_fused_aa' if aa else 'fpc_render_loss_fused', *head, P(attr), P(aidx), attr.shape[0], attr.shape[1], P(tex),
               tex.shape[0] if textured else 0, tex.shape[1] if textured else 0, P(d_ref), 1 if u8 else 0, N, rig.V, T, H, W, C, G.BG, 1.0, 0,
-              P(loss), P(g_pos), None, None, P(col_out), P(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+              P(loss), P(g_pos), None, None, P(col_out), P(adj[0]), P(adj[1]), P(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     g_ops = pos.grad
     # op-level chain against the ORACLE chain (golden ops with autograd), forward image and d loss / d pos

@@ -96,6 +96,7 @@ __device__ __forceinline__ void triangle_corner_grads(const float* m, float fx0,
 // narrowed from the 64-bit keys); the three planes g0 | g1 | g2 (d loss / d a_k per pixel) follow it, over the second half of
 // the key tile and the WarpStage records, both free by then.
 constexpr int PIX = BIN * BIN;
+constexpr int SVIS_N = 1024;          // bytes of the "id won a pixel" filter (indexed by id & 1023)
 static_assert(sizeof(unsigned long long) * PIX + sizeof(WarpStage) * FINE_WARPS >= 4 * sizeof(float) * PIX, "g planes must fit behind the ids");
 
 // 64-bit keys -> 32-bit ids in place (0xFFFFFFFF = empty); all NT threads of the CTA; ends with a barrier
@@ -148,22 +149,48 @@ __device__ __forceinline__ bool gather_moments(const int* __restrict__ ids, cons
     return seen;
 }
 
-__device__ __forceinline__ float* slot_ptr(float* slots, size_t gid, int k) { return slots + (gid * SLOTS_PER_TRI + k) * SLOT_FLOATS; }
-
-// a bin another rank renders (band split): its list entries still own slots the vertex gather reads -> zero them
-__device__ __forceinline__ void zero_bin_slots(const RasterParams& rp, float* slots, int n, int bin, int nthreads)
+// Visible list entries (window not empty, id seen by the filter) of the first `ntab` entries, bucketed by window area class
+// (floor(log2(area)), 8 classes, largest first) into vis_list; returns their number.  The order inside a class is arbitrary —
+// every entry is summed by ONE thread in a fixed pixel order, so the order in which entries are processed does not reach the
+// results.  All NT threads of the CTA; ends with a barrier.
+template <int NT>
+__device__ __forceinline__ int sort_visible_entries(const unsigned* __restrict__ ewin, const unsigned char* __restrict__ svis,
+                                                    const int* __restrict__ list, int ntab, unsigned short* __restrict__ vis_list)
 {
-    if (!slots) return;
-    const int count = rp.bin_count[(size_t)n * rp.NB + bin];
-    const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
-    const int bx = bin % rp.BW, by = bin / rp.BW;
-    for (int i = threadIdx.x; i < count; i += nthreads) {
-        const size_t gid = (size_t)n * rp.T + list[i];
-        float* o = slot_ptr(slots, gid, slot_index_k(rp.tri_info[gid], bx, by));
-#pragma unroll
-        for (int c = 0; c < SLOT_FLOATS; c++) o[c] = 0.f;
+    __shared__ int s_cls[8], s_cur[8];
+    if (threadIdx.x < 8) { s_cls[threadIdx.x] = 0; }
+    __syncthreads();
+    auto cls_of = [&](int i) -> int {
+        const unsigned win = ewin[i];
+        if ((win & EWIN_NONE) || !svis[list[i] & (SVIS_N - 1)]) return -1;
+        const int area = (int)(((win >> 6) & 63) - (win & 63) + 1) * (int)(((win >> 18) & 63) - ((win >> 12) & 63) + 1);
+        return 7 - min(31 - __clz(area), 7);                      // class 0 = the largest windows
+    };
+#ifndef FPC_EXP_NOSCAN
+    for (int i = threadIdx.x; i < ntab; i += NT) {
+        const int c = cls_of(i);
+        if (c >= 0) atomicAdd(&s_cls[c], 1);
     }
+#endif
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int c = 0; c < 8; c++) { s_cur[c] = acc; acc += s_cls[c]; }
+        s_cls[0] = acc;
+    }
+    __syncthreads();
+    const int nvis = s_cls[0];
+#ifndef FPC_EXP_NOSCAN
+    for (int i = threadIdx.x; i < ntab; i += NT) {
+        const int c = cls_of(i);
+        if (c >= 0) vis_list[atomicAdd(&s_cur[c], 1)] = (unsigned short)i;
+    }
+#endif
+    __syncthreads();
+    return nvis;
 }
+
+__device__ __forceinline__ float* slot_ptr(float* slots, size_t gid, int k) { return slots + (gid * SLOTS_PER_TRI + k) * SLOT_FLOATS; }
 
 // moments of a LARGE triangle's pixel: float REDs into the triangle's accumulator slot 1 (zeroed by k_setup)
 __device__ __forceinline__ void large_pixel_moments(float* slots, size_t gid, float g0, float g1, float g2, int px, int py, int an)
@@ -280,7 +307,6 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
 
     if (outside_band(fp, n, bin / rp.BW)) {            // another rank renders this bin row (shard.view_band_shard)
         if (threadIdx.x == 0) fp.loss_partial[(size_t)n * rp.NB + bin] = 0.0;
-        zero_bin_slots(rp, fp.slots, n, bin, FINE_THREADS);
         return;
     }
     if (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0) {      // ~2/3 of the bins of a head shot
@@ -318,7 +344,11 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-    const bool packed = raster_bin(rp, n, bin, keys, stage);
+    // gather-phase helpers filled on the way: per-entry pixel windows (raster set-up) and a 1024-way "this id won a pixel" filter
+    unsigned* ewin = reinterpret_cast<unsigned*>(sref + (size_t)PIX * C * esz);
+    unsigned char* svis = reinterpret_cast<unsigned char*>(ewin + EWIN_CAP);
+    for (int i = threadIdx.x; i < SVIS_N / 4; i += FINE_THREADS) reinterpret_cast<unsigned*>(svis)[i] = 0u;
+    const bool packed = raster_bin(rp, n, bin, keys, stage, fp.slots ? ewin : nullptr);
     if (!packed) narrow_keys<PIX, FINE_THREADS>(keys);           // rare: the bin's depth range did not fit the packed keys
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -457,6 +487,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
         if (fp.slots) {
             ids[idx] = t;
             sg0[idx] = g0; sg1[idx] = g1; sg2[idx] = g2;
+            if (fg) svis[t & (SVIS_N - 1)] = 1;
             if (any_large && fg && (g0 != 0.f || g1 != 0.f || g2 != 0.f)) {
                 const size_t gid = (size_t)n * rp.T + t;
                 if ((rp.tri_info[gid] >> 22) == 2) large_pixel_moments(fp.slots, gid, g0, g1, g2, px, py, rp.tri_anchor[gid]);
@@ -472,33 +503,88 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
         fp.loss_partial[(size_t)n * rp.NB + bin] = s;
     }
     if (!fp.slots) return;
+#ifdef FPC_EXP_NOGATHER
+    return;                       // experiment: cost of the gather phase (scripts/exp_variants.py); results are wrong
+#endif
 
-    // ---- (3) gather: one thread per entry of the bin's list sums the moments of the pixels its triangle won, in row-major
-    //          order, and stores the gradient of the triangle's three corners in the slot of (view, triangle, this bin) ----
+    // ---- (3) gather: the moments of every triangle that won pixels, summed over its pixels in a FIXED (row-major) order by
+    //          one thread, converted to the gradient of its three corners and stored in the slot of (view, triangle, this
+    //          bin).  Entries that won nothing write nothing (their slot stays invalid).  The visible entries are first
+    //          bucketed by window area (8 classes) so that the threads of a warp walk windows of similar size. ----
     const int count = rp.bin_count[(size_t)n * rp.NB + bin];
     const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
+    unsigned short* vis_list = reinterpret_cast<unsigned short*>(svis + SVIS_N);
+    const int nvis = sort_visible_entries<FINE_THREADS>(ewin, svis, list, min(count, EWIN_CAP), vis_list);
+    for (int e = threadIdx.x; e < nvis; e += FINE_THREADS) {
+        const int i = vis_list[e];
+        const int t = list[i];
+        const size_t gid = (size_t)n * rp.T + t;
+        const unsigned win = ewin[i];
+        const int wx0 = win & 63, wx1 = (win >> 6) & 63, wy0 = (win >> 12) & 63, wy1 = (win >> 18) & 63;     // tile-relative window
+        // requested now, used after the walk: the triangle's anchor and vertex indices
+        const int an = rp.tri_anchor[gid];
+        const int4 ti = tri_indices(rp, t);
+        float m[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) m[c] = 0.f;
+        bool seen = false;
+        for (int y = wy0; y <= wy1; y++) {
+            const int* idr = ids + y * BIN + wx0;
+            // which pixels of the row did the triangle win?  (branch-free pass, then only the hits are visited, left to right)
+            unsigned hit = 0u;
+            for (int x = 0; x <= wx1 - wx0; x++) hit |= (unsigned)(idr[x] == t) << x;
+            if (!hit) continue;
+            seen = true;
+            const int rowb = y * BIN + wx0;
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+            do {
+                const int x = __ffs(hit) - 1;
+                hit &= hit - 1u;
+                const float a = sg0[rowb + x], b = sg1[rowb + x], c = sg2[rowb + x];
+                const float flx = (float)x;
+                r0 += a; r1 += b; r2 += c;
+                m[3] += a * flx; m[4] += b * flx; m[5] += c * flx;
+            } while (hit);
+            const float fly = (float)(y - wy0);
+            m[0] += r0; m[1] += r1; m[2] += r2;
+            m[6] += r0 * fly; m[7] += r1 * fly; m[8] += r2 * fly;
+        }
+        if (seen) {
+            // moments about the window corner -> about the triangle's anchor pixel
+            const float dx = (float)(ox + wx0 - (an & 0xffff)), dy = (float)(oy + wy0 - (int)((unsigned)an >> 16));
+#pragma unroll
+            for (int c = 0; c < 3; c++) { m[3 + c] += dx * m[c]; m[6 + c] += dy * m[c]; }
+            const float4 p0 = ldg4(P + 4 * (size_t)ti.x), p1 = ldg4(P + 4 * (size_t)ti.y), p2 = ldg4(P + 4 * (size_t)ti.z);
+            const float fx0 = pixel_ndc(an & 0xffff, rp.xs, rp.xo), fy0 = pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo);
+            float out[9];
+            triangle_corner_grads(m, fx0, fy0, rp.xs, rp.ys, p0, p1, p2, out);
+            const int k = (win >> 24) & 3;
+            float* o = slot_ptr(fp.slots, gid, k);
+#pragma unroll
+            for (int c = 0; c < 9; c++) o[c] = out[c];
+            reinterpret_cast<unsigned char*>(rp.slot_valid + gid)[k] = 1;
+        }
+    }
+    // (more entries than the window table holds — > 1024 triangles in a 32 x 32-px bin: one thread per entry, from the binning records)
     const int bx = bin % rp.BW, by = bin / rp.BW;
-    for (int i = threadIdx.x; i < count; i += FINE_THREADS) {
+    for (int i = EWIN_CAP + threadIdx.x; i < count; i += FINE_THREADS) {
         const int t = list[i];
         const size_t gid = (size_t)n * rp.T + t;
         const ushort4 bb = rp.tri_bbox[gid];
         const int an = rp.tri_anchor[gid];
-        const int info = rp.tri_info[gid];
         float m[9];
-        const bool seen = gather_moments<BIN, BIN>(ids, sg0, sg1, sg2, t, max((int)bb.x, ox), min((int)bb.z, ox + BIN - 1), max((int)bb.y, oy),
-                                                   min((int)bb.w, oy + BIN - 1), ox, oy, ox, oy, an & 0xffff, (int)((unsigned)an >> 16), m);
-        float out[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) out[c] = 0.f;
-        if (seen) {
+        if (gather_moments<BIN, BIN>(ids, sg0, sg1, sg2, t, max((int)bb.x, ox), min((int)bb.z, ox + BIN - 1), max((int)bb.y, oy), min((int)bb.w, oy + BIN - 1),
+                                     ox, oy, ox, oy, an & 0xffff, (int)((unsigned)an >> 16), m)) {
             const int4 ti = tri_indices(rp, t);
             const float4 p0 = ldg4(P + 4 * (size_t)ti.x), p1 = ldg4(P + 4 * (size_t)ti.y), p2 = ldg4(P + 4 * (size_t)ti.z);
-            const float fx0 = pixel_ndc(an & 0xffff, rp.xs, rp.xo), fy0 = pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo);
-            triangle_corner_grads(m, fx0, fy0, rp.xs, rp.ys, p0, p1, p2, out);
-        }
-        float* o = slot_ptr(fp.slots, gid, slot_index_k(info, bx, by));
+            float out[9];
+            triangle_corner_grads(m, pixel_ndc(an & 0xffff, rp.xs, rp.xo), pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo), rp.xs, rp.ys, p0, p1, p2, out);
+            const int k = slot_index_k(rp.tri_info[gid], bx, by);
+            float* o = slot_ptr(fp.slots, gid, k);
 #pragma unroll
-        for (int c = 0; c < 9; c++) o[c] = out[c];
+            for (int c = 0; c < 9; c++) o[c] = out[c];
+            reinterpret_cast<unsigned char*>(rp.slot_valid + gid)[k] = 1;
+        }
     }
 }
 
@@ -535,36 +621,47 @@ __global__ void __launch_bounds__(256) k_vtx_gather(RasterParams rp, const float
     const int n = (int)(gv / rp.V), v = (int)(gv - (long long)n * rp.V);
     float gx = 0.f, gy = 0.f, gw = 0.f;
     const int j0 = __ldg(vadj_off + v), j1 = __ldg(vadj_off + v + 1);
-    for (int j = j0; j < j1; j++) {
-        const int item = __ldg(vadj_item + j);
-        const int t = item >> 2, corner = item & 3;
-        const size_t gid = (size_t)n * rp.T + t;
-        const int info = rp.tri_info[gid];
-        const int cls = info >> 22;
-        if (cls == 1) {
-            const float* S = slots + gid * (SLOTS_PER_TRI * SLOT_FLOATS) + 3 * corner;
-            const int nbx = (info >> 20) & 1, nby = (info >> 21) & 1;
+    // four adjacency items at a time: their (independent) index / class loads are in flight together; the sums below still run
+    // in list order
+    for (int jb = j0; jb < j1; jb += 4) {
+        int item[4], info[4];
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++)
-                if ((kk & 1) <= nbx && (kk >> 1) <= nby) { gx += S[kk * SLOT_FLOATS]; gy += S[kk * SLOT_FLOATS + 1]; gw += S[kk * SLOT_FLOATS + 2]; }
-        } else if (cls == 2) {
-            // large / near-clipped triangle: slot 1 holds its moments (float REDs), slot 2 the antialias corner terms
-            const float* M = slots + (gid * SLOTS_PER_TRI + 1) * SLOT_FLOATS;
-            float m[9];
-            bool any = false;
+        for (int u = 0; u < 4; u++) item[u] = (jb + u < j1) ? __ldg(vadj_item + jb + u) : -1;
 #pragma unroll
-            for (int c = 0; c < 9; c++) { m[c] = M[c]; any = any || (m[c] != 0.f); }
-            if (any) {
-                const int4 ti = tri_indices(rp, t);
-                const float* P = rp.pos + (size_t)n * rp.V * 4;
-                const float4 p0 = ldg4(P + 4 * (size_t)ti.x), p1 = ldg4(P + 4 * (size_t)ti.y), p2 = ldg4(P + 4 * (size_t)ti.z);
-                const int an = rp.tri_anchor[gid];
-                float out[9];
-                triangle_corner_grads(m, pixel_ndc(an & 0xffff, rp.xs, rp.xo), pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo), rp.xs, rp.ys, p0, p1, p2, out);
-                gx += out[3 * corner]; gy += out[3 * corner + 1]; gw += out[3 * corner + 2];
+        for (int u = 0; u < 4; u++) info[u] = (item[u] >= 0) ? __ldg(rp.tri_info + (size_t)n * rp.T + (item[u] >> 2)) : 0;
+        unsigned valid[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) valid[u] = ((info[u] >> 22) == 1) ? __ldg(rp.slot_valid + (size_t)n * rp.T + (item[u] >> 2)) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int t = item[u] >> 2, corner = item[u] & 3;
+            const size_t gid = (size_t)n * rp.T + t;
+            const int cls = info[u] >> 22;
+            if (cls == 1) {
+                const unsigned vm = valid[u];
+                const float* S = slots + gid * (SLOTS_PER_TRI * SLOT_FLOATS) + 3 * corner;
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)
+                    if ((vm >> (8 * kk)) & 0xffu) { gx += S[kk * SLOT_FLOATS]; gy += S[kk * SLOT_FLOATS + 1]; gw += S[kk * SLOT_FLOATS + 2]; }
+            } else if (cls == 2) {
+                // large / near-clipped triangle: slot 1 holds its moments (float REDs), slot 2 the antialias corner terms
+                const float* M = slots + (gid * SLOTS_PER_TRI + 1) * SLOT_FLOATS;
+                float m[9];
+                bool any = false;
+#pragma unroll
+                for (int c = 0; c < 9; c++) { m[c] = M[c]; any = any || (m[c] != 0.f); }
+                if (any) {
+                    const int4 ti = tri_indices(rp, t);
+                    const float* P = rp.pos + (size_t)n * rp.V * 4;
+                    const float4 p0 = ldg4(P + 4 * (size_t)ti.x), p1 = ldg4(P + 4 * (size_t)ti.y), p2 = ldg4(P + 4 * (size_t)ti.z);
+                    const int an = rp.tri_anchor[gid];
+                    float out[9];
+                    triangle_corner_grads(m, pixel_ndc(an & 0xffff, rp.xs, rp.xo), pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo), rp.xs, rp.ys, p0, p1, p2, out);
+                    gx += out[3 * corner]; gy += out[3 * corner + 1]; gw += out[3 * corner + 2];
+                }
+                const float* Aa = M + SLOT_FLOATS + 3 * corner;
+                gx += Aa[0]; gy += Aa[1]; gw += Aa[2];
             }
-            const float* Aa = M + SLOT_FLOATS + 3 * corner;
-            gx += Aa[0]; gy += Aa[1]; gw += Aa[2];
         }
     }
     reinterpret_cast<float4*>(grad_pos)[gv] = make_float4(gx, gy, 0.f, gw);
@@ -645,7 +742,12 @@ __global__ void __launch_bounds__(256) k_fused_loss_reduce(const double* __restr
 }
 
 // keys + per-warp triangle staging + the reference-frame tile (u8 or f32, C channels)
-__host__ size_t fused_smem(int C, int ref_u8) { return sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS + (size_t)BIN * BIN * C * (ref_u8 ? 1 : 4); }
+// + the gather phase's window table, visibility filter and list of visible entries
+__host__ size_t fused_smem(int C, int ref_u8)
+{
+    return sizeof(unsigned long long) * BIN * BIN + sizeof(WarpStage) * FINE_WARPS + (size_t)BIN * BIN * C * (ref_u8 ? 1 : 4) + sizeof(unsigned) * EWIN_CAP + SVIS_N +
+           sizeof(unsigned short) * EWIN_CAP;
+}
 
 template <int C, bool TEX>
 int launch_fused(const RasterParams& rp, const FusedParams& fp, cudaStream_t stream)

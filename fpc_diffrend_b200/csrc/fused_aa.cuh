@@ -41,7 +41,7 @@ constexpr int AA_REF_MARGIN = 4;               // reference tile starts 4 px lef
 constexpr int AA_REF_W = BIN + 2 * AA_REF_MARGIN;
 
 struct AASmem {
-    size_t keys, region0, col, alpha_r, alpha_u, info, coef, ref, texc, total;
+    size_t keys, region0, col, alpha_r, alpha_u, info, coef, ref, ewin, svis, vis, texc, total;
 };
 
 __host__ __device__ inline size_t aa_align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -65,6 +65,9 @@ __host__ __device__ inline AASmem aa_smem_layout(int C, int esz, bool texgrad = 
     L.info = o; o += aa_align16(AA_NT);
     L.coef = o; o += aa_align16(sizeof(float) * BIN * BIN * 3 * C);
     L.ref = o; o += aa_align16((size_t)AA_R1 * AA_REF_W * C * esz);
+    L.ewin = o; o += sizeof(unsigned) * EWIN_CAP;
+    L.svis = o; o += SVIS_N;
+    L.vis = o; o += sizeof(unsigned short) * EWIN_CAP;
     L.texc = o; if (texgrad) o += sizeof(float2) * BIN * BIN;
     L.total = o;
     return L;
@@ -130,6 +133,8 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     float* s_coef = reinterpret_cast<float*>(smem + L.coef);
     unsigned char* s_ref = smem + L.ref;
     float2* s_texc = reinterpret_cast<float2*>(smem + L.texc);
+    unsigned* ewin = reinterpret_cast<unsigned*>(smem + L.ewin);          // gather phase: per-entry pixel windows (raster set-up)
+    unsigned char* svis = smem + L.svis;                                  // gather phase: "this id won a pixel" filter
     __shared__ double red[AA_WARPS];
     __shared__ int s_nlist;
 
@@ -141,7 +146,6 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
 
     if (outside_band(fp, n, bin / rp.BW)) {            // another rank renders this bin row (shard.view_band_shard)
         if (threadIdx.x == 0) fp.loss_partial[(size_t)n * rp.NB + bin] = 0.0;
-        zero_bin_slots(rp, fp.slots, n, bin, AA_THREADS);
         return;
     }
     // bins are widened by the halo when triangles are binned: an empty list means an all-background tile
@@ -181,7 +185,8 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     }
 
     // ---- (1) visibility of the widened tile ----
-    raster_tile<AA_TW, AA_THREADS>(rp, n, bin, tx0, ty0, keys, stage);
+    for (int i = threadIdx.x; i < SVIS_N / 4; i += AA_THREADS) reinterpret_cast<unsigned*>(svis)[i] = 0u;
+    raster_tile<AA_TW, AA_THREADS>(rp, n, bin, tx0, ty0, keys, stage, true, fp.slots ? ewin : nullptr);
 
     // colour a background pixel hands to the antialias op: texture at uv = (0,0) or 0 (interpolate)
     float bgcol[C];
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
             float zw = fminf(fmaxf(sh.zw, -1.f), 1.f);
             rout = make_float4(u, v, zw, (float)(t + 1));
             slot = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned)(t + 1);
+            svis[t & (SVIS_N - 1)] = 1;
             int j0 = i0, j1 = i1, j2 = i2;
             if (fp.attr_tri4) { const int4 tj = __ldg(fp.attr_tri4 + t); j0 = tj.x; j1 = tj.y; j2 = tj.z; }
             bool ok = (unsigned)j0 < (unsigned)fp.Va && (unsigned)j1 < (unsigned)fp.Va && (unsigned)j2 < (unsigned)fp.Va;
@@ -480,15 +486,28 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
     const int bx = bin % rp.BW, by = bin / rp.BW;
     const int* idw = reinterpret_cast<const int*>(keys);            // low word of the 64-bit slot = id + 1
-    for (int i = threadIdx.x; i < count; i += AA_THREADS) {
+    unsigned short* vis_list = reinterpret_cast<unsigned short*>(smem + L.vis);
+    const int ntab = min(count, EWIN_CAP);
+    const int nvis = sort_visible_entries<AA_THREADS>(ewin, svis, list, ntab, vis_list);
+    // visible entries of the window table (bucketed by window area), then whatever the table could not hold
+    for (int e = threadIdx.x; e < nvis + max(count - EWIN_CAP, 0); e += AA_THREADS) {
+        const int i = e < nvis ? (int)vis_list[e] : EWIN_CAP + (e - nvis);
         const int t = list[i];
         const size_t gid = (size_t)n * rp.T + t;
-        const ushort4 bb = rp.tri_bbox[gid];
+        int xa, xb, ya, yb, kslot;
+        if (i < EWIN_CAP) {
+            const unsigned win = ewin[i];
+            kslot = (win >> 24) & 3;
+            xa = tx0 + (win & 63); xb = tx0 + ((win >> 6) & 63); ya = ty0 + ((win >> 12) & 63); yb = ty0 + ((win >> 18) & 63);
+        } else {                      // more entries than the window table holds: the same from the binning records
+            const ushort4 bb = rp.tri_bbox[gid];
+            kslot = slot_index_k(rp.tri_info[gid], bx, by);
+            xa = max((int)bb.x, max(tx0, 0)); xb = min((int)bb.z, tx0 + AA_TW - 1);
+            ya = max((int)bb.y, max(ty0, 0)); yb = min((int)bb.w, ty0 + AA_TW - 1);
+            if (xa > xb || ya > yb) continue;
+        }
         const int an = rp.tri_anchor[gid];
-        const int info_t = rp.tri_info[gid];
         const int anx = an & 0xffff, any = (int)((unsigned)an >> 16);
-        const int xa = max((int)bb.x, max(tx0, 0)), xb = min((int)bb.z, tx0 + AA_TW - 1);
-        const int ya = max((int)bb.y, max(ty0, 0)), yb = min((int)bb.w, ty0 + AA_TW - 1);
         float m[9], cg[9];
 #pragma unroll
         for (int c = 0; c < 9; c++) { m[c] = 0.f; cg[c] = 0.f; }
@@ -516,12 +535,18 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 }
         };
         for (int y = ya; y <= yb; y++) {
+            // which pixels of the row did the triangle win?  (branch-free pass, then only the hits are visited, left to right)
+            const int rowi = (y - ty0) * AA_TW - tx0;
+            unsigned long long hit = 0ull;
+            for (int x = xa; x <= xb; x++) hit |= (unsigned long long)(idw[2 * (rowi + x)] == t + 1) << (x - xa);
+            if (!hit) continue;
+            seen = true;
             const bool own_y = y >= oy && y < oy + BIN;
             const float fly = (float)(y - any);
-            for (int x = xa; x <= xb; x++) {
-                const int idx = (y - ty0) * AA_TW + (x - tx0);
-                if (idw[2 * idx] != t + 1) continue;
-                seen = true;
+            while (hit) {
+                const int x = xa + __ffsll((long long)hit) - 1;
+                hit &= hit - 1ull;
+                const int idx = rowi + x;
                 const bool own_x = x >= ox && x < ox + BIN;
                 if (own_x && own_y) {
                     const int ii = (y - oy) * BIN + (x - ox);
@@ -546,10 +571,9 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 }
             }
         }
+        if (!seen) continue;
         float out[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) out[c] = 0.f;
-        if (seen) {
+        {
             if (!have_p) {
                 const int4 ti = tri_indices(rp, t);
                 pc[0] = ldg4(P + 4 * (size_t)ti.x); pc[1] = ldg4(P + 4 * (size_t)ti.y); pc[2] = ldg4(P + 4 * (size_t)ti.z);
@@ -558,9 +582,10 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
 #pragma unroll
             for (int c = 0; c < 9; c++) out[c] += cg[c];
         }
-        float* o = slot_ptr(fp.slots, gid, slot_index_k(info_t, bx, by));
+        float* o = slot_ptr(fp.slots, gid, kslot);
 #pragma unroll
         for (int c = 0; c < 9; c++) o[c] = out[c];
+        reinterpret_cast<unsigned char*>(rp.slot_valid + gid)[kslot] = 1;
     }
 }
 

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
             }
         }
         rp.tri_info[gid] = info;
+        if (rp.slot_grad) rp.slot_valid[gid] = 0u;          // no gradient slot of this (view, triangle) written yet
         // large (and near-clipped) triangles are resolved by whole CTAs in every bin they touch: their gradient is accumulated
         // (float REDs) in slots 1 (moments) and 2 (antialias corner terms), which start from zero
         if (large && rp.slot_grad) {
@@ -339,6 +340,7 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_tri4 = o;        o += align_up((size_t)T * 16);
     L.off_zrange = o;      o += align_up((size_t)N * T * 8);
     L.off_bbox = o;        o += align_up((size_t)N * T * 8);
+    L.off_valid = o;       o += align_up((size_t)N * T * 4);
     L.total = o;
     return L;
 }
@@ -370,6 +372,7 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.tri4 = (int4*)(s + L.off_tri4);
     rp.tri_zrange = (uint2*)(s + L.off_zrange);
     rp.tri_bbox = (ushort4*)(s + L.off_bbox);
+    rp.slot_valid = (unsigned*)(s + L.off_valid);
     rp.idbits = 1;
     while ((1 << rp.idbits) < T) rp.idbits++;
     rp.clip_count = (int*)(s + L.off_clip_count);

@@ -73,7 +73,8 @@ struct RasterParams {
     const int32_t* pad_i_src; int4* pad_i_dst; int pad_i_n;          // nullable job for k_setup: int [n,3] -> int4 [n]
     ushort4* tri_bbox;               // [N*T] (pxa, pya, pxb, pyb): candidate pixel range of a SMALL triangle, clamped to the image
     float* slot_grad;                // nullable: [N*T*4*9] per-(view, triangle, bin k) gradient slots of fused.cu; k_setup zeroes
-                                     // the accumulator slots (1 and 2) of LARGE triangles, every other slot is written exactly once
+                                     // the accumulator slots (1 and 2) of LARGE triangles, every other slot is written at most once
+    unsigned* slot_valid;            // [N*T] (with slot_grad): byte k != 0 <=> slot k of the triangle was written; zeroed by k_setup
     uint2* tri_zrange;               // [N*T] (min, max) of depth_key(z/w) over the vertices of a SMALL triangle (k_setup)
     int idbits;                      // bits of a triangle id: ceil(log2(T))
 };
@@ -282,10 +283,17 @@ __device__ __forceinline__ void emit_any(unsigned* kp, float zd, int t, const Ke
 // The small triangles of a bin: warps claim batches of 32, every lane sets one triangle up and stages it, the warp then walks
 // the batch's (triangle, row) items.  KeyT = unsigned long long (depth_key << 32 | id, CAS-loop atomicMin) or unsigned
 // (Key32Mode, native atomicMin).
+// `ewin` (nullable, shared memory, EWIN_CAP words): the gather phase of the fused kernels wants, for list entry i, the pixel
+// window of the triangle inside this tile and the index k of this bin among the triangle's (at most 2 x 2) bins — both fall
+// out of the set-up below:  ewin[i] = (xa-ox) | (xb-ox) << 6 | (ya-oy) << 12 | (yb-oy) << 18 | k << 24, or k << 24 | EWIN_NONE
+// when the triangle has no candidate pixel in the tile.
+constexpr int EWIN_CAP = 1024;
+constexpr unsigned EWIN_NONE = 1u << 26;
+
 template <int TW, int NT, typename KeyT>
 __device__ __forceinline__ void walk_small(const RasterParams& rp, int n, const int* __restrict__ list, int count, int ox, int oy,
                                            int min_x, int min_y, int lim_x, int lim_y, KeyT* keys, WarpStage& st, int* next_batch,
-                                           const Key32Mode& km)
+                                           const Key32Mode& km, unsigned* ewin, int bin_x, int bin_y)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     (void)warp;
@@ -308,6 +316,13 @@ __device__ __forceinline__ void walk_small(const RasterParams& rp, int n, const 
             SnappedTri s;
             if (load_triangle(rp, n, t, p0, p1, p2) && setup_triangle(p0, p1, p2, rp, s)) {
                 int xa = max(s.pxa, min_x), xb = min(s.pxb, lim_x), ya = max(s.pya, min_y), yb = min(s.pyb, lim_y);
+                if (ewin && i < EWIN_CAP) {
+                    const BinRange br = bin_range(s, rp);
+                    const unsigned k = (unsigned)(((bin_y - br.by0) << 1) | (bin_x - br.bx0)) & 3u;
+                    ewin[i] = (xa <= xb && ya <= yb) ? ((unsigned)(xa - ox) | ((unsigned)(xb - ox) << 6) | ((unsigned)(ya - oy) << 12) |
+                                                        ((unsigned)(yb - oy) << 18) | (k << 24))
+                                                     : ((k << 24) | EWIN_NONE);
+                }
                 if (xa <= xb && ya <= yb) {
                     rows = yb - ya + 1;
                     // oriented vertex order (positive area): swap 1 <-> 2 when flipped
@@ -397,8 +412,9 @@ __device__ __forceinline__ void walk_small(const RasterParams& rp, int n, const 
 // Returns true when the keys were left in the packed 32-bit layout (only if `widen` is false): read them with tile_key().
 template <int TW, int NT = FINE_THREADS>
 __device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int bin, int ox, int oy, unsigned long long* keys, WarpStage* stage,
-                                            bool widen = true)
+                                            bool widen = true, unsigned* ewin = nullptr)
 {
+    const int bin_x = bin % rp.BW, bin_y = bin / rp.BW;
     const int min_x = max(ox, 0), min_y = max(oy, 0);
     const int lim_x = min(ox + TW, rp.W) - 1, lim_y = min(oy + TW, rp.H) - 1;
     const int count = rp.bin_count[(size_t)n * rp.NB + bin];
@@ -445,7 +461,7 @@ __device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int b
         unsigned* keys32 = reinterpret_cast<unsigned*>(keys);
         for (int i = threadIdx.x; i < TW * TW; i += NT) keys32[i] = 0xFFFFFFFFu;
         __syncthreads();
-        walk_small<TW, NT, unsigned>(rp, n, list, count, ox, oy, min_x, min_y, lim_x, lim_y, keys32, st, &next_batch, km);
+        walk_small<TW, NT, unsigned>(rp, n, list, count, ox, oy, min_x, min_y, lim_x, lim_y, keys32, st, &next_batch, km, ewin, bin_x, bin_y);
         __syncthreads();
         if (!s_overflow && !widen) return true;               // the caller decodes the packed keys itself (tile_key)
         if (!s_overflow) {
@@ -472,7 +488,7 @@ __device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int b
 #endif
     for (int i = threadIdx.x; i < TW * TW; i += NT) keys[i] = KEY_EMPTY;
     __syncthreads();
-    walk_small<TW, NT, unsigned long long>(rp, n, list, count, ox, oy, min_x, min_y, lim_x, lim_y, keys, st, &next_batch, km);
+    walk_small<TW, NT, unsigned long long>(rp, n, list, count, ox, oy, min_x, min_y, lim_x, lim_y, keys, st, &next_batch, km, ewin, bin_x, bin_y);
 
     // ---- large triangles: the whole CTA cooperates on each one (16 pixels per thread), int64 edge math ----
     const int* llist = rp.large_list + (size_t)n * 2 * rp.T;
@@ -507,9 +523,9 @@ __device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int b
 }
 
 // the plain bin (no halo); keys may come back packed: read them with tile_key(keys, idx, packed, rp.idbits)
-__device__ __forceinline__ bool raster_bin(const RasterParams& rp, int n, int bin, unsigned long long* keys, WarpStage* stage)
+__device__ __forceinline__ bool raster_bin(const RasterParams& rp, int n, int bin, unsigned long long* keys, WarpStage* stage, unsigned* ewin = nullptr)
 {
-    return raster_tile<BIN>(rp, n, bin, (bin % rp.BW) * BIN, (bin / rp.BW) * BIN, keys, stage, false);
+    return raster_tile<BIN>(rp, n, bin, (bin % rp.BW) * BIN, (bin / rp.BW) * BIN, keys, stage, false, ewin);
 }
 
 // key of tile pixel idx in the 64-bit convention the shading phases use (KEY_EMPTY, or the triangle id in the low 32 bits)
@@ -523,7 +539,7 @@ __device__ __forceinline__ unsigned long long tile_key(const unsigned long long*
 // Host side: scratch layout + the three binning launches.
 struct ScratchLayout {
     size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_zrange, off_bbox, off_clip_count, off_clip_verts, off_clip_parent, total;
+    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_zrange, off_bbox, off_valid, off_clip_count, off_clip_verts, off_clip_parent, total;
     int clip_cap;
 };
 

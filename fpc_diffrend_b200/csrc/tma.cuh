@@ -43,10 +43,4 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialisation attribute may start while its
-// predecessor drains; it must not touch the predecessor's results before pdl_wait(), and lets its own successor start early
-// with pdl_launch_dependents().  Both are no-ops for a kernel launched the ordinary way.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 }  // namespace fpc

@@ -64,6 +64,10 @@ class FitConfig:
     cam_slice: tuple = None               # (start, stop) camera subset rendered by this rank (camera-split mode)
     cam_band: tuple = None                # (row_lo, row_hi): of view `start` only the 32-px bin rows >= row_lo, of view `stop - 1`
                                           # only those < row_hi are rendered here (shard.view_band_shard); needs cam_slice, fused
+    shard_blend: bool = None              # camera-split mode: the ROWS of D (vertices) are sharded over the ranks — every rank blends
+                                          # V / world vertices (D is not replicated: 240 MB at config 5), the vertices are all-gathered
+                                          # and the vertex gradients reduce-scattered over NVLink.  None = on when it applies
+                                          # (cam_slice set, torch.distributed world > 1, V % world == 0, mode 'prior')
     fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
     # mesh regularisers of the shipped loss (fit.py:578-582; main.py:37-40 ships 5000 / 0 / 0.05 / 0, and fit.py:580 passes
@@ -107,8 +111,21 @@ class FitSession:
         self.N = F * C
 
         # constants
+        # row sharding of the blend under the camera split (shard.py): this rank owns vertices [v0, v1)
+        self.row_shard = None
+        if cfg.cam_slice is not None and cfg.shard_blend is not False and cfg.mode == 'prior':
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and V % dist.get_world_size() == 0:
+                r, wsz = dist.get_rank(), dist.get_world_size()
+                self.row_shard = (r * (V // wsz), (r + 1) * (V // wsz), wsz)
+        if cfg.shard_blend and self.row_shard is None:
+            raise ValueError('shard_blend needs the camera split (cam_slice), an initialised process group with V %% world == 0 and mode "prior"')
         self.v_base = torch.tensor(rig.v_base, **f32)
-        self.D = torch.tensor(rig.D, **f32).contiguous()
+        if self.row_shard is not None:
+            v0, v1, _ = self.row_shard
+            self.D = torch.tensor(rig.D[3 * v0:3 * v1], **f32).contiguous()          # only this rank's rows live on the device
+        else:
+            self.D = torch.tensor(rig.D, **f32).contiguous()
         self.pos_idx = torch.tensor(rig.pos_idx, dtype=torch.int32, device=dev).contiguous()
         self.P = torch.tensor(rig.P[c0:c1], **f32).reshape(C, 16).contiguous()
         self.A = torch.tensor(rig.A[c0:c1], **f32).reshape(C, 16).contiguous()
@@ -278,11 +295,17 @@ class FitSession:
         fg = cfg.fused_geometry
         if fg is None:
             fg = F <= 4
-        self.use_geom_fused = bool(fg and not self.use_basis and L.fpc_geometry_fused_supported(V, B, F, C))
+        self.use_geom_fused = bool(fg and not self.use_basis and self.row_shard is None and L.fpc_geometry_fused_supported(V, B, F, C))
         tc = cfg.tc_blend
         if tc is None:
             tc = F >= 8
-        self.use_tc_blend = bool(tc and not self.use_geom_fused and L.fpc_blend_tc_supported(V * 3, B, F))
+        self.use_tc_blend = bool(tc and not self.use_geom_fused and self.row_shard is None and L.fpc_blend_tc_supported(V * 3, B, F))
+        if self.row_shard is not None:
+            Vl = self.row_shard[1] - self.row_shard[0]
+            self.verts_local = torch.empty(F, Vl * 3, **f32)
+            self.verts_gathered = torch.empty(self.row_shard[2], F, Vl * 3, **f32)
+            self.d_verts_local = torch.empty(F, Vl * 3, **f32)
+            self.d_verts_scatter = torch.empty(self.row_shard[2], F, Vl * 3, **f32) if F > 1 else None
         # the tensor-core backward wants both operands K-major: a transposed copy of D, made once
         self.DT = self.D.t().contiguous() if self.use_tc_blend else None
         nbytes = max(L.fpc_blend_bwd_tc_scratch_bytes(V * 3, B, F) if self.use_tc_blend else 0,
@@ -481,6 +504,19 @@ class FitSession:
         cfg, s, call = self.cfg, self._stream(), self._timed
         F, V, B = self.F, self.V, self.B
         n = 0
+        if self.row_shard is not None:
+            # this rank's rows of D, then every rank's vertices over NVLink (one all-gather per iteration)
+            import torch.distributed as dist
+            v0, v1, wsz = self.row_shard
+            Vl = v1 - v0
+            call('blend_fwd', 'fpc_blend_fwd', _p(self.D), ctypes.c_void_p(self.v_base.data_ptr() + 12 * v0), _p(self.w), Vl * 3, B, F,
+                 _p(self.verts_local), s); n += 1
+            if F == 1:
+                dist.all_gather_into_tensor(self.verts.view(-1), self.verts_local.view(-1))
+            else:
+                dist.all_gather_into_tensor(self.verts_gathered.view(-1), self.verts_local.view(-1))
+                self.verts.view(F, wsz, Vl * 3).copy_(self.verts_gathered.permute(1, 0, 2))
+            return n + 1
         if cfg.mode != 'free':
             name = 'fpc_blend_fwd_tc' if self.use_tc_blend else 'fpc_blend_fwd'
             call('blend_fwd', name, _p(self.D), _p(self.v_base), _p(self.w), V * 3, B, F, _p(self.verts), s); n += 1
@@ -605,7 +641,19 @@ class FitSession:
              _p(self.scratch), self.scratch.numel(), s); n += 2
         if self.use_reg:
             n += self._mesh_reg(self.d_verts, 1)
-        if self.cfg.mode == 'free':
+        if self.row_shard is not None:
+            # sum of the ranks' vertex gradients, scattered by rows (one reduce-scatter per iteration); D^T on this rank's rows
+            # gives a partial d_w that the all-reduce of the packed gradient (optimizer_step) completes
+            import torch.distributed as dist
+            v0, v1, wsz = self.row_shard
+            Vl = v1 - v0
+            if F == 1:
+                dist.reduce_scatter_tensor(self.d_verts_local.view(-1), self.d_verts.view(-1))
+            else:
+                self.d_verts_scatter.copy_(self.d_verts.view(F, wsz, Vl * 3).permute(1, 0, 2))
+                dist.reduce_scatter_tensor(self.d_verts_local.view(-1), self.d_verts_scatter.view(-1))
+            call('blend_bwd', 'fpc_blend_bwd', _p(self.D), _p(self.d_verts_local), Vl * 3, B, F, _p(self.d_w), _p(self.scratch), self.scratch.numel(), s); n += 3
+        elif self.cfg.mode == 'free':
             pass                                        # no rig prior: d_w stays 0
         elif self.use_tc_blend and not self.use_reg:
             # (with mesh regularisers d_verts carries a large, strongly cancelling Laplacian component: the contraction is
@@ -773,7 +821,7 @@ class FitSession:
 
     def result_vertices(self):
         """[F, 3V] blended vertices of the current parameters (fit.py:642 `result`)."""
-        if self.use_basis or self.use_tc_blend:
+        if self.use_basis or self.use_tc_blend or self.row_shard is not None:
             self._blend_forward()
         else:
             _lib.call('fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), self.V * 3, self.B, self.F, _p(self.verts), self._stream())

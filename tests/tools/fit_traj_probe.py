@@ -39,6 +39,22 @@ def oracle_grad(w, t, q):
     return float(loss.detach()), w.grad, t.grad, q.grad
 
 
+def staged(sess):
+    """Oracle render + loss + d pos_clip fed the GPU's OWN pos_clip bits (no geometry rounding in between), and the oracle's
+    sensitivity to a 1-ulp perturbation of those positions."""
+    pc = sess.pos_clip.cpu().clone()
+    out = []
+    for pos in (pc, torch.nextafter(pc, torch.full_like(pc, float('inf')))):
+        p = pos.clone().requires_grad_(True)
+        rast, _ = G.rasterize(p, tri, (H, W))
+        col = G.interpolate(vcol[None], rast, tri)
+        img = torch.where(rast[..., 3:] > 0, col, torch.tensor(G.BG))
+        loss = sum(G.image_loss(ref_cpu[0, c], img[c]) for c in range(9)) / 9
+        loss.backward()
+        out.append((float(loss.detach()), p.grad.clone()))
+    return out
+
+
 rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-30))
 w = torch.zeros(1, rig.B); t = torch.zeros(1, 3); q = torch.tensor([[0., 0, 0, 1]])
 _, g0, _, _ = oracle_grad(w, t, q)
@@ -57,6 +73,10 @@ for it in range(iters):
     lo, gw, gt, gq = oracle_grad(*gw_params)
     print('it %d: same-params  loss gpu %.6f oracle %.6f | rel d_w %.2e  d_t %.2e  d_q %.2e' %
           (it, float(s.loss), lo, rel(s.d_w.cpu(), gw), rel(s.d_t.cpu(), gt), rel(s.d_q.cpu(), gq)))
+    (l0, g0), (l1, g1) = staged(s)
+    gp = s.g_pos.cpu()
+    print('       staged on the GPU pos_clip: loss rel %.2e, d_pos rel %.2e | oracle vs ITSELF at pos_clip + 1 ulp: d_pos rel %.2e' %
+          (abs(float(s.loss) - l0) / l0, rel(gp, g0), rel(g1, g0)))
     lf, gwf, gtf, gqf = oracle_grad(wp.detach(), tp.detach(), qp.detach())
     opt.zero_grad()
     wp.grad, tp.grad, qp.grad = gwf, gtf, gqf

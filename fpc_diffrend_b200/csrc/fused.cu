@@ -515,26 +515,33 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     const int* list = rp.pairs + (size_t)n * 4 * rp.T + rp.bin_offset[(size_t)n * rp.NB + bin];
     unsigned short* vis_list = reinterpret_cast<unsigned short*>(svis + SVIS_N);
     const int nvis = sort_visible_entries<FINE_THREADS>(ewin, svis, list, min(count, EWIN_CAP), vis_list);
-    for (int e = threadIdx.x; e < nvis; e += FINE_THREADS) {
-        const int i = vis_list[e];
-        const int t = list[i];
-        const size_t gid = (size_t)n * rp.T + t;
-        const unsigned win = ewin[i];
+    // L = 1, 2 or 4 threads per entry (as many as the CTA has to spare): thread j of an entry's group walks rows j, j + L, ...,
+    // the partial sums are combined by a fixed butterfly — fewer, shorter walks at the tail of the CTA
+    const int L = (nvis * 4 <= FINE_THREADS) ? 4 : ((nvis * 2 <= FINE_THREADS) ? 2 : 1);
+    const int sub = threadIdx.x & (L - 1);
+    for (int base = 0; base < nvis; base += FINE_THREADS / L) {
+        const int e = base + threadIdx.x / L;
+        const bool act = e < nvis;
+        const int i = act ? (int)vis_list[e] : 0;
+        const int t = act ? list[i] : -2;
+        const size_t gid = (size_t)n * rp.T + (act ? t : 0);
+        const unsigned win = act ? ewin[i] : (1u << 12);              // inactive: an empty window (wy0 > wy1)
         const int wx0 = win & 63, wx1 = (win >> 6) & 63, wy0 = (win >> 12) & 63, wy1 = (win >> 18) & 63;     // tile-relative window
         // requested now, used after the walk: the triangle's anchor and vertex indices
-        const int an = rp.tri_anchor[gid];
-        const int4 ti = tri_indices(rp, t);
+        int an = 0;
+        int4 ti = make_int4(0, 0, 0, 0);
+        if (act && sub == 0) { an = rp.tri_anchor[gid]; ti = tri_indices(rp, t); }
         float m[9];
 #pragma unroll
         for (int c = 0; c < 9; c++) m[c] = 0.f;
-        bool seen = false;
-        for (int y = wy0; y <= wy1; y++) {
+        int seen = 0;
+        for (int y = wy0 + sub; y <= wy1; y += L) {
             const int* idr = ids + y * BIN + wx0;
             // which pixels of the row did the triangle win?  (branch-free pass, then only the hits are visited, left to right)
             unsigned hit = 0u;
             for (int x = 0; x <= wx1 - wx0; x++) hit |= (unsigned)(idr[x] == t) << x;
             if (!hit) continue;
-            seen = true;
+            seen = 1;
             const int rowb = y * BIN + wx0;
             float r0 = 0.f, r1 = 0.f, r2 = 0.f;
             do {
@@ -549,7 +556,12 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             m[0] += r0; m[1] += r1; m[2] += r2;
             m[6] += r0 * fly; m[7] += r1 * fly; m[8] += r2 * fly;
         }
-        if (seen) {
+        for (int o = L >> 1; o > 0; o >>= 1) {                          // all 32 lanes get here (no early exits above)
+#pragma unroll
+            for (int c = 0; c < 9; c++) m[c] += __shfl_xor_sync(0xffffffffu, m[c], o);
+            seen |= __shfl_xor_sync(0xffffffffu, seen, o);
+        }
+        if (act && sub == 0 && seen) {
             // moments about the window corner -> about the triangle's anchor pixel
             const float dx = (float)(ox + wx0 - (an & 0xffff)), dy = (float)(oy + wy0 - (int)((unsigned)an >> 16));
 #pragma unroll

@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     unsigned char* svis = smem + L.svis;                                  // gather phase: "this id won a pixel" filter
     __shared__ double red[AA_WARPS];
     __shared__ int s_nlist;
+    __shared__ unsigned char s_rowpair[AA_TW + 4];     // tile row -> some pixel of the row is the triangle side of an accepted pair with
+                                                       // a non-zero gradient (the gather phase looks for pair terms only in such rows)
 
     const int bin = blockIdx.x, n = blockIdx.y;
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
             float zw = fminf(fmaxf(sh.zw, -1.f), 1.f);
             rout = make_float4(u, v, zw, (float)(t + 1));
             slot = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned)(t + 1);
-            svis[t & (SVIS_N - 1)] = 1;
+            if (inner) svis[t & (SVIS_N - 1)] = 1;            // triangles seen only in the halo are added by their pairs (phase 5)
             int j0 = i0, j1 = i1, j2 = i2;
             if (fp.attr_tri4) { const int4 tj = __ldg(fp.attr_tri4 + t); j0 = tj.x; j1 = tj.y; j2 = tj.z; }
             bool ok = (unsigned)j0 < (unsigned)fp.Va && (unsigned)j1 < (unsigned)fp.Va && (unsigned)j2 < (unsigned)fp.Va;
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
         }
     }
     if (threadIdx.x == 0) s_nlist = 0;
+    if (threadIdx.x < AA_TW + 4) s_rowpair[threadIdx.x] = 0;
     __syncthreads();
 
     // ---- (3a) work list of pixel pairs with different triangle ids (both pixels inside the tile and the image) ----
@@ -461,6 +464,16 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
         }
         // the pixel's own coefficient slots become its gradient terms (read only by this thread above)
         if (fp.slots) { s_coef[ii * 3 * C + 0] = g0; s_coef[ii * 3 * C + 1] = g1; s_coef[ii * 3 * C + 2] = g2; }
+        // tile rows that hold the triangle side of this pixel's pairs: its own row, and the row above for an up pair whose
+        // crossing edge belongs to the upper pixel's triangle (racing stores of the same value)
+        if (ddr != 0.f) s_rowpair[ty] = 1;
+        if (ddu != 0.f) { s_rowpair[ty] = 1; s_rowpair[ty + 1] = 1; }
+        // ... and the triangle on the far side of such a pair may have been seen in the halo only: let the gather visit it
+        if (fp.slots && (ddr != 0.f || ddu != 0.f)) {
+            const unsigned ir = (unsigned)keys[idx + 1], iu = (unsigned)keys[idx + AA_TW];
+            if (ddr != 0.f && ir) svis[(ir - 1u) & (SVIS_N - 1)] = 1;
+            if (ddu != 0.f && iu) svis[(iu - 1u) & (SVIS_N - 1)] = 1;
+        }
         ddr_[j] = ddr; ddu_[j] = ddu;
     }
     for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
@@ -489,37 +502,50 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     unsigned short* vis_list = reinterpret_cast<unsigned short*>(smem + L.vis);
     const int ntab = min(count, EWIN_CAP);
     const int nvis = sort_visible_entries<AA_THREADS>(ewin, svis, list, ntab, vis_list);
-    // visible entries of the window table (bucketed by window area), then whatever the table could not hold
-    for (int e = threadIdx.x; e < nvis + max(count - EWIN_CAP, 0); e += AA_THREADS) {
-        const int i = e < nvis ? (int)vis_list[e] : EWIN_CAP + (e - nvis);
-        const int t = list[i];
-        const size_t gid = (size_t)n * rp.T + t;
-        int xa, xb, ya, yb, kslot;
-        if (i < EWIN_CAP) {
-            const unsigned win = ewin[i];
-            kslot = (win >> 24) & 3;
-            xa = tx0 + (win & 63); xb = tx0 + ((win >> 6) & 63); ya = ty0 + ((win >> 12) & 63); yb = ty0 + ((win >> 18) & 63);
-        } else {                      // more entries than the window table holds: the same from the binning records
-            const ushort4 bb = rp.tri_bbox[gid];
-            kslot = slot_index_k(rp.tri_info[gid], bx, by);
-            xa = max((int)bb.x, max(tx0, 0)); xb = min((int)bb.z, tx0 + AA_TW - 1);
-            ya = max((int)bb.y, max(ty0, 0)); yb = min((int)bb.w, ty0 + AA_TW - 1);
-            if (xa > xb || ya > yb) continue;
+    // visible entries of the window table (bucketed by window area), then whatever the table could not hold.
+    // L = 1, 2 or 4 threads per entry (as many as the CTA has to spare): thread j of an entry's group walks rows j, j + L, ...,
+    // the partial sums are combined by a fixed butterfly — fewer, shorter walks at the tail of the CTA
+    const int ntot = nvis + max(count - EWIN_CAP, 0);
+    const int LG = (ntot * 4 <= AA_THREADS) ? 4 : ((ntot * 2 <= AA_THREADS) ? 2 : 1);
+    const int sub = threadIdx.x & (LG - 1);
+    for (int base = 0; base < ntot; base += AA_THREADS / LG) {
+        const int e = base + threadIdx.x / LG;
+        const bool act = e < ntot;
+        int t = -2, xa = 1, xb = 0, ya = 1, yb = 0, kslot = 0;
+        size_t gid = 0;
+        if (act) {
+            const int i = e < nvis ? (int)vis_list[e] : EWIN_CAP + (e - nvis);
+            t = list[i];
+            gid = (size_t)n * rp.T + t;
+            if (i < EWIN_CAP) {
+                const unsigned win = ewin[i];
+                kslot = (win >> 24) & 3;
+                xa = tx0 + (win & 63); xb = tx0 + ((win >> 6) & 63); ya = ty0 + ((win >> 12) & 63); yb = ty0 + ((win >> 18) & 63);
+            } else {                  // more entries than the window table holds: the same from the binning records
+                const ushort4 bb = rp.tri_bbox[gid];
+                kslot = slot_index_k(rp.tri_info[gid], bx, by);
+                xa = max((int)bb.x, max(tx0, 0)); xb = min((int)bb.z, tx0 + AA_TW - 1);
+                ya = max((int)bb.y, max(ty0, 0)); yb = min((int)bb.w, ty0 + AA_TW - 1);
+                if (xa > xb) { ya = 1; yb = 0; }
+            }
         }
-        const int an = rp.tri_anchor[gid];
+        // requested now, used by the pair terms and after the walk: the triangle's anchor and vertices
+        int an = 0;
+        float4 pc[3];
+        pc[0] = pc[1] = pc[2] = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (act && ya <= yb) {
+            an = rp.tri_anchor[gid];
+            const int4 ti = tri_indices(rp, t);
+            pc[0] = ldg4(P + 4 * (size_t)ti.x); pc[1] = ldg4(P + 4 * (size_t)ti.y); pc[2] = ldg4(P + 4 * (size_t)ti.z);
+        }
         const int anx = an & 0xffff, any = (int)((unsigned)an >> 16);
         float m[9], cg[9];
 #pragma unroll
         for (int c = 0; c < 9; c++) { m[c] = 0.f; cg[c] = 0.f; }
-        bool seen = false, have_p = false;
-        float4 pc[3];
+        int seen = 0;                               // the triangle has an own pixel or a pair term in this tile
         auto pair_term = [&](int apx, int apy, int d, unsigned inf, float dd) {
             if (dd == 0.f) return;
-            if (!have_p) {
-                const int4 ti = tri_indices(rp, t);
-                pc[0] = ldg4(P + 4 * (size_t)ti.x); pc[1] = ldg4(P + 4 * (size_t)ti.y); pc[2] = ldg4(P + 4 * (size_t)ti.z);
-                have_p = true;
-            }
+            seen = 1;
             const int di = inf & 3, c1 = (di + 1) % 3, c2 = (di + 2) % 3;
             float gp1[3], gp2[3];
             // (dynamic corner indices would put pc / cg in local memory: select with compares instead)
@@ -534,21 +560,22 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                     if (cnr == c2) cg[3 * cnr + c] += gp2[c];
                 }
         };
-        for (int y = ya; y <= yb; y++) {
+        for (int y = ya + sub; y <= yb; y += LG) {
             // which pixels of the row did the triangle win?  (branch-free pass, then only the hits are visited, left to right)
             const int rowi = (y - ty0) * AA_TW - tx0;
             unsigned long long hit = 0ull;
             for (int x = xa; x <= xb; x++) hit |= (unsigned long long)(idw[2 * (rowi + x)] == t + 1) << (x - xa);
             if (!hit) continue;
-            seen = true;
             const bool own_y = y >= oy && y < oy + BIN;
             const float fly = (float)(y - any);
+            const bool row_has_pairs = s_rowpair[y - ty0] != 0;
             while (hit) {
                 const int x = xa + __ffsll((long long)hit) - 1;
                 hit &= hit - 1ull;
                 const int idx = rowi + x;
                 const bool own_x = x >= ox && x < ox + BIN;
                 if (own_x && own_y) {
+                    seen = 1;
                     const int ii = (y - oy) * BIN + (x - ox);
                     const float a = s_coef[ii * 3 * C + 0], b = s_coef[ii * 3 * C + 1], c = s_coef[ii * 3 * C + 2];
                     const float flx = (float)(x - anx);
@@ -556,10 +583,13 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                     m[3] += a * flx; m[4] += b * flx; m[5] += c * flx;
                     m[6] += a * fly; m[7] += b * fly; m[8] += c * fly;
                     // this pixel's own pairs whose crossing edge belongs to its triangle (front1 == 0)
-                    const unsigned inf = s_info[idx];
-                    if ((inf & 8u) && !((inf >> 2) & 1u)) pair_term(x, y, 0, inf, s_ar[idx]);
-                    if ((inf & 0x80u) && !((inf >> 6) & 1u)) pair_term(x, y, 1, inf >> 4, s_au[idx]);
+                    if (row_has_pairs) {
+                        const unsigned inf = s_info[idx];
+                        if ((inf & 8u) && !((inf >> 2) & 1u)) pair_term(x, y, 0, inf, s_ar[idx]);
+                        if ((inf & 0x80u) && !((inf >> 6) & 1u)) pair_term(x, y, 1, inf >> 4, s_au[idx]);
+                    }
                 }
+                if (!row_has_pairs) continue;
                 // pairs owned by the left / lower neighbour (a pixel of this bin) whose crossing edge belongs to THIS pixel's triangle
                 if (own_y && x - 1 >= ox && x - 1 < ox + BIN) {
                     const unsigned inf = s_info[idx - 1];
@@ -571,21 +601,19 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                 }
             }
         }
-        if (!seen) continue;
-        float out[9];
-        {
-            if (!have_p) {
-                const int4 ti = tri_indices(rp, t);
-                pc[0] = ldg4(P + 4 * (size_t)ti.x); pc[1] = ldg4(P + 4 * (size_t)ti.y); pc[2] = ldg4(P + 4 * (size_t)ti.z);
-            }
-            triangle_corner_grads(m, pixel_ndc(anx, rp.xs, rp.xo), pixel_ndc(any, rp.ys, rp.yo), rp.xs, rp.ys, pc[0], pc[1], pc[2], out);
+        for (int o = LG >> 1; o > 0; o >>= 1) {                         // all 32 lanes get here (no early exits above)
 #pragma unroll
-            for (int c = 0; c < 9; c++) out[c] += cg[c];
+            for (int c = 0; c < 9; c++) { m[c] += __shfl_xor_sync(0xffffffffu, m[c], o); cg[c] += __shfl_xor_sync(0xffffffffu, cg[c], o); }
+            seen |= __shfl_xor_sync(0xffffffffu, seen, o);
         }
-        float* o = slot_ptr(fp.slots, gid, kslot);
+        if (act && sub == 0 && seen) {
+            float out[9];
+            triangle_corner_grads(m, pixel_ndc(anx, rp.xs, rp.xo), pixel_ndc(any, rp.ys, rp.yo), rp.xs, rp.ys, pc[0], pc[1], pc[2], out);
+            float* o = slot_ptr(fp.slots, gid, kslot);
 #pragma unroll
-        for (int c = 0; c < 9; c++) o[c] = out[c];
-        reinterpret_cast<unsigned char*>(rp.slot_valid + gid)[kslot] = 1;
+            for (int c = 0; c < 9; c++) o[c] = out[c] + cg[c];
+            reinterpret_cast<unsigned char*>(rp.slot_valid + gid)[kslot] = 1;
+        }
     }
 }
 

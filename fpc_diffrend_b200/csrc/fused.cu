@@ -225,7 +225,8 @@ __device__ __forceinline__ void tex_grad_scatter(const FusedParams& fp, unsigned
 // the reference frame (16-byte loads when the layout allows), optional image outputs are filled, nothing else runs.
 // Returns the CTA's partial loss in thread 0 via `red` (shared, FINE_WARPS doubles).
 template <int C, int NT = FINE_THREADS>
-__device__ __forceinline__ void background_bin(const RasterParams& rp, const FusedParams& fp, int n, int bin, int ox, int oy, double* red)
+__device__ __forceinline__ void background_bin(const RasterParams& rp, const FusedParams& fp, int n, int bin, int ox, int oy, double* red,
+                                               const uint4* pre = nullptr)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int esz = fp.ref_u8 ? 1 : 4;
@@ -239,7 +240,9 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
         const int cpr = (BIN * C * esz) >> 4;                    // 16-byte chunks per tile row
         for (int i = threadIdx.x; i < rows * cpr; i += NT) {
             int r = i / cpr, ch = i - r * cpr;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(rbase + ((size_t)n * rp.H + oy + r) * row_bytes + (size_t)ox * C * esz + ch * 16));
+            // (the caller may have requested this thread's first chunk before it knew the bin was empty: `pre`)
+            const uint4 v = (pre && i == (int)threadIdx.x) ? *pre
+                                                           : __ldg(reinterpret_cast<const uint4*>(rbase + ((size_t)n * rp.H + oy + r) * row_bytes + (size_t)ox * C * esz + ch * 16));
             const unsigned w4[4] = {v.x, v.y, v.z, v.w};
             float sacc = 0.f;
             if (fp.ref_u8) {
@@ -309,9 +312,25 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
         if (threadIdx.x == 0) fp.loss_partial[(size_t)n * rp.NB + bin] = 0.0;
         return;
     }
-    if (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0) {      // ~2/3 of the bins of a head shot
-        background_bin<C>(rp, fp, n, bin, ox, oy, red);
-        return;
+    {
+        // ~2/3 of the bins of a head shot hold no triangle: their only work is streaming the reference tile through the loss.  The
+        // first chunk of the tile is requested together with the counters that decide it (one memory round trip instead of two).
+        const int cnt = rp.bin_count[(size_t)n * rp.NB + bin], nlg = rp.large_count[n];
+        const int esz0 = fp.ref_u8 ? 1 : 4;
+        const unsigned char* rbase = reinterpret_cast<const unsigned char*>(fp.ref);
+        const size_t row_bytes = (size_t)rp.W * C * esz0;
+        const int cpr = (BIN * C * esz0) >> 4;
+        const bool fast = (ox + BIN <= rp.W) && (row_bytes % 16 == 0) && ((reinterpret_cast<size_t>(rbase) & 15) == 0) &&
+                          (int)threadIdx.x < min(BIN, rp.H - oy) * cpr;
+        uint4 pre = make_uint4(0u, 0u, 0u, 0u);
+        if (fast) {
+            const int r = threadIdx.x / cpr, ch = threadIdx.x - r * cpr;
+            pre = __ldg(reinterpret_cast<const uint4*>(rbase + ((size_t)n * rp.H + oy + r) * row_bytes + (size_t)ox * C * esz0 + ch * 16));
+        }
+        if (cnt == 0 && nlg == 0) {
+            background_bin<C>(rp, fp, n, bin, ox, oy, red, fast ? &pre : nullptr);
+            return;
+        }
     }
 
     // ---- (0) the tile of the reference frame starts its way into shared memory now (cp.async), so its HBM / L2

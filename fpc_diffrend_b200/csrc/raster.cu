@@ -22,7 +22,7 @@ namespace {
 // grid fits in shared memory (HIST) the CTA first histograms its triangles there and then touches each global
 // counter once, so the hot counters (a head covers only ~1/4 of the bins) see ~10x fewer global atomics.
 constexpr int BIN_TPB = 1024;
-constexpr int HIST_MAX_BINS = 8192;
+constexpr int HIST_MAX_BINS = 4096;        // three shared-memory tables of NB words each in k_setup (48 KB at 2048 x 2048)
 
 // Origin of a triangle's gradient moments (fused.cu): the pixel that holds the centroid, clamped to the image.  The position
 // gradient is assembled from sums of g_k times (pixel - origin); with the origin ON the triangle the vertex offsets stay as
@@ -38,11 +38,13 @@ __device__ __forceinline__ int moment_origin(const SnappedTri& s, const RasterPa
 template <bool HIST>
 __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
 {
-    extern __shared__ int hist[];
+    extern __shared__ int hist[];            // HIST: count [NB] | ~min depth key [NB] | max depth key [NB] of the CTA's triangles per bin
     const int n = blockIdx.y;
     const int t = blockIdx.x * BIN_TPB + threadIdx.x;
+    unsigned* s_nzlo = reinterpret_cast<unsigned*>(hist) + rp.NB;
+    unsigned* s_zhi = s_nzlo + rp.NB;
     if (HIST) {
-        for (int b = threadIdx.x; b < rp.NB; b += BIN_TPB) hist[b] = 0;
+        for (int b = threadIdx.x; b < 3 * rp.NB; b += BIN_TPB) hist[b] = 0;
         __syncthreads();
     }
     if (t < rp.T) {
@@ -67,11 +69,15 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
                         info = bx0 | (by0 << 10) | ((bx1 - bx0) << 20) | ((by1 - by0) << 21) | (1 << 22);
                         // depth window of the triangle (32-bit key mode of the fine rasterizer): the per-vertex z/w of depth_plane()
                         const unsigned k0 = depth_key(xdiv(p0.z, p0.w)), k1 = depth_key(xdiv(p1.z, p1.w)), k2 = depth_key(xdiv(p2.z, p2.w));
-                        rp.tri_zrange[gid] = make_uint2(min(k0, min(k1, k2)), max(k0, max(k1, k2)));
+                        const unsigned nzl = ~min(k0, min(k1, k2)), zh = max(k0, max(k1, k2));
                         for (int by = by0; by <= by1; by++)
                             for (int bx = bx0; bx <= bx1; bx++) {
-                                if (HIST) atomicAdd(hist + by * rp.BW + bx, 1);
-                                else atomicAdd(rp.bin_count + (size_t)n * rp.NB + by * rp.BW + bx, 1);
+                                const int b = by * rp.BW + bx;
+                                if (HIST) { atomicAdd(hist + b, 1); atomicMax(s_nzlo + b, nzl); atomicMax(s_zhi + b, zh); }
+                                else {
+                                    atomicAdd(rp.bin_count + (size_t)n * rp.NB + b, 1);
+                                    atomicMax(rp.bin_nzlo + (size_t)n * rp.NB + b, nzl); atomicMax(rp.bin_zhi + (size_t)n * rp.NB + b, zh);
+                                }
                             }
                     }
                 }
@@ -115,7 +121,11 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
         __syncthreads();
         for (int b = threadIdx.x; b < rp.NB; b += BIN_TPB) {
             int c = hist[b];
-            if (c) atomicAdd(rp.bin_count + (size_t)n * rp.NB + b, c);
+            if (c) {
+                atomicAdd(rp.bin_count + (size_t)n * rp.NB + b, c);
+                atomicMax(rp.bin_nzlo + (size_t)n * rp.NB + b, s_nzlo[b]);
+                atomicMax(rp.bin_zhi + (size_t)n * rp.NB + b, s_zhi[b]);
+            }
         }
     }
 }
@@ -327,6 +337,8 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_count = o;       o += align_up((size_t)N * NB * 4);
     L.off_cursor = o;      o += align_up((size_t)N * NB * 4);
     L.off_large_count = o; o += align_up((size_t)N * 4);
+    L.off_nzlo = o;        o += align_up((size_t)N * NB * 4);
+    L.off_zhi = o;         o += align_up((size_t)N * NB * 4);
     L.off_clip_count = o;  o += align_up(4);
     L.zero_bytes = o;
     L.off_offset = o;      o += align_up((size_t)N * NB * 4);
@@ -338,7 +350,6 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_clip_parent = o; o += align_up((size_t)L.clip_cap * 4);
     L.off_anchor = o;      o += align_up((size_t)N * T * 4);
     L.off_tri4 = o;        o += align_up((size_t)T * 16);
-    L.off_zrange = o;      o += align_up((size_t)N * T * 8);
     L.off_bbox = o;        o += align_up((size_t)N * T * 8);
     L.off_valid = o;       o += align_up((size_t)N * T * 4);
     L.total = o;
@@ -370,7 +381,8 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.large_list = (int*)(s + L.off_large);
     rp.tri_anchor = (int*)(s + L.off_anchor);
     rp.tri4 = (int4*)(s + L.off_tri4);
-    rp.tri_zrange = (uint2*)(s + L.off_zrange);
+    rp.bin_nzlo = (unsigned*)(s + L.off_nzlo);
+    rp.bin_zhi = (unsigned*)(s + L.off_zhi);
     rp.tri_bbox = (ushort4*)(s + L.off_bbox);
     rp.slot_valid = (unsigned*)(s + L.off_valid);
     rp.idbits = 1;
@@ -385,7 +397,7 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     dim3 grid(fpc_div_up(T, BIN_TPB), N);
     if (rp.NB <= HIST_MAX_BINS) {
         size_t hb = (size_t)rp.NB * sizeof(int);
-        k_setup<true><<<grid, BIN_TPB, hb, stream>>>(rp);
+        k_setup<true><<<grid, BIN_TPB, 3 * hb, stream>>>(rp);
         FPC_LAUNCH_CHECK();
         static FpcPerDeviceOnce fill_attr_set;
         if (fill_attr_set.need()) {

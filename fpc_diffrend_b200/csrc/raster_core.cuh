@@ -75,7 +75,9 @@ struct RasterParams {
     float* slot_grad;                // nullable: [N*T*4*9] per-(view, triangle, bin k) gradient slots of fused.cu; k_setup zeroes
                                      // the accumulator slots (1 and 2) of LARGE triangles, every other slot is written at most once
     unsigned* slot_valid;            // [N*T] (with slot_grad): byte k != 0 <=> slot k of the triangle was written; zeroed by k_setup
-    uint2* tri_zrange;               // [N*T] (min, max) of depth_key(z/w) over the vertices of a SMALL triangle (k_setup)
+    unsigned* bin_nzlo;              // [N*NB] ~min and
+    unsigned* bin_zhi;               // [N*NB]  max of depth_key(z/w) over the vertices of the SMALL triangles listed in the bin (k_setup;
+                                     //         zero-initialised with the counters: an empty bin reads (0xFFFFFFFF, 0))
     int idbits;                      // bits of a triangle id: ceil(log2(T))
 };
 
@@ -423,8 +425,7 @@ __device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int b
 
     __shared__ int next_batch;       // warps claim batches of 32 triangles dynamically (balances uneven batches)
     __shared__ int s_overflow;
-    __shared__ unsigned s_zlo, s_zhi;
-    if (threadIdx.x == 0) { next_batch = 0; s_overflow = 0; s_zlo = 0xFFFFFFFFu; s_zhi = 0u; }
+    if (threadIdx.x == 0) { next_batch = 0; s_overflow = 0; }
     __syncthreads();
 
     // ---- small triangles ----
@@ -437,15 +438,8 @@ __device__ __forceinline__ bool raster_tile(const RasterParams& rp, int n, int b
     // depth window of the bin from the per-triangle vertex depth ranges (k_setup); a fragment of a covered pixel lies inside its
     // triangle, so its plane depth stays within that range up to rounding: KEY32_MARGIN keys of slack on either side
     if (nlarge == 0 && count > 0 && rp.idbits <= 24) {
-        unsigned zlo = 0xFFFFFFFFu, zhi = 0u;
-        for (int i = threadIdx.x; i < count; i += NT) {
-            const uint2 zr = __ldg(rp.tri_zrange + (size_t)n * rp.T + list[i]);
-            zlo = min(zlo, zr.x); zhi = max(zhi, zr.y);
-        }
-        zlo = __reduce_min_sync(0xffffffffu, zlo); zhi = __reduce_max_sync(0xffffffffu, zhi);
-        if (lane == 0) { atomicMin(&s_zlo, zlo); atomicMax(&s_zhi, zhi); }
-        __syncthreads();
-        zlo = s_zlo; zhi = s_zhi;
+        // (k_setup accumulated the window per bin while it counted the lists: no pass over the list, no barrier here)
+        const unsigned zlo = ~rp.bin_nzlo[(size_t)n * rp.NB + bin], zhi = rp.bin_zhi[(size_t)n * rp.NB + bin];
         const unsigned span = (1u << (32 - rp.idbits)) - 1u;          // the all-ones key stays free for "empty"
         if (span > 2u * KEY32_MARGIN && zlo >= KEY32_MARGIN && zhi >= zlo && (zhi - zlo) < span - 2u * KEY32_MARGIN) {
             // clamp the window to the valid depth range [-1, 1] (see emit_fragment32)
@@ -539,7 +533,7 @@ __device__ __forceinline__ unsigned long long tile_key(const unsigned long long*
 // Host side: scratch layout + the three binning launches.
 struct ScratchLayout {
     size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_zrange, off_bbox, off_valid, off_clip_count, off_clip_verts, off_clip_parent, total;
+    size_t off_count, off_cursor, off_large_count, off_nzlo, off_zhi, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_bbox, off_valid, off_clip_count, off_clip_verts, off_clip_parent, total;
     int clip_cap;
 };
 

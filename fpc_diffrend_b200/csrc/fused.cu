@@ -190,6 +190,16 @@ __device__ __forceinline__ int sort_visible_entries(const unsigned* __restrict__
     return nvis;
 }
 
+// nine corner-gradient floats -> the slot's three float4 (x, y, w, 0) + the "written" byte
+__device__ __forceinline__ void store_slot(float* slots, unsigned* slot_valid, size_t gid, int k, const float (&out)[9])
+{
+    float4* o = reinterpret_cast<float4*>(slots + (gid * SLOTS_PER_TRI + k) * SLOT_FLOATS);
+    o[0] = make_float4(out[0], out[1], out[2], 0.f);
+    o[1] = make_float4(out[3], out[4], out[5], 0.f);
+    o[2] = make_float4(out[6], out[7], out[8], 0.f);
+    reinterpret_cast<unsigned char*>(slot_valid + gid)[k] = SLOT_WRITTEN;
+}
+
 __device__ __forceinline__ float* slot_ptr(float* slots, size_t gid, int k) { return slots + (gid * SLOTS_PER_TRI + k) * SLOT_FLOATS; }
 
 // moments of a LARGE triangle's pixel: float REDs into the triangle's accumulator slot 1 (zeroed by k_setup)
@@ -590,10 +600,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             float out[9];
             triangle_corner_grads(m, fx0, fy0, rp.xs, rp.ys, p0, p1, p2, out);
             const int k = (win >> 24) & 3;
-            float* o = slot_ptr(fp.slots, gid, k);
-#pragma unroll
-            for (int c = 0; c < 9; c++) o[c] = out[c];
-            reinterpret_cast<unsigned char*>(rp.slot_valid + gid)[k] = 1;
+            store_slot(fp.slots, rp.slot_valid, gid, k, out);
         }
     }
     // (more entries than the window table holds — > 1024 triangles in a 32 x 32-px bin: one thread per entry, from the binning records)
@@ -611,10 +618,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             float out[9];
             triangle_corner_grads(m, pixel_ndc(an & 0xffff, rp.xs, rp.xo), pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo), rp.xs, rp.ys, p0, p1, p2, out);
             const int k = slot_index_k(rp.tri_info[gid], bx, by);
-            float* o = slot_ptr(fp.slots, gid, k);
-#pragma unroll
-            for (int c = 0; c < 9; c++) o[c] = out[c];
-            reinterpret_cast<unsigned char*>(rp.slot_valid + gid)[k] = 1;
+            store_slot(fp.slots, rp.slot_valid, gid, k, out);
         }
     }
 }
@@ -655,25 +659,23 @@ __global__ void __launch_bounds__(256) k_vtx_gather(RasterParams rp, const float
     // four adjacency items at a time: their (independent) index / class loads are in flight together; the sums below still run
     // in list order
     for (int jb = j0; jb < j1; jb += 4) {
-        int item[4], info[4];
+        int item[4];
+        unsigned valid[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) item[u] = (jb + u < j1) ? __ldg(vadj_item + jb + u) : -1;
 #pragma unroll
-        for (int u = 0; u < 4; u++) info[u] = (item[u] >= 0) ? __ldg(rp.tri_info + (size_t)n * rp.T + (item[u] >> 2)) : 0;
-        unsigned valid[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) valid[u] = ((info[u] >> 22) == 1) ? __ldg(rp.slot_valid + (size_t)n * rp.T + (item[u] >> 2)) : 0u;
+        for (int u = 0; u < 4; u++) valid[u] = (item[u] >= 0) ? __ldg(rp.slot_valid + (size_t)n * rp.T + (item[u] >> 2)) : 0u;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int t = item[u] >> 2, corner = item[u] & 3;
             const size_t gid = (size_t)n * rp.T + t;
-            const int cls = info[u] >> 22;
+            const unsigned vm = valid[u];
+            const int cls = (vm >> 6) & 3;
             if (cls == 1) {
-                const unsigned vm = valid[u];
-                const float* S = slots + gid * (SLOTS_PER_TRI * SLOT_FLOATS) + 3 * corner;
+                const float4* S = reinterpret_cast<const float4*>(slots + gid * (SLOTS_PER_TRI * SLOT_FLOATS)) + corner;
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++)
-                    if ((vm >> (8 * kk)) & 0xffu) { gx += S[kk * SLOT_FLOATS]; gy += S[kk * SLOT_FLOATS + 1]; gw += S[kk * SLOT_FLOATS + 2]; }
+                    if ((vm >> (8 * kk)) & 1u) { const float4 g = __ldg(S + 3 * kk); gx += g.x; gy += g.y; gw += g.z; }
             } else if (cls == 2) {
                 // large / near-clipped triangle: slot 1 holds its moments (float REDs), slot 2 the antialias corner terms
                 const float* M = slots + (gid * SLOTS_PER_TRI + 1) * SLOT_FLOATS;
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(256) k_vtx_gather(RasterParams rp, const float
                     triangle_corner_grads(m, pixel_ndc(an & 0xffff, rp.xs, rp.xo), pixel_ndc((int)((unsigned)an >> 16), rp.ys, rp.yo), rp.xs, rp.ys, p0, p1, p2, out);
                     gx += out[3 * corner]; gy += out[3 * corner + 1]; gw += out[3 * corner + 2];
                 }
-                const float* Aa = M + SLOT_FLOATS + 3 * corner;
+                const float* Aa = M + SLOT_FLOATS + 4 * corner;
                 gx += Aa[0]; gy += Aa[1]; gw += Aa[2];
             }
         }

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
                     aa_pair_corner_grads(ap.xh, ap.yh, ldg4(P + 4 * (size_t)vi[c1]), ldg4(P + 4 * (size_t)vi[c2]), px + (d ? 0 : f1), py + (d ? f1 : 0), d, dd, gp1, gp2);
                     float* Aa = slot_ptr(fp.slots, gid, 2);
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { atomicAdd(Aa + 3 * c1 + c, gp1[c]); atomicAdd(Aa + 3 * c2 + c, gp2[c]); }
+                    for (int c = 0; c < 3; c++) { atomicAdd(Aa + 4 * c1 + c, gp1[c]); atomicAdd(Aa + 4 * c2 + c, gp2[c]); }
                 }
             }
         }
@@ -609,10 +609,9 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
         if (act && sub == 0 && seen) {
             float out[9];
             triangle_corner_grads(m, pixel_ndc(anx, rp.xs, rp.xo), pixel_ndc(any, rp.ys, rp.yo), rp.xs, rp.ys, pc[0], pc[1], pc[2], out);
-            float* o = slot_ptr(fp.slots, gid, kslot);
 #pragma unroll
-            for (int c = 0; c < 9; c++) o[c] = out[c] + cg[c];
-            reinterpret_cast<unsigned char*>(rp.slot_valid + gid)[kslot] = 1;
+            for (int c = 0; c < 9; c++) out[c] += cg[c];
+            store_slot(fp.slots, rp.slot_valid, gid, kslot, out);
         }
     }
 }

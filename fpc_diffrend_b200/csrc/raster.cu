@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(BIN_TPB) k_setup(RasterParams rp)
             }
         }
         rp.tri_info[gid] = info;
-        if (rp.slot_grad) rp.slot_valid[gid] = 0u;          // no gradient slot of this (view, triangle) written yet
+        // class of the triangle for the vertex gather; no gradient slot of this (view, triangle) written yet
+        if (rp.slot_grad) rp.slot_valid[gid] = large ? SLOT_CLASS_LARGE : ((info >> 22) == 1 ? SLOT_CLASS_SMALL : 0u);
         // large (and near-clipped) triangles are resolved by whole CTAs in every bin they touch: their gradient is accumulated
         // (float REDs) in slots 1 (moments) and 2 (antialias corner terms), which start from zero
         if (large && rp.slot_grad) {

@@ -74,7 +74,8 @@ struct RasterParams {
     ushort4* tri_bbox;               // [N*T] (pxa, pya, pxb, pyb): candidate pixel range of a SMALL triangle, clamped to the image
     float* slot_grad;                // nullable: [N*T*4*9] per-(view, triangle, bin k) gradient slots of fused.cu; k_setup zeroes
                                      // the accumulator slots (1 and 2) of LARGE triangles, every other slot is written at most once
-    unsigned* slot_valid;            // [N*T] (with slot_grad): byte k != 0 <=> slot k of the triangle was written; zeroed by k_setup
+    unsigned* slot_valid;            // [N*T] (with slot_grad): bits 6-7 of every byte = class of the triangle (0 none, 1 small, 2 large: k_setup),
+                                     //       bit 0 of byte k = slot k was written (the fused kernels)
     unsigned* bin_nzlo;              // [N*NB] ~min and
     unsigned* bin_zhi;               // [N*NB]  max of depth_key(z/w) over the vertices of the SMALL triangles listed in the bin (k_setup;
                                      //         zero-initialised with the counters: an empty bin reads (0xFFFFFFFF, 0))
@@ -547,7 +548,9 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
 
 // slot of (view n, triangle t) in bin (bx, by): k = which of the (at most 2 x 2) bins the small triangle was listed in
 __device__ __forceinline__ int slot_index_k(int info, int bx, int by) { return ((by - ((info >> 10) & 1023)) << 1) | (bx - (info & 1023)); }
-constexpr int SLOT_FLOATS = 9;       // (x, y, w) gradient of the three corners
+constexpr int SLOT_FLOATS = 12;      // three corners x float4 (d x, d y, d w, 0): one 16-byte load per (vertex, triangle, bin) in the gather
+constexpr unsigned SLOT_CLASS_SMALL = 0x40404040u, SLOT_CLASS_LARGE = 0x80808080u;   // slot_valid as k_setup leaves it (class in bits 6-7 of every byte)
+constexpr unsigned char SLOT_WRITTEN = 0x41;                                           // byte k once slot k of a small triangle holds data
 constexpr int SLOTS_PER_TRI = 4;
 
 }  // namespace fpc

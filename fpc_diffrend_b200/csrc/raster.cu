@@ -21,7 +21,10 @@ namespace {
 // k_setup / k_fill run one CTA per chunk of BIN_TPB triangles of ONE instance (grid.y = instance).  When the bin
 // grid fits in shared memory (HIST) the CTA first histograms its triangles there and then touches each global
 // counter once, so the hot counters (a head covers only ~1/4 of the bins) see ~10x fewer global atomics.
-constexpr int BIN_TPB = 1024;
+#ifndef FPC_BIN_TPB
+#define FPC_BIN_TPB 1024
+#endif
+constexpr int BIN_TPB = FPC_BIN_TPB;
 constexpr int HIST_MAX_BINS = 4096;        // three shared-memory tables of NB words each in k_setup (48 KB at 2048 x 2048)
 
 // Origin of a triangle's gradient moments (fused.cu): the pixel that holds the centroid, clamped to the image.  The position
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_fill(RasterParams rp)
         if (lane == 31) warp_tot[warp] = x;
         __syncthreads();
         if (warp == 0) {
-            int w = warp_tot[lane], xs = w;
+            int w = (lane < BIN_TPB / 32) ? warp_tot[lane] : 0, xs = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 int y = __shfl_up_sync(0xffffffffu, xs, d);

@@ -46,7 +46,8 @@ struct AASmem {
 
 __host__ __device__ inline size_t aa_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// region0 is time-shared: WarpStage records (phase 1), pair work list (phase 3), d loss / d out (phases 4-5)
+// region0 is time-shared: WarpStage records (phase 1); then pair work list (phase 3) / d loss / d out (phases 4-5) in its first
+// part and, behind them, the 3C coefficients per own pixel (written in phase 2, once the records are dead)
 // texgrad: also keep the texture coordinates of the bin's own pixels (phase 5 scatters d loss / d tex from them)
 __host__ __device__ inline AASmem aa_smem_layout(int C, int esz, bool texgrad = false)
 {
@@ -56,14 +57,15 @@ __host__ __device__ inline AASmem aa_smem_layout(int C, int esz, bool texgrad = 
     size_t r0 = sizeof(WarpStage) * AA_WARPS;
     size_t lst = sizeof(unsigned short) * 2 * AA_NT;
     size_t gc = sizeof(float) * AA_R1 * AA_R1 * C;
-    if (lst > r0) r0 = lst;
-    if (gc > r0) r0 = gc;
+    const size_t head = aa_align16(lst > gc ? lst : gc);
+    const size_t coef = aa_align16(sizeof(float) * BIN * BIN * 3 * C);
+    if (head + coef > r0) r0 = head + coef;
     L.region0 = o; o += aa_align16(r0);
+    L.coef = L.region0 + head;
     L.col = o; o += aa_align16(sizeof(float) * AA_NT * C);
     L.alpha_r = o; o += aa_align16(sizeof(float) * AA_NT);
     L.alpha_u = o; o += aa_align16(sizeof(float) * AA_NT);
     L.info = o; o += aa_align16(AA_NT);
-    L.coef = o; o += aa_align16(sizeof(float) * BIN * BIN * 3 * C);
     L.ref = o; o += aa_align16((size_t)AA_R1 * AA_REF_W * C * esz);
     L.ewin = o; o += sizeof(unsigned) * EWIN_CAP;
     L.svis = o; o += SVIS_N;

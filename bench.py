@@ -589,6 +589,7 @@ def split_parity(job, wl, ctx):
     qh = _half_pose(q)
     sess.set_parameters(0.5 * w, 0.5 * t, qh)
     sess.forward(); sess.backward()
+    torch.cuda.synchronize()
     g = sess.grads.clone()
     l = sess.loss.clone()
     dist.all_reduce(g); dist.all_reduce(l)
@@ -670,7 +671,11 @@ def run_leg(job, name, steps, warmup, frames=None):
         out.update(ms_per_step=ms, ms_per_step_steady=ms_steady, warmup=nwarm, scaling=ctx['scaling'], launches_per_iteration=launches,
                    loss_final=sess.total_loss())
         if job.world > 1 and ctx['cam_split']:
-            out['allreduce_us'] = allreduce_us(job, sess)
+            out['exchange'] = ('NVLink peer memory: blend + all-gather in one kernel, peer sums, 3 device-side barriers per iteration (csrc/peer.cu)'
+                               if getattr(sess, 'peer', None) is not None else
+                               'NCCL: all-gather of the vertices, reduce-scatter of their gradients, all-reduce of the packed gradient'
+                               if sess.row_shard is not None else 'NCCL all-reduce of the packed gradient (D replicated)')
+            out['nccl_allreduce_us'] = allreduce_us(job, sess)
             out['allreduce_floats'] = int(sess.grads.numel())
         # fused-design bound of SURVEY 8(d) for this workload, per rank
         alg = algorithmic_bytes(wl, ctx['F'], ctx['rig'].uv.shape[0], sess.C)

@@ -74,6 +74,10 @@ SIGNATURES = {
     'fpc_render_loss_fused_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'fpc_render_loss_fused': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'fpc_render_loss_fused_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'fpc_blend_fwd_bcast': (_I, [_P, _P, _P, _I, _I, ctypes.c_longlong, _P, _I, _P]),
+    'fpc_peer_store_rows': (_I, [_P, _P, _I, _I, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _P]),
+    'fpc_peer_sum_rows': (_I, [_P, _I, _I, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _P, _P]),
+    'fpc_peer_sum': (_I, [_P, _I, ctypes.c_longlong, _P, _P]),
     'fpc_vertex_adjacency_scratch_bytes': (_Z, [_I]),
     'fpc_vertex_adjacency_build': (_I, [_P, _I, _I, _P, _P, _P, _Z, _P]),
     'fpc_raster_bin_px': (_I, []),

@@ -68,6 +68,9 @@ class FitConfig:
                                           # V / world vertices (D is not replicated: 240 MB at config 5), the vertices are all-gathered
                                           # and the vertex gradients reduce-scattered over NVLink.  None = on when it applies
                                           # (cam_slice set, torch.distributed world > 1, V % world == 0, mode 'prior')
+    peer_exchange: bool = None            # row-sharded camera split: the three exchanges of an iteration go through NVLink peer memory
+                                          # (torch symmetric memory + the kernels of csrc/peer.cu, one device-side barrier each) instead of
+                                          # three NCCL collectives.  None = on when symmetric memory can be set up, else NCCL
     fused: bool = True                    # one fused render(+antialias)+loss+gradient kernel (csrc/fused.cu, fused_aa.cuh)
     ref_dtype: str = 'f32'                # 'f32' or 'u8' storage of the reference frames (8-bit cameras, fit.py:530)
     # mesh regularisers of the shipped loss (fit.py:578-582; main.py:37-40 ships 5000 / 0 / 0.05 / 0, and fit.py:580 passes
@@ -83,6 +86,45 @@ class FitConfig:
 
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _PeerExchange:
+    """Symmetric-memory buffers of the row-sharded camera split (csrc/peer.cu): ONE allocation per rank holds the blended vertices
+    [F,3V] (every rank writes its rows into every rank's copy), the rank's partial vertex gradient [F,3V] and its partial packed
+    parameter gradient; `verts` / `d_verts` / `grads` are host tables of the ranks' pointers to each section, in rank order.
+    `barrier(channel)` is the device-side barrier of torch's symmetric memory (a kernel on the current stream: capturable)."""
+
+    def __init__(self, sess):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        F, R, ng = sess.F, sess.V * 3, sess.params.numel()
+        world = sess.row_shard[2]
+        group = dist.group.WORLD
+        n = 2 * F * R + ng
+        n += (-n) % 64
+        self.buf = symm.empty(n, dtype=torch.float32, device=sess.device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(ptrs) != world:
+            raise RuntimeError('symmetric memory returned %d peer pointers for %d ranks' % (len(ptrs), world))
+        table = lambda off: (ctypes.c_void_p * world)(*[p + 4 * off for p in ptrs])
+        self.verts, self.d_verts, self.grads = table(0), table(F * R), table(2 * F * R)
+        # the session's own buffers become views of the symmetric allocation
+        sess.verts = self.buf[:F * R].view(F, R)
+        sess.d_verts = self.buf[F * R:2 * F * R].view(F, R)
+        sess.grads = self.buf[2 * F * R:2 * F * R + ng]
+        nw, nt = F * sess.B, F * 3
+        sess.d_w = sess.grads[:nw].view(F, sess.B)
+        sess.d_t = sess.grads[nw:nw + nt].view(F, 3)
+        sess.d_q = sess.grads[nw + nt:].view(F, 4)
+        self.grads_sum = torch.zeros(ng, dtype=torch.float32, device=sess.device)
+        torch.cuda.synchronize(sess.device)
+        dist.barrier()
+
+    def barrier(self, channel):
+        # device-side: every rank's stream waits here until all ranks have arrived (traps after 10 s instead of hanging)
+        self.hdl.barrier(channel=channel, timeout_ms=10000)
 
 
 class FitSession:
@@ -306,6 +348,15 @@ class FitSession:
             self.verts_gathered = torch.empty(self.row_shard[2], F, Vl * 3, **f32)
             self.d_verts_local = torch.empty(F, Vl * 3, **f32)
             self.d_verts_scatter = torch.empty(self.row_shard[2], F, Vl * 3, **f32) if F > 1 else None
+        self.peer = None
+        if self.row_shard is not None and cfg.peer_exchange is not False:
+            try:
+                self.peer = _PeerExchange(self)
+            except Exception as e:          # no symmetric memory on this box / build: the NCCL collectives do the same job
+                if cfg.peer_exchange:
+                    raise
+                self.peer_unavailable = '%s: %s' % (type(e).__name__, e)
+        self.g_total = self.grads             # the gradient vector the optimiser consumed (summed over ranks in the split modes)
         # the tensor-core backward wants both operands K-major: a transposed copy of D, made once
         self.DT = self.D.t().contiguous() if self.use_tc_blend else None
         nbytes = max(L.fpc_blend_bwd_tc_scratch_bytes(V * 3, B, F) if self.use_tc_blend else 0,
@@ -509,6 +560,17 @@ class FitSession:
             import torch.distributed as dist
             v0, v1, wsz = self.row_shard
             Vl = v1 - v0
+            if self.peer is not None:
+                # blend + all-gather in ONE kernel: the GEMV epilogue stores this rank's vertices into every rank's buffer over NVLink
+                if F == 1:
+                    call('blend_fwd', 'fpc_blend_fwd_bcast', _p(self.D), ctypes.c_void_p(self.v_base.data_ptr() + 12 * v0), _p(self.w), Vl * 3, B,
+                         3 * v0, self.peer.verts, wsz, s); n += 1
+                else:
+                    call('blend_fwd', 'fpc_blend_fwd', _p(self.D), ctypes.c_void_p(self.v_base.data_ptr() + 12 * v0), _p(self.w), Vl * 3, B, F,
+                         _p(self.verts_local), s)
+                    call('blend_fwd', 'fpc_peer_store_rows', _p(self.verts_local), self.peer.verts, wsz, F, Vl * 3, V * 3, 3 * v0, s); n += 2
+                self.peer.barrier(0)
+                return n + 1
             call('blend_fwd', 'fpc_blend_fwd', _p(self.D), ctypes.c_void_p(self.v_base.data_ptr() + 12 * v0), _p(self.w), Vl * 3, B, F,
                  _p(self.verts_local), s); n += 1
             if F == 1:
@@ -647,7 +709,11 @@ class FitSession:
             import torch.distributed as dist
             v0, v1, wsz = self.row_shard
             Vl = v1 - v0
-            if F == 1:
+            if self.peer is not None:
+                # every rank's partial vertex gradient sits in its own (mapped) buffer: sum this rank's rows over the peers
+                self.peer.barrier(1)
+                call('blend_bwd', 'fpc_peer_sum_rows', self.peer.d_verts, wsz, F, Vl * 3, V * 3, 3 * v0, _p(self.d_verts_local), s); n += 2
+            elif F == 1:
                 dist.reduce_scatter_tensor(self.d_verts_local.view(-1), self.d_verts.view(-1))
             else:
                 self.d_verts_scatter.copy_(self.d_verts.view(F, wsz, Vl * 3).permute(1, 0, 2))
@@ -694,8 +760,15 @@ class FitSession:
         cfg, s, call = self.cfg, self._stream(), self._timed
         F, B = self.F, self.B
         n = 0
-        if cfg.cam_slice is not None:
+        grads = self.grads
+        if cfg.cam_slice is not None and self.peer is not None:
+            # all-reduce over peer memory: every rank sums the ranks' partial vectors in rank order (the same bits everywhere)
+            self.peer.barrier(2)
+            call('adam', 'fpc_peer_sum', self.peer.grads, self.row_shard[2], self.grads.numel(), _p(self.peer.grads_sum), s); n += 2
+            grads = self.peer.grads_sum
+        elif cfg.cam_slice is not None:
             allreduce_gradients(self.grads)            # the only exchange of the camera-split mode: (B+7) F floats
+        self.g_total = grads
         if cfg.optimize_cam_pose:
             # shared by all frames: under frame sharding every rank holds a partial sum (camera-split ranks own their cameras)
             if cfg.cam_slice is None:
@@ -720,12 +793,12 @@ class FitSession:
                  self.basis_lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.lr_ramp, float(cfg.max_iter), _p(self.step_count), self.basis_start, s); n += 1
         nw = F * B
         if F * (B + 7) <= (1 << 22):
-            call('adam', 'fpc_adam_fused', _p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), B, F, 1 if cfg.optimize_pose else 0,
+            call('adam', 'fpc_adam_fused', _p(self.params), _p(grads), _p(self.adam_m), _p(self.adam_v), B, F, 1 if cfg.optimize_pose else 0,
                  cfg.lr_base, cfg.lr_t, cfg.lr_q, cfg.beta1, cfg.beta2, cfg.eps, cfg.lr_ramp, float(cfg.max_iter),
                  1 if cfg.quat_norm == 'frobenius' else 0, _p(self.step_count), s)
             return n + 1
         adam = lambda off, cnt, lr: call('adam', 'fpc_adam_step', ctypes.c_void_p(self.params.data_ptr() + 4 * off),
-                                         ctypes.c_void_p(self.grads.data_ptr() + 4 * off),
+                                         ctypes.c_void_p(grads.data_ptr() + 4 * off),
                                          ctypes.c_void_p(self.adam_m.data_ptr() + 4 * off),
                                          ctypes.c_void_p(self.adam_v.data_ptr() + 4 * off), cnt, lr, cfg.beta1, cfg.beta2,
                                          cfg.eps, cfg.lr_ramp, float(cfg.max_iter), _p(self.step_count), s)
@@ -820,7 +893,8 @@ class FitSession:
         self._warmed = True
 
     def result_vertices(self):
-        """[F, 3V] blended vertices of the current parameters (fit.py:642 `result`)."""
+        """[F, 3V] blended vertices of the current parameters (fit.py:642 `result`).  With the rows of D sharded over the ranks
+        (camera split) this is a collective: every rank has to call it."""
         if self.use_basis or self.use_tc_blend or self.row_shard is not None:
             self._blend_forward()
         else:

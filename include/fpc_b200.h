@@ -298,6 +298,23 @@ int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, const int32
                                const int32_t* vadj_off, const int32_t* vadj_item,
                                void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
+/* ---- camera-split exchanges over NVLink peer memory (multi-GPU part of the north-star; fit.py is single-process:
+ *      no reference counterpart).  `peers` = HOST array of `world` device pointers, entry p = rank p's copy of the buffer as
+ *      mapped into this process (symmetric memory; the caller's own buffer included at its rank).  The kernels only move
+ *      data; a device-side barrier between producer and consumer kernels is the caller's job.
+ *   fpc_blend_fwd_bcast : verts[row0 + r] = base[r] + sum_b D[r,b] w[b] for this rank's R_local rows (single frame), stored
+ *                         by the GEMV epilogue into the vertex buffer [R_total] of EVERY rank: blend + all-gather in one kernel
+ *   fpc_peer_store_rows : src [F, rows_local] -> peers[p][f * rows_total + row0 + r] for every p (frame batches)
+ *   fpc_peer_sum_rows   : out [F, rows_local] = sum_p peers[p][f * rows_total + row0 + r], rank order (reduce-scatter)
+ *   fpc_peer_sum        : out [n] = sum_p peers[p][i], rank order: the same bits on every rank (all-reduce) */
+int fpc_blend_fwd_bcast(const float* D, const float* base, const float* w, int R_local, int B, long long row0,
+                        void* const* peer_verts, int world, fpc_stream_t stream);
+int fpc_peer_store_rows(const float* src, void* const* peers, int world, int F, long long rows_local, long long rows_total,
+                        long long row0, fpc_stream_t stream);
+int fpc_peer_sum_rows(void* const* peers, int world, int F, long long rows_local, long long rows_total, long long row0,
+                      float* out, fpc_stream_t stream);
+int fpc_peer_sum(void* const* peers, int world, long long n, float* out, fpc_stream_t stream);
+
 /* ---- mesh regularisers (replaces the pytorch3d terms of fit.py:578-582: weight_laplacian * laplacian(mesh)^2 +
  *      weight_meshedge * mesh_edge_loss(mesh, target) + weight_normalconsistency * mesh_normal_consistency(mesh)) -------
  * verts [F,V,3]; static topology (fpc_diffrend_b200/topology.py): neighbour CSR nbr_off [V+1] / nbr_idx [2E] over the E

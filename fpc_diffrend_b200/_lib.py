@@ -81,6 +81,7 @@ SIGNATURES = {
     'fpc_vertex_adjacency_scratch_bytes': (_Z, [_I]),
     'fpc_vertex_adjacency_build': (_I, [_P, _I, _I, _P, _P, _P, _Z, _P]),
     'fpc_raster_bin_px': (_I, []),
+    'fpc_rasterize_clip_pieces': (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     'fpc_render_loss_fused_band': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _I, _I, _I,
                                         _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'fpc_mesh_reg_scratch_bytes': (_Z, [_I, _I, _I]),

@@ -424,6 +424,18 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
 
 extern "C" int fpc_raster_bin_px(void) { return BIN; }
 
+extern "C" int fpc_rasterize_clip_pieces(const void* scratch, int N, int T, int H, int W, int* requested, int* capacity, fpc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FPC_CHECK_ARG(scratch && requested && capacity, "rasterize_clip_pieces: null pointer argument");
+    FPC_CHECK_ARG(N > 0 && T > 0 && H > 0 && W > 0, "rasterize_clip_pieces: N, T, H, W must be positive");
+    const ScratchLayout L = raster_layout(N, T, fpc_div_up(W, BIN) * fpc_div_up(H, BIN));
+    FPC_CUDA(cudaMemcpyAsync(requested, (const char*)scratch + L.off_clip_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    FPC_CUDA(cudaStreamSynchronize(stream));
+    *capacity = L.clip_cap;
+    return FPC_OK;
+}
+
 extern "C" size_t fpc_rasterize_scratch_bytes(int N, int T, int H, int W)
 {
     if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return 256;

@@ -854,6 +854,13 @@ class FitSession:
             allreduce_gradients(l)
         return float(l)
 
+    def clip_pool_overflowed(self):
+        """True when the near-plane clipper of the last iteration ran out of pool entries (pieces were dropped: a camera inside
+        the mesh or a wildly wrong pose).  Synchronises; a validation call, not for the loop."""
+        req, cap = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.call('fpc_rasterize_clip_pieces', _p(self.scratch), self.N, self.T, self.H, self.W, ctypes.byref(req), ctypes.byref(cap), self._stream())
+        return req.value > cap.value
+
     def reset_state(self):
         """Back to the initial parameters (w = 0, t = 0, q = identity; shared parameters likewise) and a fresh optimiser:
         used between frame batches of a take and after the eager warm-up iteration that precedes a graph capture."""

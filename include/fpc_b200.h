@@ -290,6 +290,11 @@ int fpc_render_loss_fused_aa(const float* pos, const int32_t* tri, const int32_t
  * pixel pair (owned by its lower / left pixel), belongs to exactly one bin: the ranks' losses and gradients add up to those of
  * the unsplit call. */
 int fpc_raster_bin_px(void);
+/* Near-plane clipper bookkeeping of the LAST binning that used `scratch` (fpc_rasterize_fwd or a fused entry with the same
+ * N, T, H, W): pieces of triangles crossing w <= 0 live in a pool of `capacity` = N*T/32 + 1024 entries; `requested` > `capacity`
+ * means pieces were dropped (a camera inside the mesh, or a wildly wrong pose).  A validation call: it synchronises the stream
+ * and reads 4 bytes back — not for the steady-state loop. */
+int fpc_rasterize_clip_pieces(const void* scratch, int N, int T, int H, int W, int* requested, int* capacity, fpc_stream_t stream);
 int fpc_render_loss_fused_band(const float* pos, const int32_t* tri, const int32_t* tri_opp, const float* attr,
                                const int32_t* attr_tri, int Va, int A, const float* tex, int Ht, int Wt,
                                const void* ref, int ref_is_u8, int N, int V, int T, int H, int W, int C, float bg, float scale, int loss_kind,

@@ -895,3 +895,34 @@ def test_against_nvdiffrast_when_installed(dr, small_rig3):
             assert rep['tri_id_mismatch_outside_depth_ties'] == 0, rep
             assert rep['rast_uvz_max_abs'] <= 1e-5 and rep['colour_max_abs'] <= 1e-5, rep
             assert rep['grad_pos_rel'] <= 1e-4, rep
+
+
+def test_clip_pool_overflow_is_detectable(dr, small_rig3):
+    """A camera inside the mesh sends (almost) every triangle through the near-plane clipper: the pool of clipped pieces
+    (N*T/32 + 1024 entries) cannot hold them all, and fpc_rasterize_clip_pieces reports it instead of dropping pieces silently
+    (round-1 advisor finding); an ordinary view requests no piece at all."""
+    import ctypes
+    from fpc_diffrend_b200 import _lib
+    rig, H, W = small_rig3, 64, 64
+    T = rig.pos_idx.shape[0]
+    rng = np.random.default_rng(0)
+    reps = 64                                                   # many copies of the mesh so that T/32 + 1024 is small against 2T
+    tri = np.concatenate([rig.pos_idx + 0 for _ in range(reps)]).astype(np.int32)
+    for inside, want in ((False, False), (True, True)):
+        pc = clip_positions(rig)[:1].copy()
+        if inside:
+            pc[..., 3] = rng.choice([-1.0, 1.0], size=pc[..., 3].shape).astype(np.float32)     # every triangle straddles w = 0
+        d_pos, d_tri = cu(pc), cu(tri)
+        N, V, TT = 1, pc.shape[1], tri.shape[0]
+        nb = int(_lib.load().fpc_rasterize_scratch_bytes(N, TT, H, W))
+        scratch = torch.empty(nb, dtype=torch.uint8, device='cuda')
+        rast = torch.empty(N, H, W, 4, device='cuda')
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.call('fpc_rasterize_fwd', P(d_pos), P(d_tri), N, V, TT, H, W, P(rast), None, P(scratch), nb, st)
+        req, cap = ctypes.c_int(-1), ctypes.c_int(-1)
+        _lib.call('fpc_rasterize_clip_pieces', P(scratch), N, TT, H, W, ctypes.byref(req), ctypes.byref(cap), st)
+        assert cap.value == N * TT // 32 + 1024
+        assert (req.value > cap.value) == want, (inside, req.value, cap.value)
+        if not inside:
+            assert req.value == 0

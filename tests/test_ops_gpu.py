@@ -897,23 +897,22 @@ def test_against_nvdiffrast_when_installed(dr, small_rig3):
             assert rep['grad_pos_rel'] <= 1e-4, rep
 
 
-def test_clip_pool_overflow_is_detectable(dr, small_rig3):
-    """A camera inside the mesh sends (almost) every triangle through the near-plane clipper: the pool of clipped pieces
-    (N*T/32 + 1024 entries) cannot hold them all, and fpc_rasterize_clip_pieces reports it instead of dropping pieces silently
-    (round-1 advisor finding); an ordinary view requests no piece at all."""
+def test_clip_pool_overflow_is_detectable(dr):
+    """A soup of triangles that all cross the near plane in front of the camera sends every one of them through the clipper: the
+    pool of clipped pieces (N*T/32 + 1024 entries) cannot hold two pieces per triangle, and fpc_rasterize_clip_pieces reports it
+    instead of dropping pieces silently (round-1 advisor finding); the same soup entirely in front of the camera requests none."""
     import ctypes
     from fpc_diffrend_b200 import _lib
-    rig, H, W = small_rig3, 64, 64
-    T = rig.pos_idx.shape[0]
-    rng = np.random.default_rng(0)
-    reps = 64                                                   # many copies of the mesh so that T/32 + 1024 is small against 2T
-    tri = np.concatenate([rig.pos_idx + 0 for _ in range(reps)]).astype(np.int32)
-    for inside, want in ((False, False), (True, True)):
-        pc = clip_positions(rig)[:1].copy()
-        if inside:
-            pc[..., 3] = rng.choice([-1.0, 1.0], size=pc[..., 3].shape).astype(np.float32)     # every triangle straddles w = 0
+    H = W = 64
+    TT = 100000
+    a, b = 200.01 / 199.99, -4.0 / 199.99                       # z_clip = a w + b (camera.py:27-41, zn = 0.01, zf = 200)
+    tri = np.arange(3 * TT, dtype=np.int32).reshape(TT, 3)
+    for crossing in (False, True):
+        w = np.array([1.0, 1.0, -1.0 if crossing else 1.0], np.float32)
+        one = np.stack([np.array([-0.5, 0.5, 0.0], np.float32), np.array([-0.5, -0.5, 1.5], np.float32), a * w + b, w], axis=1)   # [3,4]   (y/w must vary along the crossing edges)
+        pc = np.tile(one, (TT, 1))[None].astype(np.float32)      # [1, 3T, 4]
         d_pos, d_tri = cu(pc), cu(tri)
-        N, V, TT = 1, pc.shape[1], tri.shape[0]
+        N, V = 1, 3 * TT
         nb = int(_lib.load().fpc_rasterize_scratch_bytes(N, TT, H, W))
         scratch = torch.empty(nb, dtype=torch.uint8, device='cuda')
         rast = torch.empty(N, H, W, 4, device='cuda')
@@ -923,6 +922,8 @@ def test_clip_pool_overflow_is_detectable(dr, small_rig3):
         req, cap = ctypes.c_int(-1), ctypes.c_int(-1)
         _lib.call('fpc_rasterize_clip_pieces', P(scratch), N, TT, H, W, ctypes.byref(req), ctypes.byref(cap), st)
         assert cap.value == N * TT // 32 + 1024
-        assert (req.value > cap.value) == want, (inside, req.value, cap.value)
-        if not inside:
+        if crossing:
+            assert req.value > cap.value, (req.value, cap.value)
+            assert float(rast[..., 3].max()) > 0              # the pieces that did get a pool entry are rendered
+        else:
             assert req.value == 0

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('FPC_B200_LIB') or os.path.join(_HERE, 'libfpc_b200.so')
 HEADER_PATH = os.path.join(_HERE, '..', 'include', 'fpc_b200.h')
 
-ABI_VERSION = 3        # FPC_B200_ABI_VERSION of include/fpc_b200.h these signatures were written against
+ABI_VERSION = 4        # FPC_B200_ABI_VERSION of include/fpc_b200.h these signatures were written against
 
 _lib = None
 
@@ -21,6 +21,14 @@ _I = _c.c_int
 _F = _c.c_float
 _Z = _c.c_size_t
 _L = _c.c_longlong
+
+
+
+class AdamFusedArgs(_c.Structure):
+    """fpc_adam_fused_args of include/fpc_b200.h (the optimiser step that rides in fpc_geometry_bwd)."""
+    _fields_ = [('params', _P), ('m', _P), ('v', _P), ('step_count', _P), ('optimize_pose', _I), ('quat_mode', _I),
+                ('lr_w', _F), ('lr_t', _F), ('lr_q', _F), ('b1', _F), ('b2', _F), ('eps', _F), ('lr_ramp', _F), ('max_iter', _F)]
+
 
 # name -> (restype, argtypes); kept in the order of include/fpc_b200.h
 SIGNATURES = {
@@ -68,7 +76,8 @@ SIGNATURES = {
     'fpc_geometry_fused_supported': (_I, [_I, _I, _I, _I]),
     'fpc_geometry_fwd': (_I, [_P] * 9 + [_I] * 4 + [_P] * 4),
     'fpc_geometry_bwd_scratch_bytes': (_Z, [_I, _I, _I, _I]),
-    'fpc_geometry_bwd': (_I, [_P] * 11 + [_I] * 4 + [_P] * 6 + [_Z, _P]),
+    'fpc_geometry_bwd_counter_bytes': (_Z, [_I, _I]),
+    'fpc_geometry_bwd': (_I, [_P] * 11 + [_I] * 4 + [_P] * 8 + [_Z, _P]),
     'fpc_image_loss_scratch_bytes': (_Z, [_I, _I, _I, _I]),
     'fpc_image_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _Z, _P]),
     'fpc_render_loss_fused_scratch_bytes': (_Z, [_I, _I, _I, _I]),

@@ -3,9 +3,11 @@
 //   fpc_geometry_fwd : pose -> MVP chain (fit.py:546-553)  +  blend V = base + D w (fit.py:103-129)
 //                      +  clip transform [V 1] mvp^T (camera.py:11-23)                       -> ONE kernel
 //   fpc_geometry_bwd : d pos_clip -> d V (transform_clip bwd) -> d w = D^T d V (blend bwd), d mvp -> d t, d q
-//                      (pose bwd)                                                            -> TWO kernels
+//                      (pose bwd) [-> Adam step of the packed parameters]                     -> ONE kernel: the per-CTA
+//                      partials are combined by the CTAs that arrive last (groups of 8, then the groups, then the frames:
+//                      three counters, fixed summation order), which also run the pose backward and the optimiser
 //   fpc_adam_fused   : Adam + LambdaLR for the packed [w | t | q] vector, quaternion renorm and the step
-//                      counter advance (fit.py:493-505,610-618)                              -> ONE kernel
+//                      counter advance (fit.py:493-505,610-618)                              -> ONE kernel (when not folded)
 //
 // A warp owns one vertex at a time: its three rows of D are 3B contiguous floats (HBM/L2-bound float4 stream,
 // the only large operand), reduced with warp shuffles; lanes 0..C-1 then act as the cameras of that vertex.
@@ -35,17 +37,100 @@ __device__ __forceinline__ void load_rows(const float* __restrict__ D, int v, in
     }
 }
 
+
 // ---------------------------------------------------------------------------------------------------------
-// backward, stage 1: per-CTA partials of d w [F,B] and d mvp [F*C,16]
+// Adam for the packed parameter vector [w (F*B) | t (F*3) | q (F*4)] by ONE CTA (n is small: F*(B+7)); the body of
+// k_adam_fused and of the last CTA of k_geom_bwd
+// ---------------------------------------------------------------------------------------------------------
+struct AdamArgs {
+    float* p; float* m; float* v; float* step_count;      // p == nullptr: no optimiser step
+    int pose, quat_mode;
+    float lr_w, lr_t, lr_q, b1, b2, eps, lr_ramp, max_iter;
+};
+
+__device__ __forceinline__ void adam_packed_cta(const AdamArgs& a, const float* __restrict__ g, int nw, int F, float* red /* [32] shared */)
+{
+    const float step0 = a.step_count[0];
+    const float tstep = step0 + 1.f;
+    const float ramp = powf(a.lr_ramp, step0 / a.max_iter);
+    const float bc1 = 1.f - powf(a.b1, tstep), bc2 = 1.f - powf(a.b2, tstep);
+    const int n = nw + (a.pose ? 7 * F : 0);
+    float* p = a.p;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float lr = (i < nw) ? a.lr_w : ((i < nw + 3 * F) ? a.lr_t : a.lr_q);
+        float gi = __ldcg(g + i);                           // (written by other CTAs of the same launch in the folded case)
+        float mi = a.b1 * a.m[i] + (1.f - a.b1) * gi;
+        float vi = a.b2 * a.v[i] + (1.f - a.b2) * gi * gi;
+        a.m[i] = mi;
+        a.v[i] = vi;
+        float denom = sqrtf(vi) / sqrtf(bc2) + a.eps;      // torch.optim.Adam op order (k_adam, loss_adam.cu)
+        p[i] -= (lr * ramp / bc1) * (mi / denom);
+    }
+    __syncthreads();
+    if (a.pose) {
+        float* qq = p + nw + 3 * F;
+        if (a.quat_mode == 0) {
+            for (int i = threadIdx.x; i < F; i += blockDim.x) {
+                float x = qq[4 * i], y = qq[4 * i + 1], z = qq[4 * i + 2], w = qq[4 * i + 3];
+                float s = 1.f / sqrtf(x * x + y * y + z * z + w * w);
+                qq[4 * i] = x * s; qq[4 * i + 1] = y * s; qq[4 * i + 2] = z * s; qq[4 * i + 3] = w * s;
+            }
+        } else {
+            float s = 0.f;
+            for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) s += qq[i] * qq[i];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+            __syncthreads();
+            float tot = 0.f;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) tot += red[k];
+            float inv = 1.f / sqrtf(tot);
+            for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) qq[i] *= inv;
+        }
+    }
+    if (threadIdx.x == 0) a.step_count[0] = tstep;
+}
+
+// sum of n values `stride` floats apart IN INDEX ORDER, loaded U at a time (independent L2 reads in flight; written by other CTAs
+// of this launch, hence ld.cg)
+template <int U>
+__device__ __forceinline__ float ordered_sum(const float* __restrict__ src, size_t stride, int n)
+{
+    float s = 0.f;
+    for (int k0 = 0; k0 < n; k0 += U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = (k0 + u < n) ? __ldcg(src + (size_t)(k0 + u) * stride) : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; u++) s += v[u];
+    }
+    return s;
+}
+
+// what the last-arriving CTAs of k_geom_bwd need: second-level partials, the arrival counters (zero on entry, left zero), the
+// pose chain, the outputs, and the optional optimiser step
+constexpr int GEO_GROUP = 8;
+struct GeomTail {
+    int* counters;                  // [F * ng] groups | [F] frames | [1] all
+    float* part2_w;                 // [ng][F][B]
+    float* part2_mvp;               // [ng][F][C*16]
+    const float *P, *A, *t, *q, *t_cam, *q_cam;
+    float *d_w, *d_mvp, *d_t, *d_q;
+    AdamArgs adam;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// backward: per-CTA partials of d w [F,B] and d mvp [F*C,16], then the tail (see GeomTail)
 // ---------------------------------------------------------------------------------------------------------
 template <int K>   // K = ceil(3B/4 / 32): float4 accumulators per lane
 __global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restrict__ D, const float* __restrict__ verts,
                                                           const float* __restrict__ mvp, const float* __restrict__ g_pos,
                                                           const float* __restrict__ d_verts_add, int V, int B, int F, int C,
                                                           float* __restrict__ d_verts, float* __restrict__ part_w,
-                                                          float* __restrict__ part_mvp)
+                                                          float* __restrict__ part_mvp, GeomTail tl)
 {
     extern __shared__ float sm[];
+    __shared__ int s_last;
+    __shared__ float s_red[32];
     float* s_mvp = sm;                                  // [C][16]
     float* s_w = s_mvp + C * 16;                        // [GEO_WARPS][3B]
     float* s_m = s_w + GEO_WARPS * 3 * B;               // [GEO_WARPS][C][16]
@@ -156,6 +241,68 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restric
         for (int wv = 0; wv < GEO_WARPS; wv++) s += s_m[(size_t)wv * C * 16 + i];
         part_mvp[((size_t)blockIdx.x * F + f) * C * 16 + i] = s;
     }
+
+    // ---- tail.  Level 1: the CTA that arrives last in its group of GEO_GROUP sums the group's partials (in block order) ----
+    const int nval = C * 16;
+    const int ng = (gridDim.x + GEO_GROUP - 1) / GEO_GROUP, grp = blockIdx.x / GEO_GROUP;
+    const int gsz = min(GEO_GROUP, (int)gridDim.x - grp * GEO_GROUP);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(tl.counters + f * ng + grp, 1) == gsz - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < B + nval; i += GEO_THREADS) {
+        const bool isw = i < B;
+        const float* src = isw ? part_w + ((size_t)(grp * GEO_GROUP) * F + f) * B + i : part_mvp + ((size_t)(grp * GEO_GROUP) * F + f) * nval + (i - B);
+        const size_t stride = (size_t)F * (isw ? B : nval);
+        const float s = ordered_sum<GEO_GROUP>(src, stride, gsz);
+        if (isw) tl.part2_w[((size_t)grp * F + f) * B + i] = s;
+        else tl.part2_mvp[((size_t)grp * F + f) * nval + (i - B)] = s;
+    }
+    // ---- level 2: the group that arrives last for this frame sums the groups (in group order), runs the pose backward ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(tl.counters + F * ng + f, 1) == ng - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float* s_dm = sm;                                   // [nval]   (the main loop's shared memory is free now)
+    float* s_cam = sm + nval;                           // [C][12]
+    for (int i = threadIdx.x; i < B + nval; i += GEO_THREADS) {
+        const bool isw = i < B;
+        const float* src = isw ? tl.part2_w + (size_t)f * B + i : tl.part2_mvp + (size_t)f * nval + (i - B);
+        const float s = ordered_sum<8>(src, (size_t)F * (isw ? B : nval), ng);
+        if (isw) tl.d_w[(size_t)f * B + i] = s;
+        else {
+            s_dm[i - B] = s;
+            if (tl.d_mvp) tl.d_mvp[(size_t)f * nval + (i - B)] = s;
+        }
+    }
+    for (int i = threadIdx.x; i < ng; i += GEO_THREADS) tl.counters[f * ng + i] = 0;        // left as found
+    if (threadIdx.x == 0) tl.counters[F * ng + f] = 0;
+    __syncthreads();
+    if (threadIdx.x < C) pose_backward_camera(tl.P, tl.A, tl.t_cam, tl.q_cam, s_dm + 16 * threadIdx.x, threadIdx.x, s_cam + 12 * threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float g[12] = {};
+        for (int c = 0; c < C; c++)
+#pragma unroll
+            for (int i = 0; i < 12; i++) g[i] += s_cam[12 * c + i];
+        pose_backward_finish(tl.q, f, g, tl.d_t, tl.d_q);
+    }
+    if (!tl.adam.p) return;
+    // ---- level 3: the frame that finishes last steps the optimiser on the packed [w | t | q] vector (d_w is its gradient) ----
+    __syncthreads();                                   // (d_t, d_q of this frame are written)
+    if (F > 1) {
+        __threadfence();
+        if (threadIdx.x == 0) s_last = atomicAdd(tl.counters + F * ng + F, 1) == F - 1;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (threadIdx.x == 0) tl.counters[F * ng + F] = 0;
+    }
+    adam_packed_cta(tl.adam, tl.d_w, F * B, F, s_red);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -288,129 +435,11 @@ __global__ void __launch_bounds__(GT_THREADS) k_geom_fwd_tma(const float* __rest
     }
 }
 
-// backward, stage 2: CTA (f, j < nby) sums the d w partials of columns [32 j, 32 j + 32) — 32 warps take every 32nd block,
-// then a fixed-order sum over the warps (deterministic); CTA (f, nby) sums d mvp the same way and runs the pose backward
-// with one thread per camera (camera contributions are then added in index order).
-constexpr int RED_THREADS = 1024;
-
-__global__ void __launch_bounds__(RED_THREADS) k_geom_bwd_reduce(const float* __restrict__ part_w, const float* __restrict__ part_mvp,
-                                                                 int nblk, const float* __restrict__ P, const float* __restrict__ A,
-                                                                 const float* __restrict__ t, const float* __restrict__ q,
-                                                                 const float* __restrict__ t_cam, const float* __restrict__ q_cam,
-                                                                 int B, int F, int C, float* __restrict__ d_w,
-                                                                 float* __restrict__ d_mvp, float* __restrict__ d_t, float* __restrict__ d_q)
-{
-    extern __shared__ float dyn[];                      // pose CTA: red2 [32][nval] | s_dm [nval] | s_cam [C][12]
-    __shared__ float red[32][33];
-    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (blockIdx.y < gridDim.y - 1) {
-        const int b = blockIdx.y * 32 + lane;
-        float s = 0.f;
-        if (b < B) {
-#pragma unroll 4
-            for (int k = warp; k < nblk; k += 32) s += part_w[((size_t)k * F + f) * B + b];
-        }
-        red[warp][lane] = s;
-        __syncthreads();
-        if (warp == 0 && b < B) {
-            float tot = 0.f;
-#pragma unroll
-            for (int k = 0; k < 32; k++) tot += red[k][lane];
-            d_w[(size_t)f * B + b] = tot;
-        }
-        return;
-    }
-    const int nval = C * 16;
-    float* red2 = dyn;
-    float* s_dm = dyn + 32 * nval;
-    float* s_cam = s_dm + nval;
-    // every lane keeps all its (up to 16) columns in flight per block instead of walking the blocks once per column: the
-    // same sums in the same order, a third of the dependent L2 round trips (this CTA is the long pole of the kernel)
-    {
-        constexpr int MAXP = 16;                        // nval = 16 C <= 512
-        float a[MAXP];
-#pragma unroll
-        for (int p = 0; p < MAXP; p++) a[p] = 0.f;
-        for (int k = warp; k < nblk; k += 32) {
-            const float* src = part_mvp + ((size_t)k * F + f) * nval;
-#pragma unroll
-            for (int p = 0; p < MAXP; p++) {
-                const int i = p * 32 + lane;
-                if (i < nval) a[p] += src[i];
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < MAXP; p++) {
-            const int i = p * 32 + lane;
-            if (i < nval) red2[warp * nval + i] = a[p];
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nval; i += RED_THREADS) {
-        float tot = 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; k++) tot += red2[k * nval + i];
-        s_dm[i] = tot;
-        if (d_mvp) d_mvp[(size_t)f * nval + i] = tot;
-    }
-    __syncthreads();
-    if (threadIdx.x < C) pose_backward_camera(P, A, t_cam, q_cam, s_dm + 16 * threadIdx.x, threadIdx.x, s_cam + 12 * threadIdx.x);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float g[12] = {};
-        for (int c = 0; c < C; c++)
-#pragma unroll
-            for (int i = 0; i < 12; i++) g[i] += s_cam[12 * c + i];
-        pose_backward_finish(q, f, g, d_t, d_q);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Adam for the packed parameter vector [w (F*B) | t (F*3) | q (F*4)], single CTA (n is small: F*(B+7))
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_adam_fused(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                     float* __restrict__ v, int nw, int F, int pose, float lr_w, float lr_t, float lr_q,
-                                                     float b1, float b2, float eps, float lr_ramp, float max_iter, int quat_mode,
-                                                     float* __restrict__ step_count)
+// Adam as a kernel of its own (fpc_adam_fused): a single CTA
+__global__ void __launch_bounds__(1024) k_adam_fused(AdamArgs a, const float* __restrict__ g, int nw, int F)
 {
     __shared__ float red[32];
-    const float step0 = step_count[0];
-    const float tstep = step0 + 1.f;
-    const float ramp = powf(lr_ramp, step0 / max_iter);
-    const float bc1 = 1.f - powf(b1, tstep), bc2 = 1.f - powf(b2, tstep);
-    const int n = nw + (pose ? 7 * F : 0);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        float lr = (i < nw) ? lr_w : ((i < nw + 3 * F) ? lr_t : lr_q);
-        float gi = g[i];
-        float mi = b1 * m[i] + (1.f - b1) * gi;
-        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        float denom = sqrtf(vi) / sqrtf(bc2) + eps;      // torch.optim.Adam op order (k_adam, loss_adam.cu)
-        p[i] -= (lr * ramp / bc1) * (mi / denom);
-    }
-    __syncthreads();
-    if (pose) {
-        float* qq = p + nw + 3 * F;
-        if (quat_mode == 0) {
-            for (int i = threadIdx.x; i < F; i += blockDim.x) {
-                float x = qq[4 * i], y = qq[4 * i + 1], z = qq[4 * i + 2], w = qq[4 * i + 3];
-                float s = 1.f / sqrtf(x * x + y * y + z * z + w * w);
-                qq[4 * i] = x * s; qq[4 * i + 1] = y * s; qq[4 * i + 2] = z * s; qq[4 * i + 3] = w * s;
-            }
-        } else {
-            float s = 0.f;
-            for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) s += qq[i] * qq[i];
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-            __syncthreads();
-            float tot = 0.f;
-            for (int k = 0; k < (int)(blockDim.x >> 5); k++) tot += red[k];
-            float inv = 1.f / sqrtf(tot);
-            for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) qq[i] *= inv;
-        }
-    }
-    if (threadIdx.x == 0) step_count[0] = tstep;
+    adam_packed_cta(a, g, nw, F, red);
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -465,14 +494,14 @@ int launch_fwd_tma(const GtPlan& pl, cudaStream_t stream, const float* P, const 
 
 template <int K>
 int launch_bwd(dim3 grid, size_t smem, cudaStream_t stream, const float* D, const float* verts, const float* mvp, const float* g_pos,
-               const float* d_verts_add, int V, int B, int F, int C, float* d_verts, float* part_w, float* part_mvp)
+               const float* d_verts_add, int V, int B, int F, int C, float* d_verts, float* part_w, float* part_mvp, const GeomTail& tl)
 {
     static FpcPerDeviceOnce attr_set;
     if (attr_set.need()) {
         FPC_CUDA(cudaFuncSetAttribute(k_geom_bwd<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set.done();
     }
-    k_geom_bwd<K><<<grid, GEO_THREADS, smem, stream>>>(D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp);
+    k_geom_bwd<K><<<grid, GEO_THREADS, smem, stream>>>(D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp, tl);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }
@@ -508,44 +537,61 @@ extern "C" int fpc_geometry_fwd(const float* P, const float* A, const float* t, 
 extern "C" size_t fpc_geometry_bwd_scratch_bytes(int V, int B, int F, int C)
 {
     if (V <= 0 || B <= 0 || F <= 0 || C <= 0) return 256;
-    int nblk = geom_blocks(V);
-    return align256((size_t)nblk * F * B * sizeof(float)) + align256((size_t)nblk * F * C * 16 * sizeof(float));
+    const size_t nblk = geom_blocks(V), ng = fpc_div_up((int)nblk, GEO_GROUP);
+    return align256(nblk * F * B * sizeof(float)) + align256(nblk * F * C * 16 * sizeof(float)) +
+           align256(ng * F * B * sizeof(float)) + align256(ng * F * C * 16 * sizeof(float));
+}
+
+extern "C" size_t fpc_geometry_bwd_counter_bytes(int V, int F)
+{
+    if (V <= 0 || F <= 0) return 256;
+    return align256(((size_t)F * fpc_div_up(geom_blocks(V), GEO_GROUP) + F + 1) * sizeof(int));
 }
 
 extern "C" int fpc_geometry_bwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
                                 const float* D, const float* verts, const float* mvp, const float* g_pos, const float* d_verts_add,
                                 int V, int B, int F, int C, float* d_w, float* d_t, float* d_q, float* d_verts, float* d_mvp,
+                                int32_t* counters, const fpc_adam_fused_args* adam,
                                 void* scratch, size_t scratch_bytes, fpc_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    FPC_CHECK_ARG(P && A && t && q && D && verts && mvp && g_pos && d_w && d_t && d_q, "geometry_bwd: null pointer argument");
+    FPC_CHECK_ARG(P && A && t && q && D && verts && mvp && g_pos && d_w && d_t && d_q && counters, "geometry_bwd: null pointer argument");
     FPC_CHECK_ARG((t_cam == nullptr) == (q_cam == nullptr), "geometry_bwd: t_cam and q_cam must both be given or both be NULL");
     FPC_CHECK_ARG(fpc_geometry_fused_supported(V, B, F, C),
                   "geometry_bwd: needs B %% 4 == 0, B <= 1024, F <= 65535, C <= 32 (got V=%d B=%d F=%d C=%d); use project_bwd + blend_bwd + pose_mvp_bwd", V, B, F, C);
     FPC_CHECK_ARG(scratch && scratch_bytes >= fpc_geometry_bwd_scratch_bytes(V, B, F, C), "geometry_bwd: scratch too small");
-    const int nblk = geom_blocks(V);
-    float* part_w = (float*)scratch;
-    float* part_mvp = (float*)((char*)scratch + align256((size_t)nblk * F * B * sizeof(float)));
+    const int nblk = geom_blocks(V), ng = fpc_div_up(nblk, GEO_GROUP);
+    char* sp = (char*)scratch;
+    float* part_w = (float*)sp;      sp += align256((size_t)nblk * F * B * sizeof(float));
+    float* part_mvp = (float*)sp;    sp += align256((size_t)nblk * F * C * 16 * sizeof(float));
+    GeomTail tl;
+    tl.part2_w = (float*)sp;         sp += align256((size_t)ng * F * B * sizeof(float));
+    tl.part2_mvp = (float*)sp;
+    tl.counters = counters;
+    tl.P = P; tl.A = A; tl.t = t; tl.q = q; tl.t_cam = t_cam; tl.q_cam = q_cam;
+    tl.d_w = d_w; tl.d_mvp = d_mvp; tl.d_t = d_t; tl.d_q = d_q;
+    tl.adam = AdamArgs{};
+    if (adam) {
+        // the optimiser step rides in the last CTA: the gradient must be the packed vector [d_w | d_t | d_q] the step reads
+        FPC_CHECK_ARG(adam->params && adam->m && adam->v && adam->step_count, "geometry_bwd: adam: null pointer member");
+        FPC_CHECK_ARG(d_t == d_w + (size_t)F * B && d_q == d_t + (size_t)F * 3, "geometry_bwd: adam needs d_w, d_t, d_q packed as [d_w (F*B) | d_t (F*3) | d_q (F*4)]");
+        FPC_CHECK_ARG(adam->max_iter > 0.f && adam->lr_ramp > 0.f, "geometry_bwd: adam: max_iter and lr_ramp must be positive");
+        FPC_CHECK_ARG(adam->quat_mode == 0 || adam->quat_mode == 1, "geometry_bwd: adam: quat_mode must be 0 (per row) or 1 (Frobenius)");
+        FPC_CHECK_ARG((long long)F * (B + 7) <= (1 << 22), "geometry_bwd: adam: packed parameter vector too long (%lld)", (long long)F * (B + 7));
+        tl.adam = AdamArgs{adam->params, adam->m, adam->v, adam->step_count, adam->optimize_pose ? 1 : 0, adam->quat_mode,
+                           adam->lr_w, adam->lr_t, adam->lr_q, adam->b1, adam->b2, adam->eps, adam->lr_ramp, adam->max_iter};
+    }
     const int K = fpc_div_up((3 * B) >> 2, 32);
     int st;
     const size_t lsmem = (size_t)(C * 16 + GEO_WARPS * 3 * B + GEO_WARPS * C * 16) * sizeof(float);
-#define FPC_BWD_CASE(k) case k: st = launch_bwd<k>(dim3(nblk, F), lsmem, stream, D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp); break
+#define FPC_BWD_CASE(k) case k: st = launch_bwd<k>(dim3(nblk, F), lsmem, stream, D, verts, mvp, g_pos, d_verts_add, V, B, F, C, d_verts, part_w, part_mvp, tl); break
     switch (K <= 8 ? K : (K <= 10 ? 10 : (K <= 12 ? 12 : (K <= 16 ? 16 : 24)))) {
         FPC_BWD_CASE(1); FPC_BWD_CASE(2); FPC_BWD_CASE(3); FPC_BWD_CASE(4); FPC_BWD_CASE(5); FPC_BWD_CASE(6);
         FPC_BWD_CASE(7); FPC_BWD_CASE(8); FPC_BWD_CASE(10); FPC_BWD_CASE(12); FPC_BWD_CASE(16); FPC_BWD_CASE(24);
         default: st = FPC_ERR_UNSUPPORTED; fpc_set_error("geometry_bwd: unsupported B=%d", B);
     }
 #undef FPC_BWD_CASE
-    if (st != FPC_OK) return st;
-    static FpcPerDeviceOnce red_attr_set;
-    if (red_attr_set.need()) {
-        FPC_CUDA(cudaFuncSetAttribute(k_geom_bwd_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (33 * 32 * 16 + 12 * 32) * (int)sizeof(float)));
-        red_attr_set.done();
-    }
-    k_geom_bwd_reduce<<<dim3(F, fpc_div_up(B, 32) + 1), RED_THREADS, (size_t)(33 * C * 16 + 12 * C) * sizeof(float), stream>>>(
-        part_w, part_mvp, nblk, P, A, t, q, t_cam, q_cam, B, F, C, d_w, d_mvp, d_t, d_q);
-    FPC_LAUNCH_CHECK();
-    return FPC_OK;
+    return st;
 }
 
 extern "C" int fpc_adam_fused(float* params, const float* grads, float* m, float* v, int B, int F, int optimize_pose,
@@ -557,8 +603,8 @@ extern "C" int fpc_adam_fused(float* params, const float* grads, float* m, float
     FPC_CHECK_ARG(B > 0 && F > 0 && max_iter > 0.f && lr_ramp > 0.f, "adam_fused: B, F, max_iter and lr_ramp must be positive");
     FPC_CHECK_ARG((long long)F * (B + 7) <= (1 << 22), "adam_fused: packed parameter vector too long for the single-CTA kernel (%lld)", (long long)F * (B + 7));
     FPC_CHECK_ARG(quat_mode == 0 || quat_mode == 1, "adam_fused: quat_mode must be 0 (per row) or 1 (Frobenius)");
-    k_adam_fused<<<1, 1024, 0, stream>>>(params, grads, m, v, F * B, F, optimize_pose ? 1 : 0, lr_w, lr_t, lr_q, b1, b2, eps, lr_ramp,
-                                         max_iter, quat_mode, step_count);
+    const AdamArgs a{params, m, v, step_count, optimize_pose ? 1 : 0, quat_mode, lr_w, lr_t, lr_q, b1, b2, eps, lr_ramp, max_iter};
+    k_adam_fused<<<1, 1024, 0, stream>>>(a, grads, F * B, F);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

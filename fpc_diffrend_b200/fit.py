@@ -357,6 +357,9 @@ class FitSession:
                     raise
                 self.peer_unavailable = '%s: %s' % (type(e).__name__, e)
         self.g_total = self.grads             # the gradient vector the optimiser consumed (summed over ranks in the split modes)
+        # arrival counters of the geometry backward's in-kernel reduction (zero before the first call, left zero by every call)
+        self.geom_counters = torch.zeros(int(L.fpc_geometry_bwd_counter_bytes(V, F)) // 4, dtype=torch.int32, device=self.device)
+        self._adam_struct = None
         # the tensor-core backward wants both operands K-major: a transposed copy of D, made once
         self.DT = self.D.t().contiguous() if self.use_tc_blend else None
         nbytes = max(L.fpc_blend_bwd_tc_scratch_bytes(V * 3, B, F) if self.use_tc_blend else 0,
@@ -650,12 +653,12 @@ class FitSession:
                     _p(self.vadj_off), _p(self.vadj_item), _p(self.scratch), self.scratch.numel(), s)
         return 4 + (1 if cfg.optimize_texture else 0)      # k_setup, k_fill, k_fused[_aa], k_vtx_gather (+ loss reduction) [+ memset]
 
-    def backward(self):
+    def backward(self, fold_adam=False):
         cfg, s, call = self.cfg, self._stream(), self._timed
         F, V, T, B, C, H, W, N, Ch = self.F, self.V, self.T, self.B, self.C, self.H, self.W, self.N, self.Ch
         n = 0
         if self.use_fused:
-            return self._backward_geometry()
+            return self._backward_geometry(fold_adam)
         g_colour = self.d_colour
         if cfg.antialias:
             call('antialias_bwd', 'fpc_antialias_bwd', _p(self.colour), _p(self.rast), _p(self.pos_clip), _p(self.pos_idx), _p(self.tri_opp),
@@ -684,10 +687,28 @@ class FitSession:
                  _p(self.g_pos), s); n += 2
         if cfg.antialias:
             self.g_pos.add_(self.g_pos_aa); n += 1
-        return n + self._backward_geometry()
+        return n + self._backward_geometry(fold_adam)
 
-    def _backward_geometry(self):
-        """d pos_clip -> d verts, d mvp -> d w (D^T), d t, d q."""
+    def can_fold_adam(self):
+        """True when nothing sits between the geometry backward and the optimiser step of the packed [w | t | q] vector (no
+        prior regulariser on d_w, no exchange between ranks, no other parameter group stepping on the same step counter): the
+        step then rides in the last CTA of the geometry backward (csrc/geometry.cu: GeomTail) and the iteration is one launch
+        shorter."""
+        cfg = self.cfg
+        return bool(self.use_geom_fused and not self.use_reg_prior and not cfg.optimize_cam_pose and cfg.cam_slice is None and
+                    not cfg.optimize_texture and not self.use_basis and self.F * (self.B + 7) <= (1 << 22))
+
+    def _adam_args(self):
+        cfg = self.cfg
+        if self._adam_struct is None:
+            self._adam_struct = _lib.AdamFusedArgs(
+                self.params.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.step_count.data_ptr(),
+                1 if cfg.optimize_pose else 0, 1 if cfg.quat_norm == 'frobenius' else 0,
+                cfg.lr_base, cfg.lr_t, cfg.lr_q, cfg.beta1, cfg.beta2, cfg.eps, cfg.lr_ramp, float(cfg.max_iter))
+        return ctypes.byref(self._adam_struct)
+
+    def _backward_geometry(self, fold_adam=False):
+        """d pos_clip -> d verts, d mvp -> d w (D^T), d t, d q  [-> Adam step when fold_adam]."""
         s, call = self._stream(), self._timed
         F, V, B, C = self.F, self.V, self.B, self.C
         n = 0
@@ -697,8 +718,9 @@ class FitSession:
             call('geometry_bwd', 'fpc_geometry_bwd', _p(self.P), _p(self.A), _p(self.t), _p(self.q), *self._cam(), _p(self.D), _p(self.verts),
                  _p(self.mvp), _p(self.g_pos), _p(self.d_verts_reg) if self.use_reg else None, self.V, B, F, C,
                  _p(self.d_w), _p(self.d_t), _p(self.d_q), None, _p(self.d_mvp) if self.cfg.optimize_cam_pose else None,
+                 _p(self.geom_counters), self._adam_args() if fold_adam else None,
                  _p(self.scratch), self.scratch.numel(), s)
-            return n + 2 + self._prior_reg() + self._cam_pose_bwd()
+            return n + 1 + self._prior_reg() + self._cam_pose_bwd()
         call('project_bwd', 'fpc_project_bwd', _p(self.verts), _p(self.mvp), _p(self.g_pos), F, C, V, _p(self.d_verts), _p(self.d_mvp),
              _p(self.scratch), self.scratch.numel(), s); n += 2
         if self.use_reg:
@@ -813,7 +835,12 @@ class FitSession:
     def iteration(self):
         """Enqueue one full fit iteration (forward + backward + Adam) on the current stream. Returns the number
         of kernel launches it issued."""
-        n = self.forward() + self.backward() + self.optimizer_step()
+        fold = self.can_fold_adam()
+        n = self.forward() + self.backward(fold_adam=fold)
+        if fold:
+            self.g_total = self.grads
+        else:
+            n += self.optimizer_step()
         self.launches_per_iteration = n
         return n
 

@@ -49,8 +49,9 @@ typedef enum fpc_status {
 
 typedef void* fpc_stream_t; /* cudaStream_t */
 
-#define FPC_B200_ABI_VERSION 3   /* 2: loss_kind / grad_tex arguments of the loss and fused entries, band-split entry;
-                                    3: vadj_off / vadj_item arguments of the fused entries (atomics-free gradient gather) */
+#define FPC_B200_ABI_VERSION 4   /* 2: loss_kind / grad_tex arguments of the loss and fused entries, band-split entry;
+                                    3: vadj_off / vadj_item arguments of the fused entries (atomics-free gradient gather);
+                                    4: counters / adam arguments of fpc_geometry_bwd (reduction, pose backward and Adam in its tail) */
 
 /* ---- library ------------------------------------------------------------------------------------- */
 int fpc_abi_version(void);
@@ -182,13 +183,26 @@ int fpc_geometry_fused_supported(int V, int B, int F, int C);
 int fpc_geometry_fwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
                      const float* D, const float* base, const float* w, int V, int B, int F, int C,
                      float* mvp, float* verts, float* pos_clip, fpc_stream_t stream);
+/* The optimiser step of fpc_adam_fused as a rider of fpc_geometry_bwd (same meaning member by member). */
+typedef struct fpc_adam_fused_args {
+    float* params; float* m; float* v; float* step_count;
+    int optimize_pose, quat_mode;
+    float lr_w, lr_t, lr_q, b1, b2, eps, lr_ramp, max_iter;
+} fpc_adam_fused_args;
 /* g_pos [F*C,V,4] = d loss / d pos_clip; d_verts_add [F,V,3] or NULL: extra gradient on the blended vertices
  * (mesh regularisers, fit.py:580-582) added before the D^T contraction.
- * -> d_w [F,B], d_t [F,3], d_q [F,4] (overwritten); optional outputs d_verts [F,V,3], d_mvp [F*C,16] (NULL to skip). */
+ * -> d_w [F,B], d_t [F,3], d_q [F,4] (overwritten); optional outputs d_verts [F,V,3], d_mvp [F*C,16] (NULL to skip).
+ * ONE launch: the CTAs that arrive last combine the per-CTA partials in a fixed order (bit-reproducible), run the pose
+ * backward and — when `adam` is non-NULL — the optimiser step on the packed parameters (fit.py:610-618); that needs
+ * d_w, d_t, d_q to be the packed vector [d_w | d_t | d_q].  counters: fpc_geometry_bwd_counter_bytes() bytes of device
+ * memory owned by the caller, ZERO before the first call; every call leaves them zero (calls sharing a counter buffer must not
+ * overlap in time). */
 size_t fpc_geometry_bwd_scratch_bytes(int V, int B, int F, int C);
+size_t fpc_geometry_bwd_counter_bytes(int V, int F);
 int fpc_geometry_bwd(const float* P, const float* A, const float* t, const float* q, const float* t_cam, const float* q_cam,
                      const float* D, const float* verts, const float* mvp, const float* g_pos, const float* d_verts_add,
                      int V, int B, int F, int C, float* d_w, float* d_t, float* d_q, float* d_verts, float* d_mvp,
+                     int32_t* counters, const fpc_adam_fused_args* adam,
                      void* scratch, size_t scratch_bytes, fpc_stream_t stream);
 
 /* ---- mip-mapped texturing path (reference fit.py:153-155 with enable_mip) -------------------------

@@ -98,7 +98,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), 'libfpc_b200.so does not export %s declared in include/fpc_b200.h' % n
     assert set(names) == set(_lib.SIGNATURES.keys())
-    assert lib.fpc_abi_version() == 3
+    assert lib.fpc_abi_version() == 4
 
 
 def test_argument_errors_do_not_throw_and_set_message():

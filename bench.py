@@ -504,7 +504,8 @@ def build_session(job, wl, n_frames_arg=None, keep_host=False):
     # camera split cut at bin-row granularity: 9 views balance over 2/4/8 ranks (whole views would give 5+4, 3+2+2+2, 2+1x7)
     cam_slice, cam_band = shard.view_band_shard(wl['C'], wl['H'], rank, world) if cam_split else (None, None)
     # reference frames are stored as 8-bit grey levels like the reference's camera TIFFs (fit.py:530)
-    cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype='u8', cam_slice=cam_slice, cam_band=cam_band)
+    cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype='u8', cam_slice=cam_slice, cam_band=cam_band,
+                    reorder_vertices=True)
     ref = synthesize_reference(rig, w_all[sl], t_all[sl], q_all[sl], cfg, out_dtype=torch.uint8)
     sess = FitSession(rig, F, cfg)
     sess.set_reference(ref)
@@ -828,7 +829,9 @@ def run_ours(args, wl):
                                     'frames over ranks, no data-path collective'),
                        'cache': 'L2 flushed between timed steps (a 256 MB buffer is written outside the per-step CUDA-event pairs); `steady_state` = the same K steps back to back without the flush',
                        'reference_frames': ref_dtype + ' grey levels, resident in HBM for `value`, pinned host memory for `e2e`',
-                       'launch': 'CUDA graph replay' if use_graph else 'eager', 'loss_final': loss_final, 'host_affinity': job.numa},
+                       'launch': 'CUDA graph replay' if use_graph else 'eager', 'loss_final': loss_final, 'host_affinity': job.numa,
+                       'mesh': 'rig in shuffled (authoring) order; the session renumbers its vertices along a Morton curve at set-up '
+                               '(FitConfig.reorder_vertices, as fit_take does); triangle order untouched'},
             'steady_state': {'ms_per_step': ms_steady, 'value': value * ms_per_step / ms_steady,
                              'note': 'no L2 flush: the iteration re-reads the same frames, D and geometry, part of which the 126 MB L2 retains'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_total, 'launches_per_iteration': int(launches), 'roofline': roofline, 'stages': stages,

@@ -82,10 +82,56 @@ class FitConfig:
     tc_blend: bool = None                 # frame batches: blend fwd/bwd as a TMA + tcgen05 3xTF32 GEMM (csrc/blend_tc.cu); None = auto
     fused_geometry: bool = None           # pose+blend+project in one kernel per direction (csrc/geometry.cu); None = auto
                                           # (small frame batches: D is re-read per frame there, the GEMM path is not)
+    reorder_vertices: bool = False        # renumber the vertices along a space-filling curve inside the session (reorder_rig): the
+                                          # kernels' per-vertex gathers (positions of a pixel's triangle, gradient slots around a
+                                          # vertex, rows of D of the visible vertices) then touch neighbouring memory.  Triangle ids,
+                                          # images and losses are unchanged; per-vertex tensors of the session (verts, g_pos, ...) are
+                                          # in the internal order, result_vertices() returns the rig's order
 
 
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def morton_order(points):
+    """Permutation that sorts [V,3] points along a 3-D Morton (Z-order) curve, 10 bits per axis."""
+    p = np.asarray(points, np.float64)
+    lo, span = p.min(axis=0), np.maximum(p.max(axis=0) - p.min(axis=0), 1e-30)
+    q = np.minimum(((p - lo) / span * 1024.0).astype(np.int64), 1023)
+
+    def spread(x):                      # 10 bits -> every third bit
+        x = (x | (x << 16)) & 0x030000FF
+        x = (x | (x << 8)) & 0x0300F00F
+        x = (x | (x << 4)) & 0x030C30C3
+        x = (x | (x << 2)) & 0x09249249
+        return x
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    return np.argsort(code, kind='stable')
+
+
+def reorder_rig(rig):
+    """(rig', perm): the same rig with its vertices renumbered along a Morton curve of the neutral mesh — vertex j of rig' is
+    vertex perm[j] of rig.  Rows of D, v_base and vcol are permuted, pos_idx is remapped; the TRIANGLE order (hence every
+    triangle id and depth tie) and the uv set are untouched.  Real assets come in authoring order, which scatters the
+    kernels' per-vertex gathers over memory; this is the load-time mesh optimisation a renderer does once.  Cached on the rig."""
+    hit = getattr(rig, '_fpc_reordered', None)
+    if hit is not None:
+        return hit
+    V = rig.v_base.shape[0] // 3
+    perm = morton_order(np.asarray(rig.v_base).reshape(V, 3))
+    inv = np.empty(V, np.int64)
+    inv[perm] = np.arange(V)
+    from types import SimpleNamespace
+    out = SimpleNamespace(**{k: getattr(rig, k) for k in ('uv', 'uv_idx', 'tex', 'P', 'A') if hasattr(rig, k)})
+    out.v_base = np.ascontiguousarray(np.asarray(rig.v_base).reshape(V, 3)[perm].reshape(-1))
+    out.D = np.ascontiguousarray(np.asarray(rig.D).reshape(V, 3, -1)[perm].reshape(3 * V, -1))
+    out.pos_idx = inv[np.asarray(rig.pos_idx)].astype(np.int32)
+    out.vcol = np.ascontiguousarray(np.asarray(rig.vcol)[perm])
+    try:
+        rig._fpc_reordered = (out, perm)
+    except AttributeError:
+        pass
+    return out, perm
 
 
 class _PeerExchange:
@@ -138,6 +184,13 @@ class FitSession:
             raise RuntimeError('FitSession needs a CUDA device (sm_100a); there is no CPU path')
         self.device = torch.device(device if device is not None else ('cuda:%d' % torch.cuda.current_device()))
         dev = self.device
+        self.vertex_order = None            # internal vertex j = vertex vertex_order[j] of the rig (reorder_vertices)
+        if cfg.reorder_vertices:
+            rig, perm = reorder_rig(rig)
+            inv = np.empty(perm.shape[0], np.int64)
+            inv[perm] = np.arange(perm.shape[0])
+            self.vertex_order = torch.tensor(perm, dtype=torch.int64, device=dev)
+            self._vertex_rank = torch.tensor(inv, dtype=torch.int64, device=dev)
         _lib.load()
         _check_device(torch.empty(1, device=dev))
         f32 = dict(dtype=torch.float32, device=dev)
@@ -933,6 +986,8 @@ class FitSession:
             self._blend_forward()
         else:
             _lib.call('fpc_blend_fwd', _p(self.D), _p(self.v_base), _p(self.w), self.V * 3, self.B, self.F, _p(self.verts), self._stream())
+        if self.vertex_order is not None:                 # back to the rig's vertex order
+            return self.verts.view(self.F, self.V, 3)[:, self._vertex_rank].reshape(self.F, self.V * 3)
         return self.verts.clone()
 
 

@@ -54,7 +54,7 @@ def fit_take(basemeshpath, localblpath, imdir, calibpath, out_dir=None, iters_pe
     first = dataio.read_frame(dataio.frame_path(imdir, cams[0], frames[0], digits))
     H, W = first.shape[:2]
     cfg = replace(config or FitConfig(shading='texture', antialias=True), resolution=(H, W), ref_dtype='u8',
-                  max_iter=int(max_iter or iters_per_frame))
+                  max_iter=int(max_iter or iters_per_frame), reorder_vertices=True)    # (results come back in the rig's order)
     f0, f1 = shard.frame_shard(len(frames))
     mine = frames[f0:f1]
     # parameters shared by all frames (texture, per-camera pose corrections, the learned basis of the free / combined modes)

@@ -28,7 +28,7 @@ def one(workload):
     rig, w_all, t_all, q_all = bench.make_inputs(wl, F)
     # zero learning rates: the geometry (and with it the work per iteration) stays the same for every variant
     cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype='u8',
-                    lr_base=0.0, lr_t=0.0, lr_q=0.0)
+                    lr_base=0.0, lr_t=0.0, lr_q=0.0, reorder_vertices=bool(int(os.environ.get('FPC_EXP_REORDER', '0'))))
     ref = synthesize_reference(rig, w_all, t_all, q_all, cfg, out_dtype=torch.uint8)
     sess = FitSession(rig, F, cfg)
     sess.set_reference(ref)

@@ -373,6 +373,39 @@ def test_gradients_are_bit_reproducible(small_rig3, shading, use_aa, size):
         assert r[3] == runs[0][3]
 
 
+@pytest.mark.parametrize('shading,use_aa,reg', [('vcol', False, False), ('texture', True, True)])
+def test_vertex_reordering_changes_nothing_visible(small_rig3, shading, use_aa, reg):
+    """FitConfig.reorder_vertices (what fit_take and bench.py run with): the session renumbers the vertices along a Morton curve.
+    Triangle ids do not change, so the loss of the first iteration is the same to the last bit; the per-vertex gradient is the
+    unordered session's, permuted (bit-equal: same slots, same adjacency order per vertex); the packed gradient differs only by
+    the summation order of D^T over the vertices; result_vertices() comes back in the rig's order."""
+    from dataclasses import replace
+    from fpc_diffrend_b200 import rig as rigmod
+    from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
+    rig, H, W, F = small_rig3, 152, 200, 2
+    cfg = FitConfig(resolution=(H, W), shading=shading, antialias=use_aa, lr_base=1e-2,
+                    weight_laplacian=5.0 if reg else 0.0, weight_meshedge=0.5 if reg else 0.0)
+    w_true, t_true, q_true = rigmod.make_targets(F, rig.B, seed=1)
+    ref = synthesize_reference(rig, w_true, 0.2 * t_true, q_true, cfg)
+    a, b = FitSession(rig, F, cfg), FitSession(rig, F, replace(cfg, reorder_vertices=True))
+    assert b.vertex_order is not None and not torch.equal(b.vertex_order, torch.arange(rig.V, device='cuda'))
+    for s in (a, b):
+        s.set_reference(ref)
+        s.forward(); s.backward()
+    torch.cuda.synchronize()
+    assert float(a.loss) == float(b.loss)
+    assert torch.equal(a.g_pos[:, b.vertex_order], b.g_pos)
+    rel = lambda x, y: float((x - y).abs().max() / y.abs().max().clamp_min(1e-30))
+    assert rel(b.grads, a.grads) < 2e-5, rel(b.grads, a.grads)
+    assert torch.equal(a.result_vertices(), b.result_vertices())
+    for s in (a, b):
+        for _ in range(5):
+            s.iteration()
+    torch.cuda.synchronize()
+    assert abs(float(a.loss) - float(b.loss)) <= 1e-4 * abs(float(a.loss))
+    assert rel(b.result_vertices(), a.result_vertices()) < 1e-4
+
+
 def test_fit_stream_matches_resident(tiny_rig):
     """Pipelined host-buffer API (double-buffered uploads, one graph per buffer) == resident-frame iterations."""
     from fpc_diffrend_b200 import rig as rigmod

@@ -302,6 +302,9 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
     }
 }
 
+#ifndef FPC_ORDER_MODE
+#define FPC_ORDER_MODE 1
+#endif
 #ifndef FPC_FUSED_MINBLOCKS
 #define FPC_FUSED_MINBLOCKS 8
 #endif
@@ -314,7 +317,8 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     WarpStage* stage = reinterpret_cast<WarpStage*>(smem + sizeof(unsigned long long) * BIN * BIN);
     __shared__ double red[FINE_WARPS];
 
-    const int bin = blockIdx.x, n = blockIdx.y;
+    int bin, n;
+    ordered_bin<FPC_ORDER_MODE>(rp, n, bin);           // long triangle lists first (k_fill)
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 

@@ -28,6 +28,12 @@ namespace {
 #ifndef FPC_AA_THREADS
 #define FPC_AA_THREADS 256
 #endif
+// launch order of the CTAs (raster_core.cuh: ordered_bin): identity.  Measured (round 2): longest-lists-first costs this kernel
+// 2.5 % at config 3 / 5 (neighbouring bins share texels, triangles and vertices: their CTAs are better off running together),
+// while the antialias-free kernel gains 10 % at config 2 from it
+#ifndef FPC_ORDER_MODE_AA
+#define FPC_ORDER_MODE_AA 0
+#endif
 #ifndef FPC_AA_MINBLOCKS
 #define FPC_AA_MINBLOCKS 3
 #endif
@@ -142,7 +148,8 @@ __global__ void __launch_bounds__(AA_THREADS, FPC_AA_MINBLOCKS) k_fused_aa(Raste
     __shared__ unsigned char s_rowpair[AA_TW + 4];     // tile row -> some pixel of the row is the triangle side of an accepted pair with
                                                        // a non-zero gradient (the gather phase looks for pair terms only in such rows)
 
-    const int bin = blockIdx.x, n = blockIdx.y;
+    int bin, n;
+    ordered_bin<FPC_ORDER_MODE_AA>(rp, n, bin);        // long triangle lists first (k_fill)
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
     const int tx0 = ox - AA_HALO, ty0 = oy - AA_HALO;           // tile origin (may be negative)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -90,6 +90,8 @@ __device__ __forceinline__ void adam_packed_cta(const AdamArgs& a, const float* 
     if (threadIdx.x == 0) a.step_count[0] = tstep;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // sum of n values `stride` floats apart IN INDEX ORDER, loaded U at a time (independent L2 reads in flight; written by other CTAs
 // of this launch, hence ld.cg)
 template <int U>
@@ -108,7 +110,7 @@ __device__ __forceinline__ float ordered_sum(const float* __restrict__ src, size
 
 // what the last-arriving CTAs of k_geom_bwd need: second-level partials, the arrival counters (zero on entry, left zero), the
 // pose chain, the outputs, and the optional optimiser step
-constexpr int GEO_GROUP = 8;
+constexpr int GEO_GROUP = 16;         // 296 CTAs -> 19 groups: each level sums its operands with ONE batch of loads in flight
 struct GeomTail {
     int* counters;                  // [F * ng] groups | [F] frames | [1] all
     float* part2_w;                 // [ng][F][B]
@@ -250,8 +252,7 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restric
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(tl.counters + f * ng + grp, 1) == gsz - 1;
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    if (!s_last) return;            // (the partials are read with ld.cg below: L2 is the point of coherence, as in CUDA's threadFenceReduction sample)
     for (int i = threadIdx.x; i < B + nval; i += GEO_THREADS) {
         const bool isw = i < B;
         const float* src = isw ? part_w + ((size_t)(grp * GEO_GROUP) * F + f) * B + i : part_mvp + ((size_t)(grp * GEO_GROUP) * F + f) * nval + (i - B);
@@ -266,13 +267,26 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restric
     if (threadIdx.x == 0) s_last = atomicAdd(tl.counters + F * ng + f, 1) == ng - 1;
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
+    {
+        // what the rest of the tail reads does not depend on the sums: request it now (L1 prefetch), so that the pose backward
+        // and the optimiser step do not each wait for their own round trip to L2 after the sums
+        if (threadIdx.x < C) {
+            prefetch_l1(tl.P + 16 * threadIdx.x); prefetch_l1(tl.P + 16 * threadIdx.x + 8);
+            prefetch_l1(tl.A + 16 * threadIdx.x); prefetch_l1(tl.A + 16 * threadIdx.x + 8);
+        }
+        if (threadIdx.x == 32) prefetch_l1(tl.q + 4 * f);
+        if (tl.adam.p && F == 1) {
+            const int n = B + 7;
+            if (threadIdx.x == 33) prefetch_l1(tl.adam.step_count);
+            for (int i = 8 * threadIdx.x; i < n; i += 8 * GEO_THREADS) { prefetch_l1(tl.adam.m + i); prefetch_l1(tl.adam.v + i); prefetch_l1(tl.adam.p + i); }
+        }
+    }
     float* s_dm = sm;                                   // [nval]   (the main loop's shared memory is free now)
     float* s_cam = sm + nval;                           // [C][12]
     for (int i = threadIdx.x; i < B + nval; i += GEO_THREADS) {
         const bool isw = i < B;
         const float* src = isw ? tl.part2_w + (size_t)f * B + i : tl.part2_mvp + (size_t)f * nval + (i - B);
-        const float s = ordered_sum<8>(src, (size_t)F * (isw ? B : nval), ng);
+        const float s = ordered_sum<20>(src, (size_t)F * (isw ? B : nval), ng);
         if (isw) tl.d_w[(size_t)f * B + i] = s;
         else {
             s_dm[i - B] = s;
@@ -299,7 +313,6 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geom_bwd(const float* __restric
         if (threadIdx.x == 0) s_last = atomicAdd(tl.counters + F * ng + F, 1) == F - 1;
         __syncthreads();
         if (!s_last) return;
-        __threadfence();
         if (threadIdx.x == 0) tl.counters[F * ng + F] = 0;
     }
     adam_packed_cta(tl.adam, tl.d_w, F * B, F, s_red);

@@ -214,6 +214,28 @@ __global__ void __launch_bounds__(BIN_TPB) k_fill(RasterParams rp)
             }
         }
         __syncthreads();
+        // the first CTA of the view also files the view's bins by list-length class (launch order of the fused kernels)
+        if (blockIdx.x == 0 && rp.bin_order) {
+            __shared__ int s_cls[ORDER_CLASSES], s_base[ORDER_CLASSES];
+            if (threadIdx.x < ORDER_CLASSES) s_cls[threadIdx.x] = 0;
+            __syncthreads();
+            const int any_large = rp.large_count[n] != 0;               // large triangles are walked in every bin of the view
+            const int g = n / rp.order_gv, nin = n - g * rp.order_gv;
+            int cls[HIST_MAX_BINS / BIN_TPB], rk[HIST_MAX_BINS / BIN_TPB];
+#pragma unroll
+            for (int k = 0; k < HIST_MAX_BINS / BIN_TPB; k++) {
+                const int b = threadIdx.x + k * BIN_TPB;
+                if (b < rp.NB) { cls[k] = order_class(cnt[b] + any_large); rk[k] = atomicAdd(s_cls + cls[k], 1); }
+            }
+            __syncthreads();
+            if (threadIdx.x < ORDER_CLASSES) s_base[threadIdx.x] = atomicAdd(rp.order_count + ORDER_CLASSES * g + threadIdx.x, s_cls[threadIdx.x]);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < HIST_MAX_BINS / BIN_TPB; k++) {
+                const int b = threadIdx.x + k * BIN_TPB;
+                if (b < rp.NB) rp.bin_order[((size_t)g * ORDER_CLASSES + cls[k]) * ((size_t)rp.order_gv * rp.NB) + s_base[cls[k]] + rk[k]] = nin * rp.NB + b;
+            }
+        }
     }
     int info = (t < rp.T) ? rp.tri_info[(size_t)n * rp.T + t] : 0;
     const bool small = (info >> 22) == 1;
@@ -344,6 +366,8 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_nzlo = o;        o += align_up((size_t)N * NB * 4);
     L.off_zhi = o;         o += align_up((size_t)N * NB * 4);
     L.off_clip_count = o;  o += align_up(4);
+    const size_t ngroups = ((size_t)N + ORDER_GROUP_VIEWS - 1) / ORDER_GROUP_VIEWS;
+    L.off_order_count = o; o += align_up(ngroups * ORDER_CLASSES * 4);
     L.zero_bytes = o;
     L.off_offset = o;      o += align_up((size_t)N * NB * 4);
     L.off_info = o;        o += align_up((size_t)N * T * 4);
@@ -356,6 +380,7 @@ ScratchLayout raster_layout(int N, int T, int NB)
     L.off_tri4 = o;        o += align_up((size_t)T * 16);
     L.off_bbox = o;        o += align_up((size_t)N * T * 8);
     L.off_valid = o;       o += align_up((size_t)N * T * 4);
+    L.off_order = o;       o += align_up(ngroups * ORDER_CLASSES * ORDER_GROUP_VIEWS * (size_t)NB * 4);
     L.total = o;
     return L;
 }
@@ -396,6 +421,9 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.clip_parent = (int*)(s + L.off_clip_parent);
     rp.clip_cap = L.clip_cap;
     rp.pad_i_src = pad_i_src; rp.pad_i_dst = pad_i_dst; rp.pad_i_n = pad_i_src ? pad_i_n : 0;
+    rp.order_count = (int*)(s + L.off_order_count);
+    rp.order_gv = ORDER_GROUP_VIEWS;
+    rp.bin_order = (rp.NB <= HIST_MAX_BINS) ? (int*)(s + L.off_order) : nullptr;       // (written by k_fill<true>)
     FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
     rp.slot_grad = slot_grad;
     dim3 grid(fpc_div_up(T, BIN_TPB), N);

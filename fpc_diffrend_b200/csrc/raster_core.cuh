@@ -80,7 +80,54 @@ struct RasterParams {
     unsigned* bin_zhi;               // [N*NB]  max of depth_key(z/w) over the vertices of the SMALL triangles listed in the bin (k_setup;
                                      //         zero-initialised with the counters: an empty bin reads (0xFFFFFFFF, 0))
     int idbits;                      // bits of a triangle id: ceil(log2(T))
+    // launch order of the fused kernels' CTAs (k_fill): within groups of order_gv views, bins sorted by list-length class, longest
+    // first, empty bins last — the short background CTAs fill the gaps the long ones leave at the end of the launch
+    int* order_count;                // [ngroups * ORDER_CLASSES] bins per class (zeroed with the counters)
+    int* bin_order;                  // [ngroups * ORDER_CLASSES * order_gv * NB] (view-in-group * NB + bin) per class; null: identity order
+    int order_gv;
 };
+
+constexpr int ORDER_CLASSES = 8;
+constexpr int ORDER_GROUP_VIEWS = 16;
+
+// 0: empty bin (background), 1: 1-7 triangles, 2: 8-15, 3: 16-31, ... 7: >= 256
+__device__ __forceinline__ int order_class(int count)
+{
+    if (count <= 0) return 0;
+    const int c = 32 - __clz(count) - 2;
+    return c < 1 ? 1 : (c > 7 ? 7 : c);
+}
+
+// (blockIdx.x, blockIdx.y) of a (NB, N) grid -> the (view, bin) this CTA works on.  MODE 0: identity; 1: the group's bins by class,
+// longest lists first, background bins last; 2: the same order for the non-empty bins with the background bins spread evenly
+// between them (a background CTA only streams its reference tile: it mixes well with the compute-bound ones)
+template <int MODE>
+__device__ __forceinline__ void ordered_bin(const RasterParams& rp, int& n, int& bin)
+{
+    n = blockIdx.y; bin = blockIdx.x;
+    if (MODE == 0 || !rp.bin_order) return;
+    const int g = n / rp.order_gv;
+    int r = (n - g * rp.order_gv) * rp.NB + bin;                 // rank of this CTA inside its group of views
+    const int4 hi = __ldg(reinterpret_cast<const int4*>(rp.order_count + ORDER_CLASSES * g) + 1);
+    const int4 lo = __ldg(reinterpret_cast<const int4*>(rp.order_count + ORDER_CLASSES * g));
+    const int cnt[ORDER_CLASSES] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    int cls = ORDER_CLASSES - 1;
+    if (MODE == 2 && cnt[0] > 0) {
+        const int total = min(rp.order_gv, rp.N - g * rp.order_gv) * rp.NB;
+        const int k = total / cnt[0];                            // every k-th CTA of the group is a background bin
+        const int q = r / k;
+        if (r - q * k == k - 1 && q < cnt[0]) { cls = 0; r = q; }
+        else r -= min(cnt[0], (r + 1) / k);
+    }
+    if (cls != 0) {
+#pragma unroll
+        for (int c = ORDER_CLASSES - 1; c > 0; c--)
+            if (cls == c && r >= cnt[c]) { r -= cnt[c]; cls = c - 1; }
+    }
+    const int id = __ldg(rp.bin_order + ((size_t)g * ORDER_CLASSES + cls) * ((size_t)rp.order_gv * rp.NB) + r);
+    n = g * rp.order_gv + id / rp.NB;
+    bin = id - (id / rp.NB) * rp.NB;
+}
 
 struct SnappedTri {
     int x0, y0, x1, y1, x2, y2;      // 1/16 px, ORIGINAL vertex order
@@ -534,7 +581,7 @@ __device__ __forceinline__ unsigned long long tile_key(const unsigned long long*
 // Host side: scratch layout + the three binning launches.
 struct ScratchLayout {
     size_t zero_bytes;               // leading region that must be zeroed each call
-    size_t off_count, off_cursor, off_large_count, off_nzlo, off_zhi, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_bbox, off_valid, off_clip_count, off_clip_verts, off_clip_parent, total;
+    size_t off_count, off_cursor, off_large_count, off_nzlo, off_zhi, off_offset, off_info, off_pairs, off_large, off_anchor, off_tri4, off_bbox, off_valid, off_clip_count, off_clip_verts, off_clip_parent, off_order_count, off_order, total;
     int clip_cap;
 };
 

@@ -23,7 +23,9 @@ def one(workload):
     import torch
     import bench
     from fpc_diffrend_b200.fit import FitConfig, FitSession, synthesize_reference
-    wl = bench.WORKLOADS[workload]
+    wl = dict(bench.WORKLOADS[workload])
+    if os.environ.get('FPC_EXP_SHADING'):
+        wl['shading'] = os.environ['FPC_EXP_SHADING']
     F = int(os.environ.get('FPC_EXP_FRAMES', '0')) or min(wl['F'], 4)
     rig, w_all, t_all, q_all = bench.make_inputs(wl, F)
     # zero learning rates: the geometry (and with it the work per iteration) stays the same for every variant

@@ -16,7 +16,7 @@ iters = int(sys.argv[sys.argv.index('--iters') + 1]) if '--iters' in sys.argv el
 wl = bench.WORKLOADS[workload]
 F = int(sys.argv[sys.argv.index('--frames') + 1]) if '--frames' in sys.argv else wl['F']
 rig, w_all, t_all, q_all = bench.make_inputs(wl, F)
-cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype='u8')
+cfg = FitConfig(resolution=(wl['H'], wl['W']), shading=wl['shading'], antialias=wl['aa'], ref_dtype='u8', reorder_vertices=True)   # as bench.py
 ref = synthesize_reference(rig, w_all, t_all, q_all, cfg, out_dtype=torch.uint8)
 sess = FitSession(rig, F, cfg)
 sess.set_reference(ref)

@@ -772,9 +772,8 @@ def test_packed_key_overflow_redo_path(tmp_path):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = os.path.join(root, 'fpc_diffrend_b200', 'libfpc_b200_ovf.so')
-    if not os.path.exists(lib):
-        from fpc_diffrend_b200 import build as B
-        B.build(defines=('FPC_KEY32_TEST_OVERFLOW=1',), tag='_ovf')
+    from fpc_diffrend_b200 import build as B
+    assert B.build(defines=('FPC_KEY32_TEST_OVERFLOW=1',), tag='_ovf') == lib       # incremental: recompiles what is stale
     code = r'''
 import sys, numpy as np, torch
 sys.path.insert(0, %r); sys.path.insert(0, %r)

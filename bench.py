@@ -775,7 +775,7 @@ def run_ours(args, wl):
     if top == 'render_loss_fused':
         ab = alg['render_loss_fused_as_built']
         roofline['byte_model'] = ('SURVEY 8(d) fused-path algorithmic bytes: (56+20C) B/px + geometry; the call spans its binning, '
-                                  'fused render+loss+gradient and triangle-gradient launches')
+                                  'fused render+loss+gradient and per-vertex gradient gather launches (k_setup, k_fill, k_fused[_aa], k_vtx_gather)')
         roofline['as_built_bytes_per_launch'] = ab
         roofline['as_built_GBps'] = ab / (stage_ms[top] * 1e-3) / 1e9
         roofline['frac_hbm_model'] = achieved / peak

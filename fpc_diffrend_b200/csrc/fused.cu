@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     __shared__ double red[FINE_WARPS];
 
     int bin, n;
-    ordered_bin<FPC_ORDER_MODE>(rp, n, bin);           // long triangle lists first (k_fill)
+    const int cls = ordered_bin<FPC_ORDER_MODE>(rp, n, bin);       // long triangle lists first (k_fill)
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     {
         // ~2/3 of the bins of a head shot hold no triangle: their only work is streaming the reference tile through the loss.  The
         // first chunk of the tile is requested together with the counters that decide it (one memory round trip instead of two).
-        const int cnt = rp.bin_count[(size_t)n * rp.NB + bin], nlg = rp.large_count[n];
+        // (class 0 of the launch order = no list entry and no large triangle in the view: no need to wait for the counters)
+        const bool empty = (cls >= 0) ? (cls == 0) : (rp.bin_count[(size_t)n * rp.NB + bin] == 0 && rp.large_count[n] == 0);
         const int esz0 = fp.ref_u8 ? 1 : 4;
         const unsigned char* rbase = reinterpret_cast<const unsigned char*>(fp.ref);
         const size_t row_bytes = (size_t)rp.W * C * esz0;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
             const int r = threadIdx.x / cpr, ch = threadIdx.x - r * cpr;
             pre = __ldg(reinterpret_cast<const uint4*>(rbase + ((size_t)n * rp.H + oy + r) * row_bytes + (size_t)ox * C * esz0 + ch * 16));
         }
-        if (cnt == 0 && nlg == 0) {
+        if (empty) {
             background_bin<C>(rp, fp, n, bin, ox, oy, red, fast ? &pre : nullptr);
             return;
         }

@@ -102,10 +102,10 @@ __device__ __forceinline__ int order_class(int count)
 // longest lists first, background bins last; 2: the same order for the non-empty bins with the background bins spread evenly
 // between them (a background CTA only streams its reference tile: it mixes well with the compute-bound ones)
 template <int MODE>
-__device__ __forceinline__ void ordered_bin(const RasterParams& rp, int& n, int& bin)
+__device__ __forceinline__ int ordered_bin(const RasterParams& rp, int& n, int& bin)      // returns the bin's class, -1 = unknown (identity order)
 {
     n = blockIdx.y; bin = blockIdx.x;
-    if (MODE == 0 || !rp.bin_order) return;
+    if (MODE == 0 || !rp.bin_order) return -1;
     const int g = n / rp.order_gv;
     int r = (n - g * rp.order_gv) * rp.NB + bin;                 // rank of this CTA inside its group of views
     const int4 hi = __ldg(reinterpret_cast<const int4*>(rp.order_count + ORDER_CLASSES * g) + 1);
@@ -127,6 +127,7 @@ __device__ __forceinline__ void ordered_bin(const RasterParams& rp, int& n, int&
     const int id = __ldg(rp.bin_order + ((size_t)g * ORDER_CLASSES + cls) * ((size_t)rp.order_gv * rp.NB) + r);
     n = g * rp.order_gv + id / rp.NB;
     bin = id - (id / rp.NB) * rp.NB;
+    return cls;
 }
 
 struct SnappedTri {

@@ -51,6 +51,7 @@ struct FusedParams {
 // band split of the camera-split mode: bin row `by` of view n belongs to this rank?
 __device__ __forceinline__ bool outside_band(const FusedParams& fp, int n, int by)
 {
+    if (fp.vpf <= 1 && fp.row_lo <= 0 && by < fp.row_hi) return false;          // no band split (the common case): no division
     const int c = n % fp.vpf;
     return (c == 0 && by < fp.row_lo) || (c == fp.vpf - 1 && by >= fp.row_hi);
 }
@@ -317,8 +318,16 @@ __global__ void __launch_bounds__(FINE_THREADS, FPC_FUSED_MINBLOCKS) k_fused(Ras
     WarpStage* stage = reinterpret_cast<WarpStage*>(smem + sizeof(unsigned long long) * BIN * BIN);
     __shared__ double red[FINE_WARPS];
 
-    int bin, n;
-    const int cls = ordered_bin<FPC_ORDER_MODE>(rp, n, bin);       // long triangle lists first (k_fill)
+    // which (view, bin) this CTA works on: long triangle lists first (k_fill); looked up by one thread — the look-up is ~150
+    // instructions, and for the 2/3 of the CTAs that only stream a background tile it would otherwise be their main cost
+    __shared__ int s_ticket[3];
+    if (threadIdx.x == 0) {
+        int n_, bin_;
+        s_ticket[2] = ordered_bin<FPC_ORDER_MODE>(rp, n_, bin_);
+        s_ticket[0] = n_; s_ticket[1] = bin_;
+    }
+    __syncthreads();
+    const int n = s_ticket[0], bin = s_ticket[1], cls = s_ticket[2];
     const int ox = (bin % rp.BW) * BIN, oy = (bin / rp.BW) * BIN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 

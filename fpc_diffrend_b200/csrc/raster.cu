@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_fill(RasterParams rp)
             if (threadIdx.x < ORDER_CLASSES) s_cls[threadIdx.x] = 0;
             __syncthreads();
             const int any_large = rp.large_count[n] != 0;               // large triangles are walked in every bin of the view
-            const int g = n / rp.order_gv, nin = n - g * rp.order_gv;
+            const int g = n / ORDER_GROUP_VIEWS, nin = n - g * ORDER_GROUP_VIEWS;
             int cls[HIST_MAX_BINS / BIN_TPB], rk[HIST_MAX_BINS / BIN_TPB];
 #pragma unroll
             for (int k = 0; k < HIST_MAX_BINS / BIN_TPB; k++) {
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_fill(RasterParams rp)
 #pragma unroll
             for (int k = 0; k < HIST_MAX_BINS / BIN_TPB; k++) {
                 const int b = threadIdx.x + k * BIN_TPB;
-                if (b < rp.NB) rp.bin_order[((size_t)g * ORDER_CLASSES + cls[k]) * ((size_t)rp.order_gv * rp.NB) + s_base[cls[k]] + rk[k]] = nin * rp.NB + b;
+                if (b < rp.NB) rp.bin_order[((size_t)g * ORDER_CLASSES + cls[k]) * ((size_t)ORDER_GROUP_VIEWS * rp.NB) + s_base[cls[k]] + rk[k]] = (nin << 16) | b;
             }
         }
     }
@@ -422,7 +422,6 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.clip_cap = L.clip_cap;
     rp.pad_i_src = pad_i_src; rp.pad_i_dst = pad_i_dst; rp.pad_i_n = pad_i_src ? pad_i_n : 0;
     rp.order_count = (int*)(s + L.off_order_count);
-    rp.order_gv = ORDER_GROUP_VIEWS;
     rp.bin_order = (rp.NB <= HIST_MAX_BINS) ? (int*)(s + L.off_order) : nullptr;       // (written by k_fill<true>)
     FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
     rp.slot_grad = slot_grad;

@@ -83,8 +83,7 @@ struct RasterParams {
     // launch order of the fused kernels' CTAs (k_fill): within groups of order_gv views, bins sorted by list-length class, longest
     // first, empty bins last — the short background CTAs fill the gaps the long ones leave at the end of the launch
     int* order_count;                // [ngroups * ORDER_CLASSES] bins per class (zeroed with the counters)
-    int* bin_order;                  // [ngroups * ORDER_CLASSES * order_gv * NB] (view-in-group * NB + bin) per class; null: identity order
-    int order_gv;
+    int* bin_order;                  // [ngroups * ORDER_CLASSES * ORDER_GROUP_VIEWS * NB] (view in group << 16 | bin) per class; null: identity order
 };
 
 constexpr int ORDER_CLASSES = 8;
@@ -106,14 +105,14 @@ __device__ __forceinline__ int ordered_bin(const RasterParams& rp, int& n, int& 
 {
     n = blockIdx.y; bin = blockIdx.x;
     if (MODE == 0 || !rp.bin_order) return -1;
-    const int g = n / rp.order_gv;
-    int r = (n - g * rp.order_gv) * rp.NB + bin;                 // rank of this CTA inside its group of views
+    const int g = n / ORDER_GROUP_VIEWS;
+    int r = (n - g * ORDER_GROUP_VIEWS) * rp.NB + bin;           // rank of this CTA inside its group of views
     const int4 hi = __ldg(reinterpret_cast<const int4*>(rp.order_count + ORDER_CLASSES * g) + 1);
     const int4 lo = __ldg(reinterpret_cast<const int4*>(rp.order_count + ORDER_CLASSES * g));
     const int cnt[ORDER_CLASSES] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     int cls = ORDER_CLASSES - 1;
     if (MODE == 2 && cnt[0] > 0) {
-        const int total = min(rp.order_gv, rp.N - g * rp.order_gv) * rp.NB;
+        const int total = min(ORDER_GROUP_VIEWS, rp.N - g * ORDER_GROUP_VIEWS) * rp.NB;
         const int k = total / cnt[0];                            // every k-th CTA of the group is a background bin
         const int q = r / k;
         if (r - q * k == k - 1 && q < cnt[0]) { cls = 0; r = q; }
@@ -124,9 +123,9 @@ __device__ __forceinline__ int ordered_bin(const RasterParams& rp, int& n, int& 
         for (int c = ORDER_CLASSES - 1; c > 0; c--)
             if (cls == c && r >= cnt[c]) { r -= cnt[c]; cls = c - 1; }
     }
-    const int id = __ldg(rp.bin_order + ((size_t)g * ORDER_CLASSES + cls) * ((size_t)rp.order_gv * rp.NB) + r);
-    n = g * rp.order_gv + id / rp.NB;
-    bin = id - (id / rp.NB) * rp.NB;
+    const int id = __ldg(rp.bin_order + ((size_t)g * ORDER_CLASSES + cls) * ((size_t)ORDER_GROUP_VIEWS * rp.NB) + r);    // view in group << 16 | bin
+    n = g * ORDER_GROUP_VIEWS + (id >> 16);
+    bin = id & 0xffff;
     return cls;
 }
 

@@ -9,8 +9,10 @@
 //     representable in TF32) and lo = x - hi (exact in fp32) into a twin buffer with the same swizzled layout;
 //   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=64, K=8) three times per k-step
 //     (hi*hi + hi*lo + lo*hi) into a 128x64 fp32 accumulator in TMEM; tcgen05.commit releases the stage;
-//   * the splitter warps then read the accumulator back with tcgen05.ld (one TMEM lane = one row per thread) and store
-//     it transposed, out[(z*N + n)*ldo + m], so that the lanes of a warp write consecutive addresses.
+//   * four epilogue warps read the accumulator back with tcgen05.ld (one TMEM lane = one row per thread) and store
+//     it transposed, out[(z*N + n)*ldo + m], so that the lanes of a warp write consecutive addresses;
+//   * the CTAs are persistent (one per SM) and the accumulator is double-buffered in TMEM: the epilogue of one tile overlaps
+//     the loads, splits and MMAs of the next.
 // The GEMM is far left of the tensor ridge (AI ~ 24 flop/B at F = 64): the roofline that bounds it is HBM (D is read
 // once: 48 MB at config 3); the tensor pipe only has to keep up with the stream.
 #include <cuda.h>
@@ -27,9 +29,10 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;               // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;               //  8 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // A hi | A lo | B hi | B lo
-constexpr int TC_THREADS = 192;                             // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: split + epilogue
+constexpr int TC_THREADS = 320;                             // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: split, warps 6-9: epilogue
 constexpr int TC_SPLIT_THREADS = 128;
-constexpr unsigned TC_TMEM_COLS = 64;
+constexpr int TC_EPI_THREADS = 128;
+constexpr unsigned TC_TMEM_COLS = 128;                      // two 128 x 64 fp32 accumulators
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
 // kind::tf32 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2 at bits 7-9 and 10-12), both K-major,
@@ -82,23 +85,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// C[M,N] = A[M,K] B[N,K]^T (3xTF32); grid (M tiles, N tiles, K splits); out[(z*N + n)*ldo + m] = C[m,n] (+ bias[m])
+// C[M,N] = A[M,K] B[N,K]^T (3xTF32); out[(z*N + n)*ldo + m] = C[m,n] (+ bias[m]).  PERSISTENT: one CTA per SM walks the tiles
+// (m tile, n tile, K split) blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring and the splitters run straight on into the next
+// tile, the MMA warp alternates between TWO accumulators in TMEM and a separate group of four epilogue warps drains accumulator
+// j while the MMAs of tile j + 1 are already running (round 1 had one tile per CTA: prologue, 7 k-steps and epilogue in series).
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_3xtf32(const __grid_constant__ CUtensorMap map_a,
                                                                const __grid_constant__ CUtensorMap map_b, int M, int N,
-                                                               int num_kb, int kb_per_split, const float* __restrict__ bias,
-                                                               float* __restrict__ out, int ldo)
+                                                               int num_kb, int kb_per_split, int tiles_m, int tiles_n, int total_tiles,
+                                                               const float* __restrict__ bias, float* __restrict__ out, int ldo)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(smem_raw) + 1023) & ~(size_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
-    // bars[0..S) full (TMA landed), [S..2S) ready (split done), [2S..3S) empty (MMA done), [3S] accumulator complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+    // bars[0..S) full (TMA landed), [S..2S) ready (split done), [2S..3S) empty (MMA done), [3S..3S+2) accumulator full, [3S+2..3S+4) accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 4);
     const uint32_t bar0 = smem_u32(bars);
-    const uint32_t full0 = bar0, ready0 = bar0 + 8 * TC_STAGES, empty0 = bar0 + 16 * TC_STAGES, accum_bar = bar0 + 24 * TC_STAGES;
+    const uint32_t full0 = bar0, ready0 = bar0 + 8 * TC_STAGES, empty0 = bar0 + 16 * TC_STAGES;
+    const uint32_t accf0 = bar0 + 24 * TC_STAGES, acce0 = accf0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, n_blk = blockIdx.y, z = blockIdx.z;
-    const int kb0 = z * kb_per_split;
-    const int nkb = min(kb_per_split, num_kb - kb0);            // >= 1 (host)
 
     if (threadIdx.x == 32) {
         for (int s = 0; s < TC_STAGES; s++) {
@@ -106,7 +110,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_3xtf32(const __grid_cons
             mbar_init(ready0 + 8 * s, TC_SPLIT_THREADS);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; a++) {
+            mbar_init(accf0 + 8 * a, 1);
+            mbar_init(acce0 + 8 * a, TC_EPI_THREADS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -119,93 +126,131 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_3xtf32(const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t smem0 = smem_u32(smem);
 
+    // tile -> (m block, n block, first k block, k blocks)
+    auto decode = [&](int tile, int& m_blk, int& n_blk, int& z, int& kb0, int& nkb) {
+        m_blk = tile % tiles_m;
+        const int rest = tile / tiles_m;
+        n_blk = rest % tiles_n;
+        z = rest / tiles_n;
+        kb0 = z * kb_per_split;
+        nkb = min(kb_per_split, num_kb - kb0);                  // >= 1 (host)
+    };
+
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int i = 0; i < nkb; i++) {
-                const int s = i % TC_STAGES;
-                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const uint32_t sa = smem0 + (uint32_t)s * TC_STAGE_BYTES;
-                mbar_expect_tx(full0 + 8 * s, TC_A_BYTES + TC_B_BYTES);
-                tma_load_2d(sa, &map_a, full0 + 8 * s, (kb0 + i) * TC_BK, m_blk * TC_BM);
-                tma_load_2d(sa + 2 * TC_A_BYTES, &map_b, full0 + 8 * s, (kb0 + i) * TC_BK, n_blk * TC_BN);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int m_blk, n_blk, z, kb0, nkb;
+                decode(tile, m_blk, n_blk, z, kb0, nkb);
+                for (int i = 0; i < nkb; i++, it++) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    const uint32_t sa = smem0 + (uint32_t)s * TC_STAGE_BYTES;
+                    mbar_expect_tx(full0 + 8 * s, TC_A_BYTES + TC_B_BYTES);
+                    tma_load_2d(sa, &map_a, full0 + 8 * s, (kb0 + i) * TC_BK, m_blk * TC_BM);
+                    tma_load_2d(sa + 2 * TC_A_BYTES, &map_b, full0 + 8 * s, (kb0 + i) * TC_BK, n_blk * TC_BN);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            for (int i = 0; i < nkb; i++) {
-                const int s = i % TC_STAGES;
-                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-                mbar_wait(ready0 + 8 * s, ph);
+            int it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, j++) {
+                int m_blk, n_blk, z, kb0, nkb;
+                decode(tile, m_blk, n_blk, z, kb0, nkb);
+                const int acc = j & 1;
+                mbar_wait(acce0 + 8 * acc, ((uint32_t)(j >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem0 + (uint32_t)s * TC_STAGE_BYTES;
-                const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
-                const uint64_t b_hi = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + TC_B_BYTES);
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * TC_BN);
+                for (int i = 0; i < nkb; i++, it++) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                    mbar_wait(ready0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem0 + (uint32_t)s * TC_STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
+                    const uint64_t b_hi = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + TC_B_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; k++) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);          // 32 bytes per K = 8 step inside the swizzle row
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, (i > 0 || k > 0) ? 1u : 0u);
-                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, 1u);
-                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, 1u);
+                    for (int k = 0; k < TC_BK / 8; k++) {
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);          // 32 bytes per K = 8 step inside the swizzle row
+                        umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_acc, a_hi + adv, b_lo + adv, 1u);
+                        umma_tf32(tmem_acc, a_lo + adv, b_hi + adv, 1u);
+                    }
+                    umma_commit(empty0 + 8 * s);                                    // stage free once these MMAs have read it
                 }
-                umma_commit(empty0 + 8 * s);                                    // stage free once these MMAs have read it
+                umma_commit(accf0 + 8 * acc);                                       // accumulator complete
             }
-            umma_commit(accum_bar);                                             // accumulator complete
+        }
+    } else if (warp < 2 + TC_SPLIT_THREADS / 32) {
+        // ===== splitters (hi / lo) =====
+        const int tid = threadIdx.x - 64;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int m_blk, n_blk, z, kb0, nkb;
+            decode(tile, m_blk, n_blk, z, kb0, nkb);
+            for (int i = 0; i < nkb; i++, it++) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
+                uint4* a_hi = reinterpret_cast<uint4*>(st);
+                uint4* a_lo = reinterpret_cast<uint4*>(st + TC_A_BYTES);
+                uint4* b_hi = reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES);
+                uint4* b_lo = reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+                for (int jj = 0; jj < TC_A_BYTES / 16 / TC_SPLIT_THREADS; jj++) {
+                    const int o = tid + jj * TC_SPLIT_THREADS;
+                    uint4 v = a_hi[o], h, l;
+                    h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+                    a_hi[o] = h; a_lo[o] = l;
+                }
+#pragma unroll
+                for (int jj = 0; jj < TC_B_BYTES / 16 / TC_SPLIT_THREADS; jj++) {
+                    const int o = tid + jj * TC_SPLIT_THREADS;
+                    uint4 v = b_hi[o], h, l;
+                    h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+                    b_hi[o] = h; b_lo[o] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMA (async proxy)
+                mbar_arrive(ready0 + 8 * s);
+            }
         }
     } else {
-        // ===== splitters (hi / lo), then epilogue =====
-        const int tid = threadIdx.x - 64;
-        for (int i = 0; i < nkb; i++) {
-            const int s = i % TC_STAGES;
-            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-            mbar_wait(full0 + 8 * s, ph);
-            unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-            uint4* a_hi = reinterpret_cast<uint4*>(st);
-            uint4* a_lo = reinterpret_cast<uint4*>(st + TC_A_BYTES);
-            uint4* b_hi = reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES);
-            uint4* b_lo = reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + TC_B_BYTES);
+        // ===== epilogue: TMEM lane quarter of this warp is (warp index % 4) =====
+        int j = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, j++) {
+            int m_blk, n_blk, z, kb0, nkb;
+            decode(tile, m_blk, n_blk, z, kb0, nkb);
+            const int acc = j & 1;
+            mbar_wait(accf0 + 8 * acc, (uint32_t)(j >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = 32 * (warp & 3) + lane;
+            const int m = m_blk * TC_BM + row;
+            const float bv = (bias && m < M) ? __ldg(bias + m) : 0.f;
+            float v[TC_BN];
 #pragma unroll
-            for (int j = 0; j < TC_A_BYTES / 16 / TC_SPLIT_THREADS; j++) {
-                const int o = tid + j * TC_SPLIT_THREADS;
-                uint4 v = a_hi[o], h, l;
-                h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-                l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-                l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-                l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-                l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-                a_hi[o] = h; a_lo[o] = l;
-            }
-#pragma unroll
-            for (int j = 0; j < TC_B_BYTES / 16 / TC_SPLIT_THREADS; j++) {
-                const int o = tid + j * TC_SPLIT_THREADS;
-                uint4 v = b_hi[o], h, l;
-                h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-                l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-                l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-                l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-                l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-                b_hi[o] = h; b_lo[o] = l;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMA (async proxy)
-            mbar_arrive(ready0 + 8 * s);
-        }
-        // epilogue: TMEM lane quarter of this warp is (warp index % 4)
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = 32 * (warp & 3) + lane;
-        const int m = m_blk * TC_BM + row;
-        const float bv = (bias && m < M) ? __ldg(bias + m) : 0.f;
-#pragma unroll
-        for (int half = 0; half < TC_BN / 32; half++) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(32 * half), v);
+            for (int half = 0; half < TC_BN / 32; half++)
+                tmem_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(acc * TC_BN + 32 * half), v + 32 * half);
+            // the accumulator is in registers: hand it back to the MMA warp before the (slow) global stores
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(acce0 + 8 * acc);
             if (m < M) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int n = n_blk * TC_BN + 32 * half + j;
-                    if (n < N) out[((size_t)z * N + n) * ldo + m] = v[j] + bv;
+                for (int jn = 0; jn < TC_BN; jn++) {
+                    const int n = n_blk * TC_BN + jn;
+                    if (n < N) out[((size_t)z * N + n) * ldo + m] = v[jn] + bv;
                 }
             }
         }
@@ -275,8 +320,13 @@ int launch_gemm(const float* A, const float* Bm, long long M, long long N, long 
     const int num_kb = fpc_div_up(K, TC_BK);
     const int per = fpc_div_up(num_kb, splits);
     const int zs = fpc_div_up(num_kb, per);                 // every split owns >= 1 k-block
-    dim3 grid(fpc_div_up(M, TC_BM), fpc_div_up(N, TC_BN), zs);
-    k_gemm_3xtf32<<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_b, (int)M, (int)N, num_kb, per, bias, out, ldo);
+    const int tiles_m = fpc_div_up(M, TC_BM), tiles_n = fpc_div_up(N, TC_BN);
+    const long long total = (long long)tiles_m * tiles_n * zs;
+    FPC_CHECK_ARG(total < (1LL << 30), "blend_tc: too many tiles (%lld)", total);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(total < sms ? total : sms);         // persistent: one CTA per SM (192 KB of shared memory each)
+    k_gemm_3xtf32<<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_b, (int)M, (int)N, num_kb, per, tiles_m, tiles_n, (int)total, bias, out, ldo);
     FPC_LAUNCH_CHECK();
     *splits_used = zs;
     return FPC_OK;

@@ -5,8 +5,10 @@
 // Both are C[M,N] = A[M,K] B[N,K]^T with K-major operands, computed by ONE kernel:
 //   * TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) streams 128x32 / 64x32 fp32 tiles into a 4-stage shared-memory ring;
 //   * the 1e-5 absolute tolerance of the north-star rules out plain TF32 (10-bit mantissa), so the kernel runs the
-//     3xTF32 split: four "splitter" warps rewrite every landed tile in place as hi = x & 0xFFFFE000 (exactly
-//     representable in TF32) and lo = x - hi (exact in fp32) into a twin buffer with the same swizzled layout;
+//     3xTF32 split: four "splitter" warps compute lo = x - (x & 0xFFFFE000) (exact in fp32) of every landed tile into a twin
+//     buffer with the same swizzled layout; the landed tile itself is the `hi` operand — the tensor core reads only the upper
+//     19 bits of a kind::tf32 operand, i.e. exactly x & 0xFFFFE000 (measured: bit-identical results with and without masking
+//     the tile in place, round 2);
 //   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=64, K=8) three times per k-step
 //     (hi*hi + hi*lo + lo*hi) into a 128x64 fp32 accumulator in TMEM; tcgen05.commit releases the stage;
 //   * four epilogue warps read the accumulator back with tcgen05.ld (one TMEM lane = one row per thread) and store
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_3xtf32(const __grid_cons
                     l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
                     l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
                     l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-                    a_hi[o] = h; a_lo[o] = l;
+                    a_lo[o] = l;            // (the raw tile serves as `hi`: kind::tf32 ignores the low 13 mantissa bits)
                 }
 #pragma unroll
                 for (int jj = 0; jj < TC_B_BYTES / 16 / TC_SPLIT_THREADS; jj++) {
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_3xtf32(const __grid_cons
                     l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
                     l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
                     l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-                    b_hi[o] = h; b_lo[o] = l;
+                    b_lo[o] = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMA (async proxy)
                 mbar_arrive(ready0 + 8 * s);

@@ -869,8 +869,18 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     // no accumulator is zero-filled: every gradient slot and every element of grad_pos is written exactly once (k_setup only
     // zeroes the accumulator slots of large triangles); with antialias the bins are widened by the 2-px halo the fused kernel
     // resolves around its bin
+    // Launch order of the fused kernel's CTAs (raster_core.cuh: ordered_bin): longest triangle lists first, background bins last.
+    // k_fused gains 10 % from it at config 2.  The antialias kernel LOSES 2.5 % when a rank renders all views (config 3 / 5 on one
+    // GPU, 37k - 590k CTAs: neighbouring bins share texels, triangles and vertices, and its background CTAs are slow on their own)
+    // but GAINS 6 % when a rank renders a band of ~1 view under the 8-way camera split (4.6k CTAs in the band, 10 waves of 3 CTAs
+    // per SM: there the tail of the launch is what counts): it is ordered only when few CTAs have work.
+    const int bh = fpc_div_up(H, BIN), bw = fpc_div_up(W, BIN);
+    long long ctas = (long long)N * bh * bw;
+    if (views_per_frame > 0 && row_lo >= 0 && row_hi > 0)
+        ctas = (long long)(N / views_per_frame) * ((long long)views_per_frame * bh - row_lo - (bh - row_hi)) * bw;
+    const bool launch_order = !tri_opp || ctas <= 12288;
     int st = raster_bin_triangles(who, pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, slots, tri_opp ? AA_HALO : 0,
-                                  attr_tri4 ? attr_tri : nullptr, attr_tri4, T);
+                                  attr_tri4 ? attr_tri : nullptr, attr_tri4, T, launch_order);
     if (st != FPC_OK) return st;
     FusedParams fp;
     fp.attr = attr; fp.attr_tri = attr_tri; fp.attr_tri4 = attr_tri4; fp.Va = Va; fp.A = A; fp.tex = tex; fp.Ht = Ht; fp.Wt = Wt;

@@ -28,11 +28,10 @@ namespace {
 #ifndef FPC_AA_THREADS
 #define FPC_AA_THREADS 256
 #endif
-// launch order of the CTAs (raster_core.cuh: ordered_bin): identity.  Measured (round 2): longest-lists-first costs this kernel
-// 2.5 % at config 3 / 5 (neighbouring bins share texels, triangles and vertices: their CTAs are better off running together),
-// while the antialias-free kernel gains 10 % at config 2 from it
+// launch order of the CTAs (raster_core.cuh: ordered_bin): by list length when the host asks for it (RasterParams::bin_order is
+// set only for launches with few busy CTAs, see render_loss_fused_impl), identity otherwise
 #ifndef FPC_ORDER_MODE_AA
-#define FPC_ORDER_MODE_AA 0
+#define FPC_ORDER_MODE_AA 1
 #endif
 #ifndef FPC_AA_MINBLOCKS
 #define FPC_AA_MINBLOCKS 3

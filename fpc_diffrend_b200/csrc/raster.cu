@@ -387,7 +387,7 @@ ScratchLayout raster_layout(int N, int T, int NB)
 
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                          void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
-                         float* slot_grad, int halo, const int32_t* pad_i_src, int4* pad_i_dst, int pad_i_n)
+                         float* slot_grad, int halo, const int32_t* pad_i_src, int4* pad_i_dst, int pad_i_n, bool launch_order)
 {
     FPC_CHECK_ARG(pos && tri, "%s: pos and tri must be non-null", who);
     FPC_CHECK_ARG(N > 0 && V > 0 && T > 0 && H > 0 && W > 0, "%s: N, V, T, H, W must be positive (got %d %d %d %d %d)", who, N, V, T, H, W);
@@ -422,7 +422,7 @@ int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, 
     rp.clip_cap = L.clip_cap;
     rp.pad_i_src = pad_i_src; rp.pad_i_dst = pad_i_dst; rp.pad_i_n = pad_i_src ? pad_i_n : 0;
     rp.order_count = (int*)(s + L.off_order_count);
-    rp.bin_order = (rp.NB <= HIST_MAX_BINS) ? (int*)(s + L.off_order) : nullptr;       // (written by k_fill<true>)
+    rp.bin_order = (launch_order && rp.NB <= HIST_MAX_BINS) ? (int*)(s + L.off_order) : nullptr;       // (written by k_fill<true>)
     FPC_CUDA(cudaMemsetAsync(s, 0, L.zero_bytes, stream));
     rp.slot_grad = slot_grad;
     dim3 grid(fpc_div_up(T, BIN_TPB), N);

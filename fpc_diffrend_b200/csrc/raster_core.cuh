@@ -591,7 +591,7 @@ ScratchLayout raster_layout(int N, int T, int NB);
 int raster_bin_triangles(const char* who, const float* pos, const int32_t* tri, int N, int V, int T, int H, int W,
                          void* scratch, size_t scratch_bytes, cudaStream_t stream, RasterParams& rp,
                          float* slot_grad = nullptr, int halo = 0,
-                         const int32_t* pad_i_src = nullptr, int4* pad_i_dst = nullptr, int pad_i_n = 0);
+                         const int32_t* pad_i_src = nullptr, int4* pad_i_dst = nullptr, int pad_i_n = 0, bool launch_order = false);
 
 // slot of (view n, triangle t) in bin (bx, by): k = which of the (at most 2 x 2) bins the small triangle was listed in
 __device__ __forceinline__ int slot_index_k(int info, int bx, int by) { return ((by - ((info >> 10) & 1023)) << 1) | (bx - (info & 1023)); }

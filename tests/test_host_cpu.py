@@ -222,3 +222,26 @@ def test_algorithmic_byte_model_matches_survey():
     assert abs(b['render_loss_fused'] / 1e9 - 1.0988) < 1e-3           # the figure the bench line's roofline is quoted on
     # the single-frame GEMV streams D once per direction
     assert b['geometry_fwd'] > 4 * 3 * wl['V'] * wl['B'] and b['geometry_fwd'] < 1.1 * 4 * 3 * wl['V'] * wl['B']
+
+
+def test_reorder_rig_is_a_pure_renumbering(tiny_rig):
+    """fit.reorder_rig (FitConfig.reorder_vertices): vertices renumbered along a Morton curve — a permutation; every triangle
+    keeps its position in the list and its corner positions, D / v_base / vcol rows move with their vertex, the uv set is
+    untouched; neighbouring corners end up close in index; the result is cached on the rig."""
+    from fpc_diffrend_b200.fit import morton_order, reorder_rig
+    rig = tiny_rig
+    V = rig.V
+    r2, perm = reorder_rig(rig)
+    assert sorted(perm.tolist()) == list(range(V))
+    assert np.array_equal(r2.v_base.reshape(V, 3), rig.v_base.reshape(V, 3)[perm])
+    assert np.array_equal(r2.D.reshape(V, 3, -1), rig.D.reshape(V, 3, -1)[perm])
+    assert np.array_equal(r2.vcol, rig.vcol[perm])
+    assert np.array_equal(r2.v_base.reshape(V, 3)[r2.pos_idx], rig.v_base.reshape(V, 3)[rig.pos_idx])      # same triangles, same order
+    assert r2.uv is rig.uv and r2.uv_idx is rig.uv_idx and r2.pos_idx.dtype == np.int32
+    spread = lambda idx: np.abs(idx[:, 0].astype(np.int64) - idx[:, 1]).mean()
+    assert spread(r2.pos_idx) < 0.25 * spread(rig.pos_idx)
+    assert reorder_rig(rig)[0] is r2
+    # the curve itself: points on a line come back in line order, whatever the input order
+    pts = np.stack([np.linspace(0, 1, 50)] * 3, axis=1)
+    shuffle = np.random.default_rng(0).permutation(50)
+    assert np.array_equal(shuffle[morton_order(pts[shuffle])], np.arange(50))

@@ -306,6 +306,9 @@ __device__ __forceinline__ void background_bin(const RasterParams& rp, const Fus
 #ifndef FPC_ORDER_MODE
 #define FPC_ORDER_MODE 1
 #endif
+#ifndef FPC_AA_ORDER_MAX_CTAS
+#define FPC_AA_ORDER_MAX_CTAS 20480          // the antialias kernel is launched in by-list-length order only up to this many busy CTAs
+#endif
 #ifndef FPC_FUSED_MINBLOCKS
 #define FPC_FUSED_MINBLOCKS 8
 #endif
@@ -873,12 +876,13 @@ static int render_loss_fused_impl(const char* who, const float* pos, const int32
     // k_fused gains 10 % from it at config 2.  The antialias kernel LOSES 2.5 % when a rank renders all views (config 3 / 5 on one
     // GPU, 37k - 590k CTAs: neighbouring bins share texels, triangles and vertices, and its background CTAs are slow on their own)
     // but GAINS 6 % when a rank renders a band of ~1 view under the 8-way camera split (4.6k CTAs in the band, 10 waves of 3 CTAs
-    // per SM: there the tail of the launch is what counts): it is ordered only when few CTAs have work.
+    // per SM: there the tail of the launch is what counts) and 1.3 % at 2 ranks (18.4k CTAs): it is ordered only up to
+    // FPC_AA_ORDER_MAX_CTAS busy CTAs.
     const int bh = fpc_div_up(H, BIN), bw = fpc_div_up(W, BIN);
     long long ctas = (long long)N * bh * bw;
     if (views_per_frame > 0 && row_lo >= 0 && row_hi > 0)
         ctas = (long long)(N / views_per_frame) * ((long long)views_per_frame * bh - row_lo - (bh - row_hi)) * bw;
-    const bool launch_order = !tri_opp || ctas <= 12288;
+    const bool launch_order = !tri_opp || ctas <= FPC_AA_ORDER_MAX_CTAS;
     int st = raster_bin_triangles(who, pos, tri, N, V, T, H, W, scratch, scratch_bytes, stream, rp, slots, tri_opp ? AA_HALO : 0,
                                   attr_tri4 ? attr_tri : nullptr, attr_tri4, T, launch_order);
     if (st != FPC_OK) return st;
